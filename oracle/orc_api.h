@@ -1,0 +1,123 @@
+/*
+ * orc_api.h -- the C interface shared by the two CPU checkers under oracle/.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product.
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load these libraries, and only as the checker.
+ *
+ * Two libraries export exactly this interface:
+ *   oracle/_ref/libptref.so   built by oracle/Makefile from ref_driver.cpp, which
+ *                             #includes the reference's own headers and links its
+ *                             scene.cpp / utilities.cpp where they lie under
+ *                             /root/reference (kind = "reference").
+ *   oracle/libptoracle.so     built from pt_oracle.c, a plain-C restatement with no
+ *                             glm / thrust / reference headers (kind = "port").
+ * tests/test_oracle_vs_ref.py requires them to agree bit for bit.
+ *
+ * The POD structs mirror /root/reference/src/sceneStructs.h byte for byte:
+ *   OrcGeom     <-> struct Geom      (sceneStructs.h:20-29)  236 B
+ *   OrcMaterial <-> struct Material  (sceneStructs.h:31-41)   44 B
+ *   OrcCamera   <-> struct Camera    (sceneStructs.h:43-52)   84 B
+ * Matrices are column-major (glm): m[4*c + r].
+ */
+#ifndef ORC_API_H
+#define ORC_API_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct OrcGeom {
+    int   type;            /* 0 = SPHERE, 1 = CUBE (sceneStructs.h:10-13) */
+    int   materialid;
+    float translation[3];
+    float rotation[3];
+    float scale[3];
+    float transform[16];
+    float inverseTransform[16];
+    float invTranspose[16];
+} OrcGeom;
+
+typedef struct OrcMaterial {
+    float color[3];
+    float specExponent;
+    float specColor[3];
+    float hasReflective;
+    float hasRefractive;
+    float indexOfRefraction;
+    float emittance;
+} OrcMaterial;
+
+typedef struct OrcCamera {
+    int   resolution[2];
+    float position[3];
+    float lookAt[3];
+    float view[3];
+    float up[3];
+    float right[3];
+    float fov[2];
+    float pixelLength[2];
+} OrcCamera;
+
+enum { ORC_MODE_GOLDEN_DIFFUSE = 0, ORC_MODE_FULL = 1 };
+
+/* "reference" or "port" */
+const char *orc_kind(void);
+
+/* ---- scene file -> POD (src/scene.cpp) ---- */
+void *orc_scene_load(const char *path);                 /* NULL if the file cannot be opened */
+void  orc_scene_counts(void *scene, int *ngeoms, int *nmaterials);
+void  orc_scene_get(void *scene, OrcGeom *geoms, OrcMaterial *materials, OrcCamera *cam,
+                    int *iterations, int *traceDepth, char *imageName, int nameCap);
+void  orc_scene_free(void *scene);
+
+/* camera fix-up the app performs before frame 1 (src/main.cpp:53-67, 102-120) */
+void  orc_camera_fixup(OrcCamera *cam);
+
+/* buildTransformationMatrix + glm::inverse + glm::inverseTranspose
+ * (src/utilities.cpp:65-72, src/scene.cpp:82-85) */
+void  orc_build_transform(const float t[3], const float r[3], const float s[3],
+                          float transform[16], float inverse[16], float invTranspose[16]);
+
+/* ---- hot-path pieces ---- */
+/* makeSeededRandomEngine + n draws of u01 (src/pathtrace.cu:41-45, 240-241) */
+void  orc_rng_u01(int iter, int index, int depth, int n, float *out);
+
+/* generateRayFromCamera (src/pathtrace.cu:122-143): origins/dirs are P*3 floats */
+void  orc_generate_rays(const OrcCamera *cam, float *origins, float *dirs);
+
+/* computeIntersections closest-hit loop (src/pathtrace.cu:162-211) over arbitrary rays.
+ * hit[i] = geom index or -1; t[i] = t_min or -1; normal = 3 floats; outside = flag of the
+ * winning test (the reference drops it; refraction needs it). */
+void  orc_closest_hit(const OrcGeom *geoms, int ngeoms, const float *origins, const float *dirs,
+                      int n, int *hit, float *t, float *normal, int *outside);
+
+/* calculateRandomDirectionInHemisphere (src/interactions.h:10-42) with the engine seeded
+ * by (iter[i], index[i], depth[i]) */
+void  orc_hemisphere(const float *normals, int n, const int *iter, const int *index,
+                     const int *depth, float *outDirs);
+
+/* One shade/scatter step on given inputs:
+ *   miss (hit < 0)        : colour = 0, remaining = 0
+ *   emissive material     : colour *= m.color * m.emittance, remaining = 0
+ *   otherwise             : scatter (new origin/direction, colour *= albedo), remaining -= 1,
+ *                           and colour = 0 when remaining reaches 0
+ * in/out arrays are per path; the engine is seeded by (iter[i], index[i], depth[i]). */
+void  orc_shade(const OrcMaterial *materials, int mode, int n,
+                const int *hit, const int *materialIds, const float *t,
+                const float *normal, const int *outside,
+                const int *iter, const int *index, const int *depth,
+                float *origins, float *dirs, float *colors, int *remaining);
+
+/* The normative multi-bounce loop.  image (P*3 floats) is ACCUMULATED
+ * into (+=), one iteration after another in ascending order; alivePerDepth[d] += paths that
+ * enter bounce d (traceDepth entries).  Returns the number of path segments traced. */
+long long orc_render(const OrcGeom *geoms, int ngeoms, const OrcMaterial *materials, int nmaterials,
+                     const OrcCamera *cam, int traceDepth, int mode,
+                     int iterBegin, int nIters, float *image, long long *alivePerDepth,
+                     int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
