@@ -1,0 +1,199 @@
+/*
+ * ptb200.h -- C ABI of the B200-native wavefront path tracer (libptb200.so).
+ *
+ * Drop-in boundary for the renderer core of CIS565 Project3-CUDA-Path-Tracer.  Every entry point
+ * cites the reference interface it replaces (paths relative to the reference repository).  Plain
+ * pointers and sizes only: no C++ types, no torch types, no exceptions across the boundary.
+ * All functions return PTB_OK (0) or a negative PtbError; ptb_last_error() gives the message.
+ *
+ * The reference's three C++ symbols
+ *     void pathtraceInit(Scene *scene);                       src/pathtrace.h:6
+ *     void pathtraceFree();                                   src/pathtrace.h:7
+ *     void pathtrace(uchar4 *pbo, int frame, int iteration);  src/pathtrace.h:8
+ * are provided on top of this ABI by csrc/host/pathtrace.cpp.
+ *
+ * There is NO CPU fallback: every call that renders fails with PTB_ERR_CUDA when no sm_100 device
+ * is usable.
+ */
+#ifndef PTB200_H
+#define PTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PTB_ABI_VERSION 1
+
+/* ---- POD mirrors of src/sceneStructs.h (byte-identical; matrices column-major like glm) ---- */
+typedef struct PtbGeom {            /* struct Geom, src/sceneStructs.h:20-29, 236 bytes */
+    int32_t type;                   /* enum GeomType: 0 = SPHERE, 1 = CUBE (src/sceneStructs.h:10-13) */
+    int32_t materialid;
+    float   translation[3];
+    float   rotation[3];
+    float   scale[3];
+    float   transform[16];
+    float   inverseTransform[16];
+    float   invTranspose[16];
+} PtbGeom;
+
+typedef struct PtbMaterial {        /* struct Material, src/sceneStructs.h:31-41, 44 bytes */
+    float color[3];
+    float specularExponent;
+    float specularColor[3];
+    float hasReflective;
+    float hasRefractive;
+    float indexOfRefraction;
+    float emittance;
+} PtbMaterial;
+
+typedef struct PtbCamera {          /* struct Camera, src/sceneStructs.h:43-52, 84 bytes */
+    int32_t resolution[2];
+    float   position[3];
+    float   lookAt[3];
+    float   view[3];
+    float   up[3];
+    float   right[3];
+    float   fov[2];
+    float   pixelLength[2];
+} PtbCamera;
+
+typedef struct PtbUchar4 { uint8_t x, y, z, w; } PtbUchar4;   /* CUDA uchar4 (the GL PBO texel) */
+
+/* What pathtraceInit reads from `Scene*` (src/pathtrace.cu:79-93): geoms, materials,
+ * state.camera (after main.cpp's camera fix-up, src/main.cpp:102-120) and state.traceDepth. */
+typedef struct PtbSceneDesc {
+    const PtbGeom     *geoms;
+    int32_t            numGeoms;
+    const PtbMaterial *materials;
+    int32_t            numMaterials;
+    PtbCamera          camera;
+    int32_t            traceDepth;
+} PtbSceneDesc;
+
+enum PtbBsdfMode {
+    PTB_BSDF_GOLDEN_DIFFUSE = 0,    /* every non-emissive surface is Lambertian: reproduces img/REFERENCE_cornell.5000samp.png */
+    PTB_BSDF_FULL           = 1     /* diffuse + REFL (mirror) + REFR (Schlick dielectric) */
+};
+enum PtbPipeline {
+    PTB_PIPELINE_FUSED  = 0,        /* one kernel per bounce: raygen|load -> intersect -> shade -> compact -> gather */
+    PTB_PIPELINE_STAGED = 1         /* the reference's stage structure: raygen, intersect, [sort], shade, [compact], gather */
+};
+enum PtbAccel { PTB_ACCEL_AUTO = 0, PTB_ACCEL_BRUTE = 1, PTB_ACCEL_BVH = 2 };
+
+typedef struct PtbOptions {
+    int32_t device;                 /* CUDA ordinal; -1 = current device */
+    int32_t bsdfMode;               /* PtbBsdfMode */
+    int32_t pipeline;               /* PtbPipeline */
+    int32_t accel;                  /* PtbAccel */
+    int32_t batchIters;             /* iterations traced per wavefront (fused pipeline); 0 = default */
+    int32_t compaction;             /* staged pipeline: 1 = ballot/popc stream compaction, 0 = none (skeleton layout) */
+    int32_t sortMaterials;          /* staged pipeline: 1 = sort paths by material id before shading */
+    int32_t firstBounceCache;       /* 1 = cache bounce-0 hits across iterations (INSTRUCTION.md:87-89) */
+    int32_t useGraphs;              /* 1 = replay the per-batch launch sequence as a CUDA graph */
+    int32_t reserved0;
+    void   *stream;                 /* cudaStream_t to launch on; NULL = library-owned stream */
+    float  *externalAccum;          /* device pointer to W*H*3 floats to accumulate into; NULL = library-owned */
+} PtbOptions;
+
+typedef struct PtbStats {
+    int64_t iterations;             /* iterations traced since ptb_init */
+    int64_t segments;               /* path segments traced (sum over depth of paths entering that depth) */
+    int64_t kernelLaunches;         /* kernels this library launched since ptb_init */
+    int64_t alivePerDepth[64];      /* paths entering bounce d, summed over iterations */
+    int32_t traceDepth;
+    int32_t numGeoms;
+    int32_t bvhNodes;               /* 0 when brute force */
+    int32_t batchIters;
+    int64_t pathStateBytes;         /* bytes of path state resident in HBM */
+} PtbStats;
+
+enum PtbError {
+    PTB_OK = 0,
+    PTB_ERR_INVALID = -1,           /* bad argument / not initialised */
+    PTB_ERR_CUDA = -2,              /* CUDA runtime failure (no device, launch error, ...) */
+    PTB_ERR_UNSUPPORTED = -3,
+    PTB_ERR_IO = -4
+};
+
+typedef struct PtbContext PtbContext;
+
+void        ptb_default_options(PtbOptions *opts);
+const char *ptb_last_error(void);
+int         ptb_abi_version(void);
+
+/* pathtraceInit (src/pathtrace.cu:79-101): allocate + upload + zero the accumulation buffer.
+ * The scene arrays are copied; the caller keeps ownership. */
+int ptb_create(PtbContext **ctx, const PtbSceneDesc *scene, const PtbOptions *opts);
+/* pathtraceFree (src/pathtrace.cu:103-112).  NULL is a no-op (main.cpp:126 frees before the first init). */
+int ptb_destroy(PtbContext *ctx);
+
+/* pathtrace(pbo, frame, iter) (src/pathtrace.cu:284-393): trace iteration `iter` (1-based,
+ * src/main.cpp:132), add it to the accumulation buffer, write the RGBA8 preview into the device
+ * buffer `pbo` when non-NULL (sendImageToPBO, :48-68, :386) and copy the accumulated SUM to the host
+ * array `hostImage` (W*H*3 floats, the layout of scene->state.image) when non-NULL (:389-390).
+ * `frame` is accepted and ignored exactly like the reference (src/main.cpp:136). */
+int ptb_pathtrace(PtbContext *ctx, PtbUchar4 *pbo, int frame, int iter, float *hostImage);
+
+/* Batched form of the same loop for headless use: iterations iterBegin, iterBegin+iterStride, ...
+ * (count of them) without any host round trip.  iterStride > 1 is the samples-per-pixel split
+ * across GPUs (rank r of G renders r+1, r+1+G, ...).  Asynchronous on the context's stream. */
+int ptb_render(PtbContext *ctx, int iterBegin, int count, int iterStride);
+
+/* cudaMemcpy(hst_scene->state.image <- dev_image) (src/pathtrace.cu:389-390), decoupled from the loop.
+ * Synchronises the stream. */
+int ptb_download(PtbContext *ctx, float *hostImage);
+/* sendImageToPBO (src/pathtrace.cu:48-68) on demand; `samples` is the divisor `iter`. */
+int ptb_write_pbo(PtbContext *ctx, PtbUchar4 *devicePbo, int samples);
+/* zero the accumulation buffer and statistics (what re-running pathtraceInit does, src/pathtrace.cu:84-85) */
+int ptb_reset(PtbContext *ctx);
+int ptb_sync(PtbContext *ctx);
+int ptb_stats(PtbContext *ctx, PtbStats *out);          /* synchronises */
+/* device pointer of the W*H*3 float accumulation buffer (for a collective reduce across GPUs) */
+int ptb_accum_device_ptr(PtbContext *ctx, float **devPtr);
+/* (sum / samples) -> clamp[0,1]*255 -> truncate -> RGB8 with the horizontal flip of saveImage
+ * (src/main.cpp:83-89, src/image.cpp:27-30) computed on the device; `hostRgb8` = W*H*3 bytes. */
+int ptb_resolve_rgb8(PtbContext *ctx, int samples, uint8_t *hostRgb8);
+
+/* ---- stage-level entry points (used by the parity tests; host arrays in, host arrays out) ---- */
+/* generateRayFromCamera (src/pathtrace.cu:122-143): origins/dirs = W*H*3 floats each */
+int ptb_stage_raygen(PtbContext *ctx, float *origins, float *dirs);
+/* computeIntersections (src/pathtrace.cu:149-213) over n caller-supplied rays.
+ * accel: PTB_ACCEL_BRUTE / PTB_ACCEL_BVH / PTB_ACCEL_AUTO.  hit = geom index or -1, t = -1 on miss. */
+int ptb_stage_intersect(PtbContext *ctx, int accel, const float *origins, const float *dirs, int n,
+                        int32_t *hit, float *t, float *normal, int32_t *outside);
+/* one shade/scatter step (shadeFakeMaterial's replacement + scatterRay, src/pathtrace.cu:224-266,
+ * src/interactions.h:44-79) on caller-supplied hit records; arrays are updated in place. */
+int ptb_stage_shade(PtbContext *ctx, int n, const int32_t *hit, const float *t, const float *normal,
+                    const int32_t *outside, const int32_t *iter, const int32_t *pixelIndex,
+                    const int32_t *depth, float *origins, float *dirs, float *colors, int32_t *remaining);
+/* stream compaction (the stream_compaction submodule's job, INSTRUCTION.md:183-185): keeps ids whose
+ * flag is non-zero; returns the kept ids (any order) and their count. */
+int ptb_stage_compact(PtbContext *ctx, int n, const int32_t *ids, const int32_t *flags,
+                      int32_t *outIds, int32_t *outCount);
+/* material-id sort (INSTRUCTION.md:78-86): returns a permutation of 0..n-1 grouping equal keys */
+int ptb_stage_sort_keys(PtbContext *ctx, int n, const int32_t *keys, int numKeys, int32_t *outOrder);
+/* makeSeededRandomEngine + u01 draws on the device (src/pathtrace.cu:41-45, 240-241) */
+int ptb_stage_rng(PtbContext *ctx, int iter, int index, int depth, int n, float *out);
+
+/* ---- host-side pieces of the drop-in surface (C++ in csrc/host/, reachable over the C ABI) ---- */
+/* new Scene(filename) (src/scene.cpp:7-33); PTB_ERR_IO when the file cannot be opened */
+int  ptb_scene_load(const char *path, void **sceneOut);
+int  ptb_scene_counts(void *scene, int32_t *numGeoms, int32_t *numMaterials);
+int  ptb_scene_get(void *scene, PtbGeom *geoms, PtbMaterial *materials, PtbCamera *camera,
+                   int32_t *iterations, int32_t *traceDepth, char *imageName, int nameCap);
+void ptb_scene_free(void *scene);
+/* the camera rebuild main.cpp performs before the first frame (src/main.cpp:53-67, 102-120) */
+void ptb_camera_fixup(PtbCamera *camera);
+/* saveImage + image::savePNG / saveHDR (src/main.cpp:78-99, src/image.cpp:22-45): `sum` is the W*H*3
+ * accumulated image, divided by `samples`; flipX = 1 reproduces the reference's horizontal flip.
+ * ".png" / ".hdr" is appended to baseFilename. */
+int  ptb_save_png(const char *baseFilename, int w, int h, const float *sum, float samples, int flipX);
+int  ptb_save_hdr(const char *baseFilename, int w, int h, const float *sum, float samples, int flipX);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTB200_H */

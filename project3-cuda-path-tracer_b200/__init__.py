@@ -1,0 +1,344 @@
+"""Host-side Python mirror of the reference's renderer interface over the C ABI (include/ptb200.h).
+
+The reference drives its renderer through three free functions (src/pathtrace.h:6-8):
+    pathtraceInit(Scene*)  /  pathtrace(pbo, frame, iteration)  /  pathtraceFree()
+This module exposes the same three names with the same argument meaning for tests and benchmarks,
+plus a `Renderer` object for the batched / multi-GPU entry points.  All compute happens in
+libptb200.so (hand-written sm_100a kernels); there is no Python or CPU fallback -- importing works
+without a GPU (so the symbol table can be checked), every render call raises without one.
+
+The package directory name contains '-' (it mirrors the reference's repository name), so import it
+with   importlib.import_module("project3-cuda-path-tracer_b200")   or via `ptb200_loader.py`.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libptb200.so")
+
+GEOM_DT = np.dtype([("type", "<i4"), ("materialid", "<i4"), ("translation", "<f4", 3),
+                    ("rotation", "<f4", 3), ("scale", "<f4", 3), ("transform", "<f4", 16),
+                    ("inverseTransform", "<f4", 16), ("invTranspose", "<f4", 16)])
+MATERIAL_DT = np.dtype([("color", "<f4", 3), ("specularExponent", "<f4"), ("specularColor", "<f4", 3),
+                        ("hasReflective", "<f4"), ("hasRefractive", "<f4"),
+                        ("indexOfRefraction", "<f4"), ("emittance", "<f4")])
+CAMERA_DT = np.dtype([("resolution", "<i4", 2), ("position", "<f4", 3), ("lookAt", "<f4", 3),
+                      ("view", "<f4", 3), ("up", "<f4", 3), ("right", "<f4", 3), ("fov", "<f4", 2),
+                      ("pixelLength", "<f4", 2)])
+assert GEOM_DT.itemsize == 236 and MATERIAL_DT.itemsize == 44 and CAMERA_DT.itemsize == 84
+
+BSDF_GOLDEN_DIFFUSE, BSDF_FULL = 0, 1
+PIPELINE_FUSED, PIPELINE_STAGED = 0, 1
+ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH = 0, 1, 2
+
+
+class PtbCamera(C.Structure):
+    _fields_ = [("resolution", C.c_int32 * 2), ("position", C.c_float * 3), ("lookAt", C.c_float * 3),
+                ("view", C.c_float * 3), ("up", C.c_float * 3), ("right", C.c_float * 3),
+                ("fov", C.c_float * 2), ("pixelLength", C.c_float * 2)]
+
+
+class PtbSceneDesc(C.Structure):
+    _fields_ = [("geoms", C.c_void_p), ("numGeoms", C.c_int32), ("materials", C.c_void_p),
+                ("numMaterials", C.c_int32), ("camera", PtbCamera), ("traceDepth", C.c_int32)]
+
+
+class PtbOptions(C.Structure):
+    _fields_ = [("device", C.c_int32), ("bsdfMode", C.c_int32), ("pipeline", C.c_int32), ("accel", C.c_int32),
+                ("batchIters", C.c_int32), ("compaction", C.c_int32), ("sortMaterials", C.c_int32),
+                ("firstBounceCache", C.c_int32), ("useGraphs", C.c_int32), ("reserved0", C.c_int32),
+                ("stream", C.c_void_p), ("externalAccum", C.c_void_p)]
+
+
+class PtbStats(C.Structure):
+    _fields_ = [("iterations", C.c_int64), ("segments", C.c_int64), ("kernelLaunches", C.c_int64),
+                ("alivePerDepth", C.c_int64 * 64), ("traceDepth", C.c_int32), ("numGeoms", C.c_int32),
+                ("bvhNodes", C.c_int32), ("batchIters", C.c_int32), ("pathStateBytes", C.c_int64)]
+
+
+class PtbError(RuntimeError):
+    pass
+
+
+# every symbol include/ptb200.h declares (tests/test_abi.py checks the library exports all of them)
+ABI_SYMBOLS = [
+    "ptb_default_options", "ptb_last_error", "ptb_abi_version", "ptb_create", "ptb_destroy",
+    "ptb_pathtrace", "ptb_render", "ptb_download", "ptb_write_pbo", "ptb_reset", "ptb_sync",
+    "ptb_stats", "ptb_accum_device_ptr", "ptb_resolve_rgb8", "ptb_stage_raygen", "ptb_stage_intersect",
+    "ptb_stage_shade", "ptb_stage_compact", "ptb_stage_sort_keys", "ptb_stage_rng",
+    "ptb_scene_load", "ptb_scene_counts", "ptb_scene_get", "ptb_scene_free", "ptb_camera_fixup",
+    "ptb_save_png", "ptb_save_hdr",
+]
+
+_lib = None
+
+
+def lib():
+    """Load libptb200.so; fail loudly when the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: build it with __graft_entry__.build() (nvcc, sm_100a); "
+                              "there is no fallback implementation" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.ptb_last_error.restype = C.c_char_p
+        L.ptb_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(PtbSceneDesc), C.POINTER(PtbOptions)]
+        L.ptb_destroy.argtypes = [C.c_void_p]
+        L.ptb_pathtrace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.ptb_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+        L.ptb_download.argtypes = [C.c_void_p, C.c_void_p]
+        L.ptb_write_pbo.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ptb_reset.argtypes = [C.c_void_p]
+        L.ptb_sync.argtypes = [C.c_void_p]
+        L.ptb_stats.argtypes = [C.c_void_p, C.POINTER(PtbStats)]
+        L.ptb_accum_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ptb_resolve_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ptb_stage_raygen.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ptb_stage_intersect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
+        L.ptb_stage_shade.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
+        L.ptb_stage_compact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
+        L.ptb_stage_sort_keys.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.ptb_stage_rng.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        if hasattr(L, "ptb_scene_load"):
+            L.ptb_scene_load.restype = C.c_int
+            L.ptb_scene_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
+            L.ptb_scene_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+            L.ptb_scene_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
+                                        C.POINTER(C.c_int32), C.c_char_p, C.c_int]
+            L.ptb_scene_free.argtypes = [C.c_void_p]
+            L.ptb_camera_fixup.argtypes = [C.c_void_p]
+            L.ptb_save_png.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int]
+            L.ptb_save_hdr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int]
+        _lib = L
+    return _lib
+
+
+def _check(rc):
+    if rc != 0:
+        raise PtbError("ptb200 error %d: %s" % (rc, lib().ptb_last_error().decode()))
+
+
+class Scene:
+    """Mirror of the reference's `Scene` public members (src/scene.h:20-25): geoms, materials, state."""
+
+    def __init__(self, geoms, materials, camera, iterations=5000, trace_depth=8, image_name="image"):
+        self.geoms = np.ascontiguousarray(geoms, GEOM_DT)
+        self.materials = np.ascontiguousarray(materials, MATERIAL_DT)
+        self.camera = np.ascontiguousarray(camera, CAMERA_DT).reshape(1)
+        self.iterations = int(iterations)
+        self.traceDepth = int(trace_depth)
+        self.imageName = image_name
+        # state.image: the host accumulation buffer pathtrace() fills (src/sceneStructs.h:58)
+        self.image = np.zeros((self.pixels, 3), np.float32)
+
+    @property
+    def width(self):
+        return int(self.camera["resolution"][0][0])
+
+    @property
+    def height(self):
+        return int(self.camera["resolution"][0][1])
+
+    @property
+    def pixels(self):
+        return self.width * self.height
+
+    @classmethod
+    def load(cls, filename, fixup=True):
+        """`new Scene(filename)` (src/scene.cpp:7-33) followed, when `fixup`, by the camera fix-up the
+        app performs before the first frame (src/main.cpp:53-67, 102-120).  Host C++ in libptb200.so."""
+        L = lib()
+        h = C.c_void_p()
+        _check(L.ptb_scene_load(os.fsencode(filename), C.byref(h)))
+        ng, nm = C.c_int32(), C.c_int32()
+        L.ptb_scene_counts(h, C.byref(ng), C.byref(nm))
+        geoms = np.zeros(ng.value, GEOM_DT)
+        mats = np.zeros(nm.value, MATERIAL_DT)
+        cam = np.zeros(1, CAMERA_DT)
+        it, dp = C.c_int32(), C.c_int32()
+        name = C.create_string_buffer(256)
+        L.ptb_scene_get(h, geoms.ctypes.data, mats.ctypes.data, cam.ctypes.data, C.byref(it), C.byref(dp), name, 256)
+        L.ptb_scene_free(h)
+        if fixup:
+            L.ptb_camera_fixup(cam.ctypes.data)
+        return cls(geoms, mats, cam, it.value, dp.value, name.value.decode())
+
+
+class Renderer:
+    """One device context (PtbContext).  Keyword options map 1:1 onto PtbOptions."""
+
+    def __init__(self, scene, device=-1, bsdf=BSDF_FULL, pipeline=PIPELINE_FUSED, accel=ACCEL_AUTO,
+                 batch_iters=0, compaction=1, sort_materials=0, first_bounce_cache=0, use_graphs=1,
+                 stream=None, external_accum=None, trace_depth=None):
+        L = lib()
+        self.scene = scene
+        self._keep = (scene.geoms, scene.materials)
+        desc = PtbSceneDesc()
+        desc.geoms = scene.geoms.ctypes.data
+        desc.numGeoms = len(scene.geoms)
+        desc.materials = scene.materials.ctypes.data
+        desc.numMaterials = len(scene.materials)
+        C.memmove(C.addressof(desc.camera), scene.camera.ctypes.data, 84)
+        desc.traceDepth = scene.traceDepth if trace_depth is None else int(trace_depth)
+        opt = PtbOptions()
+        L.ptb_default_options(C.byref(opt))
+        opt.device, opt.bsdfMode, opt.pipeline, opt.accel = device, bsdf, pipeline, accel
+        opt.batchIters, opt.compaction, opt.sortMaterials = batch_iters, compaction, sort_materials
+        opt.firstBounceCache, opt.useGraphs = first_bounce_cache, use_graphs
+        opt.stream = stream
+        opt.externalAccum = external_accum
+        self.trace_depth = desc.traceDepth
+        self._h = C.c_void_p()
+        _check(L.ptb_create(C.byref(self._h), C.byref(desc), C.byref(opt)))
+
+    def close(self):
+        if self._h:
+            lib().ptb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- the reference's loop ----
+    def pathtrace(self, pbo, frame, iteration, host_image=None):
+        ptr = host_image.ctypes.data if host_image is not None else None
+        _check(lib().ptb_pathtrace(self._h, pbo, frame, iteration, ptr))
+
+    def render(self, iter_begin, count, iter_stride=1):
+        _check(lib().ptb_render(self._h, iter_begin, count, iter_stride))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.zeros((self.scene.pixels, 3), np.float32)
+        _check(lib().ptb_download(self._h, out.ctypes.data))
+        return out
+
+    def write_pbo(self, device_ptr, samples):
+        _check(lib().ptb_write_pbo(self._h, device_ptr, samples))
+
+    def reset(self):
+        _check(lib().ptb_reset(self._h))
+
+    def sync(self):
+        _check(lib().ptb_sync(self._h))
+
+    def stats(self):
+        s = PtbStats()
+        _check(lib().ptb_stats(self._h, C.byref(s)))
+        return {"iterations": s.iterations, "segments": s.segments, "kernel_launches": s.kernelLaunches,
+                "alive_per_depth": [int(s.alivePerDepth[d]) for d in range(s.traceDepth)],
+                "trace_depth": s.traceDepth, "num_geoms": s.numGeoms, "bvh_nodes": s.bvhNodes,
+                "batch_iters": s.batchIters, "path_state_bytes": s.pathStateBytes}
+
+    def accum_device_ptr(self):
+        p = C.c_void_p()
+        _check(lib().ptb_accum_device_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def resolve_rgb8(self, samples):
+        out = np.zeros((self.scene.height, self.scene.width, 3), np.uint8)
+        _check(lib().ptb_resolve_rgb8(self._h, samples, out.ctypes.data))
+        return out
+
+    # ---- stage-level entry points ----
+    def stage_raygen(self):
+        o = np.zeros((self.scene.pixels, 3), np.float32)
+        d = np.zeros((self.scene.pixels, 3), np.float32)
+        _check(lib().ptb_stage_raygen(self._h, o.ctypes.data, d.ctypes.data))
+        return o, d
+
+    def stage_intersect(self, origins, dirs, accel=ACCEL_AUTO):
+        o = np.ascontiguousarray(origins, np.float32)
+        d = np.ascontiguousarray(dirs, np.float32)
+        n = o.shape[0]
+        hit = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float32)
+        nrm = np.zeros((n, 3), np.float32)
+        outside = np.zeros(n, np.int32)
+        _check(lib().ptb_stage_intersect(self._h, accel, o.ctypes.data, d.ctypes.data, n, hit.ctypes.data,
+                                         t.ctypes.data, nrm.ctypes.data, outside.ctypes.data))
+        return hit, t, nrm, outside
+
+    def stage_shade(self, hit, t, normal, outside, it, pixel_index, depth, origins, dirs, colors, remaining):
+        i32 = lambda a: np.ascontiguousarray(a, np.int32)
+        hit, outside, it, pixel_index, depth = map(i32, (hit, outside, it, pixel_index, depth))
+        t = np.ascontiguousarray(t, np.float32)
+        normal = np.ascontiguousarray(normal, np.float32)
+        o = np.array(origins, np.float32, copy=True, order="C")
+        d = np.array(dirs, np.float32, copy=True, order="C")
+        c = np.array(colors, np.float32, copy=True, order="C")
+        rem = np.array(remaining, np.int32, copy=True)
+        _check(lib().ptb_stage_shade(self._h, len(hit), hit.ctypes.data, t.ctypes.data, normal.ctypes.data,
+                                     outside.ctypes.data, it.ctypes.data, pixel_index.ctypes.data,
+                                     depth.ctypes.data, o.ctypes.data, d.ctypes.data, c.ctypes.data, rem.ctypes.data))
+        return o, d, c, rem
+
+    def stage_compact(self, ids, flags):
+        ids = np.ascontiguousarray(ids, np.int32)
+        flags = np.ascontiguousarray(flags, np.int32)
+        out = np.zeros(len(ids), np.int32)
+        cnt = C.c_int32()
+        _check(lib().ptb_stage_compact(self._h, len(ids), ids.ctypes.data, flags.ctypes.data, out.ctypes.data, C.byref(cnt)))
+        return out[:cnt.value], cnt.value
+
+    def stage_sort_keys(self, keys, num_keys):
+        keys = np.ascontiguousarray(keys, np.int32)
+        order = np.zeros(len(keys), np.int32)
+        _check(lib().ptb_stage_sort_keys(self._h, len(keys), keys.ctypes.data, num_keys, order.ctypes.data))
+        return order
+
+    def stage_rng(self, it, index, depth, n):
+        out = np.zeros(n, np.float32)
+        _check(lib().ptb_stage_rng(self._h, it, index, depth, n, out.ctypes.data))
+        return out
+
+
+# ---- the reference's three entry points (src/pathtrace.h:6-8), global-state form ----
+_current = None
+_current_opts = {}
+
+
+def set_options(**kw):
+    """Options applied by the next pathtraceInit (the reference has compile-time toggles instead)."""
+    _current_opts.clear()
+    _current_opts.update(kw)
+
+
+def pathtraceInit(scene):
+    global _current
+    if _current is not None:
+        _current.close()
+    _current = Renderer(scene, **_current_opts)
+
+
+def pathtraceFree():
+    """No-op when nothing is initialised: the app frees before the first init (src/main.cpp:126)."""
+    global _current
+    if _current is not None:
+        _current.close()
+        _current = None
+
+
+def pathtrace(pbo, frame, iteration):
+    """Traces iteration `iteration` and leaves the accumulated SUM in scene.image, exactly the
+    post-condition of the reference (src/pathtrace.cu:276, 389-390)."""
+    if _current is None:
+        raise PtbError("pathtrace() before pathtraceInit()")
+    _current.pathtrace(pbo, frame, iteration, _current.scene.image)
+
+
+def save_png(filename_base, width, height, image_sum, samples, flip_x=True):
+    """saveImage + image::savePNG (src/main.cpp:78-99, src/image.cpp:22-39): writes <base>.png"""
+    img = np.ascontiguousarray(image_sum, np.float32)
+    _check(lib().ptb_save_png(os.fsencode(filename_base), width, height, img.ctypes.data, float(samples), int(flip_x)))

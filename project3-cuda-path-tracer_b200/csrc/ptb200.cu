@@ -1,0 +1,652 @@
+// ptb200.cu -- implementation of the C ABI in include/ptb200.h: device memory, launch sequences,
+// CUDA-graph replay of the per-batch bounce loop.  Host orchestration only; the kernels are in
+// ptb_kernels.cuh.  Replaces the host side of src/pathtrace.cu (pathtraceInit :79-101,
+// pathtraceFree :103-112, pathtrace :284-393) of the reference.
+#include "../../include/ptb200.h"
+#include "ptb_kernels.cuh"
+#include "ptb_bvh.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace ptb;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_lastError = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(PTB_ERR_CUDA, "CUDA error (%s:%d): %s: %s", "ptb200.cu", __LINE__, #call,  \
+                        cudaGetErrorString(e_));                                                   \
+    } while (0)
+
+template <typename T> struct DevBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    cudaError_t alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return cudaSuccess;
+        return cudaMalloc(&p, count * sizeof(T));
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+};
+
+} // namespace
+
+struct PtbContext {
+    int device = 0;
+    PtbOptions opt{};
+    cudaStream_t stream = nullptr;
+    bool ownStream = false;
+    int numSMs = 148;
+
+    // scene
+    int W = 0, H = 0, traceDepth = 0;
+    uint32_t numPixels = 0;
+    int pixBits = 0;
+    int batch = 1;                       // slots per wavefront
+    bool useBvh = false;
+    std::vector<int> sceneMaterial;      // scene geom index -> material id
+    std::vector<int> slotOfScene;
+    DevBuf<GeomRec> geoms;
+    DevBuf<GeomRec> geomsScene;          // scene order (brute force), kept for ptb_stage_intersect(BRUTE)
+    DevBuf<BvhNode> bvh;
+    int numNodes = 0, smemNodes = 0;
+    DevBuf<float4> mats;
+    DevBuf<int> sceneMatDev;
+    int numGeoms = 0, numMats = 0;
+
+    // state
+    DevBuf<float> image;
+    float *imagePtr = nullptr;           // own or external
+    DevBuf<float4> A[2], B[2];
+    DevBuf<float2> C[2];
+    DevBuf<float4> hitTn;
+    DevBuf<int> hitMeta, sortKeys, sortOrder;
+    DevBuf<uint32_t> sortHist;
+    DevBuf<Control> ctrl;
+    DevBuf<uint8_t> rgb8;
+
+    Params base{};
+    int gridFused = 0, gridStaged = 0;
+    size_t smemBrute = 0, smemBvh = 0;
+
+    cudaGraphExec_t graphExec = nullptr;
+    int64_t launches = 0;
+    int64_t hostIterations = 0;
+
+    ~PtbContext() {
+        if (graphExec) cudaGraphExecDestroy(graphExec);
+        geoms.release(); geomsScene.release(); bvh.release(); mats.release(); sceneMatDev.release();
+        image.release();
+        for (int i = 0; i < 2; ++i) { A[i].release(); B[i].release(); C[i].release(); }
+        hitTn.release(); hitMeta.release(); sortKeys.release(); sortOrder.release(); sortHist.release();
+        ctrl.release(); rgb8.release();
+        if (ownStream && stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+GeomRec packGeom(const PtbGeom &g, int sceneIndex) {
+    GeomRec r;
+    auto row = [](const float *m, int k) { return make_float4(m[0 + k], m[4 + k], m[8 + k], m[12 + k]); };
+    r.inv.r0 = row(g.inverseTransform, 0); r.inv.r1 = row(g.inverseTransform, 1); r.inv.r2 = row(g.inverseTransform, 2);
+    r.fwd.r0 = row(g.transform, 0); r.fwd.r1 = row(g.transform, 1); r.fwd.r2 = row(g.transform, 2);
+    r.nrm.r0 = row(g.invTranspose, 0); r.nrm.r1 = row(g.invTranspose, 1); r.nrm.r2 = row(g.invTranspose, 2);
+    r.tag = make_int4(g.type, g.materialid, sceneIndex, 0);
+    return r;
+}
+
+Params makeParams(PtbContext *c, int inBuf) {
+    Params p = c->base;
+    p.in.A = c->A[inBuf].p; p.in.B = c->B[inBuf].p; p.in.C = c->C[inBuf].p;
+    p.out.A = c->A[inBuf ^ 1].p; p.out.B = c->B[inBuf ^ 1].p; p.out.C = c->C[inBuf ^ 1].p;
+    return p;
+}
+
+template <typename K> int setSmem(K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+        if (e != cudaSuccess) return fail(PTB_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e));
+    }
+    return PTB_OK;
+}
+
+// ---- launch sequences -------------------------------------------------------------------------
+// fused: traceDepth bounce kernels + the advance kernel.  Buffers ping-pong per bounce.
+int launchFusedBatch(PtbContext *c) {
+    const size_t smem = c->useBvh ? c->smemBvh : c->smemBrute;
+    for (int d = 0; d < c->traceDepth; ++d) {
+        // bounce d reads buffer (d-1)&1... bounce 0 reads nothing and writes buffer 0
+        Params p = makeParams(c, d == 0 ? 1 : ((d - 1) & 1));
+        if (d == 0) {
+            if (c->useBvh) bounce_kernel<true, true><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+            else           bounce_kernel<true, false><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+        } else {
+            if (c->useBvh) bounce_kernel<false, true><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+            else           bounce_kernel<false, false><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+        }
+        c->launches++;
+    }
+    advance_kernel<<<1, 32, 0, c->stream>>>(c->ctrl.p, c->traceDepth, c->numPixels);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PTB_ERR_CUDA, "fused batch launch: %s", cudaGetErrorString(e));
+    return PTB_OK;
+}
+
+// staged: raygen, then per bounce intersect -> [sort] -> shade -> [compact], then gather.
+int launchStagedBatch(PtbContext *c) {
+    const size_t smem = c->useBvh ? c->smemBvh : c->smemBrute;
+    const int grid = c->gridStaged;
+    int cur = 0;
+    Params p = makeParams(c, cur);
+    raygen_kernel<<<grid, kBlock, 0, c->stream>>>(p);
+    c->launches++;
+    const int compaction = c->opt.compaction;
+    for (int d = 0; d < c->traceDepth; ++d) {
+        p = makeParams(c, cur);
+        if (c->useBvh) intersect_kernel<true><<<grid, kBlock, smem, c->stream>>>(p, d);
+        else           intersect_kernel<false><<<grid, kBlock, smem, c->stream>>>(p, d);
+        c->launches++;
+        const int *order = nullptr;
+        if (c->opt.sortMaterials) {
+            const int numKeys = c->numMats + 1;
+            cudaMemsetAsync(c->sortHist.p, 0, sizeof(uint32_t) * numKeys, c->stream);
+            sort_keys_kernel<<<grid, kBlock, 0, c->stream>>>(p, d, c->sortKeys.p);
+            sort_hist_dev_kernel<<<grid, kBlock, sizeof(uint32_t) * numKeys, c->stream>>>(c->sortKeys.p, c->ctrl.p, d, numKeys, c->sortHist.p);
+            sort_scan_kernel<<<1, 32, 0, c->stream>>>(c->sortHist.p, numKeys);
+            sort_scatter_dev_kernel<<<grid, kBlock, 0, c->stream>>>(c->sortKeys.p, c->ctrl.p, d, c->sortHist.p, c->sortOrder.p);
+            c->launches += 4;
+            order = c->sortOrder.p;
+        }
+        shade_kernel<<<grid, kBlock, 0, c->stream>>>(p, d, order, compaction ? 1 : 0);
+        c->launches++;
+        if (compaction) {
+            compact_kernel<<<grid, kBlock, 0, c->stream>>>(p, d);
+            cur ^= 1;
+        } else {
+            carry_count_kernel<<<1, 32, 0, c->stream>>>(c->ctrl.p, d);
+        }
+        c->launches++;
+    }
+    if (!compaction) {
+        p = makeParams(c, cur);
+        gather_kernel<<<grid, kBlock, 0, c->stream>>>(p, c->numPixels * (uint32_t)c->batch);
+        c->launches++;
+    }
+    advance_kernel<<<1, 32, 0, c->stream>>>(c->ctrl.p, c->traceDepth, c->numPixels);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PTB_ERR_CUDA, "staged batch launch: %s", cudaGetErrorString(e));
+    return PTB_OK;
+}
+
+int launchBatch(PtbContext *c) {
+    return c->opt.pipeline == PTB_PIPELINE_STAGED ? launchStagedBatch(c) : launchFusedBatch(c);
+}
+
+int kernelsPerBatch(const PtbContext *c) {
+    if (c->opt.pipeline == PTB_PIPELINE_STAGED) {
+        int per = 1 /*intersect*/ + 1 /*shade*/ + 1 /*compact or carry*/ + (c->opt.sortMaterials ? 4 : 0);
+        return 1 + per * c->traceDepth + (c->opt.compaction ? 0 : 1) + 1;
+    }
+    return c->traceDepth + 1;
+}
+
+int buildGraph(PtbContext *c) {
+    if (c->graphExec) return PTB_OK;
+    cudaGraph_t graph = nullptr;
+    CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    const int64_t before = c->launches;
+    int rc = launchBatch(c);
+    c->launches = before;                         // capture does not execute anything
+    cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+    if (rc != PTB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return fail(PTB_ERR_CUDA, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&c->graphExec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return fail(PTB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    return PTB_OK;
+}
+
+int runBatches(PtbContext *c, int iterBegin, int count, int iterStride) {
+    int done = 0;
+    while (done < count) {
+        const int b = std::min(c->batch, count - done);
+        set_control_kernel<<<1, 32, 0, c->stream>>>(c->ctrl.p, iterBegin + done * iterStride, iterStride, b);
+        c->launches++;
+        // full batches replay back to back: advance_kernel moves iterBase on the device
+        int reps = (b == c->batch) ? (count - done) / c->batch : 1;
+        for (int r = 0; r < reps; ++r) {
+            if (c->opt.useGraphs) {
+                int rc = buildGraph(c);
+                if (rc != PTB_OK) return rc;
+                CU(cudaGraphLaunch(c->graphExec, c->stream));
+                c->launches += kernelsPerBatch(c);
+            } else {
+                int rc = launchBatch(c);
+                if (rc != PTB_OK) return rc;
+            }
+        }
+        done += reps * b;
+    }
+    c->hostIterations += count;
+    return PTB_OK;
+}
+
+} // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char *ptb_last_error(void) { return g_lastError.c_str(); }
+int ptb_abi_version(void) { return PTB_ABI_VERSION; }
+
+void ptb_default_options(PtbOptions *o) {
+    if (!o) return;
+    memset(o, 0, sizeof *o);
+    o->device = -1;
+    o->bsdfMode = PTB_BSDF_FULL;
+    o->pipeline = PTB_PIPELINE_FUSED;
+    o->accel = PTB_ACCEL_AUTO;
+    o->batchIters = 0;
+    o->compaction = 1;
+    o->sortMaterials = 0;
+    o->firstBounceCache = 0;
+    o->useGraphs = 1;
+}
+
+int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *optIn) {
+    if (!out || !scene) return fail(PTB_ERR_INVALID, "ptb_create: null argument");
+    *out = nullptr;
+    PtbOptions opt;
+    if (optIn) opt = *optIn; else ptb_default_options(&opt);
+    if (scene->numGeoms < 0 || scene->numMaterials <= 0 || (scene->numGeoms > 0 && !scene->geoms) || !scene->materials)
+        return fail(PTB_ERR_INVALID, "ptb_create: scene needs geoms[%d] and materials[%d]", scene->numGeoms, scene->numMaterials);
+    const int W = scene->camera.resolution[0], H = scene->camera.resolution[1];
+    if (W <= 0 || H <= 0 || (int64_t)W * H > (1ll << 30)) return fail(PTB_ERR_INVALID, "ptb_create: bad resolution %dx%d", W, H);
+    if (scene->traceDepth < 1 || scene->traceDepth > 64) return fail(PTB_ERR_INVALID, "ptb_create: traceDepth %d outside [1,64]", scene->traceDepth);
+    for (int i = 0; i < scene->numGeoms; ++i) {
+        if (scene->geoms[i].type != 0 && scene->geoms[i].type != 1) return fail(PTB_ERR_INVALID, "ptb_create: geom %d has unknown type %d", i, scene->geoms[i].type);
+        if (scene->geoms[i].materialid < 0 || scene->geoms[i].materialid >= scene->numMaterials)
+            return fail(PTB_ERR_INVALID, "ptb_create: geom %d references material %d of %d", i, scene->geoms[i].materialid, scene->numMaterials);
+    }
+
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    if (ndev <= 0) return fail(PTB_ERR_CUDA, "no CUDA device (this library has no CPU fallback)");
+    int dev = opt.device;
+    if (dev < 0) CU(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(PTB_ERR_INVALID, "device %d of %d", dev, ndev);
+    CU(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, dev));
+
+    PtbContext *c = new PtbContext();
+    c->device = dev;
+    c->opt = opt;
+    c->numSMs = prop.multiProcessorCount;
+    c->W = W; c->H = H; c->traceDepth = scene->traceDepth;
+    c->numPixels = (uint32_t)W * (uint32_t)H;
+    c->numGeoms = scene->numGeoms; c->numMats = scene->numMaterials;
+    int bits = 1;
+    while ((1ull << bits) < c->numPixels) ++bits;
+    c->pixBits = bits;
+    const int maxSlots = 1 << std::min(31 - bits, 12);
+    int batch = opt.batchIters > 0 ? opt.batchIters : 8;
+    if (opt.pipeline == PTB_PIPELINE_STAGED && opt.batchIters <= 0) batch = 1;
+    // keep the wavefront within 2^31 paths and a sane memory budget (2 x 40 B per path)
+    while (batch > 1 && ((uint64_t)batch * c->numPixels > (1ull << 30) || batch > maxSlots)) batch >>= 1;
+    c->batch = std::max(1, batch);
+
+    auto bail = [&](int rc) { delete c; return rc; };
+#define CUB(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return bail(fail(PTB_ERR_CUDA, "CUDA error (%s:%d): %s: %s", "ptb200.cu", __LINE__, #call, cudaGetErrorString(e_))); \
+    } while (0)
+
+    if (opt.stream) { c->stream = (cudaStream_t)opt.stream; c->ownStream = false; }
+    else { CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->ownStream = true; }
+
+    // ---- scene upload (src/pathtrace.cu:89-93) in the device layout ----
+    c->useBvh = opt.accel == PTB_ACCEL_BVH || (opt.accel == PTB_ACCEL_AUTO && scene->numGeoms > 64);
+    const size_t bruteBytes = (size_t)std::max(1, scene->numGeoms) * sizeof(GeomRec);
+    if (!c->useBvh && bruteBytes > 200 * 1024) c->useBvh = true;
+    c->sceneMaterial.resize(scene->numGeoms);
+    std::vector<GeomRec> sceneOrder(std::max(1, scene->numGeoms));
+    memset(sceneOrder.data(), 0, sceneOrder.size() * sizeof(GeomRec));
+    for (int i = 0; i < scene->numGeoms; ++i) { sceneOrder[i] = packGeom(scene->geoms[i], i); c->sceneMaterial[i] = scene->geoms[i].materialid; }
+    CUB(c->geomsScene.alloc(sceneOrder.size()));
+    CUB(cudaMemcpy(c->geomsScene.p, sceneOrder.data(), sceneOrder.size() * sizeof(GeomRec), cudaMemcpyHostToDevice));
+    CUB(c->sceneMatDev.alloc(std::max(1, scene->numGeoms)));
+    if (scene->numGeoms) CUB(cudaMemcpy(c->sceneMatDev.p, c->sceneMaterial.data(), scene->numGeoms * sizeof(int), cudaMemcpyHostToDevice));
+
+    // the BVH is always built when there is more than one geom so that ptb_stage_intersect can compare
+    // both traversals on any scene; the render path uses it only when useBvh is set
+    {
+        HostBvh hb;
+        buildBvh(scene->geoms, scene->numGeoms, 4, hb);
+        static_assert(sizeof(HostBvhNode) == sizeof(BvhNode), "bvh node");
+        c->numNodes = (int)hb.nodes.size();
+        CUB(c->bvh.alloc(hb.nodes.size()));
+        CUB(cudaMemcpy(c->bvh.p, hb.nodes.data(), hb.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
+        std::vector<GeomRec> leafOrder(std::max(1, scene->numGeoms));
+        memset(leafOrder.data(), 0, leafOrder.size() * sizeof(GeomRec));
+        for (int s = 0; s < scene->numGeoms; ++s) leafOrder[s] = sceneOrder[hb.order[s]];
+        CUB(c->geoms.alloc(leafOrder.size()));
+        CUB(cudaMemcpy(c->geoms.p, leafOrder.data(), leafOrder.size() * sizeof(GeomRec), cudaMemcpyHostToDevice));
+        c->smemNodes = std::min(c->numNodes, 511);
+    }
+    std::vector<float4> mats(3 * (size_t)scene->numMaterials);
+    for (int i = 0; i < scene->numMaterials; ++i) {
+        const PtbMaterial &m = scene->materials[i];
+        mats[3 * i + 0] = make_float4(m.color[0], m.color[1], m.color[2], m.emittance);
+        mats[3 * i + 1] = make_float4(m.specularColor[0], m.specularColor[1], m.specularColor[2], m.hasReflective);
+        mats[3 * i + 2] = make_float4(m.hasRefractive, m.indexOfRefraction, m.specularExponent, 0.f);
+    }
+    CUB(c->mats.alloc(mats.size()));
+    CUB(cudaMemcpy(c->mats.p, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice));
+
+    // ---- state (src/pathtrace.cu:84-87, 95-96) ----
+    if (opt.externalAccum) c->imagePtr = opt.externalAccum;
+    else { CUB(c->image.alloc((size_t)c->numPixels * 3)); c->imagePtr = c->image.p; CUB(cudaMemset(c->imagePtr, 0, (size_t)c->numPixels * 3 * sizeof(float))); }
+    const size_t maxPaths = (size_t)c->numPixels * c->batch;
+    for (int i = 0; i < 2; ++i) {
+        CUB(c->A[i].alloc(maxPaths)); CUB(c->B[i].alloc(maxPaths)); CUB(c->C[i].alloc(maxPaths));
+    }
+    if (opt.pipeline == PTB_PIPELINE_STAGED) {
+        CUB(c->hitTn.alloc(maxPaths)); CUB(c->hitMeta.alloc(maxPaths));
+        if (opt.sortMaterials) { CUB(c->sortKeys.alloc(maxPaths)); CUB(c->sortOrder.alloc(maxPaths)); CUB(c->sortHist.alloc(scene->numMaterials + 2)); }
+    }
+    CUB(c->ctrl.alloc(1));
+    CUB(cudaMemset(c->ctrl.p, 0, sizeof(Control)));
+
+    // ---- launch geometry ----
+    c->smemBrute = bruteBytes;
+    c->smemBvh = (size_t)std::max(1, c->smemNodes) * sizeof(BvhNode);
+    int rc = PTB_OK;
+    rc |= setSmem(bounce_kernel<true, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false>, c->smemBrute);
+    rc |= setSmem(intersect_kernel<false>, c->smemBrute); rc |= setSmem(stage_intersect_kernel<false>, c->smemBrute);
+    if (rc != PTB_OK && !c->useBvh && bruteBytes <= 200 * 1024) return bail(rc);
+    int occ = 0;
+    const size_t smem = c->useBvh ? c->smemBvh : c->smemBrute;
+    if (c->useBvh) CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, true>, kBlock, smem));
+    else           CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, false>, kBlock, smem));
+    c->gridFused = c->numSMs * std::max(1, occ);
+    c->gridStaged = c->numSMs * 8;
+
+    Params &p = c->base;
+    memset(&p, 0, sizeof p);
+    const PtbCamera &cam = scene->camera;
+    p.cam = CameraParams{cam.position[0], cam.position[1], cam.position[2], cam.view[0], cam.view[1], cam.view[2],
+                         cam.up[0], cam.up[1], cam.up[2], cam.right[0], cam.right[1], cam.right[2],
+                         cam.pixelLength[0], cam.pixelLength[1], W, H};
+    p.geoms = c->useBvh ? c->geoms.p : c->geomsScene.p;
+    p.numGeoms = scene->numGeoms;
+    p.bvh = c->bvh.p; p.numNodes = c->numNodes; p.smemNodes = c->smemNodes;
+    p.mats = c->mats.p; p.numMats = scene->numMaterials;
+    p.image = c->imagePtr;
+    p.ctrl = c->ctrl.p;
+    p.hits.tn = c->hitTn.p; p.hits.meta = c->hitMeta.p;
+    p.traceDepth = c->traceDepth;
+    p.bsdfMode = opt.bsdfMode;
+    p.pixBits = c->pixBits;
+    p.numPixels = c->numPixels;
+    p.atomicGather = c->batch > 1 ? 1 : 0;
+    CUB(cudaDeviceSynchronize());
+#undef CUB
+    *out = c;
+    return PTB_OK;
+}
+
+int ptb_destroy(PtbContext *c) {
+    if (!c) return PTB_OK;                          // pathtraceFree before any pathtraceInit (src/main.cpp:126)
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    delete c;
+    return PTB_OK;
+}
+
+int ptb_render(PtbContext *c, int iterBegin, int count, int iterStride) {
+    if (!c) return fail(PTB_ERR_INVALID, "ptb_render: not initialised");
+    if (count < 0 || iterStride < 1 || iterBegin < 0) return fail(PTB_ERR_INVALID, "ptb_render: bad range");
+    // makeSeededRandomEngine packs iter into 22 bits and depth into 9 (src/pathtrace.cu:43)
+    if ((int64_t)iterBegin + (int64_t)(count - 1) * iterStride >= (1 << 22)) return fail(PTB_ERR_INVALID, "ptb_render: iteration beyond 2^22 aliases the RNG seed");
+    CU(cudaSetDevice(c->device));
+    return runBatches(c, iterBegin, count, iterStride);
+}
+
+int ptb_write_pbo(PtbContext *c, PtbUchar4 *pbo, int samples) {
+    if (!c || !pbo) return fail(PTB_ERR_INVALID, "ptb_write_pbo: null argument");
+    CU(cudaSetDevice(c->device));
+    pbo_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(reinterpret_cast<uchar4 *>(pbo), c->imagePtr, c->numPixels, samples);
+    c->launches++;
+    CU(cudaGetLastError());
+    return PTB_OK;
+}
+
+int ptb_download(PtbContext *c, float *hostImage) {
+    if (!c || !hostImage) return fail(PTB_ERR_INVALID, "ptb_download: null argument");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemcpyAsync(hostImage, c->imagePtr, (size_t)c->numPixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+int ptb_pathtrace(PtbContext *c, PtbUchar4 *pbo, int frame, int iter, float *hostImage) {
+    (void)frame;                                     // unused by the reference as well (src/main.cpp:136)
+    if (!c) return fail(PTB_ERR_INVALID, "ptb_pathtrace: not initialised");
+    if (iter < 0) return fail(PTB_ERR_INVALID, "ptb_pathtrace: iter %d", iter);
+    int rc = ptb_render(c, iter, 1, 1);
+    if (rc != PTB_OK) return rc;
+    if (pbo) { rc = ptb_write_pbo(c, pbo, iter); if (rc != PTB_OK) return rc; }
+    if (hostImage) return ptb_download(c, hostImage);
+    return PTB_OK;
+}
+
+int ptb_reset(PtbContext *c) {
+    if (!c) return fail(PTB_ERR_INVALID, "ptb_reset: not initialised");
+    CU(cudaSetDevice(c->device));
+    CU(cudaMemsetAsync(c->imagePtr, 0, (size_t)c->numPixels * 3 * sizeof(float), c->stream));
+    CU(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Control), c->stream));
+    c->hostIterations = 0;
+    return PTB_OK;
+}
+
+int ptb_sync(PtbContext *c) {
+    if (!c) return fail(PTB_ERR_INVALID, "ptb_sync: not initialised");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+int ptb_stats(PtbContext *c, PtbStats *out) {
+    if (!c || !out) return fail(PTB_ERR_INVALID, "ptb_stats: null argument");
+    CU(cudaSetDevice(c->device));
+    Control h;
+    CU(cudaMemcpyAsync(&h, c->ctrl.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    memset(out, 0, sizeof *out);
+    out->iterations = (int64_t)h.iterations;
+    out->segments = (int64_t)h.segments;
+    out->kernelLaunches = c->launches;
+    for (int d = 0; d < 64; ++d) out->alivePerDepth[d] = (int64_t)h.aliveTotals[d];
+    out->traceDepth = c->traceDepth;
+    out->numGeoms = c->numGeoms;
+    out->bvhNodes = c->useBvh ? c->numNodes : 0;
+    out->batchIters = c->batch;
+    out->pathStateBytes = (int64_t)c->numPixels * c->batch * 40 * 2;
+    return PTB_OK;
+}
+
+int ptb_accum_device_ptr(PtbContext *c, float **devPtr) {
+    if (!c || !devPtr) return fail(PTB_ERR_INVALID, "ptb_accum_device_ptr: null argument");
+    *devPtr = c->imagePtr;
+    return PTB_OK;
+}
+
+int ptb_resolve_rgb8(PtbContext *c, int samples, uint8_t *hostRgb8) {
+    if (!c || !hostRgb8 || samples <= 0) return fail(PTB_ERR_INVALID, "ptb_resolve_rgb8: bad argument");
+    CU(cudaSetDevice(c->device));
+    if (!c->rgb8.p) CU(c->rgb8.alloc((size_t)c->numPixels * 3));
+    resolve_rgb8_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(c->rgb8.p, c->imagePtr, c->W, c->H, (float)samples);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hostRgb8, c->rgb8.p, (size_t)c->numPixels * 3, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+
+// ---- stage-level entry points ---------------------------------------------------------------------
+int ptb_stage_raygen(PtbContext *c, float *origins, float *dirs) {
+    if (!c || !origins || !dirs) return fail(PTB_ERR_INVALID, "ptb_stage_raygen: null argument");
+    CU(cudaSetDevice(c->device));
+    const size_t n = (size_t)c->numPixels * 3;
+    DevBuf<float> o, d;
+    CU(o.alloc(n)); CU(d.alloc(n));
+    stage_raygen_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(c->base, o.p, d.p);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(origins, o.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaMemcpyAsync(dirs, d.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    o.release(); d.release();
+    return PTB_OK;
+}
+
+int ptb_stage_intersect(PtbContext *c, int accel, const float *origins, const float *dirs, int n,
+                        int32_t *hit, float *t, float *normal, int32_t *outside) {
+    if (!c || !origins || !dirs || !hit || !t || !normal || !outside || n < 0) return fail(PTB_ERR_INVALID, "ptb_stage_intersect: bad argument");
+    CU(cudaSetDevice(c->device));
+    bool bvh = accel == PTB_ACCEL_BVH || (accel == PTB_ACCEL_AUTO && c->useBvh);
+    if (!bvh && c->smemBrute > 200 * 1024) return fail(PTB_ERR_UNSUPPORTED, "brute force needs %zu B of shared memory", c->smemBrute);
+    DevBuf<float> o, d, dt, dn; DevBuf<int> dh, dout;
+    CU(o.alloc((size_t)n * 3)); CU(d.alloc((size_t)n * 3)); CU(dt.alloc(n)); CU(dn.alloc((size_t)n * 3)); CU(dh.alloc(n)); CU(dout.alloc(n));
+    if (n) {
+        CU(cudaMemcpyAsync(o.p, origins, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(d.p, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
+        Params p = c->base;
+        if (bvh) { p.geoms = c->geoms.p; stage_intersect_kernel<true><<<c->gridStaged, kBlock, c->smemBvh, c->stream>>>(p, o.p, d.p, n, dh.p, dt.p, dn.p, dout.p); }
+        else { p.geoms = c->geomsScene.p; stage_intersect_kernel<false><<<c->gridStaged, kBlock, c->smemBrute, c->stream>>>(p, o.p, d.p, n, dh.p, dt.p, dn.p, dout.p); }
+        c->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(hit, dh.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(t, dt.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(normal, dn.p, (size_t)n * 12, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(outside, dout.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    o.release(); d.release(); dt.release(); dn.release(); dh.release(); dout.release();
+    return PTB_OK;
+}
+
+int ptb_stage_shade(PtbContext *c, int n, const int32_t *hit, const float *t, const float *normal,
+                    const int32_t *outside, const int32_t *iter, const int32_t *pixelIndex,
+                    const int32_t *depth, float *origins, float *dirs, float *colors, int32_t *remaining) {
+    if (!c || n < 0) return fail(PTB_ERR_INVALID, "ptb_stage_shade: bad argument");
+    CU(cudaSetDevice(c->device));
+    DevBuf<int> dh, dout, dit, dpx, ddp, drem; DevBuf<float> dt, dn, o, d, col;
+    CU(dh.alloc(n)); CU(dout.alloc(n)); CU(dit.alloc(n)); CU(dpx.alloc(n)); CU(ddp.alloc(n)); CU(drem.alloc(n));
+    CU(dt.alloc(n)); CU(dn.alloc((size_t)n * 3)); CU(o.alloc((size_t)n * 3)); CU(d.alloc((size_t)n * 3)); CU(col.alloc((size_t)n * 3));
+    if (n) {
+        auto up = [&](void *dst, const void *src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream); };
+        CU(up(dh.p, hit, (size_t)n * 4)); CU(up(dout.p, outside, (size_t)n * 4)); CU(up(dit.p, iter, (size_t)n * 4));
+        CU(up(dpx.p, pixelIndex, (size_t)n * 4)); CU(up(ddp.p, depth, (size_t)n * 4)); CU(up(drem.p, remaining, (size_t)n * 4));
+        CU(up(dt.p, t, (size_t)n * 4)); CU(up(dn.p, normal, (size_t)n * 12)); CU(up(o.p, origins, (size_t)n * 12));
+        CU(up(d.p, dirs, (size_t)n * 12)); CU(up(col.p, colors, (size_t)n * 12));
+        stage_shade_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(c->base, n, dh.p, c->sceneMatDev.p, dt.p, dn.p, dout.p, dit.p, dpx.p, ddp.p,
+                                                                   o.p, d.p, col.p, drem.p);
+        c->launches++;
+        CU(cudaGetLastError());
+        auto down = [&](void *dst, const void *src, size_t bytes) { return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, c->stream); };
+        CU(down(origins, o.p, (size_t)n * 12)); CU(down(dirs, d.p, (size_t)n * 12)); CU(down(colors, col.p, (size_t)n * 12));
+        CU(down(remaining, drem.p, (size_t)n * 4));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    dh.release(); dout.release(); dit.release(); dpx.release(); ddp.release(); drem.release();
+    dt.release(); dn.release(); o.release(); d.release(); col.release();
+    return PTB_OK;
+}
+
+int ptb_stage_compact(PtbContext *c, int n, const int32_t *ids, const int32_t *flags, int32_t *outIds, int32_t *outCount) {
+    if (!c || n < 0 || !outCount) return fail(PTB_ERR_INVALID, "ptb_stage_compact: bad argument");
+    CU(cudaSetDevice(c->device));
+    DevBuf<int> di, df, dout; DevBuf<uint32_t> cnt;
+    CU(di.alloc(n)); CU(df.alloc(n)); CU(dout.alloc(n)); CU(cnt.alloc(1));
+    CU(cudaMemsetAsync(cnt.p, 0, 4, c->stream));
+    if (n) {
+        CU(cudaMemcpyAsync(di.p, ids, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(df.p, flags, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        stage_compact_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(n, di.p, df.p, dout.p, cnt.p);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
+    uint32_t k = 0;
+    CU(cudaMemcpyAsync(&k, cnt.p, 4, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    if (k && outIds) CU(cudaMemcpy(outIds, dout.p, (size_t)k * 4, cudaMemcpyDeviceToHost));
+    *outCount = (int32_t)k;
+    di.release(); df.release(); dout.release(); cnt.release();
+    return PTB_OK;
+}
+
+int ptb_stage_sort_keys(PtbContext *c, int n, const int32_t *keys, int numKeys, int32_t *outOrder) {
+    if (!c || n < 0 || numKeys <= 0 || numKeys > 8192) return fail(PTB_ERR_INVALID, "ptb_stage_sort_keys: bad argument");
+    for (int i = 0; i < n; ++i) if (keys[i] < 0 || keys[i] >= numKeys) return fail(PTB_ERR_INVALID, "ptb_stage_sort_keys: key %d out of range", keys[i]);
+    CU(cudaSetDevice(c->device));
+    DevBuf<int> dk, dord; DevBuf<uint32_t> hist;
+    CU(dk.alloc(n)); CU(dord.alloc(n)); CU(hist.alloc(numKeys));
+    CU(cudaMemsetAsync(hist.p, 0, sizeof(uint32_t) * numKeys, c->stream));
+    if (n) {
+        CU(cudaMemcpyAsync(dk.p, keys, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        sort_hist_kernel<<<c->gridStaged, kBlock, sizeof(uint32_t) * numKeys, c->stream>>>(dk.p, (uint32_t)n, numKeys, hist.p);
+        sort_scan_kernel<<<1, 32, 0, c->stream>>>(hist.p, numKeys);
+        sort_scatter_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(dk.p, (uint32_t)n, hist.p, dord.p);
+        c->launches += 3;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(outOrder, dord.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    dk.release(); dord.release(); hist.release();
+    return PTB_OK;
+}
+
+int ptb_stage_rng(PtbContext *c, int iter, int index, int depth, int n, float *out) {
+    if (!c || n < 0 || !out) return fail(PTB_ERR_INVALID, "ptb_stage_rng: bad argument");
+    CU(cudaSetDevice(c->device));
+    DevBuf<float> d;
+    CU(d.alloc(n));
+    if (n) {
+        stage_rng_kernel<<<1, 32, 0, c->stream>>>(iter, index, depth, n, d.p);
+        c->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(out, d.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    d.release();
+    return PTB_OK;
+}
+
+} // extern "C"

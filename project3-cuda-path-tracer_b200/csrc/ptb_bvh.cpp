@@ -1,0 +1,169 @@
+// ptb_bvh.cpp -- see ptb_bvh.h.  Pure host C++.
+#include "ptb_bvh.h"
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <queue>
+
+namespace ptb {
+
+// Both reference tests return a hit point computed in float and placed 1e-4 object-space units short
+// of the surface (getPointOnRay, src/intersections.h:27-29), so the point can lie slightly outside
+// the exact world box of the primitive.  The pad covers that shortfall mapped through the transform
+// (<= 1e-4 * sum|column|), float rounding of the object-space round trip, and the pruning slab test.
+void geomBounds(const PtbGeom &g, float lo[3], float hi[3]) {
+    const float *m = g.transform;                       // column-major
+    for (int r = 0; r < 3; ++r) {
+        const double c = m[12 + r];
+        const double e = 0.5 * (std::fabs((double)m[0 + r]) + std::fabs((double)m[4 + r]) + std::fabs((double)m[8 + r]));
+        const double rowAbs = 2.0 * e;
+        const double pad = 4e-4 * rowAbs + 1e-3 + 2e-5 * (std::fabs(c) + e);
+        lo[r] = (float)(c - e - pad);
+        hi[r] = (float)(c + e + pad);
+    }
+}
+
+namespace {
+struct Box {
+    float lo[3], hi[3];
+    void reset() { for (int a = 0; a < 3; ++a) { lo[a] = FLT_MAX; hi[a] = -FLT_MAX; } }
+    void grow(const Box &b) { for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    float area() const {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (dx < 0 || dy < 0 || dz < 0) return 0.f;
+        return 2.f * (dx * dy + dy * dz + dz * dx);
+    }
+};
+struct Prim { Box box; float cen[3]; int32_t index; };
+struct BuildNode { Box box; int first, count; int left = -1, right = -1; };   // leaf when left < 0
+
+struct Builder {
+    std::vector<Prim> prims;
+    std::vector<BuildNode> nodes;
+    int maxLeaf;
+    int maxDepth = 0;
+
+    int build(int first, int count, int depth) {
+        BuildNode nd;
+        nd.first = first; nd.count = count;
+        nd.box.reset();
+        Box cb; cb.reset();
+        for (int i = first; i < first + count; ++i) {
+            nd.box.grow(prims[i].box);
+            for (int a = 0; a < 3; ++a) { cb.lo[a] = std::min(cb.lo[a], prims[i].cen[a]); cb.hi[a] = std::max(cb.hi[a], prims[i].cen[a]); }
+        }
+        const int me = (int)nodes.size();
+        nodes.push_back(nd);
+        maxDepth = std::max(maxDepth, depth);
+        if (count <= maxLeaf || depth > 56) {
+            if (count <= 8 || depth > 56) return me;                    // forced leaf (bounded by the 64-entry stack)
+        }
+        // binned SAH over the widest centroid axis, falling back to a median split
+        int axis = 0;
+        float ext = cb.hi[0] - cb.lo[0];
+        for (int a = 1; a < 3; ++a) if (cb.hi[a] - cb.lo[a] > ext) { ext = cb.hi[a] - cb.lo[a]; axis = a; }
+        int mid = first + count / 2;
+        if (ext > 0.f) {
+            constexpr int NB = 16;
+            Box bb[NB]; int bc[NB];
+            for (int b = 0; b < NB; ++b) { bb[b].reset(); bc[b] = 0; }
+            const float k = NB * (1.f - 1e-6f) / ext;
+            for (int i = first; i < first + count; ++i) {
+                int b = (int)((prims[i].cen[axis] - cb.lo[axis]) * k);
+                b = std::min(std::max(b, 0), NB - 1);
+                bb[b].grow(prims[i].box); bc[b]++;
+            }
+            float leftA[NB], rightA[NB]; int leftC[NB], rightC[NB];
+            Box acc; acc.reset(); int c = 0;
+            for (int b = 0; b < NB; ++b) { acc.grow(bb[b]); c += bc[b]; leftA[b] = acc.area(); leftC[b] = c; }
+            acc.reset(); c = 0;
+            for (int b = NB - 1; b >= 0; --b) { acc.grow(bb[b]); c += bc[b]; rightA[b] = acc.area(); rightC[b] = c; }
+            float bestCost = FLT_MAX; int bestB = -1;
+            for (int b = 0; b + 1 < NB; ++b) {
+                if (leftC[b] == 0 || rightC[b + 1] == 0) continue;
+                float cost = leftA[b] * leftC[b] + rightA[b + 1] * rightC[b + 1];
+                if (cost < bestCost) { bestCost = cost; bestB = b; }
+            }
+            if (bestB >= 0) {
+                if (count <= maxLeaf && bestCost >= nd.box.area() * count) return me;   // a leaf is cheaper
+                auto it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](const Prim &p) {
+                    int b = (int)((p.cen[axis] - cb.lo[axis]) * k);
+                    b = std::min(std::max(b, 0), NB - 1);
+                    return b <= bestB;
+                });
+                mid = (int)(it - prims.begin());
+            }
+        }
+        if (mid <= first || mid >= first + count) {
+            if (count <= maxLeaf) return me;
+            mid = first + count / 2;
+            std::nth_element(prims.begin() + first, prims.begin() + mid, prims.begin() + first + count,
+                             [&](const Prim &a, const Prim &b) { return a.cen[axis] < b.cen[axis]; });
+        }
+        const int l = build(first, mid - first, depth + 1);
+        const int r = build(mid, first + count - mid, depth + 1);
+        nodes[me].left = l; nodes[me].right = r;
+        return me;
+    }
+};
+} // namespace
+
+void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out) {
+    Builder b;
+    b.maxLeaf = std::max(1, std::min(maxLeaf, 8));
+    b.prims.resize(n);
+    for (int i = 0; i < n; ++i) {
+        geomBounds(geoms[i], b.prims[i].box.lo, b.prims[i].box.hi);
+        for (int a = 0; a < 3; ++a) b.prims[i].cen[a] = 0.5f * (b.prims[i].box.lo[a] + b.prims[i].box.hi[a]);
+        b.prims[i].index = i;
+    }
+    out.nodes.clear(); out.order.clear();
+    if (n == 0) {
+        HostBvhNode e{};
+        e.lref = -1; e.rref = -1;
+        out.nodes.push_back(e);
+        return;
+    }
+    const int root = b.build(0, n, 0);
+    out.maxDepth = b.maxDepth;
+    out.order.resize(n);
+    // scene order inside every leaf keeps ties deterministic without relying on the tie rule alone
+    for (const BuildNode &nd : b.nodes)
+        if (nd.left < 0)
+            std::sort(b.prims.begin() + nd.first, b.prims.begin() + nd.first + nd.count,
+                      [](const Prim &x, const Prim &y) { return x.index < y.index; });
+    for (int i = 0; i < n; ++i) out.order[i] = b.prims[i].index;
+
+    auto fill = [&](int child, float lo[3], int32_t &ref, float hi[3], int32_t &count, int interiorIndex) {
+        const BuildNode &c = b.nodes[child];
+        for (int a = 0; a < 3; ++a) { lo[a] = c.box.lo[a]; hi[a] = c.box.hi[a]; }
+        if (c.left < 0) { ref = c.first; count = c.count; }
+        else { ref = interiorIndex; count = 0; }
+    };
+    if (b.nodes[root].left < 0) {                         // the whole scene is one leaf
+        HostBvhNode e{};
+        fill(root, e.llo, e.lref, e.lhi, e.lcount, -1);
+        e.rref = -1; e.rcount = 0;
+        for (int a = 0; a < 3; ++a) { e.rlo[a] = FLT_MAX; e.rhi[a] = -FLT_MAX; }
+        out.nodes.push_back(e);
+        return;
+    }
+    // breadth-first emission of interior nodes: index = order of discovery
+    std::vector<int> bfs;                                // build-node ids of interior nodes in BFS order
+    std::vector<int> outIndex(b.nodes.size(), -1);
+    bfs.push_back(root); outIndex[root] = 0;
+    for (size_t h = 0; h < bfs.size(); ++h) {
+        const BuildNode &nd = b.nodes[bfs[h]];
+        for (int child : {nd.left, nd.right})
+            if (b.nodes[child].left >= 0) { outIndex[child] = (int)bfs.size(); bfs.push_back(child); }
+    }
+    out.nodes.resize(bfs.size());
+    for (size_t h = 0; h < bfs.size(); ++h) {
+        const BuildNode &nd = b.nodes[bfs[h]];
+        HostBvhNode &e = out.nodes[h];
+        fill(nd.left, e.llo, e.lref, e.lhi, e.lcount, outIndex[nd.left]);
+        fill(nd.right, e.rlo, e.rref, e.rhi, e.rcount, outIndex[nd.right]);
+    }
+}
+
+} // namespace ptb

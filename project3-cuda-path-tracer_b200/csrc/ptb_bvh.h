@@ -1,0 +1,29 @@
+// ptb_bvh.h -- host-side builder of the flat BVH used for large scenes (BASELINE.json configs[4]).
+// The reference has no acceleration structure (its loop is brute force, src/pathtrace.cu:176-199;
+// a hierarchical structure is an assignment ask, INSTRUCTION.md:123-140).
+#pragma once
+#include <cstdint>
+#include <vector>
+#include "../../include/ptb200.h"
+
+namespace ptb {
+
+struct HostBvhNode {             // mirrors ptb::BvhNode (64 B)
+    float llo[3]; int32_t lref; float lhi[3]; int32_t lcount;
+    float rlo[3]; int32_t rref; float rhi[3]; int32_t rcount;
+};
+static_assert(sizeof(HostBvhNode) == 64, "node layout");
+
+struct HostBvh {
+    std::vector<HostBvhNode> nodes;      // BFS order: the first 2^k-1 entries are the top k levels
+    std::vector<int32_t>     order;      // order[slot] = scene geom index
+    int                      maxDepth = 0;
+};
+
+// Padded world-space box of one geom (unit cube / sphere under Geom::transform).
+void geomBounds(const PtbGeom &g, float lo[3], float hi[3]);
+
+// Binned-SAH top-down build; leaves hold at most `maxLeaf` geoms.
+void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out);
+
+} // namespace ptb

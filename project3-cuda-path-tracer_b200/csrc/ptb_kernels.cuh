@@ -1,0 +1,709 @@
+// ptb_kernels.cuh -- every stage of the per-bounce loop as a hand-written sm_100a kernel.
+//
+//   stage (reference)                               kernel here
+//   generateRayFromCamera   src/pathtrace.cu:122    raygen_kernel            (and bounce_kernel<FIRST>)
+//   computeIntersections    src/pathtrace.cu:149    intersect_kernel         (brute force in smem / flat BVH)
+//   shadeFakeMaterial+scatterRay  :224, interactions.h:69   shade_kernel
+//   stream compaction (absent, :313-315,:376)       compact_kernel           (ballot/popc + aggregated atomics)
+//   material sort (absent, INSTRUCTION.md:78-86)    sort_hist/scan/scatter kernels
+//   finalGather             src/pathtrace.cu:269    gather_kernel            (or deposit-at-termination)
+//   sendImageToPBO          src/pathtrace.cu:48     pbo_kernel
+//   all of the above in one pass per bounce         bounce_kernel            (the fast path)
+//
+// Path state lives in HBM as three SoA planes, 40 B per path, moved with 128/128/64-bit accesses:
+//   A[i] = (o.x, o.y, o.z, d.x)   B[i] = (d.y, d.z, c.x, c.y)   C[i] = (c.z, id)
+//   id   = pixelIndex | slot << pixBits | dead << 31      (slot = which iteration of the batch)
+// remainingBounces is not stored: every live path at bounce d has traceDepth - d left
+// (src/pathtrace.cu:141 sets it once; nothing but the bounce loop changes it).
+#pragma once
+#include "ptb_math.cuh"
+#include <cfloat>
+
+namespace ptb {
+
+constexpr int kBlock = 256;
+constexpr uint32_t kDeadBit = 0x80000000u;
+
+struct BvhNode {                 // 64 B = four 128-bit loads: a binary node holding BOTH child boxes
+    float4 llo, lhi;             // left  child: min.xyz | ref (int bits), max.xyz | count (int bits)
+    float4 rlo, rhi;             // right child: same.  count > 0: leaf, ref = first geom slot;
+};                               //              count == 0: interior, ref = node index; ref < 0: empty
+
+struct PathPlanes { float4 *A; float4 *B; float2 *C; };
+
+struct HitPlanes {               // staged pipeline only: ShadeableIntersection (src/sceneStructs.h:72-76) as SoA, 20 B
+    float4 *tn;                  // t, n.x, n.y, n.z
+    int    *meta;                // -1 = miss, else geom slot | outside << 30
+};
+
+struct Control {                 // device-resident loop control: no host round trip inside a batch
+    int      iterBase;           // iteration number of slot 0
+    int      iterStride;         // iteration distance between slots (G for a G-GPU spp split)
+    int      batch;              // slots in this wavefront
+    int      pad;
+    uint32_t counts[68];         // counts[d] = paths entering bounce d of the current batch
+    unsigned long long aliveTotals[64];
+    unsigned long long segments;
+    unsigned long long iterations;
+};
+
+struct CameraParams {
+    float px, py, pz;            // position
+    float vx, vy, vz;            // view
+    float ux, uy, uz;            // up
+    float rx, ry, rz;            // right
+    float plx, ply;              // pixelLength
+    int   W, H;
+};
+
+struct Params {
+    CameraParams cam;
+    const GeomRec *geoms;        // brute force: scene order; BVH: leaf order (tag.z = scene index)
+    int            numGeoms;
+    const BvhNode *bvh;
+    int            numNodes;
+    int            smemNodes;    // leading BVH nodes (BFS order = top levels) staged in shared memory
+    const float4  *mats;         // 3 float4 per material
+    int            numMats;
+    float         *image;        // W*H*3 accumulation (layout of scene->state.image)
+    Control       *ctrl;
+    PathPlanes     in, out;
+    HitPlanes      hits;
+    int            traceDepth;
+    int            bsdfMode;
+    int            pixBits;
+    uint32_t       numPixels;
+    int            atomicGather; // 1 when several slots may deposit into one pixel concurrently
+};
+
+// ------------------------------------------------------------------------------------------------
+// shared device pieces
+// ------------------------------------------------------------------------------------------------
+// generateRayFromCamera body, src/pathtrace.cu:131-138
+PTB_DEV void cameraRay(const CameraParams &c, uint32_t pix, f3 &o, f3 &d) {
+    const int y = (int)(pix / (uint32_t)c.W);
+    const int x = (int)(pix - (uint32_t)y * (uint32_t)c.W);
+    o = mk3(c.px, c.py, c.pz);
+    const float fx = sub((float)x, mul((float)c.W, 0.5f));
+    const float fy = sub((float)y, mul((float)c.H, 0.5f));
+    f3 a = scale3(scale3(mk3(c.rx, c.ry, c.rz), c.plx), fx);
+    f3 b = scale3(scale3(mk3(c.ux, c.uy, c.uz), c.ply), fy);
+    d = normalize3(sub3(sub3(mk3(c.vx, c.vy, c.vz), a), b));
+}
+
+struct Candidate {               // what must survive the geom loop to build the winner's normal
+    float t;
+    int   slot;                  // position in the geoms array, -1 = none
+    int   outside;
+    float a, b, c;               // box: face normal code; sphere: object-space hit point
+};
+
+PTB_DEV void testGeom(const GeomRec &g, int slot, f3 o, f3 d, Candidate &best, int bestOrig, int &bestOrigOut, bool tieByIndex) {
+    float t; int outside = 1; float a, b, c;
+    if (g.tag.x == 1) {          // CUBE
+        BoxFace f;
+        t = boxTest(g, o, d, f, outside);
+        a = f.nx; b = f.ny; c = f.nz;
+    } else {                     // SPHERE
+        f3 objP = mk3(0.f, 0.f, 0.f);
+        t = sphereTest(g, o, d, objP, outside);
+        a = objP.x; b = objP.y; c = objP.z;
+    }
+    // src/pathtrace.cu:192: `t > 0.0f && t_min > t` visited in index order == lowest index wins ties.
+    bool take = t > 0.0f && best.t > t;
+    if (tieByIndex && t > 0.0f && best.t == t && g.tag.z < bestOrig) take = true;
+    if (take) {
+        best.t = t; best.slot = slot; best.outside = outside; best.a = a; best.b = b; best.c = c;
+        bestOrigOut = g.tag.z;
+    }
+}
+
+PTB_DEV f3 candidateNormal(const GeomRec &g, const Candidate &c) {
+    if (g.tag.x == 1) { BoxFace f; f.nx = c.a; f.ny = c.b; f.nz = c.c; return boxNormal(g, f); }
+    return sphereNormal(g, mk3(c.a, c.b, c.c), c.outside);
+}
+
+// closest hit, brute force over shared-memory geoms (warp-uniform loop => broadcast reads)
+PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, Candidate &best) {
+    best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
+    int orig = 0x7fffffff;
+    for (int g = 0; g < numGeoms; ++g) testGeom(sg[g], g, o, d, best, orig, orig, false);
+}
+
+// Conservative ray/AABB test for pruning only.  The boxes are padded on the host (ptb_bvh.cpp) to cover
+// the reference's rounding and its 1e-4 fall-short (src/intersections.h:27-29); tNear is the entry
+// parameter along the ray in units of |d|.  fminf/fmaxf drop the NaNs that 0*inf produces when the
+// origin lies on a slab plane, which errs on the side of visiting.
+PTB_DEV bool slabNear(float4 lo, float4 hi, f3 o, f3 inv, float &tNear) {
+    float tx0 = (lo.x - o.x) * inv.x, tx1 = (hi.x - o.x) * inv.x;
+    float ty0 = (lo.y - o.y) * inv.y, ty1 = (hi.y - o.y) * inv.y;
+    float tz0 = (lo.z - o.z) * inv.z, tz1 = (hi.z - o.z) * inv.z;
+    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
+    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
+    tNear = tn;
+    return tn <= tf * 1.00001f + 1e-5f;
+}
+
+PTB_DEV GeomRec loadGeom(const GeomRec *gp) {
+    GeomRec g;
+    const float4 *src = reinterpret_cast<const float4 *>(gp);
+    float4 *dst = reinterpret_cast<float4 *>(&g);
+#pragma unroll
+    for (int q = 0; q < 10; ++q) dst[q] = __ldg(src + q);
+    return g;
+}
+
+// closest hit through the flat BVH.  Leaves run the reference-exact tests; pruning uses padded boxes
+// and a slackened distance bound, so the winner is the same (t, scene index)-lexicographic minimum
+// that the reference's index-ordered loop finds (src/pathtrace.cu:176-199).
+PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, f3 o, f3 d, Candidate &best) {
+    best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
+    int bestOrig = 0x7fffffff;
+    const float dl = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z) * 0.9999f;
+    const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    int stack[64];
+    int sp = 0;
+    int node = 0;
+    for (;;) {
+        float4 llo, lhi, rlo, rhi;
+        if (node < p.smemNodes) { llo = snodes[node].llo; lhi = snodes[node].lhi; rlo = snodes[node].rlo; rhi = snodes[node].rhi; }
+        else {
+            const float4 *np = reinterpret_cast<const float4 *>(p.bvh + node);
+            llo = __ldg(np); lhi = __ldg(np + 1); rlo = __ldg(np + 2); rhi = __ldg(np + 3);
+        }
+        float tl, tr;
+        // tNear*|d| (slackened) is a lower bound of the world distance of anything inside the box
+        bool vl = __float_as_int(llo.w) >= 0 && slabNear(llo, lhi, o, inv, tl) && tl * dl - 1e-4f <= best.t;
+        bool vr = __float_as_int(rlo.w) >= 0 && slabNear(rlo, rhi, o, inv, tr) && tr * dl - 1e-4f <= best.t;
+        int nextL = -1, nextR = -1;
+        if (vl) {
+            const int cnt = __float_as_int(lhi.w), ref = __float_as_int(llo.w);
+            if (cnt > 0) { for (int k = 0; k < cnt; ++k) testGeom(loadGeom(p.geoms + ref + k), ref + k, o, d, best, bestOrig, bestOrig, true); }
+            else nextL = ref;
+        }
+        if (vr && tr * dl - 1e-4f <= best.t) {
+            const int cnt = __float_as_int(rhi.w), ref = __float_as_int(rlo.w);
+            if (cnt > 0) { for (int k = 0; k < cnt; ++k) testGeom(loadGeom(p.geoms + ref + k), ref + k, o, d, best, bestOrig, bestOrig, true); }
+            else nextR = ref;
+        }
+        if (nextL >= 0 && nextR >= 0) {
+            if (tl <= tr) { if (sp < 64) stack[sp++] = nextR; node = nextL; }
+            else          { if (sp < 64) stack[sp++] = nextL; node = nextR; }
+        } else if (nextL >= 0) node = nextL;
+        else if (nextR >= 0) node = nextR;
+        else {
+            if (sp == 0) break;
+            node = stack[--sp];
+        }
+    }
+}
+
+struct Mat { f3 color; float emittance; f3 spec; float refl; float refr; float ior; };
+PTB_DEV Mat loadMat(const float4 *mats, int id) {
+    float4 a = __ldg(&mats[3 * id]), b = __ldg(&mats[3 * id + 1]), c = __ldg(&mats[3 * id + 2]);
+    Mat m;
+    m.color = mk3(a.x, a.y, a.z); m.emittance = a.w;
+    m.spec = mk3(b.x, b.y, b.z); m.refl = b.w;
+    m.refr = c.x; m.ior = c.y;
+    return m;
+}
+
+// calculateRandomDirectionInHemisphere, src/interactions.h:10-42
+PTB_DEV f3 hemisphere(f3 n, Rng &rng) {
+    float up = fsqrt(u01(rng));
+    float over = fsqrt(sub(1.0f, mul(up, up)));
+    float around = mul(u01(rng), 6.2831853071795864769252867665590057683943f);
+    f3 notNormal;
+    if (fabsf(n.x) < 0.5773502691896257645091487805019574556476f) notNormal = mk3(1.f, 0.f, 0.f);
+    else if (fabsf(n.y) < 0.5773502691896257645091487805019574556476f) notNormal = mk3(0.f, 1.f, 0.f);
+    else notNormal = mk3(0.f, 0.f, 1.f);
+    f3 p1 = normalize3(cross3(n, notNormal));
+    f3 p2 = normalize3(cross3(n, p1));
+    float s, c;
+    sincosf(around, &s, &c);      // full-precision libdevice path (no fast-math); ulp-level vs glibc
+    return add3(add3(scale3(n, up), scale3(p1, mul(c, over))), scale3(p2, mul(s, over)));
+}
+
+// glm::reflect, func_geometric.inl:176-179: I - N * dot(N, I) * 2
+PTB_DEV f3 reflect3(f3 I, f3 N) { return sub3(I, scale3(scale3(N, dot3(N, I)), 2.0f)); }
+
+// One shade step.  Returns true while the path stays alive; when it returns
+// false, `c` holds the radiance this path contributes (zero for a miss or an exhausted path).
+PTB_DEV bool shadeStep(const Params &p, int depth, int iter, uint32_t pix, bool isHit, int matId,
+                       float t, f3 n, int outside, f3 &o, f3 &d, f3 &c, int remainingBefore) {
+    if (!isHit) { c = mk3(0.f, 0.f, 0.f); return false; }                 // src/pathtrace.cu:262-264
+    const Mat m = loadMat(p.mats, matId);
+    if (m.emittance > 0.0f) {                                             // src/pathtrace.cu:247-249
+        c = mul3(c, scale3(m.color, m.emittance));
+        return false;
+    }
+    if (remainingBefore <= 1) {                                           // bounce budget exhausted:
+        c = mk3(0.f, 0.f, 0.f);                                           // the scattered ray is never used
+        return false;
+    }
+    Rng rng = seedRng(iter, (int)pix, depth);                             // src/pathtrace.cu:240, keyed by pixelIndex
+    const f3 P = pointOnRay(o, d, t);
+    if (p.bsdfMode == 1 && m.refr > 0.0f) {
+        const f3 I = normalize3(d);
+        const float eta = outside ? fdiv(1.0f, m.ior) : m.ior;
+        const float cosi = -dot3(n, I);
+        float r0 = fdiv(sub(1.0f, m.ior), add(1.0f, m.ior));
+        r0 = mul(r0, r0);
+        const float c1 = sub(1.0f, cosi);
+        const float c2 = mul(c1, c1);
+        const float c5 = mul(mul(c2, c2), c1);
+        const float R = add(r0, mul(sub(1.0f, r0), c5));
+        const float u = u01(rng);
+        const float dotNI = dot3(n, I);
+        const float k = sub(1.0f, mul(mul(eta, eta), sub(1.0f, mul(dotNI, dotNI))));
+        const bool tir = !(k >= 0.0f);
+        if (tir || u < R) {
+            d = reflect3(I, n);
+            o = P;
+            c = mul3(c, m.spec);
+        } else {
+            // glm::refract, func_geometric.inl:193-200
+            const float f = add(mul(eta, dotNI), fsqrt(k));
+            const f3 T = scale3(sub3(scale3(I, eta), scale3(n, f)), 1.0f);
+            o = pointOnRay(o, d, add(t, 0.0002f));
+            d = T;
+            c = mul3(c, m.color);
+        }
+    } else if (p.bsdfMode == 1 && m.refl > 0.0f) {
+        d = reflect3(d, n);
+        o = P;
+        c = mul3(c, m.spec);
+    } else {
+        d = hemisphere(n, rng);
+        o = P;
+        c = mul3(c, m.color);
+    }
+    return true;
+}
+
+// image[pixelIndex] += color (src/pathtrace.cu:276).  A zero colour is skipped: x + 0 == x.
+PTB_DEV void deposit(const Params &p, uint32_t pix, f3 c) {
+    if (c.x == 0.0f && c.y == 0.0f && c.z == 0.0f) return;
+    float *px = p.image + 3 * (size_t)pix;
+    if (p.atomicGather) {
+        atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
+    } else {
+        px[0] = add(px[0], c.x); px[1] = add(px[1], c.y); px[2] = add(px[2], c.z);
+    }
+}
+
+PTB_DEV void loadPath(const PathPlanes &s, uint32_t i, f3 &o, f3 &d, f3 &c, uint32_t &id) {
+    const float4 a = s.A[i], b = s.B[i];
+    const float2 e = s.C[i];
+    o = mk3(a.x, a.y, a.z); d = mk3(a.w, b.x, b.y); c = mk3(b.z, b.w, e.x); id = __float_as_uint(e.y);
+}
+PTB_DEV void storePath(const PathPlanes &s, uint32_t i, f3 o, f3 d, f3 c, uint32_t id) {
+    s.A[i] = make_float4(o.x, o.y, o.z, d.x);
+    s.B[i] = make_float4(d.y, d.z, c.x, c.y);
+    s.C[i] = make_float2(c.z, __uint_as_float(id));
+}
+
+// cooperative copy of the scene tables into shared memory (geoms for brute force, BVH top levels)
+PTB_DEV void stageShared(float4 *dst, const float4 *src, int nFloat4) {
+    for (int i = threadIdx.x; i < nFloat4; i += blockDim.x) dst[i] = __ldg(src + i);
+    __syncthreads();
+}
+
+// Block-wide stream compaction slot: warp ballot + popc prefix, one aggregated atomic per block.
+// Returns the destination index for threads with keep == true.
+PTB_DEV uint32_t compactSlot(bool keep, uint32_t *counter, int *warpTotals, uint32_t *blockBase) {
+    const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int prefix = __popc(ballot & ((1u << lane) - 1u));
+    if (lane == 0) warpTotals[warp] = __popc(ballot);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        // one warp scans the (<= 32) warp totals and issues the single atomic of this tile
+        const int nw = blockDim.x >> 5;
+        int v = threadIdx.x < nw ? warpTotals[threadIdx.x] : 0;
+        int incl = v;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            int y = __shfl_up_sync(0xffffffffu, incl, s);
+            if (lane >= s) incl += y;
+        }
+        const int total = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t base = 0;
+        if (lane == 0 && total > 0) base = atomicAdd(counter, (uint32_t)total);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (threadIdx.x < nw) warpTotals[threadIdx.x] = incl - v;      // exclusive offsets
+        if (lane == 0) *blockBase = base;
+    }
+    __syncthreads();
+    const uint32_t dst = *blockBase + (uint32_t)warpTotals[warp] + (uint32_t)prefix;
+    __syncthreads();                                                     // smem is reused by the next tile
+    return dst;
+}
+
+// ------------------------------------------------------------------------------------------------
+// THE FAST PATH: one launch per bounce.  FIRST = bounce 0 (camera rays generated in registers, no
+// path-state read); USE_BVH selects the flat BVH over the brute-force shared-memory loop.
+// Persistent grid (a multiple of the SM count), grid-stride over 256-path tiles; the number of live
+// paths is read from device memory, so the host never synchronises inside an iteration.
+// ------------------------------------------------------------------------------------------------
+template <bool FIRST, bool USE_BVH>
+__global__ void __launch_bounds__(kBlock) bounce_kernel(const __grid_constant__ Params p, const int depth) {
+    extern __shared__ float4 smem4[];
+    __shared__ int warpTotals[kBlock / 32];
+    __shared__ uint32_t blockBase;
+
+    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), p.smemNodes * 4);
+    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * 10);
+    const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
+    const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
+
+    Control *ctrl = p.ctrl;
+    const int iterBase = ctrl->iterBase, iterStride = ctrl->iterStride;
+    const uint32_t nIn = FIRST ? p.numPixels * (uint32_t)ctrl->batch : ctrl->counts[depth];
+    const int remainingBefore = p.traceDepth - depth;
+    const uint32_t pixMask = (1u << p.pixBits) - 1u;
+
+    for (uint32_t base = blockIdx.x * kBlock; base < nIn; base += gridDim.x * kBlock) {
+        const uint32_t i = base + threadIdx.x;
+        bool alive = false;
+        f3 o, d, c; uint32_t id = 0;
+        if (i < nIn) {
+            uint32_t pix, slot;
+            if (FIRST) {
+                slot = i / p.numPixels;
+                pix = i - slot * p.numPixels;
+                id = pix | (slot << p.pixBits);
+                cameraRay(p.cam, pix, o, d);
+                c = mk3(1.0f, 1.0f, 1.0f);                                // src/pathtrace.cu:132
+            } else {
+                loadPath(p.in, i, o, d, c, id);
+                pix = id & pixMask;
+                slot = (id & ~kDeadBit) >> p.pixBits;
+            }
+            Candidate best;
+            if (USE_BVH) closestHitBvh(p, snodes, o, d, best);
+            else         closestHitBrute(sgeoms, p.numGeoms, o, d, best);
+            const bool isHit = best.slot >= 0;
+            f3 n = mk3(0.f, 0.f, 0.f); int matId = 0;
+            if (isHit) {
+                if (USE_BVH) {
+                    const GeomRec g = loadGeom(p.geoms + best.slot);
+                    n = candidateNormal(g, best); matId = g.tag.y;
+                } else {
+                    n = candidateNormal(sgeoms[best.slot], best); matId = sgeoms[best.slot].tag.y;
+                }
+            }
+            const int iter = iterBase + (int)slot * iterStride;
+            alive = shadeStep(p, depth, iter, pix, isHit, matId, best.t, n, best.outside, o, d, c, remainingBefore);
+            if (!alive) deposit(p, pix, c);                               // gather at termination
+        }
+        const uint32_t dst = compactSlot(alive, &ctrl->counts[depth + 1], warpTotals, &blockBase);
+        if (alive) storePath(p.out, dst, o, d, c, id);
+    }
+}
+
+// End of a batch: fold the per-depth counts into the running statistics, clear them for the next
+// batch and advance the iteration base -- keeps the whole multi-batch loop on the device.
+__global__ void advance_kernel(Control *ctrl, int traceDepth, uint32_t numPixels) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctrl->counts[0] = numPixels * (uint32_t)ctrl->batch;
+    unsigned long long seg = 0;
+    for (int d = 0; d < traceDepth; ++d) { ctrl->aliveTotals[d] += ctrl->counts[d]; seg += ctrl->counts[d]; }
+    for (int d = 0; d <= traceDepth + 1 && d < 68; ++d) ctrl->counts[d] = 0;
+    ctrl->segments += seg;
+    ctrl->iterations += (unsigned long long)ctrl->batch;
+    ctrl->iterBase += ctrl->batch * ctrl->iterStride;
+}
+__global__ void set_control_kernel(Control *ctrl, int iterBase, int iterStride, int batch) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctrl->iterBase = iterBase; ctrl->iterStride = iterStride; ctrl->batch = batch;
+    for (int d = 0; d < 68; ++d) ctrl->counts[d] = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// THE STAGED PIPELINE: the reference's kernel structure, one stage per launch.
+// ------------------------------------------------------------------------------------------------
+// generateRayFromCamera (src/pathtrace.cu:122-143)
+__global__ void __launch_bounds__(kBlock) raygen_kernel(const __grid_constant__ Params p) {
+    const uint32_t n = p.numPixels * (uint32_t)p.ctrl->batch;
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        const uint32_t slot = i / p.numPixels, pix = i - slot * p.numPixels;
+        f3 o, d;
+        cameraRay(p.cam, pix, o, d);
+        storePath(p.in, i, o, d, mk3(1.0f, 1.0f, 1.0f), pix | (slot << p.pixBits));
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) p.ctrl->counts[0] = n;
+}
+
+// computeIntersections (src/pathtrace.cu:149-213): writes one hit record per live path
+template <bool USE_BVH>
+__global__ void __launch_bounds__(kBlock) intersect_kernel(const __grid_constant__ Params p, const int depth) {
+    extern __shared__ float4 smem4[];
+    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), p.smemNodes * 4);
+    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * 10);
+    const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
+    const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
+    const uint32_t nIn = p.ctrl->counts[depth];
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < nIn; i += gridDim.x * kBlock) {
+        f3 o, d, c; uint32_t id;
+        loadPath(p.in, i, o, d, c, id);
+        if (id & kDeadBit) { p.hits.meta[i] = -1; continue; }            // no-compaction mode: dead path stays in place
+        Candidate best;
+        if (USE_BVH) closestHitBvh(p, snodes, o, d, best);
+        else         closestHitBrute(sgeoms, p.numGeoms, o, d, best);
+        if (best.slot < 0) {
+            p.hits.tn[i] = make_float4(-1.0f, 0.f, 0.f, 0.f);             // src/pathtrace.cu:203
+            p.hits.meta[i] = -1;
+        } else {
+            const GeomRec &g = USE_BVH ? p.geoms[best.slot] : sgeoms[best.slot];
+            const f3 n = candidateNormal(g, best);
+            p.hits.tn[i] = make_float4(best.t, n.x, n.y, n.z);
+            p.hits.meta[i] = best.slot | (best.outside << 30);
+        }
+    }
+}
+
+// shading + scatterRay.  order != NULL: paths are visited in material-sorted order.
+// depositAtTermination: 1 = add radiance when the path ends (needed once dead paths are compacted
+// away), 0 = leave it in the path's colour for gather_kernel (the reference's finalGather layout).
+__global__ void __launch_bounds__(kBlock) shade_kernel(const __grid_constant__ Params p, const int depth,
+                                                       const int *order, const int depositAtTermination) {
+    const uint32_t nIn = p.ctrl->counts[depth];
+    const int iterBase = p.ctrl->iterBase, iterStride = p.ctrl->iterStride;
+    const uint32_t pixMask = (1u << p.pixBits) - 1u;
+    for (uint32_t j = blockIdx.x * kBlock + threadIdx.x; j < nIn; j += gridDim.x * kBlock) {
+        const uint32_t i = order ? (uint32_t)order[j] : j;
+        f3 o, d, c; uint32_t id;
+        loadPath(p.in, i, o, d, c, id);
+        if (id & kDeadBit) continue;
+        const uint32_t pix = id & pixMask, slot = id >> p.pixBits;
+        const int meta = p.hits.meta[i];
+        const bool isHit = meta >= 0;
+        float t = -1.0f; f3 n = mk3(0.f, 0.f, 0.f); int matId = 0, outside = 1;
+        if (isHit) {
+            const float4 tn = p.hits.tn[i];
+            t = tn.x; n = mk3(tn.y, tn.z, tn.w);
+            outside = (meta >> 30) & 1;
+            matId = p.geoms[meta & 0x3fffffff].tag.y;
+        }
+        const bool alive = shadeStep(p, depth, iterBase + (int)slot * iterStride, pix, isHit, matId, t, n, outside,
+                                     o, d, c, p.traceDepth - depth);
+        if (!alive) {
+            if (depositAtTermination) deposit(p, pix, c);
+            id |= kDeadBit;
+        }
+        storePath(p.in, i, o, d, c, id);
+    }
+}
+
+// stream compaction of the path array (replaces the stream_compaction submodule): live paths of
+// `in` are packed into `out`; counts[depth+1] receives their number.
+__global__ void __launch_bounds__(kBlock) compact_kernel(const __grid_constant__ Params p, const int depth) {
+    __shared__ int warpTotals[kBlock / 32];
+    __shared__ uint32_t blockBase;
+    const uint32_t nIn = p.ctrl->counts[depth];
+    for (uint32_t base = blockIdx.x * kBlock; base < nIn; base += gridDim.x * kBlock) {
+        const uint32_t i = base + threadIdx.x;
+        f3 o, d, c; uint32_t id = kDeadBit;
+        if (i < nIn) loadPath(p.in, i, o, d, c, id);
+        const bool keep = !(id & kDeadBit);
+        const uint32_t dst = compactSlot(keep, &p.ctrl->counts[depth + 1], warpTotals, &blockBase);
+        if (keep) storePath(p.out, dst, o, d, c, id);
+    }
+}
+// without compaction the next bounce still sees every slot
+__global__ void carry_count_kernel(Control *ctrl, int depth) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) ctrl->counts[depth + 1] = ctrl->counts[depth];
+}
+
+// finalGather (src/pathtrace.cu:269-278): image[pixelIndex] += color for every path slot.
+// Paths that never ended on a light carry colour 0 by then.
+__global__ void __launch_bounds__(kBlock) gather_kernel(const __grid_constant__ Params p, const uint32_t nPaths) {
+    const uint32_t pixMask = (1u << p.pixBits) - 1u;
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < nPaths; i += gridDim.x * kBlock) {
+        f3 o, d, c; uint32_t id;
+        loadPath(p.in, i, o, d, c, id);
+        if (!(id & kDeadBit)) c = mk3(0.f, 0.f, 0.f);      // still alive after the last bounce: exhausted
+        deposit(p, id & pixMask, c);
+    }
+}
+
+// ---- material-id sort: histogram -> scan -> scatter (counting sort; keys are tiny integers) ----
+__global__ void __launch_bounds__(kBlock) sort_hist_kernel(const int *keys, uint32_t n, int numKeys, uint32_t *hist) {
+    extern __shared__ uint32_t sh[];
+    for (int k = threadIdx.x; k < numKeys; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) atomicAdd(&sh[keys[i]], 1u);
+    __syncthreads();
+    for (int k = threadIdx.x; k < numKeys; k += blockDim.x) if (sh[k]) atomicAdd(&hist[k], sh[k]);
+}
+__global__ void sort_scan_kernel(uint32_t *hist, int numKeys) {     // exclusive scan, numKeys is small
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        uint32_t run = 0;
+        for (int k = 0; k < numKeys; ++k) { uint32_t v = hist[k]; hist[k] = run; run += v; }
+    }
+}
+__global__ void __launch_bounds__(kBlock) sort_scatter_kernel(const int *keys, uint32_t n, uint32_t *cursor, int *order) {
+    for (uint32_t base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
+        const uint32_t i = base + threadIdx.x;
+        const bool valid = i < n;
+        const int key = valid ? keys[i] : -1;
+        // warp-aggregated atomics per key: lanes with the same key share one atomicAdd
+        const unsigned active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned peers = __match_any_sync(active, key);
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(peers) - 1;
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t pos = 0;
+            if (lane == leader) pos = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+            pos = __shfl_sync(peers, pos, leader);
+            order[pos + rank] = (int)i;
+        }
+    }
+}
+// key of a path for the material sort: its hit material, or numMats for misses / dead slots
+__global__ void __launch_bounds__(kBlock) sort_keys_kernel(const __grid_constant__ Params p, const int depth, int *keys) {
+    const uint32_t nIn = p.ctrl->counts[depth];
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < nIn; i += gridDim.x * kBlock) {
+        const int meta = p.hits.meta[i];
+        keys[i] = meta < 0 ? p.numMats : p.geoms[meta & 0x3fffffff].tag.y;
+    }
+}
+// material sort with the path count living on the device
+__global__ void __launch_bounds__(kBlock) sort_hist_dev_kernel(const int *keys, const Control *ctrl, int depth, int numKeys, uint32_t *hist) {
+    extern __shared__ uint32_t sh[];
+    const uint32_t n = ctrl->counts[depth];
+    for (int k = threadIdx.x; k < numKeys; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) atomicAdd(&sh[keys[i]], 1u);
+    __syncthreads();
+    for (int k = threadIdx.x; k < numKeys; k += blockDim.x) if (sh[k]) atomicAdd(&hist[k], sh[k]);
+}
+__global__ void __launch_bounds__(kBlock) sort_scatter_dev_kernel(const int *keys, const Control *ctrl, int depth, uint32_t *cursor, int *order) {
+    const uint32_t n = ctrl->counts[depth];
+    for (uint32_t base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
+        const uint32_t i = base + threadIdx.x;
+        const bool valid = i < n;
+        const int key = valid ? keys[i] : -1;
+        const unsigned active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            const unsigned peers = __match_any_sync(active, key);
+            const int lane = threadIdx.x & 31;
+            const int leader = __ffs(peers) - 1;
+            const int rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t pos = 0;
+            if (lane == leader) pos = atomicAdd(&cursor[key], (uint32_t)__popc(peers));
+            pos = __shfl_sync(peers, pos, leader);
+            order[pos + rank] = (int)i;
+        }
+    }
+}
+
+// sendImageToPBO (src/pathtrace.cu:48-68): clamp((int)(pix / iter * 255.0), 0, 255) -- the multiply is
+// in double precision because the literal 255.0 is a double.
+__global__ void __launch_bounds__(kBlock) pbo_kernel(uchar4 *pbo, const float *image, uint32_t numPixels, int iter) {
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < numPixels; i += gridDim.x * kBlock) {
+        const float fi = (float)iter;
+        int r = (int)((double)fdiv(image[3 * (size_t)i + 0], fi) * 255.0);
+        int g = (int)((double)fdiv(image[3 * (size_t)i + 1], fi) * 255.0);
+        int b = (int)((double)fdiv(image[3 * (size_t)i + 2], fi) * 255.0);
+        r = min(max(r, 0), 255); g = min(max(g, 0), 255); b = min(max(b, 0), 255);
+        pbo[i] = make_uchar4((unsigned char)r, (unsigned char)g, (unsigned char)b, 0);
+    }
+}
+
+// saveImage + image::savePNG on the device (src/main.cpp:83-89, src/image.cpp:27-30):
+// out(W-1-x, y) = (unsigned char)(clamp(sum / samples, 0, 1) * 255.f)
+__global__ void __launch_bounds__(kBlock) resolve_rgb8_kernel(uint8_t *rgb, const float *image, int W, int H, float samples) {
+    const uint32_t n = (uint32_t)W * (uint32_t)H;
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        const int y = (int)(i / (uint32_t)W), x = (int)(i - (uint32_t)y * (uint32_t)W);
+        const size_t dst = (size_t)y * W + (size_t)(W - 1 - x);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            float v = fdiv(image[3 * (size_t)i + k], samples);
+            v = v < 0.0f ? 0.0f : (v > 1.0f ? 1.0f : v);     // glm::clamp = min(max(x, lo), hi); NaN stays NaN -> cast 0
+            rgb[3 * dst + k] = (uint8_t)mul(v, 255.f);
+        }
+    }
+}
+
+// ---- stage-level test kernels (host arrays in / out through ptb_stage_*) ----
+template <bool USE_BVH>
+__global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_constant__ Params p, const float *origins,
+        const float *dirs, int n, int *hit, float *t, float *normal, int *outside) {
+    extern __shared__ float4 smem4[];
+    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), p.smemNodes * 4);
+    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * 10);
+    const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
+    const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        const f3 o = mk3(origins[3 * (size_t)i], origins[3 * (size_t)i + 1], origins[3 * (size_t)i + 2]);
+        const f3 d = mk3(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2]);
+        Candidate best;
+        if (USE_BVH) closestHitBvh(p, snodes, o, d, best);
+        else         closestHitBrute(sgeoms, p.numGeoms, o, d, best);
+        if (best.slot < 0) {
+            hit[i] = -1; t[i] = -1.0f; outside[i] = 1;
+            normal[3 * (size_t)i] = normal[3 * (size_t)i + 1] = normal[3 * (size_t)i + 2] = 0.f;
+        } else {
+            const GeomRec &g = USE_BVH ? p.geoms[best.slot] : sgeoms[best.slot];
+            const f3 nn = candidateNormal(g, best);
+            hit[i] = g.tag.z; t[i] = best.t; outside[i] = best.outside;
+            normal[3 * (size_t)i] = nn.x; normal[3 * (size_t)i + 1] = nn.y; normal[3 * (size_t)i + 2] = nn.z;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) stage_raygen_kernel(const __grid_constant__ Params p, float *origins, float *dirs) {
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < p.numPixels; i += gridDim.x * kBlock) {
+        f3 o, d;
+        cameraRay(p.cam, i, o, d);
+        origins[3 * (size_t)i] = o.x; origins[3 * (size_t)i + 1] = o.y; origins[3 * (size_t)i + 2] = o.z;
+        dirs[3 * (size_t)i] = d.x; dirs[3 * (size_t)i + 1] = d.y; dirs[3 * (size_t)i + 2] = d.z;
+    }
+}
+
+// hit[] holds SCENE geom indices here (as the oracle reports them); sceneMat maps them to materials
+__global__ void __launch_bounds__(kBlock) stage_shade_kernel(const __grid_constant__ Params p, int n, const int *hit,
+        const int *sceneMat, const float *t, const float *normal, const int *outside, const int *iter,
+        const int *pixelIndex, const int *depth, float *origins, float *dirs, float *colors, int *remaining) {
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        f3 o = mk3(origins[3 * (size_t)i], origins[3 * (size_t)i + 1], origins[3 * (size_t)i + 2]);
+        f3 d = mk3(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2]);
+        f3 c = mk3(colors[3 * (size_t)i], colors[3 * (size_t)i + 1], colors[3 * (size_t)i + 2]);
+        const f3 nn = mk3(normal[3 * (size_t)i], normal[3 * (size_t)i + 1], normal[3 * (size_t)i + 2]);
+        const bool isHit = hit[i] >= 0;
+        const int rem = remaining[i];
+        const bool alive = shadeStep(p, depth[i], iter[i], (uint32_t)pixelIndex[i], isHit, isHit ? sceneMat[hit[i]] : 0,
+                                     t[i], nn, outside[i], o, d, c, rem);
+        // orc_shade contract: miss / emissive -> remaining 0; scatter -> remaining - 1 (0 => colour 0)
+        int newRem = 0;
+        if (alive) newRem = rem - 1;
+        origins[3 * (size_t)i] = o.x; origins[3 * (size_t)i + 1] = o.y; origins[3 * (size_t)i + 2] = o.z;
+        dirs[3 * (size_t)i] = d.x; dirs[3 * (size_t)i + 1] = d.y; dirs[3 * (size_t)i + 2] = d.z;
+        colors[3 * (size_t)i] = c.x; colors[3 * (size_t)i + 1] = c.y; colors[3 * (size_t)i + 2] = c.z;
+        remaining[i] = newRem;
+    }
+}
+
+__global__ void __launch_bounds__(kBlock) stage_compact_kernel(int n, const int *ids, const int *flags, int *outIds, uint32_t *counter) {
+    __shared__ int warpTotals[kBlock / 32];
+    __shared__ uint32_t blockBase;
+    for (int base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {
+        const int i = base + threadIdx.x;
+        const bool keep = i < n && flags[i] != 0;
+        const uint32_t dst = compactSlot(keep, counter, warpTotals, &blockBase);
+        if (keep) outIds[dst] = ids[i];
+    }
+}
+
+__global__ void stage_rng_kernel(int iter, int index, int depth, int n, float *out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        Rng r = seedRng(iter, index, depth);
+        for (int i = 0; i < n; ++i) out[i] = u01(r);
+    }
+}
+
+} // namespace ptb
