@@ -108,6 +108,7 @@ typedef struct PtbStats {
     int32_t bvhNodes;               /* 0 when brute force */
     int32_t batchIters;
     int64_t pathStateBytes;         /* bytes of path state resident in HBM */
+    int64_t sceneUploadBytes;       /* host->device bytes of the last ptb_create / ptb_update_scene */
 } PtbStats;
 
 enum PtbError {
@@ -127,6 +128,10 @@ int         ptb_abi_version(void);
 /* pathtraceInit (src/pathtrace.cu:79-101): allocate + upload + zero the accumulation buffer.
  * The scene arrays are copied; the caller keeps ownership. */
 int ptb_create(PtbContext **ctx, const PtbSceneDesc *scene, const PtbOptions *opts);
+/* Re-upload geoms / materials / camera into an existing context and zero the accumulation: what the
+ * app does on a camera move by calling pathtraceFree + pathtraceInit (src/main.cpp:125-128), without
+ * reallocating.  Counts, resolution and traceDepth must equal those given to ptb_create. */
+int ptb_update_scene(PtbContext *ctx, const PtbSceneDesc *scene);
 /* pathtraceFree (src/pathtrace.cu:103-112).  NULL is a no-op (main.cpp:126 frees before the first init). */
 int ptb_destroy(PtbContext *ctx);
 

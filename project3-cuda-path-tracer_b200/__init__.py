@@ -55,7 +55,8 @@ class PtbOptions(C.Structure):
 class PtbStats(C.Structure):
     _fields_ = [("iterations", C.c_int64), ("segments", C.c_int64), ("kernelLaunches", C.c_int64),
                 ("alivePerDepth", C.c_int64 * 64), ("traceDepth", C.c_int32), ("numGeoms", C.c_int32),
-                ("bvhNodes", C.c_int32), ("batchIters", C.c_int32), ("pathStateBytes", C.c_int64)]
+                ("bvhNodes", C.c_int32), ("batchIters", C.c_int32), ("pathStateBytes", C.c_int64),
+                ("sceneUploadBytes", C.c_int64)]
 
 
 class PtbError(RuntimeError):
@@ -64,7 +65,7 @@ class PtbError(RuntimeError):
 
 # every symbol include/ptb200.h declares (tests/test_abi.py checks the library exports all of them)
 ABI_SYMBOLS = [
-    "ptb_default_options", "ptb_last_error", "ptb_abi_version", "ptb_create", "ptb_destroy",
+    "ptb_default_options", "ptb_last_error", "ptb_abi_version", "ptb_create", "ptb_update_scene", "ptb_destroy",
     "ptb_pathtrace", "ptb_render", "ptb_download", "ptb_write_pbo", "ptb_reset", "ptb_sync",
     "ptb_stats", "ptb_accum_device_ptr", "ptb_resolve_rgb8", "ptb_stage_raygen", "ptb_stage_intersect",
     "ptb_stage_shade", "ptb_stage_compact", "ptb_stage_sort_keys", "ptb_stage_rng",
@@ -86,6 +87,7 @@ def lib():
         L.ptb_last_error.restype = C.c_char_p
         L.ptb_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(PtbSceneDesc), C.POINTER(PtbOptions)]
         L.ptb_destroy.argtypes = [C.c_void_p]
+        L.ptb_update_scene.argtypes = [C.c_void_p, C.POINTER(PtbSceneDesc)]
         L.ptb_pathtrace.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.ptb_render.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
         L.ptb_download.argtypes = [C.c_void_p, C.c_void_p]
@@ -174,14 +176,8 @@ class Renderer:
                  stream=None, external_accum=None, trace_depth=None):
         L = lib()
         self.scene = scene
-        self._keep = (scene.geoms, scene.materials)
-        desc = PtbSceneDesc()
-        desc.geoms = scene.geoms.ctypes.data
-        desc.numGeoms = len(scene.geoms)
-        desc.materials = scene.materials.ctypes.data
-        desc.numMaterials = len(scene.materials)
-        C.memmove(C.addressof(desc.camera), scene.camera.ctypes.data, 84)
-        desc.traceDepth = scene.traceDepth if trace_depth is None else int(trace_depth)
+        self.trace_depth = scene.traceDepth if trace_depth is None else int(trace_depth)
+        desc = self._desc(scene)
         opt = PtbOptions()
         L.ptb_default_options(C.byref(opt))
         opt.device, opt.bsdfMode, opt.pipeline, opt.accel = device, bsdf, pipeline, accel
@@ -189,9 +185,26 @@ class Renderer:
         opt.firstBounceCache, opt.useGraphs = first_bounce_cache, use_graphs
         opt.stream = stream
         opt.externalAccum = external_accum
-        self.trace_depth = desc.traceDepth
         self._h = C.c_void_p()
         _check(L.ptb_create(C.byref(self._h), C.byref(desc), C.byref(opt)))
+
+    def _desc(self, scene):
+        self._keep = (scene.geoms, scene.materials)
+        desc = PtbSceneDesc()
+        desc.geoms = scene.geoms.ctypes.data
+        desc.numGeoms = len(scene.geoms)
+        desc.materials = scene.materials.ctypes.data
+        desc.numMaterials = len(scene.materials)
+        C.memmove(C.addressof(desc.camera), scene.camera.ctypes.data, 84)
+        desc.traceDepth = self.trace_depth
+        return desc
+
+    def update_scene(self, scene):
+        """Re-upload geoms/materials/camera (same counts and resolution) and reset the accumulation:
+        the camera-move path of the app (src/main.cpp:125-128) without reallocating."""
+        desc = self._desc(scene)
+        _check(lib().ptb_update_scene(self._h, C.byref(desc)))
+        self.scene = scene
 
     def close(self):
         if self._h:
@@ -224,6 +237,10 @@ class Renderer:
         _check(lib().ptb_download(self._h, out.ctypes.data))
         return out
 
+    def download_to(self, host_ptr):
+        """ptb_download into caller-owned host memory given as a raw address (e.g. a pinned buffer)."""
+        _check(lib().ptb_download(self._h, host_ptr))
+
     def write_pbo(self, device_ptr, samples):
         _check(lib().ptb_write_pbo(self._h, device_ptr, samples))
 
@@ -239,7 +256,8 @@ class Renderer:
         return {"iterations": s.iterations, "segments": s.segments, "kernel_launches": s.kernelLaunches,
                 "alive_per_depth": [int(s.alivePerDepth[d]) for d in range(s.traceDepth)],
                 "trace_depth": s.traceDepth, "num_geoms": s.numGeoms, "bvh_nodes": s.bvhNodes,
-                "batch_iters": s.batchIters, "path_state_bytes": s.pathStateBytes}
+                "batch_iters": s.batchIters, "path_state_bytes": s.pathStateBytes,
+                "scene_upload_bytes": s.sceneUploadBytes}
 
     def accum_device_ptr(self):
         p = C.c_void_p()

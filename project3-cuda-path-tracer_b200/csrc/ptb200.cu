@@ -72,7 +72,11 @@ struct PtbContext {
     int numNodes = 0, smemNodes = 0;
     DevBuf<float4> mats;
     DevBuf<int> sceneMatDev;
+    DevBuf<SceneHeader> hdr;
     int numGeoms = 0, numMats = 0;
+    uint8_t *pinned = nullptr;           // pinned staging for scene uploads (H2D from pinned memory)
+    size_t pinnedBytes = 0;
+    int64_t h2dBytes = 0;                // bytes copied host->device by the last ptb_create / ptb_update_scene
 
     // state
     DevBuf<float> image;
@@ -99,7 +103,8 @@ struct PtbContext {
         image.release();
         for (int i = 0; i < 2; ++i) { A[i].release(); B[i].release(); C[i].release(); }
         hitTn.release(); hitMeta.release(); sortKeys.release(); sortOrder.release(); sortHist.release();
-        ctrl.release(); rgb8.release();
+        ctrl.release(); rgb8.release(); hdr.release();
+        if (pinned) cudaFreeHost(pinned);
         if (ownStream && stream) cudaStreamDestroy(stream);
     }
 };
@@ -128,6 +133,73 @@ template <typename K> int setSmem(K kernel, size_t bytes) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) return fail(PTB_ERR_CUDA, "cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e));
     }
+    return PTB_OK;
+}
+
+int validateScene(const PtbSceneDesc *scene) {
+    if (scene->numGeoms < 0 || scene->numMaterials <= 0 || (scene->numGeoms > 0 && !scene->geoms) || !scene->materials)
+        return fail(PTB_ERR_INVALID, "scene needs geoms[%d] and materials[%d]", scene->numGeoms, scene->numMaterials);
+    for (int i = 0; i < scene->numGeoms; ++i) {
+        if (scene->geoms[i].type != 0 && scene->geoms[i].type != 1) return fail(PTB_ERR_INVALID, "geom %d has unknown type %d", i, scene->geoms[i].type);
+        if (scene->geoms[i].materialid < 0 || scene->geoms[i].materialid >= scene->numMaterials)
+            return fail(PTB_ERR_INVALID, "geom %d references material %d of %d", i, scene->geoms[i].materialid, scene->numMaterials);
+    }
+    return PTB_OK;
+}
+
+// Packs the scene into the device layout inside the pinned staging buffer and copies it to the
+// device on the context's stream (src/pathtrace.cu:89-93 uploads the AoS structs instead).
+int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
+    const int G = scene->numGeoms, M = scene->numMaterials, Gp = std::max(1, G);
+    const size_t bytesGeoms = (size_t)Gp * sizeof(GeomRec), bytesNodes = (size_t)Gp * sizeof(BvhNode);
+    const size_t bytesMats = (size_t)M * 3 * sizeof(float4), bytesSm = (size_t)Gp * sizeof(int);
+    const size_t total = 2 * bytesGeoms + bytesNodes + bytesMats + bytesSm + sizeof(SceneHeader);
+    if (c->pinnedBytes < total) {
+        if (c->pinned) cudaFreeHost(c->pinned);
+        c->pinned = nullptr; c->pinnedBytes = 0;
+        CU(cudaMallocHost(&c->pinned, total));
+        c->pinnedBytes = total;
+    }
+    uint8_t *q = c->pinned;
+    GeomRec *sceneOrder = reinterpret_cast<GeomRec *>(q); q += bytesGeoms;
+    GeomRec *leafOrder = reinterpret_cast<GeomRec *>(q); q += bytesGeoms;
+    BvhNode *nodes = reinterpret_cast<BvhNode *>(q); q += bytesNodes;
+    float4 *mats = reinterpret_cast<float4 *>(q); q += bytesMats;
+    int *sceneMat = reinterpret_cast<int *>(q); q += bytesSm;
+    SceneHeader *hdr = reinterpret_cast<SceneHeader *>(q);
+    memset(c->pinned, 0, total);
+
+    c->sceneMaterial.resize(G);
+    for (int i = 0; i < G; ++i) { sceneOrder[i] = packGeom(scene->geoms[i], i); sceneMat[i] = c->sceneMaterial[i] = scene->geoms[i].materialid; }
+    // the BVH is always built so that ptb_stage_intersect can compare both traversals on any scene;
+    // the render path uses it only when useBvh is set
+    HostBvh hb;
+    buildBvh(scene->geoms, G, 4, hb);
+    static_assert(sizeof(HostBvhNode) == sizeof(BvhNode), "bvh node");
+    if ((int)hb.nodes.size() > Gp) return fail(PTB_ERR_INVALID, "BVH has %zu nodes for %d geoms", hb.nodes.size(), G);
+    memcpy(nodes, hb.nodes.data(), hb.nodes.size() * sizeof(BvhNode));
+    for (int sIdx = 0; sIdx < G; ++sIdx) leafOrder[sIdx] = sceneOrder[hb.order[sIdx]];
+    c->numNodes = (int)hb.nodes.size();
+    c->smemNodes = std::min(c->numNodes, 511);
+    for (int i = 0; i < M; ++i) {
+        const PtbMaterial &m = scene->materials[i];
+        mats[3 * i + 0] = make_float4(m.color[0], m.color[1], m.color[2], m.emittance);
+        mats[3 * i + 1] = make_float4(m.specularColor[0], m.specularColor[1], m.specularColor[2], m.hasReflective);
+        mats[3 * i + 2] = make_float4(m.hasRefractive, m.indexOfRefraction, m.specularExponent, 0.f);
+    }
+    const PtbCamera &cam = scene->camera;
+    hdr->cam = CameraParams{cam.position[0], cam.position[1], cam.position[2], cam.view[0], cam.view[1], cam.view[2],
+                            cam.up[0], cam.up[1], cam.up[2], cam.right[0], cam.right[1], cam.right[2],
+                            cam.pixelLength[0], cam.pixelLength[1], c->W, c->H};
+    hdr->numNodes = c->numNodes; hdr->smemNodes = c->smemNodes;
+
+    CU(cudaMemcpyAsync(c->geomsScene.p, sceneOrder, bytesGeoms, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->geoms.p, leafOrder, bytesGeoms, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->bvh.p, nodes, bytesNodes, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->mats.p, mats, bytesMats, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->sceneMatDev.p, sceneMat, bytesSm, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->hdr.p, hdr, sizeof(SceneHeader), cudaMemcpyHostToDevice, c->stream));
+    c->h2dBytes = (int64_t)total;
     return PTB_OK;
 }
 
@@ -281,16 +353,10 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     *out = nullptr;
     PtbOptions opt;
     if (optIn) opt = *optIn; else ptb_default_options(&opt);
-    if (scene->numGeoms < 0 || scene->numMaterials <= 0 || (scene->numGeoms > 0 && !scene->geoms) || !scene->materials)
-        return fail(PTB_ERR_INVALID, "ptb_create: scene needs geoms[%d] and materials[%d]", scene->numGeoms, scene->numMaterials);
+    { int vrc = validateScene(scene); if (vrc != PTB_OK) return vrc; }
     const int W = scene->camera.resolution[0], H = scene->camera.resolution[1];
     if (W <= 0 || H <= 0 || (int64_t)W * H > (1ll << 30)) return fail(PTB_ERR_INVALID, "ptb_create: bad resolution %dx%d", W, H);
     if (scene->traceDepth < 1 || scene->traceDepth > 64) return fail(PTB_ERR_INVALID, "ptb_create: traceDepth %d outside [1,64]", scene->traceDepth);
-    for (int i = 0; i < scene->numGeoms; ++i) {
-        if (scene->geoms[i].type != 0 && scene->geoms[i].type != 1) return fail(PTB_ERR_INVALID, "ptb_create: geom %d has unknown type %d", i, scene->geoms[i].type);
-        if (scene->geoms[i].materialid < 0 || scene->geoms[i].materialid >= scene->numMaterials)
-            return fail(PTB_ERR_INVALID, "ptb_create: geom %d references material %d of %d", i, scene->geoms[i].materialid, scene->numMaterials);
-    }
 
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
@@ -334,40 +400,13 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     c->useBvh = opt.accel == PTB_ACCEL_BVH || (opt.accel == PTB_ACCEL_AUTO && scene->numGeoms > 64);
     const size_t bruteBytes = (size_t)std::max(1, scene->numGeoms) * sizeof(GeomRec);
     if (!c->useBvh && bruteBytes > 200 * 1024) c->useBvh = true;
-    c->sceneMaterial.resize(scene->numGeoms);
-    std::vector<GeomRec> sceneOrder(std::max(1, scene->numGeoms));
-    memset(sceneOrder.data(), 0, sceneOrder.size() * sizeof(GeomRec));
-    for (int i = 0; i < scene->numGeoms; ++i) { sceneOrder[i] = packGeom(scene->geoms[i], i); c->sceneMaterial[i] = scene->geoms[i].materialid; }
-    CUB(c->geomsScene.alloc(sceneOrder.size()));
-    CUB(cudaMemcpy(c->geomsScene.p, sceneOrder.data(), sceneOrder.size() * sizeof(GeomRec), cudaMemcpyHostToDevice));
-    CUB(c->sceneMatDev.alloc(std::max(1, scene->numGeoms)));
-    if (scene->numGeoms) CUB(cudaMemcpy(c->sceneMatDev.p, c->sceneMaterial.data(), scene->numGeoms * sizeof(int), cudaMemcpyHostToDevice));
-
-    // the BVH is always built when there is more than one geom so that ptb_stage_intersect can compare
-    // both traversals on any scene; the render path uses it only when useBvh is set
     {
-        HostBvh hb;
-        buildBvh(scene->geoms, scene->numGeoms, 4, hb);
-        static_assert(sizeof(HostBvhNode) == sizeof(BvhNode), "bvh node");
-        c->numNodes = (int)hb.nodes.size();
-        CUB(c->bvh.alloc(hb.nodes.size()));
-        CUB(cudaMemcpy(c->bvh.p, hb.nodes.data(), hb.nodes.size() * sizeof(BvhNode), cudaMemcpyHostToDevice));
-        std::vector<GeomRec> leafOrder(std::max(1, scene->numGeoms));
-        memset(leafOrder.data(), 0, leafOrder.size() * sizeof(GeomRec));
-        for (int s = 0; s < scene->numGeoms; ++s) leafOrder[s] = sceneOrder[hb.order[s]];
-        CUB(c->geoms.alloc(leafOrder.size()));
-        CUB(cudaMemcpy(c->geoms.p, leafOrder.data(), leafOrder.size() * sizeof(GeomRec), cudaMemcpyHostToDevice));
-        c->smemNodes = std::min(c->numNodes, 511);
+        const size_t Gp = (size_t)std::max(1, scene->numGeoms);
+        CUB(c->geomsScene.alloc(Gp)); CUB(c->geoms.alloc(Gp)); CUB(c->bvh.alloc(Gp)); CUB(c->sceneMatDev.alloc(Gp));
+        CUB(c->mats.alloc((size_t)scene->numMaterials * 3)); CUB(c->hdr.alloc(1));
+        int urc = uploadScene(c, scene);
+        if (urc != PTB_OK) return bail(urc);
     }
-    std::vector<float4> mats(3 * (size_t)scene->numMaterials);
-    for (int i = 0; i < scene->numMaterials; ++i) {
-        const PtbMaterial &m = scene->materials[i];
-        mats[3 * i + 0] = make_float4(m.color[0], m.color[1], m.color[2], m.emittance);
-        mats[3 * i + 1] = make_float4(m.specularColor[0], m.specularColor[1], m.specularColor[2], m.hasReflective);
-        mats[3 * i + 2] = make_float4(m.hasRefractive, m.indexOfRefraction, m.specularExponent, 0.f);
-    }
-    CUB(c->mats.alloc(mats.size()));
-    CUB(cudaMemcpy(c->mats.p, mats.data(), mats.size() * sizeof(float4), cudaMemcpyHostToDevice));
 
     // ---- state (src/pathtrace.cu:84-87, 95-96) ----
     if (opt.externalAccum) c->imagePtr = opt.externalAccum;
@@ -385,7 +424,7 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
 
     // ---- launch geometry ----
     c->smemBrute = bruteBytes;
-    c->smemBvh = (size_t)std::max(1, c->smemNodes) * sizeof(BvhNode);
+    c->smemBvh = (size_t)511 * sizeof(BvhNode);     // fixed: the node count may change in ptb_update_scene
     int rc = PTB_OK;
     rc |= setSmem(bounce_kernel<true, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false>, c->smemBrute);
     rc |= setSmem(intersect_kernel<false>, c->smemBrute); rc |= setSmem(stage_intersect_kernel<false>, c->smemBrute);
@@ -399,13 +438,10 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
 
     Params &p = c->base;
     memset(&p, 0, sizeof p);
-    const PtbCamera &cam = scene->camera;
-    p.cam = CameraParams{cam.position[0], cam.position[1], cam.position[2], cam.view[0], cam.view[1], cam.view[2],
-                         cam.up[0], cam.up[1], cam.up[2], cam.right[0], cam.right[1], cam.right[2],
-                         cam.pixelLength[0], cam.pixelLength[1], W, H};
+    p.hdr = c->hdr.p;
     p.geoms = c->useBvh ? c->geoms.p : c->geomsScene.p;
     p.numGeoms = scene->numGeoms;
-    p.bvh = c->bvh.p; p.numNodes = c->numNodes; p.smemNodes = c->smemNodes;
+    p.bvh = c->bvh.p;
     p.mats = c->mats.p; p.numMats = scene->numMaterials;
     p.image = c->imagePtr;
     p.ctrl = c->ctrl.p;
@@ -419,6 +455,20 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
 #undef CUB
     *out = c;
     return PTB_OK;
+}
+
+int ptb_update_scene(PtbContext *c, const PtbSceneDesc *scene) {
+    if (!c || !scene) return fail(PTB_ERR_INVALID, "ptb_update_scene: null argument");
+    int rc = validateScene(scene);
+    if (rc != PTB_OK) return rc;
+    if (scene->numGeoms != c->numGeoms || scene->numMaterials != c->numMats || scene->camera.resolution[0] != c->W ||
+        scene->camera.resolution[1] != c->H || scene->traceDepth != c->traceDepth)
+        return fail(PTB_ERR_INVALID, "ptb_update_scene: geometry/material counts, resolution and depth must match ptb_create");
+    CU(cudaSetDevice(c->device));
+    CU(cudaStreamSynchronize(c->stream));           // the pinned staging buffer is about to be rewritten
+    rc = uploadScene(c, scene);
+    if (rc != PTB_OK) return rc;
+    return ptb_reset(c);
 }
 
 int ptb_destroy(PtbContext *c) {
@@ -498,6 +548,7 @@ int ptb_stats(PtbContext *c, PtbStats *out) {
     out->bvhNodes = c->useBvh ? c->numNodes : 0;
     out->batchIters = c->batch;
     out->pathStateBytes = (int64_t)c->numPixels * c->batch * 40 * 2;
+    out->sceneUploadBytes = c->h2dBytes;
     return PTB_OK;
 }
 

@@ -56,13 +56,17 @@ struct CameraParams {
     int   W, H;
 };
 
-struct Params {
+struct SceneHeader {             // device-resident, rewritten by ptb_update_scene without touching launch parameters
     CameraParams cam;
+    int          numNodes;
+    int          smemNodes;      // leading BVH nodes (BFS order = top levels) staged in shared memory
+};
+
+struct Params {
+    const SceneHeader *hdr;
     const GeomRec *geoms;        // brute force: scene order; BVH: leaf order (tag.z = scene index)
     int            numGeoms;
     const BvhNode *bvh;
-    int            numNodes;
-    int            smemNodes;    // leading BVH nodes (BFS order = top levels) staged in shared memory
     const float4  *mats;         // 3 float4 per material
     int            numMats;
     float         *image;        // W*H*3 accumulation (layout of scene->state.image)
@@ -123,11 +127,42 @@ PTB_DEV f3 candidateNormal(const GeomRec &g, const Candidate &c) {
     return sphereNormal(g, mk3(c.a, c.b, c.c), c.outside);
 }
 
-// closest hit, brute force over shared-memory geoms (warp-uniform loop => broadcast reads)
+// Closest hit, brute force over shared-memory geoms, in two phases:
+//   1. a warp-uniform loop classifies every geom with cheap approximate arithmetic (MUFU reciprocals,
+//      fused multiply-adds) into sure-miss / candidate and brackets the distance each candidate would
+//      return; a candidate survives only if its lower bound does not exceed the smallest upper bound of
+//      a sure hit;
+//   2. each lane runs the reference-exact test (ptb_math.cuh) on ITS OWN surviving candidates -- one
+//      for almost every ray -- in ascending index order, so `t > 0 && t_min > t` (src/pathtrace.cu:192)
+//      keeps its lowest-index-wins tie rule.
+// Phase 1 only prunes; every output value comes from phase 2.  Scenes of up to 64 geoms take this path.
 PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, Candidate &best) {
     best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
     int orig = 0x7fffffff;
-    for (int g = 0; g < numGeoms; ++g) testGeom(sg[g], g, o, d, best, orig, orig, false);
+    const float rdLen = sqrtf(fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z)));
+    const float roMag = fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f;
+    float minHi = 3.0e38f;
+    for (int g0 = 0; g0 < numGeoms; g0 += 64) {                  // 64 candidates per mask word
+        const int g1 = min(numGeoms, g0 + 64);
+        unsigned long long mask = 0ull;
+        for (int g = g0; g < g1; ++g) {
+            // object-space origin / direction with the EXACT operation order: the signs of the slab
+            // numerators and denominators then equal those of the exact test
+            const f3 qo = mulMV(sg[g].inv, o, 1.0f);
+            const f3 u = mulMV(sg[g].inv, d, 0.0f);
+            float lo, hi;
+            const int cls = sg[g].tag.x == 1 ? classifyBox(qo, u, rdLen, roMag, lo, hi) : classifySphere(qo, u, rdLen, roMag, lo, hi);
+            if (cls != 0 && lo <= minHi) {
+                mask |= 1ull << (g - g0);
+                if (cls == 2) minHi = fminf(minHi, hi);
+            }
+        }
+        while (mask) {
+            const int g = g0 + __ffsll((long long)mask) - 1;
+            mask &= mask - 1ull;
+            testGeom(sg[g], g, o, d, best, orig, orig, false);
+        }
+    }
 }
 
 // Conservative ray/AABB test for pruning only.  The boxes are padded on the host (ptb_bvh.cpp) to cover
@@ -156,7 +191,7 @@ PTB_DEV GeomRec loadGeom(const GeomRec *gp) {
 // closest hit through the flat BVH.  Leaves run the reference-exact tests; pruning uses padded boxes
 // and a slackened distance bound, so the winner is the same (t, scene index)-lexicographic minimum
 // that the reference's index-ordered loop finds (src/pathtrace.cu:176-199).
-PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, f3 o, f3 d, Candidate &best) {
+PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, const int smemNodes, f3 o, f3 d, Candidate &best) {
     best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
     int bestOrig = 0x7fffffff;
     const float dl = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z) * 0.9999f;
@@ -166,7 +201,7 @@ PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, f3 o, f3 d, C
     int node = 0;
     for (;;) {
         float4 llo, lhi, rlo, rhi;
-        if (node < p.smemNodes) { llo = snodes[node].llo; lhi = snodes[node].lhi; rlo = snodes[node].rlo; rhi = snodes[node].rhi; }
+        if (node < smemNodes) { llo = snodes[node].llo; lhi = snodes[node].lhi; rlo = snodes[node].rlo; rhi = snodes[node].rhi; }
         else {
             const float4 *np = reinterpret_cast<const float4 *>(p.bvh + node);
             llo = __ldg(np); lhi = __ldg(np + 1); rlo = __ldg(np + 2); rhi = __ldg(np + 3);
@@ -352,12 +387,15 @@ __global__ void __launch_bounds__(kBlock) bounce_kernel(const __grid_constant__ 
     __shared__ int warpTotals[kBlock / 32];
     __shared__ uint32_t blockBase;
 
-    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), p.smemNodes * 4);
+    const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
+    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
     else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * 10);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
     const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
 
     Control *ctrl = p.ctrl;
+    CameraParams cam;
+    if (FIRST) cam = p.hdr->cam;
     const int iterBase = ctrl->iterBase, iterStride = ctrl->iterStride;
     const uint32_t nIn = FIRST ? p.numPixels * (uint32_t)ctrl->batch : ctrl->counts[depth];
     const int remainingBefore = p.traceDepth - depth;
@@ -373,7 +411,7 @@ __global__ void __launch_bounds__(kBlock) bounce_kernel(const __grid_constant__ 
                 slot = i / p.numPixels;
                 pix = i - slot * p.numPixels;
                 id = pix | (slot << p.pixBits);
-                cameraRay(p.cam, pix, o, d);
+                cameraRay(cam, pix, o, d);
                 c = mk3(1.0f, 1.0f, 1.0f);                                // src/pathtrace.cu:132
             } else {
                 loadPath(p.in, i, o, d, c, id);
@@ -381,7 +419,7 @@ __global__ void __launch_bounds__(kBlock) bounce_kernel(const __grid_constant__ 
                 slot = (id & ~kDeadBit) >> p.pixBits;
             }
             Candidate best;
-            if (USE_BVH) closestHitBvh(p, snodes, o, d, best);
+            if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, best);
             else         closestHitBrute(sgeoms, p.numGeoms, o, d, best);
             const bool isHit = best.slot >= 0;
             f3 n = mk3(0.f, 0.f, 0.f); int matId = 0;
@@ -425,11 +463,12 @@ __global__ void set_control_kernel(Control *ctrl, int iterBase, int iterStride, 
 // ------------------------------------------------------------------------------------------------
 // generateRayFromCamera (src/pathtrace.cu:122-143)
 __global__ void __launch_bounds__(kBlock) raygen_kernel(const __grid_constant__ Params p) {
+    const CameraParams cam = p.hdr->cam;
     const uint32_t n = p.numPixels * (uint32_t)p.ctrl->batch;
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
         const uint32_t slot = i / p.numPixels, pix = i - slot * p.numPixels;
         f3 o, d;
-        cameraRay(p.cam, pix, o, d);
+        cameraRay(cam, pix, o, d);
         storePath(p.in, i, o, d, mk3(1.0f, 1.0f, 1.0f), pix | (slot << p.pixBits));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) p.ctrl->counts[0] = n;
@@ -439,7 +478,8 @@ __global__ void __launch_bounds__(kBlock) raygen_kernel(const __grid_constant__ 
 template <bool USE_BVH>
 __global__ void __launch_bounds__(kBlock) intersect_kernel(const __grid_constant__ Params p, const int depth) {
     extern __shared__ float4 smem4[];
-    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), p.smemNodes * 4);
+    const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
+    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
     else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * 10);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
     const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
@@ -449,7 +489,7 @@ __global__ void __launch_bounds__(kBlock) intersect_kernel(const __grid_constant
         loadPath(p.in, i, o, d, c, id);
         if (id & kDeadBit) { p.hits.meta[i] = -1; continue; }            // no-compaction mode: dead path stays in place
         Candidate best;
-        if (USE_BVH) closestHitBvh(p, snodes, o, d, best);
+        if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, best);
         else         closestHitBrute(sgeoms, p.numGeoms, o, d, best);
         if (best.slot < 0) {
             p.hits.tn[i] = make_float4(-1.0f, 0.f, 0.f, 0.f);             // src/pathtrace.cu:203
@@ -634,7 +674,8 @@ template <bool USE_BVH>
 __global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_constant__ Params p, const float *origins,
         const float *dirs, int n, int *hit, float *t, float *normal, int *outside) {
     extern __shared__ float4 smem4[];
-    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), p.smemNodes * 4);
+    const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
+    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
     else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * 10);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
     const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
@@ -642,7 +683,7 @@ __global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_co
         const f3 o = mk3(origins[3 * (size_t)i], origins[3 * (size_t)i + 1], origins[3 * (size_t)i + 2]);
         const f3 d = mk3(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2]);
         Candidate best;
-        if (USE_BVH) closestHitBvh(p, snodes, o, d, best);
+        if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, best);
         else         closestHitBrute(sgeoms, p.numGeoms, o, d, best);
         if (best.slot < 0) {
             hit[i] = -1; t[i] = -1.0f; outside[i] = 1;
@@ -657,9 +698,10 @@ __global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_co
 }
 
 __global__ void __launch_bounds__(kBlock) stage_raygen_kernel(const __grid_constant__ Params p, float *origins, float *dirs) {
+    const CameraParams cam = p.hdr->cam;
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < p.numPixels; i += gridDim.x * kBlock) {
         f3 o, d;
-        cameraRay(p.cam, i, o, d);
+        cameraRay(cam, i, o, d);
         origins[3 * (size_t)i] = o.x; origins[3 * (size_t)i + 1] = o.y; origins[3 * (size_t)i + 2] = o.z;
         dirs[3 * (size_t)i] = d.x; dirs[3 * (size_t)i + 1] = d.y; dirs[3 * (size_t)i + 2] = d.z;
     }
@@ -678,7 +720,7 @@ __global__ void __launch_bounds__(kBlock) stage_shade_kernel(const __grid_consta
         const int rem = remaining[i];
         const bool alive = shadeStep(p, depth[i], iter[i], (uint32_t)pixelIndex[i], isHit, isHit ? sceneMat[hit[i]] : 0,
                                      t[i], nn, outside[i], o, d, c, rem);
-        // orc_shade contract: miss / emissive -> remaining 0; scatter -> remaining - 1 (0 => colour 0)
+        // stage contract: miss / emissive -> remaining 0; scatter -> remaining - 1 (0 => colour 0)
         int newRem = 0;
         if (alive) newRem = rem - 1;
         origins[3 * (size_t)i] = o.x; origins[3 * (size_t)i + 1] = o.y; origins[3 * (size_t)i + 2] = o.z;

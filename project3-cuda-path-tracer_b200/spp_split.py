@@ -1,0 +1,31 @@
+"""Samples-per-pixel split across the GPUs of one node.
+
+Iterations are independent: the RNG depends only on (iter, pixelIndex, depth) (src/pathtrace.cu:41-45)
+and the only cross-iteration state is the additive accumulation buffer (src/pathtrace.cu:276).  Rank r
+of G renders iterations r+1, r+1+G, ... into a private W*H*3 float buffer; ONE sum-reduce of that
+buffer to rank 0 per output frame is the only collective (NCCL over NVLink/NVSwitch on GPUs, gloo in
+the CPU tests).  One process per GPU; torch.distributed is plumbing only.
+"""
+
+
+def rank_iterations(first_iter, total_iters, rank, world):
+    """(iterBegin, count, iterStride) for ptb_render on `rank`: the interleaved split keeps every
+    prefix of the sample sequence balanced.  The union over ranks is exactly
+    first_iter .. first_iter + total_iters - 1, each iteration once."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world %r/%r" % (rank, world))
+    count = (total_iters - rank + world - 1) // world if total_iters > rank else 0
+    return first_iter + rank, count, world
+
+
+def reduce_frame(accum, frame=None, dst=0, group=None):
+    """Sum the per-rank accumulation buffers into `frame` on rank `dst` (a copy first: the private
+    partial sums keep growing across frames, so they must not be overwritten by the total)."""
+    import torch.distributed as dist
+    if frame is None:
+        frame = accum.clone()
+    else:
+        frame.copy_(accum)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.reduce(frame, dst=dst, op=dist.ReduceOp.SUM, group=group)
+    return frame

@@ -1,0 +1,140 @@
+"""GPU tests at BASELINE.json's full sizes, through size-independent properties, plus the BVH on the
+synthetic many-object scene (configs[4]) and convergence towards the reference's golden image."""
+import numpy as np
+import pytest
+
+import orclib
+import scenes
+from common import pkg, golden_image, same_bits, rel_err_lit
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def m():
+    return pkg()
+
+
+@pytest.fixture(scope="module")
+def port():
+    return orclib.load("port")
+
+
+@pytest.fixture(scope="module")
+def synthetic(m, tmp_path_factory):
+    d = tmp_path_factory.mktemp("syn")
+    p = d / "synthetic.txt"
+    p.write_text(scenes.synthetic_text(n_objects=100000, res=(1920, 1080), depth=16))
+    return str(p)
+
+
+def test_bvh_equals_brute_force_on_20k_objects(m, port, tmp_path):
+    """The flat BVH must return exactly what the reference's index-ordered brute-force loop returns
+    (same t, same scene index under ties, same normal bits)."""
+    p = tmp_path / "syn20k.txt"
+    p.write_text(scenes.synthetic_text(n_objects=20000, res=(640, 360), depth=4, seed=99))
+    s = m.Scene.load(str(p))
+    os_ = port.load_scene(str(p))
+    with m.Renderer(s, device=0, bsdf=1, accel=m.ACCEL_BVH) as r:
+        o, d = r.stage_raygen()
+        bvh = r.stage_intersect(o, d, m.ACCEL_BVH)
+        # oracle (CPU brute force, ~1e7 tests/s/core) spot-checks a few thousand rays
+        sel = np.random.RandomState(1).choice(len(o), 3000, replace=False)
+        want = port.closest_hit(os_.geoms, o[sel], d[sel])
+        assert np.array_equal(bvh[0][sel], want[0]) and same_bits(bvh[1][sel], want[1])
+        assert same_bits(bvh[2][sel], want[2]) and np.array_equal(bvh[3][sel], want[3])
+        # secondary rays: scattered from the first hits (incoherent, many start inside boxes' pads)
+        hitmask = bvh[0] >= 0
+        rs = np.random.RandomState(2)
+        so = (o + d * (bvh[1][:, None] - 1e-3))[hitmask]
+        sd = rs.normal(size=so.shape).astype(np.float32)
+        sd /= np.linalg.norm(sd, axis=1, keepdims=True).astype(np.float32)
+        b2 = r.stage_intersect(so, sd, m.ACCEL_BVH)
+        sel2 = rs.choice(len(so), 3000, replace=False)
+        want2 = port.closest_hit(os_.geoms, so[sel2], sd[sel2])
+        assert np.array_equal(b2[0][sel2], want2[0]) and same_bits(b2[1][sel2], want2[1])
+        assert same_bits(b2[2][sel2], want2[2]) and np.array_equal(b2[3][sel2], want2[3])
+    # GPU brute force over all rays is feasible for 1k objects: exhaustive BVH == brute comparison
+    p2 = tmp_path / "syn1k.txt"
+    p2.write_text(scenes.synthetic_text(n_objects=1000, res=(640, 360), depth=4, seed=98))
+    s2 = m.Scene.load(str(p2))
+    with m.Renderer(s2, device=0, bsdf=1) as r:
+        o, d = r.stage_raygen()
+        a = r.stage_intersect(o, d, m.ACCEL_BVH)
+        b = r.stage_intersect(o, d, m.ACCEL_BRUTE)
+        assert np.array_equal(a[0], b[0]) and same_bits(a[1], b[1]) and same_bits(a[2], b[2]) and np.array_equal(a[3], b[3])
+        hitmask = a[0] >= 0
+        so = (o + d * (a[1][:, None] - 1e-3))[hitmask]
+        sd = np.random.RandomState(3).normal(size=so.shape).astype(np.float32)
+        a2 = r.stage_intersect(so, sd, m.ACCEL_BVH)
+        b2 = r.stage_intersect(so, sd, m.ACCEL_BRUTE)
+        assert np.array_equal(a2[0], b2[0]) and same_bits(a2[1], b2[1]) and same_bits(a2[2], b2[2])
+
+
+def test_synthetic_100k_full_size_properties(m, port, synthetic):
+    """configs[4]: 100k objects, 1920x1080, depth 16.  Properties: per-depth counts are non-increasing,
+    segments == their sum, the image is finite and non-negative, rendering [1..4] equals rendering
+    [1..2] then [3..4] (additivity), and an oracle spot check of the first bounce."""
+    s = m.Scene.load(synthetic)
+    os_ = port.load_scene(synthetic)
+    assert len(s.geoms) == 100000 and s.traceDepth == 16
+    with m.Renderer(s, device=0, bsdf=1, batch_iters=1) as r:
+        st0 = r.stats()
+        assert st0["bvh_nodes"] > 0
+        o, d = r.stage_raygen()
+        hit, t, n, outside = r.stage_intersect(o, d)
+        sel = np.random.RandomState(4).choice(len(o), 1500, replace=False)
+        want = port.closest_hit(os_.geoms, o[sel], d[sel])
+        assert np.array_equal(hit[sel], want[0]) and same_bits(t[sel], want[1]) and same_bits(n[sel], want[2])
+        r.render(1, 4)
+        whole = r.download()
+        st = r.stats()
+        alive = np.array(st["alive_per_depth"])
+        assert alive[0] == 4 * s.pixels and np.all(np.diff(alive) <= 0) and st["segments"] == alive.sum()
+        assert np.isfinite(whole).all() and (whole >= 0).all() and whole.any()
+        r.reset()
+        r.render(1, 2)
+        r.render(3, 2)
+        assert same_bits(whole, r.download())
+
+
+def test_4k_cornell_properties(m):
+    """configs[3] resolution (3840x2160): linearity of the accumulation and interleaved spp split."""
+    import tempfile, os
+    d = tempfile.mkdtemp()
+    p = os.path.join(d, "cornell4k.txt")
+    open(p, "w").write(scenes.cornell_text(res=(3840, 2160)))
+    s = m.Scene.load(p)
+    with m.Renderer(s, device=0, bsdf=1, batch_iters=2) as r:
+        r.render(1, 4)
+        whole = r.download()
+        st = r.stats()
+        assert st["alive_per_depth"][0] == 4 * s.pixels
+        # the 2-GPU split: rank 0 renders 1,3 and rank 1 renders 2,4; their sum is the whole
+        r.reset(); r.render(1, 2, 2); a = r.download()
+        r.reset(); r.render(2, 2, 2); b = r.download()
+    assert np.allclose(a + b, whole, rtol=2e-6, atol=0)
+    # every row of pixels is left/right symmetric in hit pattern only for the walls; cheap sanity: light is saturated
+    assert whole.max() > 4.9 * 4
+
+
+def test_converges_to_the_reference_image(m, scene_dir):
+    """img/REFERENCE_cornell.5000samp.png is a diffuse-only 5000-spp render.
+    Metric (SURVEY.md section 7 hard part 5): RMSE on [0,1] pixels after the same clamp+truncate,
+    normalised by the golden's RMS, on 16x16 block means (per-pixel numbers are noise-floor bound:
+    two independent 5000-spp renders differ by ~0.0155 RMS per pixel).  north_star: <= 1e-2."""
+    gold = golden_image().astype(np.float64) / 255.0
+    s = m.Scene.load(scene_dir + "/cornell.txt")
+    with m.Renderer(s, device=0, bsdf=m.BSDF_GOLDEN_DIFFUSE, batch_iters=8) as r:
+        r.render(1, 5000)
+        ours = r.resolve_rgb8(5000).astype(np.float64) / 255.0
+    rms = np.sqrt((gold ** 2).mean())
+    assert abs(rms - 0.1804) < 2e-3
+    blk = lambda a: a.reshape(50, 16, 50, 16, 3).mean((1, 3))
+    rel_rmse_blocks = np.sqrt(((blk(ours) - blk(gold)) ** 2).mean()) / rms
+    rel_rmse_pixels = np.sqrt(((ours - gold) ** 2).mean()) / rms
+    mean_ratio = ours.mean((0, 1)) / gold.mean((0, 1))
+    print("rel-RMSE 16x16 blocks %.5f, per pixel %.5f (noise floor ~0.086), mean ratio %s" % (rel_rmse_blocks, rel_rmse_pixels, mean_ratio))
+    assert rel_rmse_blocks <= 1e-2
+    assert np.all(np.abs(mean_ratio - 1) < 5e-3)
+    assert rel_rmse_pixels < 0.12          # 0.0155 / 0.1804 = 0.086 is the seed-to-seed floor

@@ -1,0 +1,146 @@
+"""CPU tests of the product's host side (no compute calls): the C-ABI library loads and exports every
+symbol include/ptb200.h declares, the C++ scene loader / camera fix-up / PNG writer behave like the
+reference's, and rendering fails loudly without a GPU (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import orclib
+import scenes
+from common import pkg, golden, has_gpu, ROOT
+
+
+def test_library_exports_every_declared_symbol():
+    m = pkg()
+    L = m.lib()
+    header = open(os.path.join(ROOT, "include", "ptb200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(ptb_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    assert declared == set(m.ABI_SYMBOLS), declared ^ set(m.ABI_SYMBOLS)
+    for name in sorted(declared):
+        assert hasattr(L, name), "libptb200.so does not export %s" % name
+    L.ptb_abi_version.restype = C.c_int
+    assert L.ptb_abi_version() == 1
+
+
+def test_struct_sizes_match_reference_layout():
+    m = pkg()
+    assert m.GEOM_DT.itemsize == 236 and m.MATERIAL_DT.itemsize == 44 and m.CAMERA_DT.itemsize == 84
+    assert C.sizeof(m.PtbCamera) == 84
+    o = m.PtbOptions()
+    m.lib().ptb_default_options(C.byref(o))
+    assert o.device == -1 and o.bsdfMode == m.BSDF_FULL and o.pipeline == m.PIPELINE_FUSED and o.useGraphs == 1
+
+
+def test_scene_loader_matches_reference_pod(scene_dir):
+    m = pkg()
+    g = golden()
+    for name in ("cornell", "sphere"):
+        raw = m.Scene.load("%s/%s.txt" % (scene_dir, name), fixup=False)
+        fixed = m.Scene.load("%s/%s.txt" % (scene_dir, name), fixup=True)
+        assert raw.geoms.tobytes() == g["scene_%s_geoms" % name].tobytes()
+        assert raw.materials.tobytes() == g["scene_%s_materials" % name].tobytes()
+        assert raw.camera.tobytes() == g["scene_%s_camera_raw" % name].tobytes()
+        assert fixed.camera.tobytes() == g["scene_%s_camera_fixed" % name].tobytes()
+        assert [raw.iterations, raw.traceDepth] == list(g["scene_%s_meta" % name])
+        assert raw.imageName == name
+
+
+def test_scene_loader_matches_oracle_on_generated_scenes(tmp_path):
+    m = pkg()
+    port = orclib.load("port")
+    p = tmp_path / "syn.txt"
+    p.write_text(scenes.synthetic_text(n_objects=2000, seed=11))
+    a = m.Scene.load(str(p))
+    b = port.load_scene(str(p))
+    assert len(a.geoms) == 2000
+    assert a.geoms.tobytes() == b.geoms.tobytes() and a.materials.tobytes() == b.materials.tobytes()
+    assert a.camera.tobytes() == b.camera.tobytes()
+
+
+def test_loader_quirks(tmp_path):
+    m = pkg()
+    base = scenes.cornell_text()
+    (tmp_path / "crlf.txt").write_text(base.replace("\n", "\r\n"))
+    (tmp_path / "cr.txt").write_text(base.replace("\n", "\r"))
+    (tmp_path / "notrail.txt").write_text(base.rstrip("\n"))
+    ref = m.Scene.load(str(_write(tmp_path, "lf.txt", base)))
+    for f in ("crlf.txt", "cr.txt", "notrail.txt"):
+        s = m.Scene.load(str(tmp_path / f))
+        assert s.geoms.tobytes() == ref.geoms.tobytes() and s.camera.tobytes() == ref.camera.tobytes()
+    # a trailing blank after the type keyword defeats the whole-line compare (src/scene.cpp:48,51):
+    # the object keeps the default type, as in the reference
+    odd = base.replace("\nsphere\n", "\nsphere \n")
+    s = m.Scene.load(str(_write(tmp_path, "odd.txt", odd)))
+    assert len(s.geoms) == 7
+    # out-of-sequence ids are skipped (src/scene.cpp:37-39)
+    skipped = base.replace("OBJECT 6", "OBJECT 9")
+    s = m.Scene.load(str(_write(tmp_path, "skip.txt", skipped)))
+    assert len(s.geoms) == 6
+    with pytest.raises(m.PtbError):
+        m.Scene.load(str(tmp_path / "missing.txt"))
+
+
+def _write(d, name, text):
+    p = d / name
+    p.write_text(text)
+    return p
+
+
+def test_png_writer_follows_image_cpp(tmp_path):
+    from PIL import Image
+    m = pkg()
+    w, h = 13, 7
+    rs = np.random.RandomState(3)
+    summed = rs.uniform(-0.5, 3.0, (w * h, 3)).astype(np.float32) * 4
+    m.save_png(str(tmp_path / "out"), w, h, summed, 4, flip_x=True)
+    got = np.asarray(Image.open(str(tmp_path / "out.png")).convert("RGB"))
+    assert got.shape == (h, w, 3)
+    # src/main.cpp:83-89 (x flip, / samples) then src/image.cpp:27-30 (clamp, *255, truncate)
+    pix = (summed / np.float32(4)).reshape(h, w, 3)[:, ::-1, :]
+    want = (np.clip(pix, 0, 1) * np.float32(255)).astype(np.uint8)
+    assert np.array_equal(got, want)
+    m.save_png(str(tmp_path / "noflip"), w, h, summed, 4, flip_x=False)
+    got2 = np.asarray(Image.open(str(tmp_path / "noflip.png")).convert("RGB"))
+    assert np.array_equal(got2, want[:, ::-1, :])
+
+
+def test_hdr_writer(tmp_path):
+    m = pkg()
+    img = np.linspace(0, 6, 5 * 4 * 3, dtype=np.float32).reshape(20, 3)
+    rc = m.lib().ptb_save_hdr(str(tmp_path / "o").encode(), 5, 4, img.ctypes.data, C.c_float(1.0), 0)
+    assert rc == 0
+    data = open(str(tmp_path / "o.hdr"), "rb").read()
+    assert data.startswith(b"#?RADIANCE") and data.endswith(bytes(0)) and len(data) > 80
+
+
+@pytest.mark.skipif(has_gpu(), reason="only meaningful on a machine without a GPU")
+def test_render_fails_loudly_without_gpu(scene_dir):
+    m = pkg()
+    s = m.Scene.load(scene_dir + "/cornell.txt")
+    with pytest.raises(m.PtbError) as e:
+        m.Renderer(s)
+    assert "CUDA" in str(e.value)
+    # the reference-named entry points behave the same
+    with pytest.raises(m.PtbError):
+        m.pathtraceInit(s)
+    m.pathtraceFree()          # free before/without init is a no-op (src/main.cpp:126)
+    with pytest.raises(m.PtbError):
+        m.pathtrace(None, 0, 1)
+
+
+def test_product_does_not_touch_the_oracle():
+    """No product source may reference oracle/ (parity would be void)."""
+    pkgdir = os.path.join(ROOT, "project3-cuda-path-tracer_b200")
+    for base, _, files in os.walk(pkgdir):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                assert "libptoracle" not in text and "libptref" not in text and "orc_" not in text, os.path.join(base, f)
+    import subprocess
+    out = subprocess.run(["ldd", os.path.join(pkgdir, "libptb200.so")], capture_output=True, text=True).stdout
+    assert "ptoracle" not in out and "ptref" not in out
