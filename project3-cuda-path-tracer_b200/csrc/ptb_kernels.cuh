@@ -132,10 +132,12 @@ PTB_DEV f3 candidateNormal(const GeomRec &g, const Candidate &c) {
 //      fused multiply-adds) into sure-miss / candidate and brackets the distance each candidate would
 //      return; a candidate survives only if its lower bound does not exceed the smallest upper bound of
 //      a sure hit;
-//   2. each lane runs the reference-exact test (ptb_math.cuh) on ITS OWN surviving candidates -- one
-//      for almost every ray -- in ascending index order, so `t > 0 && t_min > t` (src/pathtrace.cu:192)
-//      keeps its lowest-index-wins tie rule.
-// Phase 1 only prunes; every output value comes from phase 2.  Scenes of up to 64 geoms take this path.
+//   2. each lane runs the reference-exact test (ptb_math.cuh) on ITS OWN candidate with the smallest
+//      lower bound -- the winner for almost every ray -- and looks at the other candidates only when
+//      the second-smallest lower bound does not exceed that exact distance.  Ties go to the lowest
+//      scene index, as `t > 0 && t_min > t` visited in index order does (src/pathtrace.cu:192).
+// Phase 1 only prunes; every output value comes from phase 2.  Scenes of up to 64 geoms take this
+// path in one mask word; larger ones are walked in chunks of 64.
 PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, Candidate &best) {
     best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
     int orig = 0x7fffffff;
@@ -145,6 +147,8 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, Candid
     for (int g0 = 0; g0 < numGeoms; g0 += 64) {                  // 64 candidates per mask word
         const int g1 = min(numGeoms, g0 + 64);
         unsigned long long mask = 0ull;
+        float lo1 = 3.0e38f, lo2 = 3.0e38f;                      // smallest / second-smallest lower bound
+        int first = -1;
         for (int g = g0; g < g1; ++g) {
             // object-space origin / direction with the EXACT operation order: the signs of the slab
             // numerators and denominators then equal those of the exact test
@@ -155,12 +159,19 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, Candid
             if (cls != 0 && lo <= minHi) {
                 mask |= 1ull << (g - g0);
                 if (cls == 2) minHi = fminf(minHi, hi);
+                if (lo < lo1) { lo2 = lo1; lo1 = lo; first = g; }
+                else lo2 = fminf(lo2, lo);
             }
+        }
+        if (first >= 0) {
+            testGeom(sg[first], first, o, d, best, orig, orig, true);
+            mask &= ~(1ull << (first - g0));
+            if (!(lo2 <= best.t)) mask = 0ull;                    // nobody else can reach the exact winner
         }
         while (mask) {
             const int g = g0 + __ffsll((long long)mask) - 1;
             mask &= mask - 1ull;
-            testGeom(sg[g], g, o, d, best, orig, orig, false);
+            testGeom(sg[g], g, o, d, best, orig, orig, true);
         }
     }
 }
