@@ -1,7 +1,7 @@
 // host_abi.cpp -- C-ABI access to the host-side pieces (scene loader, camera fix-up, image writer)
 // so that non-C++ callers (the Python tests, other FFI users) reach the same code the headless
 // driver uses.  Declared in include/ptb200.h.
-#include "../../../include/ptb200.h"
+#include "ptb200.h"
 #include "scene.h"
 #include "image.h"
 #include <cstring>

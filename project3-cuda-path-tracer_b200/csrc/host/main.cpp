@@ -1,0 +1,128 @@
+// main.cpp -- headless driver: the reference app's main loop (src/main.cpp:33-76 start-up, :101-147
+// runCuda, :78-99 saveImage) without GLFW/GLEW/OpenGL.  The reference has no headless mode; the GL
+// preview (src/preview.cpp, glslUtility.cpp) is display only and out of scope.
+//
+//   ptb200_headless SCENEFILE.txt [--iters N] [--depth D] [--bsdf full|golden-diffuse] [--batch B]
+//                   [--per-iteration] [--out BASENAME] [--hdr] [--staged] [--sort] [--no-compaction]
+//                   [--device K] [--quiet]
+//
+// Default: renders state.iterations iterations (ITERATIONS of the scene file) through the batched
+// loop and writes <FILE>.<UTC start time>.<N>samp.png exactly like saveImage().  --per-iteration uses
+// the reference's pathtrace(pbo, frame, iteration) call, one call and one image download per iteration.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <iostream>
+#include <sstream>
+#include <string>
+
+#include "ptb200.h"
+#include "image.h"
+#include "pathtrace.h"
+#include "scene.h"
+
+static std::string currentTimeString() {                    // src/preview.cpp:13-19
+    time_t now;
+    time(&now);
+    char buf[sizeof "0000-00-00_00-00-00z"];
+    strftime(buf, sizeof buf, "%Y-%m-%d_%H-%M-%Sz", gmtime(&now));
+    return std::string(buf);
+}
+
+static Scene *scene;
+static RenderState *renderState;
+static int iteration;
+static int width, height;
+static std::string startTimeString;
+
+static void saveImage(const std::string &outBase, bool hdr, bool quiet) {   // src/main.cpp:78-99
+    float samples = (float)iteration;
+    image img(width, height);
+    for (int x = 0; x < width; x++)
+        for (int y = 0; y < height; y++) {
+            int index = x + (y * width);
+            glm::vec3 pix = renderState->image[index];
+            img.setPixel(width - 1 - x, y, glm::vec3(pix) / samples);
+        }
+    std::string filename = outBase;
+    if (filename.empty()) {
+        std::ostringstream ss;
+        ss << renderState->imageName << "." << startTimeString << "." << samples << "samp";
+        filename = ss.str();
+    }
+    if (hdr) img.saveHDR(filename, quiet); else img.savePNG(filename, quiet);
+}
+
+int main(int argc, char **argv) {
+    startTimeString = currentTimeString();
+    if (argc < 2) { printf("Usage: %s SCENEFILE.txt [options]\n", argv[0]); return 1; }
+    const char *sceneFile = argv[1];
+    int iters = -1, depth = -1, batch = 0, device = -1;
+    bool perIteration = false, hdr = false, quiet = false;
+    std::string outBase;
+    PtbOptions opt;
+    ptb_default_options(&opt);
+    for (int i = 2; i < argc; ++i) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char * { return i + 1 < argc ? argv[++i] : ""; };
+        if (a == "--iters") iters = atoi(next());
+        else if (a == "--depth") depth = atoi(next());
+        else if (a == "--batch") batch = atoi(next());
+        else if (a == "--device") device = atoi(next());
+        else if (a == "--out") outBase = next();
+        else if (a == "--bsdf") opt.bsdfMode = strcmp(next(), "golden-diffuse") == 0 ? PTB_BSDF_GOLDEN_DIFFUSE : PTB_BSDF_FULL;
+        else if (a == "--per-iteration") perIteration = true;
+        else if (a == "--hdr") hdr = true;
+        else if (a == "--staged") opt.pipeline = PTB_PIPELINE_STAGED;
+        else if (a == "--sort") opt.sortMaterials = 1;
+        else if (a == "--no-compaction") opt.compaction = 0;
+        else if (a == "--quiet") quiet = true;
+        else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
+    }
+    opt.batchIters = perIteration ? 1 : batch;
+    opt.device = device;
+
+    scene = new Scene(sceneFile, !quiet);                      // src/main.cpp:44
+    if (!scene->ok) { fprintf(stderr, "Error reading from file - aborting!\n"); return 1; }
+    iteration = 0;
+    renderState = &scene->state;
+    Camera &cam = renderState->camera;
+    width = cam.resolution.x;
+    height = cam.resolution.y;
+    if (iters >= 0) renderState->iterations = (unsigned)iters;
+    if (depth > 0) renderState->traceDepth = depth;
+
+    // src/main.cpp:53-67 + :102-120 -- the camera is rebuilt from (zoom, phi, theta) before frame 1
+    ptb_camera_fixup(reinterpret_cast<PtbCamera *>(&cam));
+
+    pathtraceSetOptions(&opt);
+    pathtraceFree();                                           // src/main.cpp:126-127 (free precedes the first init)
+    pathtraceInit(scene);
+
+    auto t0 = std::chrono::steady_clock::now();
+    if (perIteration) {
+        while (iteration < (int)renderState->iterations) {     // src/main.cpp:131-140
+            iteration++;
+            pathtrace(NULL, 0, iteration);
+        }
+    } else {
+        pathtraceBatch(1, (int)renderState->iterations);
+        iteration = (int)renderState->iterations;
+        pathtraceDownload();
+    }
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+    PtbStats st;
+    ptb_stats(pathtraceContext(), &st);
+    if (!quiet) {
+        printf("%d iterations in %.3f s: %.1f iterations/s, %.4e path segments/s\n", iteration, secs, iteration / secs, st.segments / secs);
+        printf("paths entering each bounce (per iteration):");
+        for (int d = 0; d < st.traceDepth; ++d) printf(" %.0f", (double)st.alivePerDepth[d] / (double)(st.iterations ? st.iterations : 1));
+        printf("\n");
+    }
+    if (iteration > 0) saveImage(outBase, hdr, quiet);         // src/main.cpp:141-142
+    pathtraceFree();
+    return 0;
+}

@@ -4,7 +4,7 @@
 // put the reference's src/ first on the include path) -- see INTEGRATION.md.
 // Error behaviour follows checkCUDAError (src/pathtrace.cu:21-39): print and exit(EXIT_FAILURE).
 #include "pathtrace.h"
-#include "../../../include/ptb200.h"
+#include "ptb200.h"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>

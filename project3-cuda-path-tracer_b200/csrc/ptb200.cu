@@ -2,7 +2,7 @@
 // CUDA-graph replay of the per-batch bounce loop.  Host orchestration only; the kernels are in
 // ptb_kernels.cuh.  Replaces the host side of src/pathtrace.cu (pathtraceInit :79-101,
 // pathtraceFree :103-112, pathtrace :284-393) of the reference.
-#include "../../include/ptb200.h"
+#include "ptb200.h"
 #include "ptb_kernels.cuh"
 #include "ptb_bvh.h"
 
@@ -425,10 +425,12 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     // ---- launch geometry ----
     c->smemBrute = bruteBytes;
     c->smemBvh = (size_t)511 * sizeof(BvhNode);     // fixed: the node count may change in ptb_update_scene
-    int rc = PTB_OK;
-    rc |= setSmem(bounce_kernel<true, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false>, c->smemBrute);
-    rc |= setSmem(intersect_kernel<false>, c->smemBrute); rc |= setSmem(stage_intersect_kernel<false>, c->smemBrute);
-    if (rc != PTB_OK && !c->useBvh && bruteBytes <= 200 * 1024) return bail(rc);
+    if (bruteBytes <= 200 * 1024) {                  // brute force is only launchable when the geoms fit in shared memory
+        int rc = PTB_OK;
+        rc |= setSmem(bounce_kernel<true, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false>, c->smemBrute);
+        rc |= setSmem(intersect_kernel<false>, c->smemBrute); rc |= setSmem(stage_intersect_kernel<false>, c->smemBrute);
+        if (rc != PTB_OK) return bail(rc);
+    }
     int occ = 0;
     const size_t smem = c->useBvh ? c->smemBvh : c->smemBrute;
     if (c->useBvh) CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, true>, kBlock, smem));

@@ -4,7 +4,7 @@
 #pragma once
 #include <cstdint>
 #include <vector>
-#include "../../include/ptb200.h"
+#include "ptb200.h"
 
 namespace ptb {
 
