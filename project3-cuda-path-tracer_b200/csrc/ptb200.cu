@@ -118,6 +118,18 @@ GeomRec packGeom(const PtbGeom &g, int sceneIndex) {
     r.fwd.r0 = row(g.transform, 0); r.fwd.r1 = row(g.transform, 1); r.fwd.r2 = row(g.transform, 2);
     r.nrm.r0 = row(g.invTranspose, 0); r.nrm.r1 = row(g.invTranspose, 1); r.nrm.r2 = row(g.invTranspose, 2);
     r.tag = make_int4(g.type, g.materialid, sceneIndex, 0);
+    // conservative world-space pruning bound (phase 1 of the brute-force closest hit)
+    if (g.type == 1) {
+        float lo[3], hi[3];
+        geomBounds(g, lo, hi);
+        r.b0 = make_float4(lo[0], lo[1], lo[2], 0.f);
+        r.b1 = make_float4(hi[0], hi[1], hi[2], 0.f);
+    } else {
+        float c[3], r2;
+        sphereBounds(g, c, &r2);
+        r.b0 = make_float4(c[0], c[1], c[2], r2);
+        r.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     return r;
 }
 

@@ -23,6 +23,33 @@ void geomBounds(const PtbGeom &g, float lo[3], float hi[3]) {
     }
 }
 
+// The unit-radius-0.5 sphere under the linear part A of Geom::transform lies inside the ball of radius
+// 0.5 * sigma_max(A) around the translation; sigma_max by power iteration on A^T A (3x3, double).
+// Padded like geomBounds for the 1e-4 fall-short and float rounding of the reference's hit point.
+void sphereBounds(const PtbGeom &g, float centre[3], float *radius2) {
+    const float *m = g.transform;
+    double A[3][3];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) A[r][c] = m[4 * c + r];
+    double S[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { S[i][j] = 0; for (int k = 0; k < 3; ++k) S[i][j] += A[k][i] * A[k][j]; }
+    double v[3] = {0.577, 0.577, 0.577}, lambda = 0;
+    for (int it = 0; it < 64; ++it) {
+        double w[3] = {0, 0, 0};
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) w[i] += S[i][j] * v[j];
+        const double n = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        if (!(n > 0)) break;
+        lambda = n;
+        for (int i = 0; i < 3; ++i) v[i] = w[i] / n;
+    }
+    // power iteration converges from below; the Frobenius norm caps it from above
+    const double frob = std::sqrt(S[0][0] + S[1][1] + S[2][2]);
+    double sigma = std::min(frob, std::sqrt(lambda) * 1.001);
+    double cmag = std::fabs((double)m[12]) + std::fabs((double)m[13]) + std::fabs((double)m[14]);
+    const double R = 0.5 * sigma * (1.0 + 1e-4) + 4e-4 * sigma + 1e-3 + 2e-5 * (cmag + sigma);
+    centre[0] = m[12]; centre[1] = m[13]; centre[2] = m[14];
+    *radius2 = (float)(R * R * (1.0 + 1e-6));
+}
+
 namespace {
 struct Box {
     float lo[3], hi[3];

@@ -22,6 +22,8 @@ struct HostBvh {
 
 // Padded world-space box of one geom (unit cube / sphere under Geom::transform).
 void geomBounds(const PtbGeom &g, float lo[3], float hi[3]);
+// Padded world-space bounding sphere of a SPHERE geom: centre and squared radius.
+void sphereBounds(const PtbGeom &g, float centre[3], float *radius2);
 
 // Binned-SAH top-down build; leaves hold at most `maxLeaf` geoms.
 void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out);

@@ -102,76 +102,65 @@ struct Candidate {               // what must survive the geom loop to build the
     float a, b, c;               // box: face normal code; sphere: object-space hit point
 };
 
-PTB_DEV void testGeom(const GeomRec &g, int slot, f3 o, f3 d, Candidate &best, int bestOrig, int &bestOrigOut, bool tieByIndex) {
-    float t; int outside = 1; float a, b, c;
-    if (g.tag.x == 1) {          // CUBE
-        BoxFace f;
-        t = boxTest(g, o, d, f, outside);
-        a = f.nx; b = f.ny; c = f.nz;
-    } else {                     // SPHERE
-        f3 objP = mk3(0.f, 0.f, 0.f);
-        t = sphereTest(g, o, d, objP, outside);
-        a = objP.x; b = objP.y; c = objP.z;
-    }
-    // src/pathtrace.cu:192: `t > 0.0f && t_min > t` visited in index order == lowest index wins ties.
-    bool take = t > 0.0f && best.t > t;
-    if (tieByIndex && t > 0.0f && best.t == t && g.tag.z < bestOrig) take = true;
+PTB_DEV void testGeom(const GeomRec &g, int slot, f3 o, f3 d, Candidate &best, int &bestOrig) {
+    int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
+    const float t = exactTest(g, o, d, outside, a, b, c);
+    // src/pathtrace.cu:192 visits the geoms in index order with `t > 0.0f && t_min > t`: the smallest t
+    // wins and, among equal t, the lowest scene index.  Candidates arrive here in arbitrary order.
+    const bool take = t > 0.0f && (best.t > t || (best.t == t && g.tag.z < bestOrig));
     if (take) {
         best.t = t; best.slot = slot; best.outside = outside; best.a = a; best.b = b; best.c = c;
-        bestOrigOut = g.tag.z;
+        bestOrig = g.tag.z;
     }
 }
 
-PTB_DEV f3 candidateNormal(const GeomRec &g, const Candidate &c) {
-    if (g.tag.x == 1) { BoxFace f; f.nx = c.a; f.ny = c.b; f.nz = c.c; return boxNormal(g, f); }
-    return sphereNormal(g, mk3(c.a, c.b, c.c), c.outside);
-}
+PTB_DEV f3 candidateNormal(const GeomRec &g, const Candidate &c) { return exactNormal(g, c.outside, c.a, c.b, c.c); }
 
-// Closest hit, brute force over shared-memory geoms, in two phases:
-//   1. a warp-uniform loop classifies every geom with cheap approximate arithmetic (MUFU reciprocals,
-//      fused multiply-adds) into sure-miss / candidate and brackets the distance each candidate would
-//      return; a candidate survives only if its lower bound does not exceed the smallest upper bound of
-//      a sure hit;
-//   2. each lane runs the reference-exact test (ptb_math.cuh) on ITS OWN candidate with the smallest
-//      lower bound -- the winner for almost every ray -- and looks at the other candidates only when
-//      the second-smallest lower bound does not exceed that exact distance.  Ties go to the lowest
-//      scene index, as `t > 0 && t_min > t` visited in index order does (src/pathtrace.cu:192).
-// Phase 1 only prunes; every output value comes from phase 2.  Scenes of up to 64 geoms take this
-// path in one mask word; larger ones are walked in chunks of 64.
+// Closest hit, brute force over the shared-memory geoms, in two phases:
+//   1. a warp-uniform loop over all geoms evaluates a cheap conservative world-space bound (padded
+//      AABB for cubes, padded bounding sphere for spheres, ~25 approximate instructions each) and
+//      records, per lane, which primitives the ray can reach and the smallest / second-smallest entry
+//      distance;
+//   2. each lane then runs the reference-exact test (ptb_math.cuh) on ITS OWN nearest candidate -- the
+//      data-dependent shared-memory reads keep the warp on one code path -- and looks at the remaining
+//      candidates only if the second-smallest lower bound does not exceed that exact distance.
+// Phase 1 only prunes and orders; every output value comes from phase 2.
 PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, Candidate &best) {
     best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
     int orig = 0x7fffffff;
-    const float rdLen = sqrtf(fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z)));
+    const float dd = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
+    const float rinv = rsqrtApprox(dd);
+    const float rdLen = dd * rinv;
+    const f3 dn = mk3(d.x * rinv, d.y * rinv, d.z * rinv);
+    const f3 invD = mk3(rcpApprox(d.x), rcpApprox(d.y), rcpApprox(d.z));
+    // slack on every lower bound: rounding of the bound itself plus the deviation of the exact hit
+    // point from the ideal ray (a few ulp of the coordinates involved)
     const float roMag = fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f;
-    float minHi = 3.0e38f;
     for (int g0 = 0; g0 < numGeoms; g0 += 64) {                  // 64 candidates per mask word
         const int g1 = min(numGeoms, g0 + 64);
         unsigned long long mask = 0ull;
         float lo1 = 3.0e38f, lo2 = 3.0e38f;                      // smallest / second-smallest lower bound
         int first = -1;
         for (int g = g0; g < g1; ++g) {
-            // object-space origin / direction with the EXACT operation order: the signs of the slab
-            // numerators and denominators then equal those of the exact test
-            const f3 qo = mulMV(sg[g].inv, o, 1.0f);
-            const f3 u = mulMV(sg[g].inv, d, 0.0f);
-            float lo, hi;
-            const int cls = sg[g].tag.x == 1 ? classifyBox(qo, u, rdLen, roMag, lo, hi) : classifySphere(qo, u, rdLen, roMag, lo, hi);
-            if (cls != 0 && lo <= minHi) {
-                mask |= 1ull << (g - g0);
-                if (cls == 2) minHi = fminf(minHi, hi);
-                if (lo < lo1) { lo2 = lo1; lo1 = lo; first = g; }
-                else lo2 = fminf(lo2, lo);
+            float lo = boundEntry(sg[g], o, invD, dn, rdLen);
+            if (lo >= 0.0f) {
+                lo = lo * 0.99998f - 2e-5f * roMag;
+                if (lo <= best.t) {                              // best.t is exact: carried over from earlier chunks
+                    mask |= 1ull << (g - g0);
+                    if (lo < lo1) { lo2 = lo1; lo1 = lo; first = g; }
+                    else lo2 = fminf(lo2, lo);
+                }
             }
         }
         if (first >= 0) {
-            testGeom(sg[first], first, o, d, best, orig, orig, true);
+            testGeom(sg[first], first, o, d, best, orig);
             mask &= ~(1ull << (first - g0));
             if (!(lo2 <= best.t)) mask = 0ull;                    // nobody else can reach the exact winner
         }
         while (mask) {
             const int g = g0 + __ffsll((long long)mask) - 1;
             mask &= mask - 1ull;
-            testGeom(sg[g], g, o, d, best, orig, orig, true);
+            testGeom(sg[g], g, o, d, best, orig);
         }
     }
 }
@@ -195,7 +184,8 @@ PTB_DEV GeomRec loadGeom(const GeomRec *gp) {
     const float4 *src = reinterpret_cast<const float4 *>(gp);
     float4 *dst = reinterpret_cast<float4 *>(&g);
 #pragma unroll
-    for (int q = 0; q < 10; ++q) dst[q] = __ldg(src + q);
+    for (int q = 0; q < 10; ++q) dst[q] = __ldg(src + q);      // the pruning bound (b0, b1) is not needed at a BVH leaf
+    g.b0 = g.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
     return g;
 }
 
@@ -224,12 +214,12 @@ PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, const int sme
         int nextL = -1, nextR = -1;
         if (vl) {
             const int cnt = __float_as_int(lhi.w), ref = __float_as_int(llo.w);
-            if (cnt > 0) { for (int k = 0; k < cnt; ++k) testGeom(loadGeom(p.geoms + ref + k), ref + k, o, d, best, bestOrig, bestOrig, true); }
+            if (cnt > 0) { for (int k = 0; k < cnt; ++k) testGeom(loadGeom(p.geoms + ref + k), ref + k, o, d, best, bestOrig); }
             else nextL = ref;
         }
         if (vr && tr * dl - 1e-4f <= best.t) {
             const int cnt = __float_as_int(rhi.w), ref = __float_as_int(rlo.w);
-            if (cnt > 0) { for (int k = 0; k < cnt; ++k) testGeom(loadGeom(p.geoms + ref + k), ref + k, o, d, best, bestOrig, bestOrig, true); }
+            if (cnt > 0) { for (int k = 0; k < cnt; ++k) testGeom(loadGeom(p.geoms + ref + k), ref + k, o, d, best, bestOrig); }
             else nextR = ref;
         }
         if (nextL >= 0 && nextR >= 0) {
@@ -400,7 +390,7 @@ __global__ void __launch_bounds__(kBlock) bounce_kernel(const __grid_constant__ 
 
     const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
     if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
-    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * 10);
+    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
     const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
 
@@ -491,7 +481,7 @@ __global__ void __launch_bounds__(kBlock) intersect_kernel(const __grid_constant
     extern __shared__ float4 smem4[];
     const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
     if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
-    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * 10);
+    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
     const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
     const uint32_t nIn = p.ctrl->counts[depth];
@@ -687,7 +677,7 @@ __global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_co
     extern __shared__ float4 smem4[];
     const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
     if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
-    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * 10);
+    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
     const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
     for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
