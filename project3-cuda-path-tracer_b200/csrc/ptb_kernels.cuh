@@ -102,9 +102,7 @@ struct Candidate {               // what must survive the geom loop to build the
     float a, b, c;               // box: face normal code; sphere: object-space hit point
 };
 
-PTB_DEV void testGeom(const GeomRec &g, int slot, f3 o, f3 d, Candidate &best, int &bestOrig) {
-    int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
-    const float t = exactTest(g, o, d, outside, a, b, c);
+PTB_DEV void acceptHit(const GeomRec &g, int slot, float t, int outside, float a, float b, float c, Candidate &best, int &bestOrig) {
     // src/pathtrace.cu:192 visits the geoms in index order with `t > 0.0f && t_min > t`: the smallest t
     // wins and, among equal t, the lowest scene index.  Candidates arrive here in arbitrary order.
     const bool take = t > 0.0f && (best.t > t || (best.t == t && g.tag.z < bestOrig));
@@ -113,18 +111,33 @@ PTB_DEV void testGeom(const GeomRec &g, int slot, f3 o, f3 d, Candidate &best, i
         bestOrig = g.tag.z;
     }
 }
+PTB_DEV void testGeom(const GeomRec &g, int slot, f3 o, f3 d, Candidate &best, int &bestOrig) {
+    int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
+    const float t = exactTest(g, o, d, outside, a, b, c);
+    acceptHit(g, slot, t, outside, a, b, c, best, bestOrig);
+}
+// brute-force phase 2: object-space sure-miss filter, then the exact test on the same object-space ray
+PTB_DEV void testCandidate(const GeomRec &g, int slot, f3 o, f3 d, Candidate &best, int &bestOrig) {
+    f3 qo, qu;
+    objectRay(g, o, d, qo, qu);
+    if (sureMiss(g, qo, qu)) return;
+    int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
+    const float t = exactTestQ(g, o, qo, qu, outside, a, b, c);
+    acceptHit(g, slot, t, outside, a, b, c, best, bestOrig);
+}
 
 PTB_DEV f3 candidateNormal(const GeomRec &g, const Candidate &c) { return exactNormal(g, c.outside, c.a, c.b, c.c); }
 
 // Closest hit, brute force over the shared-memory geoms, in two phases:
 //   1. a warp-uniform loop over all geoms evaluates a cheap conservative world-space bound (padded
-//      AABB for cubes, padded bounding sphere for spheres, ~25 approximate instructions each) and
-//      records, per lane, which primitives the ray can reach and the smallest / second-smallest entry
-//      distance;
-//   2. each lane then runs the reference-exact test (ptb_math.cuh) on ITS OWN nearest candidate -- the
-//      data-dependent shared-memory reads keep the warp on one code path -- and looks at the remaining
-//      candidates only if the second-smallest lower bound does not exceed that exact distance.
-// Phase 1 only prunes and orders; every output value comes from phase 2.
+//      AABB for cubes, padded bounding sphere for spheres, ~35 approximate instructions each) and keeps,
+//      per lane, the three reachable primitives with the smallest entry distance, sorted (anything
+//      beyond three goes to an overflow mask);
+//   2. each lane walks ITS OWN candidates nearest first -- the data-dependent shared-memory reads keep
+//      the warp on one code path -- stopping as soon as the next lower bound exceeds the exact distance
+//      found so far.  A candidate first meets the object-space sure-miss filter (the primitive a bounce
+//      ray just left is always "reachable" for the world-space bound) and only then the exact test.
+// Phase 1 only prunes and orders; every output value comes from the exact test.
 PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, Candidate &best) {
     best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
     int orig = 0x7fffffff;
@@ -135,32 +148,39 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, Candid
     const f3 invD = mk3(rcpApprox(d.x), rcpApprox(d.y), rcpApprox(d.z));
     // slack on every lower bound: rounding of the bound itself plus the deviation of the exact hit
     // point from the ideal ray (a few ulp of the coordinates involved)
-    const float roMag = fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f;
-    for (int g0 = 0; g0 < numGeoms; g0 += 64) {                  // 64 candidates per mask word
+    const float slack = 2e-5f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f);
+    for (int g0 = 0; g0 < numGeoms; g0 += 64) {                  // 64 geoms per overflow-mask word
         const int g1 = min(numGeoms, g0 + 64);
-        unsigned long long mask = 0ull;
-        float lo1 = 3.0e38f, lo2 = 3.0e38f;                      // smallest / second-smallest lower bound
-        int first = -1;
+        unsigned long long overflow = 0ull;
+        float l0 = 3.0e38f, l1 = 3.0e38f, l2 = 3.0e38f;          // three smallest lower bounds, ascending
+        int c0 = -1, c1 = -1, c2 = -1;
         for (int g = g0; g < g1; ++g) {
             float lo = boundEntry(sg[g], o, invD, dn, rdLen);
             if (lo >= 0.0f) {
-                lo = lo * 0.99998f - 2e-5f * roMag;
-                if (lo <= best.t) {                              // best.t is exact: carried over from earlier chunks
-                    mask |= 1ull << (g - g0);
-                    if (lo < lo1) { lo2 = lo1; lo1 = lo; first = g; }
-                    else lo2 = fminf(lo2, lo);
+                lo = lo * 0.99998f - slack;
+                if (lo < l2) {
+                    if (c2 >= 0) overflow |= 1ull << (c2 - g0);
+                    if (lo < l0)      { l2 = l1; c2 = c1; l1 = l0; c1 = c0; l0 = lo; c0 = g; }
+                    else if (lo < l1) { l2 = l1; c2 = c1; l1 = lo; c1 = g; }
+                    else              { l2 = lo; c2 = g; }
+                } else {
+                    overflow |= 1ull << (g - g0);
                 }
             }
         }
-        if (first >= 0) {
-            testGeom(sg[first], first, o, d, best, orig);
-            mask &= ~(1ull << (first - g0));
-            if (!(lo2 <= best.t)) mask = 0ull;                    // nobody else can reach the exact winner
+#pragma unroll 1
+        for (int k = 0; k < 3; ++k) {                             // one copy of the test code
+            const int g = k == 0 ? c0 : (k == 1 ? c1 : c2);
+            const float lo = k == 0 ? l0 : (k == 1 ? l1 : l2);
+            if (g < 0 || !(lo <= best.t)) break;                  // sorted: nothing further can win
+            testCandidate(sg[g], g, o, d, best, orig);
         }
-        while (mask) {
-            const int g = g0 + __ffsll((long long)mask) - 1;
-            mask &= mask - 1ull;
-            testGeom(sg[g], g, o, d, best, orig);
+        if (!(l2 <= best.t)) overflow = 0ull;                     // every overflow bound is >= l2
+        while (overflow) {
+            const int g = g0 + __ffsll((long long)overflow) - 1;
+            overflow &= overflow - 1ull;
+            const float lo = boundEntry(sg[g], o, invD, dn, rdLen) * 0.99998f - slack;
+            if (lo <= best.t) testCandidate(sg[g], g, o, d, best, orig);
         }
     }
 }
@@ -383,7 +403,7 @@ PTB_DEV uint32_t compactSlot(bool keep, uint32_t *counter, int *warpTotals, uint
 // paths is read from device memory, so the host never synchronises inside an iteration.
 // ------------------------------------------------------------------------------------------------
 template <bool FIRST, bool USE_BVH>
-__global__ void __launch_bounds__(kBlock) bounce_kernel(const __grid_constant__ Params p, const int depth) {
+__global__ void __launch_bounds__(kBlock, 4) bounce_kernel(const __grid_constant__ Params p, const int depth) {
     extern __shared__ float4 smem4[];
     __shared__ int warpTotals[kBlock / 32];
     __shared__ uint32_t blockBase;
