@@ -91,7 +91,8 @@ typedef struct PtbOptions {
     int32_t batchIters;             /* iterations traced per wavefront (fused pipeline); 0 = default */
     int32_t compaction;             /* staged pipeline: 1 = ballot/popc stream compaction, 0 = none (skeleton layout) */
     int32_t sortMaterials;          /* staged pipeline: 1 = sort paths by material id before shading */
-    int32_t firstBounceCache;       /* 1 = cache bounce-0 hits across iterations (INSTRUCTION.md:87-89) */
+    int32_t firstBounceCache;       /* fused pipeline: 1 = cache the bounce-0 hit record of every pixel across iterations
+                                       (INSTRUCTION.md:87-89); refilled after ptb_create / ptb_update_scene */
     int32_t useGraphs;              /* 1 = replay the per-batch launch sequence as a CUDA graph */
     int32_t reserved0;
     void   *stream;                 /* cudaStream_t to launch on; NULL = library-owned stream */
@@ -182,6 +183,12 @@ int ptb_stage_compact(PtbContext *ctx, int n, const int32_t *ids, const int32_t 
 int ptb_stage_sort_keys(PtbContext *ctx, int n, const int32_t *keys, int numKeys, int32_t *outOrder);
 /* makeSeededRandomEngine + u01 draws on the device (src/pathtrace.cu:41-45, 240-241) */
 int ptb_stage_rng(PtbContext *ctx, int iter, int index, int depth, int n, float *out);
+
+/* the device arithmetic the exact tests are built from (csrc/ptb_math.cuh: IEEE division, square root and
+ * glm::normalize with a shared range check) on caller-supplied operands: quot[i] = a[i] / b[i],
+ * root[i] = sqrt(|a[i]|), normY[i] = normalize(vec3(a[i], b[i], a[i])).y -- checked against correctly
+ * rounded host arithmetic (the glm operations of src/intersections.h:48-144 are built from exactly these) */
+int ptb_stage_arith(PtbContext *ctx, int n, const float *a, const float *b, float *quot, float *root, float *normY);
 
 /* ---- host-side pieces of the drop-in surface (C++ in csrc/host/, reachable over the C ABI) ---- */
 /* new Scene(filename) (src/scene.cpp:7-33); PTB_ERR_IO when the file cannot be opened */

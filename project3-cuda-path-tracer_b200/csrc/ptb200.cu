@@ -9,6 +9,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -83,9 +84,12 @@ struct PtbContext {
     float *imagePtr = nullptr;           // own or external
     DevBuf<float4> A[2], B[2];
     DevBuf<float2> C[2];
-    DevBuf<float4> hitTn;
+    DevBuf<float4> hitTn, fbTn;           // fbTn / fbMeta: first-bounce cache (INSTRUCTION.md:87-89)
+    DevBuf<int> fbMeta;
+    bool fbValid = false;
     DevBuf<int> hitMeta, sortKeys, sortOrder;
-    DevBuf<uint32_t> sortHist;
+    DevBuf<uint32_t> sortHist, segCounts;
+    uint32_t segCap = 0;
     DevBuf<Control> ctrl;
     DevBuf<uint8_t> rgb8;
 
@@ -102,7 +106,7 @@ struct PtbContext {
         geoms.release(); geomsScene.release(); bvh.release(); mats.release(); sceneMatDev.release();
         image.release();
         for (int i = 0; i < 2; ++i) { A[i].release(); B[i].release(); C[i].release(); }
-        hitTn.release(); hitMeta.release(); sortKeys.release(); sortOrder.release(); sortHist.release();
+        hitTn.release(); hitMeta.release(); sortKeys.release(); sortOrder.release(); sortHist.release(); segCounts.release(); fbTn.release(); fbMeta.release();
         ctrl.release(); rgb8.release(); hdr.release();
         if (pinned) cudaFreeHost(pinned);
         if (ownStream && stream) cudaStreamDestroy(stream);
@@ -313,7 +317,21 @@ int buildGraph(PtbContext *c) {
     return PTB_OK;
 }
 
+// (re)fills the first-bounce cache after a scene / camera upload
+int ensureFirstBounceCache(PtbContext *c) {
+    if (!c->opt.firstBounceCache || c->opt.pipeline != PTB_PIPELINE_FUSED || c->fbValid) return PTB_OK;
+    Params p = c->base;
+    if (c->useBvh) fb_cache_kernel<true><<<c->gridStaged, kBlock, c->smemBvh, c->stream>>>(p, c->fbTn.p, c->fbMeta.p);
+    else           fb_cache_kernel<false><<<c->gridStaged, kBlock, c->smemBrute, c->stream>>>(p, c->fbTn.p, c->fbMeta.p);
+    c->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(PTB_ERR_CUDA, "first-bounce cache fill: %s", cudaGetErrorString(e));
+    c->fbValid = true;
+    return PTB_OK;
+}
+
 int runBatches(PtbContext *c, int iterBegin, int count, int iterStride) {
+    { int rc = ensureFirstBounceCache(c); if (rc != PTB_OK) return rc; }
     int done = 0;
     while (done < count) {
         const int b = std::min(c->batch, count - done);
@@ -420,20 +438,6 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
         if (urc != PTB_OK) return bail(urc);
     }
 
-    // ---- state (src/pathtrace.cu:84-87, 95-96) ----
-    if (opt.externalAccum) c->imagePtr = opt.externalAccum;
-    else { CUB(c->image.alloc((size_t)c->numPixels * 3)); c->imagePtr = c->image.p; CUB(cudaMemset(c->imagePtr, 0, (size_t)c->numPixels * 3 * sizeof(float))); }
-    const size_t maxPaths = (size_t)c->numPixels * c->batch;
-    for (int i = 0; i < 2; ++i) {
-        CUB(c->A[i].alloc(maxPaths)); CUB(c->B[i].alloc(maxPaths)); CUB(c->C[i].alloc(maxPaths));
-    }
-    if (opt.pipeline == PTB_PIPELINE_STAGED) {
-        CUB(c->hitTn.alloc(maxPaths)); CUB(c->hitMeta.alloc(maxPaths));
-        if (opt.sortMaterials) { CUB(c->sortKeys.alloc(maxPaths)); CUB(c->sortOrder.alloc(maxPaths)); CUB(c->sortHist.alloc(scene->numMaterials + 2)); }
-    }
-    CUB(c->ctrl.alloc(1));
-    CUB(cudaMemset(c->ctrl.p, 0, sizeof(Control)));
-
     // ---- launch geometry ----
     c->smemBrute = bruteBytes;
     c->smemBvh = (size_t)511 * sizeof(BvhNode);     // fixed: the node count may change in ptb_update_scene
@@ -441,14 +445,40 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
         int rc = PTB_OK;
         rc |= setSmem(bounce_kernel<true, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false>, c->smemBrute);
         rc |= setSmem(intersect_kernel<false>, c->smemBrute); rc |= setSmem(stage_intersect_kernel<false>, c->smemBrute);
+        rc |= setSmem(fb_cache_kernel<false>, c->smemBrute);
         if (rc != PTB_OK) return bail(rc);
     }
     int occ = 0;
     const size_t smem = c->useBvh ? c->smemBvh : c->smemBrute;
     if (c->useBvh) CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, true>, kBlock, smem));
     else           CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, false>, kBlock, smem));
-    c->gridFused = c->numSMs * std::max(1, occ);
+    // 4 CTAs per resident slot: the CTA-owned segments cannot be rebalanced inside a launch, so a few
+    // waves of smaller CTAs keep the tail short (measured: x1 142 us, x2 138, x4 134.5, x8 135.4, x16 142 per cornell iteration)
+    int gridMult = 4;
+    if (const char *e = getenv("PTB_GRID_MULT")) gridMult = std::max(1, atoi(e));           // tuning knob (experiments)
+    c->gridFused = c->numSMs * std::max(1, occ) * gridMult;
     c->gridStaged = c->numSMs * 8;
+
+    // ---- state (src/pathtrace.cu:84-87, 95-96) ----
+    if (opt.externalAccum) c->imagePtr = opt.externalAccum;
+    else { CUB(c->image.alloc((size_t)c->numPixels * 3)); c->imagePtr = c->image.p; CUB(cudaMemset(c->imagePtr, 0, (size_t)c->numPixels * 3 * sizeof(float))); }
+    const size_t maxPaths = (size_t)c->numPixels * c->batch;
+    // fused pipeline: every CTA owns a segment of ceil(tiles / grid) 256-path tiles of the path buffers
+    const size_t tiles = (maxPaths + kBlock - 1) / kBlock;
+    c->segCap = (uint32_t)(((tiles + c->gridFused - 1) / c->gridFused) * kBlock);
+    const size_t pathSlots = std::max(maxPaths, (size_t)c->segCap * c->gridFused);
+    for (int i = 0; i < 2; ++i) {
+        CUB(c->A[i].alloc(pathSlots)); CUB(c->B[i].alloc(pathSlots)); CUB(c->C[i].alloc(pathSlots));
+    }
+    CUB(c->segCounts.alloc((size_t)2 * c->gridFused));
+    CUB(cudaMemset(c->segCounts.p, 0, sizeof(uint32_t) * 2 * c->gridFused));
+    if (opt.pipeline == PTB_PIPELINE_STAGED) {
+        CUB(c->hitTn.alloc(maxPaths)); CUB(c->hitMeta.alloc(maxPaths));
+        if (opt.sortMaterials) { CUB(c->sortKeys.alloc(maxPaths)); CUB(c->sortOrder.alloc(maxPaths)); CUB(c->sortHist.alloc(scene->numMaterials + 2)); }
+    }
+    if (opt.firstBounceCache && opt.pipeline == PTB_PIPELINE_FUSED) { CUB(c->fbTn.alloc(c->numPixels)); CUB(c->fbMeta.alloc(c->numPixels)); }
+    CUB(c->ctrl.alloc(1));
+    CUB(cudaMemset(c->ctrl.p, 0, sizeof(Control)));
 
     Params &p = c->base;
     memset(&p, 0, sizeof p);
@@ -465,6 +495,9 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     p.pixBits = c->pixBits;
     p.numPixels = c->numPixels;
     p.atomicGather = c->batch > 1 ? 1 : 0;
+    p.segCounts = c->segCounts.p;
+    p.segCap = c->segCap;
+    p.fbTn = c->fbTn.p; p.fbMeta = c->fbMeta.p;          // NULL when the cache is off
     CUB(cudaDeviceSynchronize());
 #undef CUB
     *out = c;
@@ -482,6 +515,7 @@ int ptb_update_scene(PtbContext *c, const PtbSceneDesc *scene) {
     CU(cudaStreamSynchronize(c->stream));           // the pinned staging buffer is about to be rewritten
     rc = uploadScene(c, scene);
     if (rc != PTB_OK) return rc;
+    c->fbValid = false;                              // new geometry / camera: the cached bounce-0 hits are stale
     return ptb_reset(c);
 }
 
@@ -695,6 +729,26 @@ int ptb_stage_sort_keys(PtbContext *c, int n, const int32_t *keys, int numKeys, 
     }
     CU(cudaStreamSynchronize(c->stream));
     dk.release(); dord.release(); hist.release();
+    return PTB_OK;
+}
+
+int ptb_stage_arith(PtbContext *c, int n, const float *a, const float *b, float *quot, float *root, float *normY) {
+    if (!c || n < 0 || !a || !b || !quot || !root || !normY) return fail(PTB_ERR_INVALID, "ptb_stage_arith: bad argument");
+    CU(cudaSetDevice(c->device));
+    DevBuf<float> da, db, dq, dr, dn;
+    CU(da.alloc(n)); CU(db.alloc(n)); CU(dq.alloc(n)); CU(dr.alloc(n)); CU(dn.alloc(n));
+    if (n) {
+        CU(cudaMemcpyAsync(da.p, a, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        CU(cudaMemcpyAsync(db.p, b, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        stage_arith_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(n, da.p, db.p, dq.p, dr.p, dn.p);
+        c->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(quot, dq.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(root, dr.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(normY, dn.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    da.release(); db.release(); dq.release(); dr.release(); dn.release();
     return PTB_OK;
 }
 

@@ -21,7 +21,13 @@
 
 namespace ptb {
 
-constexpr int kBlock = 256;
+#ifndef PTB_BLOCK
+#define PTB_BLOCK 256
+#endif
+#ifndef PTB_MINBLOCKS
+#define PTB_MINBLOCKS 4
+#endif
+constexpr int kBlock = PTB_BLOCK;
 constexpr uint32_t kDeadBit = 0x80000000u;
 
 struct BvhNode {                 // 64 B = four 128-bit loads: a binary node holding BOTH child boxes
@@ -78,6 +84,10 @@ struct Params {
     int            pixBits;
     uint32_t       numPixels;
     int            atomicGather; // 1 when several slots may deposit into one pixel concurrently
+    const float4  *fbTn;         // first-bounce cache (INSTRUCTION.md:87-89), NULL = off: per pixel t, n.xyz ...
+    const int     *fbMeta;       // ... and geom slot | outside << 30, -1 = miss
+    uint32_t      *segCounts;    // fused pipeline: 2 x grid per-CTA survivor counts (ping-pong by depth parity)
+    uint32_t       segCap;       // fused pipeline: path slots per CTA segment
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -116,29 +126,27 @@ PTB_DEV void testGeom(const GeomRec &g, int slot, f3 o, f3 d, Candidate &best, i
     const float t = exactTest(g, o, d, outside, a, b, c);
     acceptHit(g, slot, t, outside, a, b, c, best, bestOrig);
 }
-// brute-force phase 2: object-space sure-miss filter, then the exact test on the same object-space ray
-PTB_DEV void testCandidate(const GeomRec &g, int slot, f3 o, f3 d, Candidate &best, int &bestOrig) {
-    f3 qo, qu;
-    objectRay(g, o, d, qo, qu);
-    if (sureMiss(g, qo, qu)) return;
-    int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
-    const float t = exactTestQ(g, o, qo, qu, outside, a, b, c);
-    acceptHit(g, slot, t, outside, a, b, c, best, bestOrig);
-}
-
 PTB_DEV f3 candidateNormal(const GeomRec &g, const Candidate &c) { return exactNormal(g, c.outside, c.a, c.b, c.c); }
 
-// Closest hit, brute force over the shared-memory geoms, in two phases:
-//   1. a warp-uniform loop over all geoms evaluates a cheap conservative world-space bound (padded
-//      AABB for cubes, padded bounding sphere for spheres, ~35 approximate instructions each) and keeps,
-//      per lane, the three reachable primitives with the smallest entry distance, sorted (anything
-//      beyond three goes to an overflow mask);
-//   2. each lane walks ITS OWN candidates nearest first -- the data-dependent shared-memory reads keep
-//      the warp on one code path -- stopping as soon as the next lower bound exceeds the exact distance
-//      found so far.  A candidate first meets the object-space sure-miss filter (the primitive a bounce
-//      ray just left is always "reachable" for the world-space bound) and only then the exact test.
+// Closest hit, brute force over the shared-memory geoms, in two phases per chunk of 32 geoms:
+//   1. a warp-uniform loop over the geoms evaluates a cheap conservative world-space bound (padded
+//      AABB for cubes, padded bounding sphere for spheres, approximate instructions) and keeps, per
+//      lane, the three reachable primitives with the smallest entry distance as SORTED PACKED KEYS:
+//      key = bits(lower bound) with the five low mantissa bits replaced by the geom's index in the
+//      chunk (clearing mantissa bits only lowers a non-negative bound), so one unsigned min/max
+//      network (5 instructions) does the sorted insert and no per-lane branch is taken;
+//   2. each lane walks ITS OWN keys nearest first.  A cheap inner loop skips candidates the
+//      object-space sure-miss filter rejects (the primitive a bounce ray just left is always
+//      "reachable" for the world-space bound), so that the lanes of a warp arrive TOGETHER at the one
+//      copy of the exact test; the walk stops as soon as the next lower bound exceeds the exact
+//      distance found so far.
+// When more than three primitives are reachable and the third bound did not end the walk (rare), the
+// same two phases run again over the keys above the last one consumed.
 // Phase 1 only prunes and orders; every output value comes from the exact test.
-PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, Candidate &best) {
+constexpr uint32_t kNoCand = 0xffffffffu;
+
+// `valid` = this lane carries a ray (callers keep their loops warp-uniform).
+PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, bool valid, Candidate &best) {
     best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
     int orig = 0x7fffffff;
     const float dd = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
@@ -149,38 +157,43 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, Candid
     // slack on every lower bound: rounding of the bound itself plus the deviation of the exact hit
     // point from the ideal ray (a few ulp of the coordinates involved)
     const float slack = 2e-5f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f);
-    for (int g0 = 0; g0 < numGeoms; g0 += 64) {                  // 64 geoms per overflow-mask word
-        const int g1 = min(numGeoms, g0 + 64);
-        unsigned long long overflow = 0ull;
-        float l0 = 3.0e38f, l1 = 3.0e38f, l2 = 3.0e38f;          // three smallest lower bounds, ascending
-        int c0 = -1, c1 = -1, c2 = -1;
-        for (int g = g0; g < g1; ++g) {
-            float lo = boundEntry(sg[g], o, invD, dn, rdLen);
-            if (lo >= 0.0f) {
-                lo = lo * 0.99998f - slack;
-                if (lo < l2) {
-                    if (c2 >= 0) overflow |= 1ull << (c2 - g0);
-                    if (lo < l0)      { l2 = l1; c2 = c1; l1 = l0; c1 = c0; l0 = lo; c0 = g; }
-                    else if (lo < l1) { l2 = l1; c2 = c1; l1 = lo; c1 = g; }
-                    else              { l2 = lo; c2 = g; }
-                } else {
-                    overflow |= 1ull << (g - g0);
-                }
+    for (int g0 = 0; g0 < numGeoms; g0 += 32) {
+        const int g1 = min(numGeoms, g0 + 32);
+        uint32_t floorKey = 0u;                                   // keys below it were consumed by an earlier round
+        for (;;) {
+            uint32_t k0 = kNoCand, k1 = kNoCand, k2 = kNoCand;
+            int nAbove = 0;
+            for (int g = g0; g < g1; ++g) {
+                const float e = boundEntry(sg[g], o, invD, dn, rdLen);
+                const float lo = fmaxf(fmaf(e, 0.99998f, -slack), 0.0f);
+                uint32_t key = (__float_as_uint(lo) & ~31u) | (uint32_t)(g - g0);
+                key = (valid && e >= 0.0f && key >= floorKey) ? key : kNoCand;
+                nAbove += key != kNoCand;
+                const uint32_t a = min(k0, key), b = max(k0, key);  // sorted insert, the largest of four falls out
+                const uint32_t c = min(k1, b), f = max(k1, b);
+                k0 = a; k1 = c; k2 = min(k2, f);
             }
-        }
-#pragma unroll 1
-        for (int k = 0; k < 3; ++k) {                             // one copy of the test code
-            const int g = k == 0 ? c0 : (k == 1 ? c1 : c2);
-            const float lo = k == 0 ? l0 : (k == 1 ? l1 : l2);
-            if (g < 0 || !(lo <= best.t)) break;                  // sorted: nothing further can win
-            testCandidate(sg[g], g, o, d, best, orig);
-        }
-        if (!(l2 <= best.t)) overflow = 0ull;                     // every overflow bound is >= l2
-        while (overflow) {
-            const int g = g0 + __ffsll((long long)overflow) - 1;
-            overflow &= overflow - 1ull;
-            const float lo = boundEntry(sg[g], o, invD, dn, rdLen) * 0.99998f - slack;
-            if (lo <= best.t) testCandidate(sg[g], g, o, d, best, orig);
+            uint32_t lastKey = 0u;
+            bool exhausted = true;                                // all three keys consumed without the bound ending the walk
+            for (;;) {
+                int g = -1;
+                f3 qo, qu;
+                while (k0 != kNoCand) {
+                    const float lo = __uint_as_float(k0 & ~31u);
+                    if (!(lo <= best.t)) { exhausted = false; k0 = kNoCand; break; }   // sorted: nothing further can win
+                    const int cand = g0 + (int)(k0 & 31u);
+                    lastKey = k0;
+                    k0 = k1; k1 = k2; k2 = kNoCand;
+                    objectRay(sg[cand], o, d, qo, qu);
+                    if (!sureMiss(sg[cand], qo, qu)) { g = cand; break; }
+                }
+                if (g < 0) break;
+                int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
+                const float t = exactTestQ(sg[g], o, qo, qu, outside, a, b, c);
+                acceptHit(sg[g], g, t, outside, a, b, c, best, orig);
+            }
+            if (!(exhausted && nAbove > 3)) break;
+            floorKey = lastKey + 1u;
         }
     }
 }
@@ -399,17 +412,27 @@ PTB_DEV uint32_t compactSlot(bool keep, uint32_t *counter, int *warpTotals, uint
 // ------------------------------------------------------------------------------------------------
 // THE FAST PATH: one launch per bounce.  FIRST = bounce 0 (camera rays generated in registers, no
 // path-state read); USE_BVH selects the flat BVH over the brute-force shared-memory loop.
-// Persistent grid (a multiple of the SM count), grid-stride over 256-path tiles; the number of live
-// paths is read from device memory, so the host never synchronises inside an iteration.
+//
+// Persistent grid (SM count x resident CTAs).  Every CTA owns one SEGMENT of the path buffers
+// (segCap slots at blockIdx * segCap): it reads the paths it wrote at the previous bounce and packs
+// its survivors at the front of the same segment of the other buffer.  Stream compaction is therefore
+// CTA-local: a warp ballot + popc prefix gives each survivor its rank inside the warp, and ONE
+// warp-aggregated shared-memory atomic reserves the warp's run of output slots -- no __syncthreads and
+// no global atomic per tile, so the eight warps of a CTA never wait for each other.  Warps pull
+// 32-path chunks of the CTA's segment from a shared-memory ticket counter.  The per-CTA survivor
+// counts live in device memory (segCounts, ping-pong by depth parity); their sum goes to
+// ctrl->counts[depth + 1] with one atomic per CTA at the end of the kernel, so the host never
+// synchronises inside an iteration.  At bounce 0 tile t of 256 camera paths belongs to CTA t mod grid,
+// which gives every CTA a uniform sample of the image and keeps the segments balanced.
 // ------------------------------------------------------------------------------------------------
 template <bool FIRST, bool USE_BVH>
-__global__ void __launch_bounds__(kBlock, 4) bounce_kernel(const __grid_constant__ Params p, const int depth) {
+__global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __grid_constant__ Params p, const int depth) {
     extern __shared__ float4 smem4[];
-    __shared__ int warpTotals[kBlock / 32];
-    __shared__ uint32_t blockBase;
+    __shared__ uint32_t sNextChunk, sOutCount;
 
+    if (threadIdx.x == 0) { sNextChunk = 0u; sOutCount = 0u; }
     const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
-    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
+    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);      // ends with __syncthreads
     else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
     const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
@@ -418,46 +441,130 @@ __global__ void __launch_bounds__(kBlock, 4) bounce_kernel(const __grid_constant
     CameraParams cam;
     if (FIRST) cam = p.hdr->cam;
     const int iterBase = ctrl->iterBase, iterStride = ctrl->iterStride;
-    const uint32_t nIn = FIRST ? p.numPixels * (uint32_t)ctrl->batch : ctrl->counts[depth];
     const int remainingBefore = p.traceDepth - depth;
     const uint32_t pixMask = (1u << p.pixBits) - 1u;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t segBase = blockIdx.x * p.segCap;
+    const uint32_t *segIn = p.segCounts + ((depth + 1) & 1) * gridDim.x;
+    uint32_t *segOut = p.segCounts + (depth & 1) * gridDim.x;
 
-    for (uint32_t base = blockIdx.x * kBlock; base < nIn; base += gridDim.x * kBlock) {
-        const uint32_t i = base + threadIdx.x;
-        bool alive = false;
+    uint32_t total = 0, nChunks;
+    if (FIRST) {
+        total = p.numPixels * (uint32_t)ctrl->batch;
+        const uint32_t tiles = (total + kBlock - 1) / kBlock;
+        const uint32_t myTiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+        nChunks = myTiles * (kBlock / 32);
+    } else {
+        total = segIn[blockIdx.x];
+        nChunks = (total + 31u) / 32u;
+    }
+
+    for (;;) {
+        uint32_t chunk = 0;
+        if (lane == 0) chunk = atomicAdd(&sNextChunk, 1u);
+        chunk = __shfl_sync(0xffffffffu, chunk, 0);
+        if (chunk >= nChunks) break;
+
+        bool alive = false, valid;
         f3 o, d, c; uint32_t id = 0;
-        if (i < nIn) {
-            uint32_t pix, slot;
-            if (FIRST) {
+        uint32_t pix = 0, slot = 0;
+        o = d = c = mk3(0.f, 0.f, 0.f);
+        if (FIRST) {
+            const uint32_t tile = blockIdx.x + (chunk / (kBlock / 32)) * gridDim.x;
+            const uint32_t i = tile * kBlock + (chunk % (kBlock / 32)) * 32u + lane;
+            valid = i < total;
+            if (valid) {
                 slot = i / p.numPixels;
                 pix = i - slot * p.numPixels;
                 id = pix | (slot << p.pixBits);
                 cameraRay(cam, pix, o, d);
                 c = mk3(1.0f, 1.0f, 1.0f);                                // src/pathtrace.cu:132
-            } else {
-                loadPath(p.in, i, o, d, c, id);
+            }
+        } else {
+            const uint32_t k = chunk * 32u + lane;
+            valid = k < total;
+            if (valid) {
+                loadPath(p.in, segBase + k, o, d, c, id);
                 pix = id & pixMask;
                 slot = (id & ~kDeadBit) >> p.pixBits;
             }
-            Candidate best;
-            if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, best);
-            else         closestHitBrute(sgeoms, p.numGeoms, o, d, best);
-            const bool isHit = best.slot >= 0;
+        }
+        Candidate best;
+        const bool cached = FIRST && p.fbTn != nullptr;            // warp-uniform
+        if (!USE_BVH && !cached) closestHitBrute(sgeoms, p.numGeoms, o, d, valid, best);
+        if (valid) {
             f3 n = mk3(0.f, 0.f, 0.f); int matId = 0;
-            if (isHit) {
-                if (USE_BVH) {
-                    const GeomRec g = loadGeom(p.geoms + best.slot);
-                    n = candidateNormal(g, best); matId = g.tag.y;
-                } else {
-                    n = candidateNormal(sgeoms[best.slot], best); matId = sgeoms[best.slot].tag.y;
+            bool isHit;
+            if (cached) {
+                // camera rays do not depend on the iteration (src/pathtrace.cu:122-143 ignores `iter`),
+                // so the bounce-0 hit record of this pixel is the one fb_cache_kernel stored
+                const int meta = __ldg(p.fbMeta + pix);
+                isHit = meta >= 0;
+                best.t = -1.0f; best.outside = 1;
+                if (isHit) {
+                    const float4 tn = __ldg(p.fbTn + pix);
+                    best.t = tn.x; n = mk3(tn.y, tn.z, tn.w);
+                    best.outside = (meta >> 30) & 1;
+                    matId = USE_BVH ? p.geoms[meta & 0x3fffffff].tag.y : sgeoms[meta & 0x3fffffff].tag.y;
+                }
+            } else {
+                if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, best);
+                isHit = best.slot >= 0;
+                if (isHit) {
+                    if (USE_BVH) {
+                        const GeomRec g = loadGeom(p.geoms + best.slot);
+                        n = candidateNormal(g, best); matId = g.tag.y;
+                    } else {
+                        n = candidateNormal(sgeoms[best.slot], best); matId = sgeoms[best.slot].tag.y;
+                    }
                 }
             }
             const int iter = iterBase + (int)slot * iterStride;
             alive = shadeStep(p, depth, iter, pix, isHit, matId, best.t, n, best.outside, o, d, c, remainingBefore);
             if (!alive) deposit(p, pix, c);                               // gather at termination
         }
-        const uint32_t dst = compactSlot(alive, &ctrl->counts[depth + 1], warpTotals, &blockBase);
-        if (alive) storePath(p.out, dst, o, d, c, id);
+        // CTA-local stream compaction: ballot + popc prefix, one shared-memory atomic per warp
+        const unsigned ballot = __ballot_sync(0xffffffffu, alive);
+        if (ballot) {
+            uint32_t off = 0;
+            if (lane == 0) off = atomicAdd(&sOutCount, (uint32_t)__popc(ballot));
+            off = __shfl_sync(0xffffffffu, off, 0);
+            if (alive) storePath(p.out, segBase + off + (uint32_t)__popc(ballot & ((1u << lane) - 1u)), o, d, c, id);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t n = sOutCount;
+        segOut[blockIdx.x] = n;
+        if (n) atomicAdd(&ctrl->counts[depth + 1], n);
+    }
+}
+
+// First-bounce cache fill (INSTRUCTION.md:87-89): the bounce-0 hit record of every pixel, computed once
+// per scene/camera upload with the same closest-hit code the bounce kernels run.
+template <bool USE_BVH>
+__global__ void __launch_bounds__(kBlock) fb_cache_kernel(const __grid_constant__ Params p, float4 *tnOut, int *metaOut) {
+    extern __shared__ float4 smem4[];
+    const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
+    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
+    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
+    const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
+    const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
+    const CameraParams cam = p.hdr->cam;
+    for (uint32_t base = blockIdx.x * kBlock; base < p.numPixels; base += gridDim.x * kBlock) {   // warp-uniform trip count
+        const uint32_t pix = base + threadIdx.x;
+        const bool valid = pix < p.numPixels;
+        f3 o = mk3(0.f, 0.f, 0.f), d = o;
+        if (valid) cameraRay(cam, pix, o, d);
+        Candidate best;
+        if (USE_BVH) { if (valid) closestHitBvh(p, snodes, smemNodes, o, d, best); }
+        else         closestHitBrute(sgeoms, p.numGeoms, o, d, valid, best);
+        if (!valid) continue;
+        if (best.slot < 0) { tnOut[pix] = make_float4(-1.0f, 0.f, 0.f, 0.f); metaOut[pix] = -1; continue; }
+        const GeomRec &g = USE_BVH ? p.geoms[best.slot] : sgeoms[best.slot];
+        const f3 n = candidateNormal(g, best);
+        tnOut[pix] = make_float4(best.t, n.x, n.y, n.z);
+        metaOut[pix] = best.slot | (best.outside << 30);
     }
 }
 
@@ -505,13 +612,16 @@ __global__ void __launch_bounds__(kBlock) intersect_kernel(const __grid_constant
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
     const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
     const uint32_t nIn = p.ctrl->counts[depth];
-    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < nIn; i += gridDim.x * kBlock) {
-        f3 o, d, c; uint32_t id;
-        loadPath(p.in, i, o, d, c, id);
-        if (id & kDeadBit) { p.hits.meta[i] = -1; continue; }            // no-compaction mode: dead path stays in place
+    for (uint32_t base = blockIdx.x * kBlock; base < nIn; base += gridDim.x * kBlock) {   // warp-uniform trip count
+        const uint32_t i = base + threadIdx.x;
+        f3 o = mk3(0.f, 0.f, 0.f), d = o, c; uint32_t id = kDeadBit;
+        if (i < nIn) loadPath(p.in, i, o, d, c, id);
+        const bool valid = !(id & kDeadBit);                             // no-compaction mode: dead path stays in place
         Candidate best;
-        if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, best);
-        else         closestHitBrute(sgeoms, p.numGeoms, o, d, best);
+        if (USE_BVH) { if (valid) closestHitBvh(p, snodes, smemNodes, o, d, best); }
+        else         closestHitBrute(sgeoms, p.numGeoms, o, d, valid, best);
+        if (i >= nIn) continue;
+        if (!valid) { p.hits.meta[i] = -1; continue; }
         if (best.slot < 0) {
             p.hits.tn[i] = make_float4(-1.0f, 0.f, 0.f, 0.f);             // src/pathtrace.cu:203
             p.hits.meta[i] = -1;
@@ -700,12 +810,18 @@ __global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_co
     else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
     const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
-    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
-        const f3 o = mk3(origins[3 * (size_t)i], origins[3 * (size_t)i + 1], origins[3 * (size_t)i + 2]);
-        const f3 d = mk3(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2]);
+    for (int base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {          // warp-uniform trip count
+        const int i = base + threadIdx.x;
+        const bool valid = i < n;
+        f3 o = mk3(0.f, 0.f, 0.f), d = o;
+        if (valid) {
+            o = mk3(origins[3 * (size_t)i], origins[3 * (size_t)i + 1], origins[3 * (size_t)i + 2]);
+            d = mk3(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2]);
+        }
         Candidate best;
-        if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, best);
-        else         closestHitBrute(sgeoms, p.numGeoms, o, d, best);
+        if (USE_BVH) { if (valid) closestHitBvh(p, snodes, smemNodes, o, d, best); }
+        else         closestHitBrute(sgeoms, p.numGeoms, o, d, valid, best);
+        if (!valid) continue;
         if (best.slot < 0) {
             hit[i] = -1; t[i] = -1.0f; outside[i] = 1;
             normal[3 * (size_t)i] = normal[3 * (size_t)i + 1] = normal[3 * (size_t)i + 2] = 0.f;
@@ -759,6 +875,21 @@ __global__ void __launch_bounds__(kBlock) stage_compact_kernel(int n, const int 
         const bool keep = i < n && flags[i] != 0;
         const uint32_t dst = compactSlot(keep, counter, warpTotals, &blockBase);
         if (keep) outIds[dst] = ids[i];
+    }
+}
+
+// the grouped IEEE helpers of ptb_math.cuh on caller-supplied operands: quot = a / b, root = sqrt(|a|),
+// ninv = the reciprocal length normalize3 multiplies by for the vector (a, b, a)
+__global__ void __launch_bounds__(kBlock) stage_arith_kernel(int n, const float *a, const float *b, float *quot, float *root, float *ninv) {
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        const float x = a[i], y = b[i];
+        const float lo = fminf(fabsf(x), fabsf(y)), hi = fmaxf(fabsf(x), fabsf(y));
+        quot[i] = moderate(lo, hi) ? divRefined(x, y, rcpRefined(y)) : fdiv(x, y);
+        const float ax = fabsf(x);
+        root[i] = moderate(ax, ax) ? sqrtRefined(ax) : fsqrt(ax);
+        const f3 v = normalize3(mk3(x, y, x));
+        ninv[i] = fdiv(v.y, y);        // not compared bit-for-bit by the test; keeps normalize3 alive
+        if (y != 0.0f) ninv[i] = v.y;
     }
 }
 

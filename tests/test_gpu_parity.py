@@ -13,7 +13,7 @@ import pytest
 
 import orclib
 import scenes
-from common import pkg, golden, crc, same_bits, densify, rel_err_lit
+from common import pkg, golden, crc, bits, same_bits, densify, rel_err_lit
 
 pytestmark = pytest.mark.gpu
 
@@ -45,6 +45,40 @@ def test_rng_bit_exact(m, port, cornell):
             assert same_bits(r.stage_rng(int(a), int(b), int(c), 4), want)
         # long stream incl. the wrap of the LCG state
         assert same_bits(r.stage_rng(4194303, (1 << 23) - 1, 511, 2000), port.rng_u01(4194303, (1 << 23) - 1, 511, 2000))
+
+
+def test_ieee_helpers_bit_exact(m, cornell):
+    """csrc/ptb_math.cuh groups IEEE divisions / square roots under one range check and runs the
+    refinement sequences without the per-operation slow-path branch.  They must equal correctly
+    rounded arithmetic (numpy float32 = IEEE on the host) bit for bit: the reference's tests are
+    built from exactly these operations (src/intersections.h:60-62, glm::normalize, glm::length)."""
+    rs = np.random.RandomState(11)
+    n = 1 << 21
+    # operands across the whole exponent range, incl. zeros, denormals, infinities and the range-check edges
+    mant = rs.uniform(1.0, 2.0, (2, n)).astype(np.float32)
+    expo = rs.randint(-149, 128, (2, n))
+    a = np.ldexp(mant[0], expo[0]).astype(np.float32) * rs.choice(np.float32([-1, 1]), n)
+    b = np.ldexp(mant[1], expo[1]).astype(np.float32) * rs.choice(np.float32([-1, 1]), n)
+    a[:2000] = rs.uniform(-12, 12, 2000); b[:2000] = rs.uniform(-1, 1, 2000)       # the slab-test regime
+    special = np.float32([0.0, -0.0, np.inf, -np.inf, 1.0, 2.0 ** -40, 2.0 ** 40, 2.0 ** -41, 2.0 ** 41, 1e-45, 3.0])
+    a[2000:2000 + 121] = np.repeat(special, 11); b[2000:2000 + 121] = np.tile(special, 11)
+    half = n // 2                                                                      # moderate operands: the fast path
+    a[half:] = np.ldexp(mant[0][half:], rs.randint(-39, 39, n - half)).astype(np.float32)
+    b[half:] = np.ldexp(mant[1][half:], rs.randint(-39, 39, n - half)).astype(np.float32) * rs.choice(np.float32([-1, 1]), n - half)
+    with m.Renderer(cornell, device=0) as r:
+        q, root, ny = r.stage_arith(a, b)
+    with np.errstate(all="ignore"):
+        wq = (a / b).astype(np.float32)
+        wr = np.sqrt(np.abs(a)).astype(np.float32)
+        dd = ((a * a).astype(np.float32) + (b * b).astype(np.float32)).astype(np.float32)
+        dd = (dd + (a * a).astype(np.float32)).astype(np.float32)
+        inv = (np.float32(1.0) / np.sqrt(dd).astype(np.float32)).astype(np.float32)
+        wn = (b * inv).astype(np.float32)
+    nan = np.isnan(wq)
+    assert np.array_equal(np.isnan(q), nan) and np.array_equal(bits(q)[~nan], bits(wq)[~nan])
+    assert np.array_equal(bits(root), bits(wr))
+    ok = (b != 0) & ~np.isnan(wn)
+    assert np.array_equal(bits(ny)[ok], bits(wn)[ok])
 
 
 # --------------------------------------------------------------------------------- raygen + bounce 0
@@ -211,6 +245,30 @@ def test_batched_wavefront_matches_sequential(m, scene_dir):
         sb = r.stats()
     assert sa["alive_per_depth"] == sb["alive_per_depth"] and sa["iterations"] == sb["iterations"] == 12
     assert np.allclose(a, b, rtol=2e-6, atol=0)
+
+
+@pytest.mark.parametrize("scene,accel", [("cornell", 0), ("glass", 0), ("glass", 2)])
+def test_first_bounce_cache_is_result_neutral(m, scene_dir, scene, accel):
+    """INSTRUCTION.md:87-89: the bounce-0 intersections are the same every iteration (no AA in
+    generateRayFromCamera, src/pathtrace.cu:134), so caching them must not change a single bit; a scene
+    upload (camera move, src/main.cpp:125-128) must invalidate the cache."""
+    s = m.Scene.load(scene_dir + "/%s.txt" % scene)
+    out = []
+    for cache in (0, 1):
+        with m.Renderer(s, device=0, bsdf=1, batch_iters=1, accel=accel, first_bounce_cache=cache) as r:
+            r.render(1, 3)
+            a, sa = r.download(), r.stats()
+            moved = m.Scene.load(scene_dir + "/%s.txt" % scene)
+            moved.camera["position"][0][0] += 0.75
+            moved.camera["view"][0][:] = [0.05, -0.02, -1.0]
+            r.update_scene(moved)
+            r.render(1, 2)
+            b, sb = r.download(), r.stats()
+            out.append((a, sa["alive_per_depth"], b, sb["alive_per_depth"], sa["kernel_launches"]))
+    assert same_bits(out[0][0], out[1][0]) and out[0][1] == out[1][1]
+    assert same_bits(out[0][2], out[1][2]) and out[0][3] == out[1][3]
+    assert not same_bits(out[0][0] * (2.0 / 3.0), out[0][2])           # the moved camera really renders another image
+    assert out[1][4] == out[0][4] + 1                                   # one cache-fill launch
 
 
 def test_every_bounce_hits_bit_exact_on_gpu_rays(m, port, scene_dir):
