@@ -34,8 +34,10 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 WORKLOAD = "scenes/cornell.txt 800x800 traceDepth 8 (BASELINE.json configs[2] scene/size; configs[0] on the CPU arm)"
 METRIC = "path_segments_per_s"
 UNIT = "segments/s"
-SPP_PER_STEP = 128            # iterations per step (frame)
-BATCH_ITERS = 16              # iterations per wavefront: 10.24 M paths, 2 x 410 MB of path state (> 126 MB L2)
+SPP_PER_STEP = 256            # iterations per step (frame)
+BATCH_ITERS = 64              # iterations per wavefront: 40.96 M paths, 2 x 1.64 GB of path state (>> 126 MB L2)
+CPU_ITERS = 16                # BASELINE.json configs[0]: 16 iterations through the reference's host functions
+FLOP_PER_SEGMENT = 700        # ~7 ray-primitive tests + scatter, FMA counted as 2
 BYTES_PER_SEGMENT = 88        # 44 B read + 44 B write of path state
 BYTES_PER_PIXEL_ITER = 24     # accumulation read + write
 
@@ -138,8 +140,8 @@ def run_reference_arm(args):
         return 0
     tmp = tempfile.mkdtemp()
     scene_path = write_scene(tmp)
-    iters = 2                                   # one step = a bounded sample: 2 iterations (~5 M segments)
-    cpu_reference_run(scene_path, 1, max(1, args.warmup))      # warm-up steps
+    iters = CPU_ITERS                           # one step = BASELINE.json configs[0]: 16 iterations (~39.6 M segments, ~1.2 s on 16 cores)
+    cpu_reference_run(scene_path, 2, max(1, args.warmup))      # warm-up steps
     t0 = time.perf_counter()
     val, kind, cores, sample, secs, seg_per_iter = cpu_reference_run(scene_path, iters, args.steps)
     ms_per_step = secs / args.steps * 1e3
@@ -308,6 +310,26 @@ def main():
         dropin = {"iters_per_s": n_it / dt, "segments_per_s": sdi["segments"] / sdi["iterations"] * n_it / dt,
                   "d2h_bytes_per_iter": P * 12, "note": "ptb_pathtrace with a host image every iteration (src/pathtrace.cu:389-390 semantic)"}
 
+    # the same device-resident loop with the first-bounce cache on (INSTRUCTION.md:87-89; result-neutral,
+    # tests/test_gpu_parity.py::test_first_bounce_cache_is_result_neutral) -- reported beside `value`, not as `value`
+    r.close()
+    r = m.Renderer(scene, device=local, bsdf=m.BSDF_FULL, pipeline=m.PIPELINE_FUSED, batch_iters=args.batch_iters,
+                   stream=stream.cuda_stream, external_accum=accum.data_ptr(), first_bounce_cache=1)
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sc0 = r.stats()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record(stream)
+    for _ in range(args.steps):
+        device_step()
+    c1.record(stream)
+    barrier()
+    ms_fbc = allmax(c0.elapsed_time(c1))
+    sc1 = r.stats()
+    seg_fbc = allsum(sc1["segments"] - sc0["segments"])
+    iters_fbc = allsum(sc1["iterations"] - sc0["iterations"])
+
     if rank == 0:
         hbm_peak, peak_src, sm_max = load_peaks()
         alg_bytes = BYTES_PER_SEGMENT * seg_all + BYTES_PER_PIXEL_ITER * P * iters_all
@@ -335,16 +357,20 @@ def main():
             "e2e": {"value": seg_e2e_all / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s / e2e_steps * 1e3, "steps": e2e_steps},
             "e2e_per_iteration_dropin": dropin,
+            "first_bounce_cache": {"value": seg_fbc / (ms_fbc * 1e-3), "unit": UNIT, "iters_per_s": iters_fbc / (ms_fbc * 1e-3),
+                                   "note": "PtbOptions.firstBounceCache = 1: bounce-0 hit records reused across iterations (bit-identical images)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "peak_source": peak_src, "kernel": "ptb::bounce_kernel",
                          "algorithmic_bytes": "88 B/segment + 24 B/pixel/iteration (SURVEY.md 8(d))",
                          "launches_in_timed_region_per_gpu": bounce_launches,
                          "avg_launch_us": ms * 1e3 / max(1.0, bounce_launches),
-                         "fp32_note": "the bounce kernel is FP32-issue bound, not HBM bound (no FMA allowed: bit-exact parity); see DESIGN.md"},
+                         "fp32": {"achieved_tflops": FLOP_PER_SEGMENT * seg_all / (ms * 1e-3) / 1e12 / world,
+                                  "peak_tflops": 148 * 128 * 2 * sm_max * 1e6 / 1e12, "flop_per_segment": FLOP_PER_SEGMENT,
+                                  "note": "the bounce kernel is instruction-issue bound, not HBM bound: bit-exact parity forbids FFMA in the exact tests (DESIGN.md 4.4)"}},
         }
         if not args.no_cpu_baseline and world == 1:
             try:
-                val, kind, cores, sample, secs, _ = cpu_reference_run(scene_path, 4, 2)
+                val, kind, cores, sample, secs, _ = cpu_reference_run(scene_path, CPU_ITERS, 8)     # ~10 s of CPU work
                 line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "seconds": secs}
             except Exception as ex:                                     # the checker is optional for the bench line
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}

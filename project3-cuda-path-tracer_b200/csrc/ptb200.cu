@@ -409,7 +409,10 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     while ((1ull << bits) < c->numPixels) ++bits;
     c->pixBits = bits;
     const int maxSlots = 1 << std::min(31 - bits, 12);
-    int batch = opt.batchIters > 0 ? opt.batchIters : 8;
+    // default wavefront: about 40 M paths (1.6 GB per path buffer), a power of two between 1 and 64 iterations
+    int autoBatch = 1;
+    while (autoBatch < 64 && (uint64_t)(autoBatch * 2) * c->numPixels <= 40000000ull) autoBatch <<= 1;
+    int batch = opt.batchIters > 0 ? opt.batchIters : autoBatch;
     if (opt.pipeline == PTB_PIPELINE_STAGED && opt.batchIters <= 0) batch = 1;
     // keep the wavefront within 2^31 paths and a sane memory budget (2 x 40 B per path)
     while (batch > 1 && ((uint64_t)batch * c->numPixels > (1ull << 30) || batch > maxSlots)) batch >>= 1;

@@ -217,23 +217,92 @@ PTB_DEV GeomRec loadGeom(const GeomRec *gp) {
     const float4 *src = reinterpret_cast<const float4 *>(gp);
     float4 *dst = reinterpret_cast<float4 *>(&g);
 #pragma unroll
-    for (int q = 0; q < 10; ++q) dst[q] = __ldg(src + q);      // the pruning bound (b0, b1) is not needed at a BVH leaf
+    for (int q = 0; q < 10; ++q) dst[q] = __ldg(src + q);      // the pruning bound (b0, b1) is not needed for the normal
     g.b0 = g.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
     return g;
 }
 
-// closest hit through the flat BVH.  Leaves run the reference-exact tests; pruning uses padded boxes
-// and a slackened distance bound, so the winner is the same (t, scene index)-lexicographic minimum
-// that the reference's index-ordered loop finds (src/pathtrace.cu:176-199).
-PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, const int smemNodes, f3 o, f3 d, Candidate &best) {
+// Closest hit through the flat BVH.  Warp-collective (all 32 lanes call it; `valid` = the lane carries a
+// ray).  Three kinds of work alternate, and the expensive one is entered by the lanes TOGETHER:
+//   A. traversal steps: fetch a 64-byte node (shared memory for the top levels), slab-test both child
+//      boxes, descend into the nearer child and push the other (interior node index, or an encoded
+//      leaf) on the per-lane stack;
+//   B. per-primitive pruning of the pending leaf: the padded world-space bound of the primitive
+//      (48 bytes: tag, b0, b1), then -- only when that lower bound can still beat the best distance
+//      -- the exact object-space ray (48 more bytes) and the sure-miss filter;
+//   C. the reference-exact test of a primitive that survived B.
+// A lane runs A/B in a cheap loop until it HAS a candidate for C (or is finished); `__any_sync` then
+// brings the lanes together and every lane with a candidate runs the one copy of the exact test.  With
+// the exact test inlined in the traversal loop (one lane at a leaf, 31 waiting) only 4 of 32 lanes
+// were active on the 100 k-object scene.
+// Pruning uses padded boxes and slackened distance bounds only; the winner is the same
+// (t, scene index)-lexicographic minimum that the reference's index-ordered loop finds
+// (src/pathtrace.cu:176-199).
+PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, const int smemNodes, f3 o, f3 d, bool valid, Candidate &best) {
     best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
     int bestOrig = 0x7fffffff;
-    const float dl = sqrtf(d.x * d.x + d.y * d.y + d.z * d.z) * 0.9999f;
-    const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+    const float dd = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
+    const float rinv = rsqrtApprox(dd);
+    const float rdLen = dd * rinv;                                // |d|
+    const f3 dn = mk3(d.x * rinv, d.y * rinv, d.z * rinv);
+    const f3 invD = mk3(rcpApprox(d.x), rcpApprox(d.y), rcpApprox(d.z));
+    const float dl = rdLen * 0.9999f;
+    const float slack = 2e-5f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f);
     int stack[64];
     int sp = 0;
-    int node = 0;
+    int node = valid ? 0 : -1;                                    // -1: take the next entry from the stack
+    bool done = !valid;
+    int primRef = 0, primCnt = 0;                                 // pending leaf: geoms[primRef .. primRef + primCnt)
+    int cand = -1;                                                // primitive waiting for the exact test
+    f3 qo = mk3(0.f, 0.f, 0.f), qu = qo;
+    bool candCube = false;
+    // One warp-uniform loop; the votes at its head make the lanes reconverge EVERY step (a per-lane
+    // `while` with early exits lets divergent groups drift apart for the whole traversal).
     for (;;) {
+        const unsigned waiting = __ballot_sync(0xffffffffu, cand >= 0);
+        const unsigned working = __ballot_sync(0xffffffffu, cand < 0 && !done);
+        if (!(waiting | working)) break;
+        if (waiting && (!working || __popc(waiting) >= 8)) {
+            if (cand >= 0) {
+                // ---- C: the reference-exact test
+                const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + cand);
+                Affine fwd;
+                fwd.r0 = __ldg(gp + 3); fwd.r1 = __ldg(gp + 4); fwd.r2 = __ldg(gp + 5);
+                const int origIndex = __ldg(reinterpret_cast<const int *>(gp + 9) + 2);
+                int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
+                const float t = exactTestCore(candCube, fwd, o, qo, qu, outside, a, b, c);
+                const bool take = t > 0.0f && (best.t > t || (best.t == t && origIndex < bestOrig));   // src/pathtrace.cu:192 + index tie rule
+                if (take) { best.t = t; best.slot = cand; best.outside = outside; best.a = a; best.b = b; best.c = c; bestOrig = origIndex; }
+                cand = -1;
+            }
+            continue;
+        }
+        if (cand >= 0 || done) continue;
+        if (primCnt > 0) {
+            // ---- B: prune one primitive of the pending leaf
+            const int slot = primRef;
+            ++primRef; --primCnt;
+            const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + slot);
+            const int4 tag = __ldg(reinterpret_cast<const int4 *>(gp + 9));
+            const float4 b0 = __ldg(gp + 10), b1 = __ldg(gp + 11);
+            const bool isCube = tag.x == 1;
+            const float e = boundEntryRaw(isCube, b0, b1, o, invD, dn, rdLen);
+            if (e >= 0.0f && fmaf(e, 0.99998f, -slack) <= best.t) {
+                Affine inv;
+                inv.r0 = __ldg(gp); inv.r1 = __ldg(gp + 1); inv.r2 = __ldg(gp + 2);
+                qo = mulMVPoint(inv, o);
+                qu = mulMV(inv, d, 0.0f);
+                if (!sureMissT(isCube, qo, qu)) { cand = slot; candCube = isCube; }
+            }
+            continue;
+        }
+        // ---- A: one traversal step
+        if (node < 0) {
+            if (sp == 0) { done = true; continue; }
+            const int e = stack[--sp];
+            if (e < 0) { const int enc = ~e; primRef = enc & 0x7ffffff; primCnt = enc >> 27; continue; }
+            node = e;
+        }
         float4 llo, lhi, rlo, rhi;
         if (node < smemNodes) { llo = snodes[node].llo; lhi = snodes[node].lhi; rlo = snodes[node].rlo; rhi = snodes[node].rhi; }
         else {
@@ -241,28 +310,25 @@ PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, const int sme
             llo = __ldg(np); lhi = __ldg(np + 1); rlo = __ldg(np + 2); rhi = __ldg(np + 3);
         }
         float tl, tr;
-        // tNear*|d| (slackened) is a lower bound of the world distance of anything inside the box
-        bool vl = __float_as_int(llo.w) >= 0 && slabNear(llo, lhi, o, inv, tl) && tl * dl - 1e-4f <= best.t;
-        bool vr = __float_as_int(rlo.w) >= 0 && slabNear(rlo, rhi, o, inv, tr) && tr * dl - 1e-4f <= best.t;
-        int nextL = -1, nextR = -1;
-        if (vl) {
-            const int cnt = __float_as_int(lhi.w), ref = __float_as_int(llo.w);
-            if (cnt > 0) { for (int k = 0; k < cnt; ++k) testGeom(loadGeom(p.geoms + ref + k), ref + k, o, d, best, bestOrig); }
-            else nextL = ref;
-        }
-        if (vr && tr * dl - 1e-4f <= best.t) {
-            const int cnt = __float_as_int(rhi.w), ref = __float_as_int(rlo.w);
-            if (cnt > 0) { for (int k = 0; k < cnt; ++k) testGeom(loadGeom(p.geoms + ref + k), ref + k, o, d, best, bestOrig); }
-            else nextR = ref;
-        }
-        if (nextL >= 0 && nextR >= 0) {
-            if (tl <= tr) { if (sp < 64) stack[sp++] = nextR; node = nextL; }
-            else          { if (sp < 64) stack[sp++] = nextL; node = nextR; }
-        } else if (nextL >= 0) node = nextL;
-        else if (nextR >= 0) node = nextR;
-        else {
-            if (sp == 0) break;
-            node = stack[--sp];
+        // tNear * |d| (slackened) is a lower bound of the world distance of anything inside the box
+        const bool vl = __float_as_int(llo.w) >= 0 && slabNear(llo, lhi, o, invD, tl) && tl * dl - 1e-4f <= best.t;
+        const bool vr = __float_as_int(rlo.w) >= 0 && slabNear(rlo, rhi, o, invD, tr) && tr * dl - 1e-4f <= best.t;
+        // children as stack entries: interior -> node index (>= 0), leaf -> ~(ref | count << 27) (< 0)
+        const int cl = __float_as_int(lhi.w) > 0 ? ~(__float_as_int(llo.w) | (__float_as_int(lhi.w) << 27)) : __float_as_int(llo.w);
+        const int cr = __float_as_int(rhi.w) > 0 ? ~(__float_as_int(rlo.w) | (__float_as_int(rhi.w) << 27)) : __float_as_int(rlo.w);
+        int next = 0;
+        bool haveNext = true;
+        if (vl && vr) {
+            const bool leftFirst = tl <= tr;
+            next = leftFirst ? cl : cr;
+            if (sp < 64) stack[sp++] = leftFirst ? cr : cl;
+        } else if (vl) next = cl;
+        else if (vr) next = cr;
+        else haveNext = false;
+        node = -1;
+        if (haveNext) {
+            if (next < 0) { const int enc = ~next; primRef = enc & 0x7ffffff; primCnt = enc >> 27; }
+            else node = next;
         }
     }
 }
@@ -492,6 +558,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
         Candidate best;
         const bool cached = FIRST && p.fbTn != nullptr;            // warp-uniform
         if (!USE_BVH && !cached) closestHitBrute(sgeoms, p.numGeoms, o, d, valid, best);
+        if (USE_BVH && !cached) closestHitBvh(p, snodes, smemNodes, o, d, valid, best);
         if (valid) {
             f3 n = mk3(0.f, 0.f, 0.f); int matId = 0;
             bool isHit;
@@ -508,7 +575,6 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
                     matId = USE_BVH ? p.geoms[meta & 0x3fffffff].tag.y : sgeoms[meta & 0x3fffffff].tag.y;
                 }
             } else {
-                if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, best);
                 isHit = best.slot >= 0;
                 if (isHit) {
                     if (USE_BVH) {
@@ -557,7 +623,7 @@ __global__ void __launch_bounds__(kBlock) fb_cache_kernel(const __grid_constant_
         f3 o = mk3(0.f, 0.f, 0.f), d = o;
         if (valid) cameraRay(cam, pix, o, d);
         Candidate best;
-        if (USE_BVH) { if (valid) closestHitBvh(p, snodes, smemNodes, o, d, best); }
+        if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, valid, best);
         else         closestHitBrute(sgeoms, p.numGeoms, o, d, valid, best);
         if (!valid) continue;
         if (best.slot < 0) { tnOut[pix] = make_float4(-1.0f, 0.f, 0.f, 0.f); metaOut[pix] = -1; continue; }
@@ -618,7 +684,7 @@ __global__ void __launch_bounds__(kBlock) intersect_kernel(const __grid_constant
         if (i < nIn) loadPath(p.in, i, o, d, c, id);
         const bool valid = !(id & kDeadBit);                             // no-compaction mode: dead path stays in place
         Candidate best;
-        if (USE_BVH) { if (valid) closestHitBvh(p, snodes, smemNodes, o, d, best); }
+        if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, valid, best);
         else         closestHitBrute(sgeoms, p.numGeoms, o, d, valid, best);
         if (i >= nIn) continue;
         if (!valid) { p.hits.meta[i] = -1; continue; }
@@ -819,7 +885,7 @@ __global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_co
             d = mk3(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2]);
         }
         Candidate best;
-        if (USE_BVH) { if (valid) closestHitBvh(p, snodes, smemNodes, o, d, best); }
+        if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, valid, best);
         else         closestHitBrute(sgeoms, p.numGeoms, o, d, valid, best);
         if (!valid) continue;
         if (best.slot < 0) {
