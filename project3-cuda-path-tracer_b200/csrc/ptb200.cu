@@ -68,7 +68,8 @@ struct PtbContext {
     std::vector<int> sceneMaterial;      // scene geom index -> material id
     std::vector<int> slotOfScene;
     DevBuf<GeomRec> geoms;
-    DevBuf<GeomRec> geomsScene;          // scene order (brute force), kept for ptb_stage_intersect(BRUTE)
+    DevBuf<GeomRec> geomsScene;          // brute-force table (cubes first, then spheres), also used by ptb_stage_intersect(BRUTE)
+    int numCubes = 0;
     DevBuf<BvhNode> bvh;
     int numNodes = 0, smemNodes = 0;
     DevBuf<float4> mats;
@@ -136,6 +137,18 @@ GeomRec packGeom(const PtbGeom &g, int sceneIndex) {
     }
     return r;
 }
+// brute-force table record: a cube's padded box as [lo, hi, lo] per axis in the nine words from tag.w on
+// (sign-selected near / far plane loads in closestHitBrute)
+GeomRec packGeomBrute(const PtbGeom &g, int sceneIndex) {
+    GeomRec r = packGeom(g, sceneIndex);
+    if (g.type == 1) {
+        static_assert(offsetof(GeomRec, tag) + 12 == kPruneWord0 * 4 && sizeof(GeomRec) == (kPruneWord0 + 9) * 4, "prune words");
+        const float lo[3] = {r.b0.x, r.b0.y, r.b0.z}, hi[3] = {r.b1.x, r.b1.y, r.b1.z};
+        float *w = reinterpret_cast<float *>(&r) + kPruneWord0;
+        for (int ax = 0; ax < 3; ++ax) { w[3 * ax] = lo[ax]; w[3 * ax + 1] = hi[ax]; w[3 * ax + 2] = lo[ax]; }
+    }
+    return r;
+}
 
 Params makeParams(PtbContext *c, int inBuf) {
     Params p = c->base;
@@ -177,7 +190,7 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
         c->pinnedBytes = total;
     }
     uint8_t *q = c->pinned;
-    GeomRec *sceneOrder = reinterpret_cast<GeomRec *>(q); q += bytesGeoms;
+    GeomRec *bruteOrder = reinterpret_cast<GeomRec *>(q); q += bytesGeoms;
     GeomRec *leafOrder = reinterpret_cast<GeomRec *>(q); q += bytesGeoms;
     BvhNode *nodes = reinterpret_cast<BvhNode *>(q); q += bytesNodes;
     float4 *mats = reinterpret_cast<float4 *>(q); q += bytesMats;
@@ -186,7 +199,13 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     memset(c->pinned, 0, total);
 
     c->sceneMaterial.resize(G);
-    for (int i = 0; i < G; ++i) { sceneOrder[i] = packGeom(scene->geoms[i], i); sceneMat[i] = c->sceneMaterial[i] = scene->geoms[i].materialid; }
+    for (int i = 0; i < G; ++i) sceneMat[i] = c->sceneMaterial[i] = scene->geoms[i].materialid;
+    // brute-force table: cubes first, then spheres, each in scene order (tag.z keeps the scene index for the tie rule)
+    int numCubes = 0;
+    for (int i = 0; i < G; ++i) if (scene->geoms[i].type == 1) bruteOrder[numCubes++] = packGeomBrute(scene->geoms[i], i);
+    for (int i = 0, k = numCubes; i < G; ++i) if (scene->geoms[i].type != 1) bruteOrder[k++] = packGeomBrute(scene->geoms[i], i);
+    c->numCubes = numCubes;
+    hdr->numCubes = numCubes;
     // the BVH is always built so that ptb_stage_intersect can compare both traversals on any scene;
     // the render path uses it only when useBvh is set
     HostBvh hb;
@@ -194,7 +213,7 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     static_assert(sizeof(HostBvhNode) == sizeof(BvhNode), "bvh node");
     if ((int)hb.nodes.size() > Gp) return fail(PTB_ERR_INVALID, "BVH has %zu nodes for %d geoms", hb.nodes.size(), G);
     memcpy(nodes, hb.nodes.data(), hb.nodes.size() * sizeof(BvhNode));
-    for (int sIdx = 0; sIdx < G; ++sIdx) leafOrder[sIdx] = sceneOrder[hb.order[sIdx]];
+    for (int sIdx = 0; sIdx < G; ++sIdx) leafOrder[sIdx] = packGeom(scene->geoms[hb.order[sIdx]], hb.order[sIdx]);
     c->numNodes = (int)hb.nodes.size();
     c->smemNodes = std::min(c->numNodes, 511);
     for (int i = 0; i < M; ++i) {
@@ -209,7 +228,7 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
                             cam.pixelLength[0], cam.pixelLength[1], c->W, c->H};
     hdr->numNodes = c->numNodes; hdr->smemNodes = c->smemNodes;
 
-    CU(cudaMemcpyAsync(c->geomsScene.p, sceneOrder, bytesGeoms, cudaMemcpyHostToDevice, c->stream));
+    CU(cudaMemcpyAsync(c->geomsScene.p, bruteOrder, bytesGeoms, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->geoms.p, leafOrder, bytesGeoms, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->bvh.p, nodes, bytesNodes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->mats.p, mats, bytesMats, cudaMemcpyHostToDevice, c->stream));

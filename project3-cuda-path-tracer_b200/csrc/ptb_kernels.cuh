@@ -66,6 +66,7 @@ struct SceneHeader {             // device-resident, rewritten by ptb_update_sce
     CameraParams cam;
     int          numNodes;
     int          smemNodes;      // leading BVH nodes (BFS order = top levels) staged in shared memory
+    int          numCubes;       // brute-force table: the cubes come first (this many), then the spheres
 };
 
 struct Params {
@@ -134,7 +135,8 @@ PTB_DEV f3 candidateNormal(const GeomRec &g, const Candidate &c) { return exactN
 //      lane, the three reachable primitives with the smallest entry distance as SORTED PACKED KEYS:
 //      key = bits(lower bound) with the five low mantissa bits replaced by the geom's index in the
 //      chunk (clearing mantissa bits only lowers a non-negative bound), so one unsigned min/max
-//      network (5 instructions) does the sorted insert and no per-lane branch is taken;
+//      network (5 instructions) does the sorted insert and no per-lane branch is taken.  A miss is the
+//      key of +infinity, which sorts behind every reachable primitive and ends the walk by itself;
 //   2. each lane walks ITS OWN keys nearest first.  A cheap inner loop skips candidates the
 //      object-space sure-miss filter rejects (the primitive a bounce ray just left is always
 //      "reachable" for the world-space bound), so that the lanes of a warp arrive TOGETHER at the one
@@ -143,36 +145,94 @@ PTB_DEV f3 candidateNormal(const GeomRec &g, const Candidate &c) { return exactN
 // When more than three primitives are reachable and the third bound did not end the walk (rare), the
 // same two phases run again over the keys above the last one consumed.
 // Phase 1 only prunes and orders; every output value comes from the exact test.
+//
+// The phase-1 loop is bound by the ALU pipe (min/max, compares, selects: one warp instruction per two
+// cycles), not by the FMA pipe, so it is laid out to need as few of those as possible:
+//   * the brute-force geom table is ordered cubes first (Params::numCubes of them), then spheres, so
+//     each type has its own branch-free loop (the scene index for the tie rule lives in tag.z);
+//   * a cube's padded world box is stored as [lo, hi, lo] per axis (GeomRec::pruneWords): a lane reads
+//     its NEAR plane at word s and its FAR plane at word s + 1, s = sign bit of the direction
+//     component, so the six per-axis min/max of a slab test disappear (two distinct words of one
+//     geom per load: different banks, one shared-memory wavefront);
+//   * entry = max3, exit = min3 (FMNMX3).
 constexpr uint32_t kNoCand = 0xffffffffu;
+constexpr uint32_t kMissKey = 0x7f800000u;                        // bits(+inf): every key at or above it is "not reachable"
+
+struct BruteRay {                                                 // per-lane constants of phase 1
+    f3 o, invD, dn;
+    float rdLen, slack;
+    uint32_t sx, sy, sz;                                          // sign bits of the direction components
+};
+
+// sorted insert of `key` into (k0 <= k1 <= k2); the largest of the four falls out
+PTB_DEV void insertKey(uint32_t key, uint32_t &k0, uint32_t &k1, uint32_t &k2) {
+    const uint32_t a = min(k0, key), b = max(k0, key);
+    const uint32_t c = min(k1, b), f = max(k1, b);
+    k0 = a; k1 = c; k2 = min(k2, f);
+}
+// lower-bound key of one primitive: e = entry distance (world units) or +inf for a sure miss (`reach` false)
+template <bool RESCAN>
+PTB_DEV void pushBound(float e, bool reach, int idx, const BruteRay &r, uint32_t floorKey, uint32_t &k0, uint32_t &k1, uint32_t &k2, int &nAbove) {
+    const float lo = fmaxf(fmaf(e, 0.99998f, -r.slack), 0.0f);    // inf stays inf
+    uint32_t key = (__float_as_uint(lo) & ~31u) | (uint32_t)idx;
+    if (RESCAN) { reach = reach && key >= floorKey; key = reach ? key : kNoCand; }
+    if (reach) ++nAbove;
+    insertKey(key, k0, k1, k2);
+}
+template <bool RESCAN>
+PTB_DEV void boundsPhase(const GeomRec *sg, int g0, int c1, int g1, const BruteRay &r, uint32_t floorKey,
+                         uint32_t &k0, uint32_t &k1, uint32_t &k2, int &nAbove) {
+    const float inf = __uint_as_float(kMissKey);
+    constexpr int kStride = (int)(sizeof(GeomRec) / 4);
+    // cubes [g0, c1): sign-selected near / far planes
+    const float *wx = reinterpret_cast<const float *>(sg + g0) + kPruneWord0 + r.sx;
+    const float *wy = reinterpret_cast<const float *>(sg + g0) + kPruneWord0 + 3 + r.sy;
+    const float *wz = reinterpret_cast<const float *>(sg + g0) + kPruneWord0 + 6 + r.sz;
+#pragma unroll 2
+    for (int i = 0; i < c1 - g0; ++i, wx += kStride, wy += kStride, wz += kStride) {
+        const float nx = (wx[0] - r.o.x) * r.invD.x, fx = (wx[1] - r.o.x) * r.invD.x;
+        const float ny = (wy[0] - r.o.y) * r.invD.y, fy = (wy[1] - r.o.y) * r.invD.y;
+        const float nz = (wz[0] - r.o.z) * r.invD.z, fz = (wz[1] - r.o.z) * r.invD.z;
+        // fminf / fmaxf drop the NaN of 0 * inf (origin exactly on a padded plane, direction component 0):
+        // that errs towards "reachable"
+        const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
+        const float tf = fminf(fminf(fx, fy), fz);
+        const bool reach = tn <= fmaf(tf, 1.00002f, 1e-6f);
+        pushBound<RESCAN>(reach ? tn * r.rdLen : inf, reach, i, r, floorKey, k0, k1, k2, nAbove);
+    }
+    // spheres [max(g0, c1), g1): padded bounding sphere
+#pragma unroll 1
+    for (int g = max(g0, c1); g < g1; ++g) {
+        const float e = boundEntryRaw(false, sg[g].b0, sg[g].b1, r.o, r.invD, r.dn, r.rdLen);
+        pushBound<RESCAN>(e >= 0.0f ? e : inf, e >= 0.0f, g - g0, r, floorKey, k0, k1, k2, nAbove);
+    }
+}
 
 // `valid` = this lane carries a ray (callers keep their loops warp-uniform).
-PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, bool valid, Candidate &best) {
+PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o, f3 d, bool valid, Candidate &best) {
     best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
     int orig = 0x7fffffff;
+    BruteRay r;
     const float dd = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
     const float rinv = rsqrtApprox(dd);
-    const float rdLen = dd * rinv;
-    const f3 dn = mk3(d.x * rinv, d.y * rinv, d.z * rinv);
-    const f3 invD = mk3(rcpApprox(d.x), rcpApprox(d.y), rcpApprox(d.z));
+    r.o = o;
+    r.rdLen = dd * rinv;
+    r.dn = mk3(d.x * rinv, d.y * rinv, d.z * rinv);
+    r.invD = mk3(rcpApprox(d.x), rcpApprox(d.y), rcpApprox(d.z));
+    r.sx = __float_as_uint(d.x) >> 31; r.sy = __float_as_uint(d.y) >> 31; r.sz = __float_as_uint(d.z) >> 31;
     // slack on every lower bound: rounding of the bound itself plus the deviation of the exact hit
     // point from the ideal ray (a few ulp of the coordinates involved)
-    const float slack = 2e-5f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f);
+    r.slack = 2e-5f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f);
     for (int g0 = 0; g0 < numGeoms; g0 += 32) {
         const int g1 = min(numGeoms, g0 + 32);
+        const int c1 = min(max(numCubes, g0), g1);                // cubes of this chunk: [g0, c1)
         uint32_t floorKey = 0u;                                   // keys below it were consumed by an earlier round
         for (;;) {
             uint32_t k0 = kNoCand, k1 = kNoCand, k2 = kNoCand;
             int nAbove = 0;
-            for (int g = g0; g < g1; ++g) {
-                const float e = boundEntry(sg[g], o, invD, dn, rdLen);
-                const float lo = fmaxf(fmaf(e, 0.99998f, -slack), 0.0f);
-                uint32_t key = (__float_as_uint(lo) & ~31u) | (uint32_t)(g - g0);
-                key = (valid && e >= 0.0f && key >= floorKey) ? key : kNoCand;
-                nAbove += key != kNoCand;
-                const uint32_t a = min(k0, key), b = max(k0, key);  // sorted insert, the largest of four falls out
-                const uint32_t c = min(k1, b), f = max(k1, b);
-                k0 = a; k1 = c; k2 = min(k2, f);
-            }
+            if (floorKey == 0u) boundsPhase<false>(sg, g0, c1, g1, r, 0u, k0, k1, k2, nAbove);
+            else                boundsPhase<true>(sg, g0, c1, g1, r, floorKey, k0, k1, k2, nAbove);
+            if (!valid) k0 = kNoCand;
             uint32_t lastKey = 0u;
             bool exhausted = true;                                // all three keys consumed without the bound ending the walk
             for (;;) {
@@ -180,7 +240,7 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, bool v
                 f3 qo, qu;
                 while (k0 != kNoCand) {
                     const float lo = __uint_as_float(k0 & ~31u);
-                    if (!(lo <= best.t)) { exhausted = false; k0 = kNoCand; break; }   // sorted: nothing further can win
+                    if (!(lo <= best.t)) { exhausted = false; k0 = kNoCand; break; }   // sorted: nothing further can win (+inf = miss keys too)
                     const int cand = g0 + (int)(k0 & 31u);
                     lastKey = k0;
                     k0 = k1; k1 = k2; k2 = kNoCand;
@@ -192,7 +252,7 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, f3 o, f3 d, bool v
                 const float t = exactTestQ(sg[g], o, qo, qu, outside, a, b, c);
                 acceptHit(sg[g], g, t, outside, a, b, c, best, orig);
             }
-            if (!(exhausted && nAbove > 3)) break;
+            if (!(valid && exhausted && nAbove > 3)) break;
             floorKey = lastKey + 1u;
         }
     }
@@ -498,6 +558,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
 
     if (threadIdx.x == 0) { sNextChunk = 0u; sOutCount = 0u; }
     const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
+    const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
     if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);      // ends with __syncthreads
     else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
@@ -557,7 +618,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
         }
         Candidate best;
         const bool cached = FIRST && p.fbTn != nullptr;            // warp-uniform
-        if (!USE_BVH && !cached) closestHitBrute(sgeoms, p.numGeoms, o, d, valid, best);
+        if (!USE_BVH && !cached) closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
         if (USE_BVH && !cached) closestHitBvh(p, snodes, smemNodes, o, d, valid, best);
         if (valid) {
             f3 n = mk3(0.f, 0.f, 0.f); int matId = 0;
@@ -612,6 +673,7 @@ template <bool USE_BVH>
 __global__ void __launch_bounds__(kBlock) fb_cache_kernel(const __grid_constant__ Params p, float4 *tnOut, int *metaOut) {
     extern __shared__ float4 smem4[];
     const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
+    const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
     if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
     else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
@@ -624,7 +686,7 @@ __global__ void __launch_bounds__(kBlock) fb_cache_kernel(const __grid_constant_
         if (valid) cameraRay(cam, pix, o, d);
         Candidate best;
         if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, valid, best);
-        else         closestHitBrute(sgeoms, p.numGeoms, o, d, valid, best);
+        else         closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
         if (!valid) continue;
         if (best.slot < 0) { tnOut[pix] = make_float4(-1.0f, 0.f, 0.f, 0.f); metaOut[pix] = -1; continue; }
         const GeomRec &g = USE_BVH ? p.geoms[best.slot] : sgeoms[best.slot];
@@ -673,6 +735,7 @@ template <bool USE_BVH>
 __global__ void __launch_bounds__(kBlock) intersect_kernel(const __grid_constant__ Params p, const int depth) {
     extern __shared__ float4 smem4[];
     const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
+    const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
     if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
     else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
@@ -685,7 +748,7 @@ __global__ void __launch_bounds__(kBlock) intersect_kernel(const __grid_constant
         const bool valid = !(id & kDeadBit);                             // no-compaction mode: dead path stays in place
         Candidate best;
         if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, valid, best);
-        else         closestHitBrute(sgeoms, p.numGeoms, o, d, valid, best);
+        else         closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
         if (i >= nIn) continue;
         if (!valid) { p.hits.meta[i] = -1; continue; }
         if (best.slot < 0) {
@@ -872,6 +935,7 @@ __global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_co
         const float *dirs, int n, int *hit, float *t, float *normal, int *outside) {
     extern __shared__ float4 smem4[];
     const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
+    const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
     if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
     else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
@@ -886,7 +950,7 @@ __global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_co
         }
         Candidate best;
         if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, valid, best);
-        else         closestHitBrute(sgeoms, p.numGeoms, o, d, valid, best);
+        else         closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
         if (!valid) continue;
         if (best.slot < 0) {
             hit[i] = -1; t[i] = -1.0f; outside[i] = 1;
