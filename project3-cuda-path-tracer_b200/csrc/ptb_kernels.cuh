@@ -245,7 +245,14 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
                     lastKey = k0;
                     k0 = k1; k1 = k2; k2 = kNoCand;
                     objectRay(sg[cand], o, d, qo, qu);
-                    if (!sureMiss(sg[cand], qo, qu)) { g = cand; break; }
+                    // The cube filter runs for every lane and the sphere filter overrides it inside a plain `if`
+                    // (no break / continue in either arm), so the lanes reconverge right here.  With the filters
+                    // in the two arms of a type branch that both lead to the loop exits, the lanes holding a
+                    // sphere candidate (2 of 32 on the cornell box, in two warps out of three) went through
+                    // the whole exact test as a separate pass.
+                    bool miss = boxSureMiss(qo, qu);
+                    if (sg[cand].tag.x != 1) miss = sphereSureMiss(qo, qu);
+                    if (!miss) { g = cand; break; }
                 }
                 if (g < 0) break;
                 int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
