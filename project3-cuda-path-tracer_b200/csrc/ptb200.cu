@@ -209,7 +209,9 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     // the BVH is always built so that ptb_stage_intersect can compare both traversals on any scene;
     // the render path uses it only when useBvh is set
     HostBvh hb;
-    buildBvh(scene->geoms, G, 4, hb);
+    int maxLeaf = 1;                     // one primitive per leaf: its padded bound IS the leaf box (measured: 4 -> 7.28, 2 -> 6.62, 1 -> 6.29 ms per iteration of the 100k-object scene)
+    if (const char *e = getenv("PTB_BVH_LEAF")) maxLeaf = std::max(1, atoi(e));                       // tuning knob (experiments)
+    buildBvh(scene->geoms, G, maxLeaf, hb);
     static_assert(sizeof(HostBvhNode) == sizeof(BvhNode), "bvh node");
     if ((int)hb.nodes.size() > Gp) return fail(PTB_ERR_INVALID, "BVH has %zu nodes for %d geoms", hb.nodes.size(), G);
     memcpy(nodes, hb.nodes.data(), hb.nodes.size() * sizeof(BvhNode));
@@ -245,12 +247,19 @@ int launchFusedBatch(PtbContext *c) {
     for (int d = 0; d < c->traceDepth; ++d) {
         // bounce d reads buffer (d-1)&1... bounce 0 reads nothing and writes buffer 0
         Params p = makeParams(c, d == 0 ? 1 : ((d - 1) & 1));
-        if (d == 0) {
-            if (c->useBvh) bounce_kernel<true, true><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
-            else           bounce_kernel<true, false><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+        if (c->useBvh) {
+            // closest hit first (persistent threads, dynamic ray fetch), then shade / scatter / compact
+            const bool cached = d == 0 && p.fbTn != nullptr;
+            if (!cached) {
+                if (d == 0) trace_bvh_kernel<true><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+                else        trace_bvh_kernel<false><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+                c->launches++;
+            }
+            if (d == 0) bounce_kernel<true, true><<<c->gridFused, kBlock, 0, c->stream>>>(p, d);
+            else        bounce_kernel<false, true><<<c->gridFused, kBlock, 0, c->stream>>>(p, d);
         } else {
-            if (c->useBvh) bounce_kernel<false, true><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
-            else           bounce_kernel<false, false><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+            if (d == 0) bounce_kernel<true, false><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+            else        bounce_kernel<false, false><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
         }
         c->launches++;
     }
@@ -317,6 +326,7 @@ int kernelsPerBatch(const PtbContext *c) {
         int per = 1 /*intersect*/ + 1 /*shade*/ + 1 /*compact or carry*/ + (c->opt.sortMaterials ? 4 : 0);
         return 1 + per * c->traceDepth + (c->opt.compaction ? 0 : 1) + 1;
     }
+    if (c->useBvh) return 2 * c->traceDepth + 1 - (c->opt.firstBounceCache ? 1 : 0);   // trace + bounce per depth
     return c->traceDepth + 1;
 }
 
@@ -472,7 +482,7 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     }
     int occ = 0;
     const size_t smem = c->useBvh ? c->smemBvh : c->smemBrute;
-    if (c->useBvh) CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, true>, kBlock, smem));
+    if (c->useBvh) CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_bvh_kernel<false>, kBlock, smem));
     else           CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, false>, kBlock, smem));
     // 4 CTAs per resident slot: the CTA-owned segments cannot be rebalanced inside a launch, so a few
     // waves of smaller CTAs keep the tail short (measured: x1 142 us, x2 138, x4 134.5, x8 135.4, x16 142 per cornell iteration)
@@ -494,8 +504,8 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     }
     CUB(c->segCounts.alloc((size_t)2 * c->gridFused));
     CUB(cudaMemset(c->segCounts.p, 0, sizeof(uint32_t) * 2 * c->gridFused));
-    if (opt.pipeline == PTB_PIPELINE_STAGED) {
-        CUB(c->hitTn.alloc(maxPaths)); CUB(c->hitMeta.alloc(maxPaths));
+    if (opt.pipeline == PTB_PIPELINE_STAGED || c->useBvh) {
+        CUB(c->hitTn.alloc(pathSlots)); CUB(c->hitMeta.alloc(pathSlots));
         if (opt.sortMaterials) { CUB(c->sortKeys.alloc(maxPaths)); CUB(c->sortOrder.alloc(maxPaths)); CUB(c->sortHist.alloc(scene->numMaterials + 2)); }
     }
     if (opt.firstBounceCache && opt.pipeline == PTB_PIPELINE_FUSED) { CUB(c->fbTn.alloc(c->numPixels)); CUB(c->fbMeta.alloc(c->numPixels)); }

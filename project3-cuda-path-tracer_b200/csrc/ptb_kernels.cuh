@@ -543,6 +543,199 @@ PTB_DEV uint32_t compactSlot(bool keep, uint32_t *counter, int *warpTotals, uint
 }
 
 // ------------------------------------------------------------------------------------------------
+// BVH scenes, fused pipeline: closest hit as its own PERSISTENT-THREADS kernel with dynamic ray fetch.
+//
+// The traversal length of a ray through the 100 k-object scene varies by an order of magnitude, and a
+// warp that owns 32 fixed rays runs until its longest one is finished: measured on the fused bounce
+// kernel, 545 traversal steps per warp against 170 per ray, 8.9 of 32 lanes active.  Here a lane that
+// finishes its ray writes the raw hit record and goes idle; as soon as kRefillLanes lanes of the warp are
+// idle (or all of them) the warp takes that many tickets from the CTA's queue with ONE shared-memory atomic
+// and the idle lanes start new rays, so the warp stays populated until the CTA's rays run out.
+// The rays of a CTA are the paths of its own segment (bounce_kernel's CTA-owned path segments), so the
+// hit record of path slot i lands at hits[i] and the bounce kernel that follows (USE_BVH: shade, scatter,
+// compact) reads it back with the path: 20 B written + 20 B read per segment, against ~10^4 thread
+// instructions of traversal.
+// Raw hit record: hits.tn[i] = (t, a, b, c) -- (a, b, c) is what the deferred normal needs (Candidate) --
+// and hits.meta[i] = geom slot | outside << 30, or -1 for a miss.
+// The traversal itself is closestHitBvh's A / B / C state machine.
+// ------------------------------------------------------------------------------------------------
+#ifndef PTB_REFILL_LANES
+#define PTB_REFILL_LANES 8
+#endif
+constexpr int kRefillLanes = PTB_REFILL_LANES;
+#ifndef PTB_EXACT_LANES
+#define PTB_EXACT_LANES 8
+#endif
+constexpr int kExactLanes = PTB_EXACT_LANES;                       // lanes that must wait before the exact test runs (unless nobody can work)
+
+template <bool FIRST>
+__global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const __grid_constant__ Params p, const int depth) {
+    extern __shared__ float4 smem4[];
+    __shared__ uint32_t sNextTicket;
+    if (threadIdx.x == 0) sNextTicket = 0u;
+    const int smemNodes = p.hdr->smemNodes;
+    stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);      // ends with __syncthreads
+    const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
+    CameraParams cam;
+    if (FIRST) cam = p.hdr->cam;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t laneBelow = (1u << lane) - 1u;
+    const uint32_t segBase = blockIdx.x * p.segCap;
+    uint32_t total, nTickets;
+    if (FIRST) {
+        total = p.numPixels * (uint32_t)p.ctrl->batch;
+        const uint32_t tiles = (total + kBlock - 1) / kBlock;
+        nTickets = (tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u) * kBlock;
+    } else {
+        total = p.segCounts[((depth + 1) & 1) * gridDim.x + blockIdx.x];
+        nTickets = total;
+    }
+
+    // per-lane ray and traversal state
+    f3 o = mk3(0.f, 0.f, 0.f), d = o, invD = o, dn = o;
+    float rdLen = 0.f, dl = 0.f, slack = 0.f;
+    Candidate best;
+    best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
+    int bestOrig = 0x7fffffff;
+    int stack[64];
+    int sp = 0, node = -1;
+    int primRef = 0, primCnt = 0;                                 // pending leaf: geoms[primRef .. primRef + primCnt)
+    int cand = -1;                                                // primitive waiting for the exact test
+    f3 qo = o, qu = o;
+    bool candCube = false;
+    bool done = true;                                             // the lane holds no ray
+    bool drained = false;                                         // warp-uniform: the CTA's queue is empty
+    uint32_t idx = 0;                                             // hit-record index of the lane's ray
+
+    for (;;) {
+        // ---- refill: idle lanes take tickets
+        const unsigned idle = __ballot_sync(0xffffffffu, done);
+        if (!drained && (idle == 0xffffffffu || __popc(idle) >= kRefillLanes)) {
+            const uint32_t want = (uint32_t)__popc(idle);
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&sNextTicket, want);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            drained = base + want >= nTickets;
+            if (done) {
+                const uint32_t k = base + (uint32_t)__popc(idle & laneBelow);
+                bool have = k < nTickets;
+                if (have) {
+                    if (FIRST) {
+                        const uint32_t tile = blockIdx.x + (k / kBlock) * gridDim.x;
+                        idx = tile * kBlock + (k % kBlock);
+                        have = idx < total;
+                        if (have) cameraRay(cam, idx % p.numPixels, o, d);
+                    } else {
+                        idx = segBase + k;
+                        const float4 a = p.in.A[idx], b = p.in.B[idx];
+                        o = mk3(a.x, a.y, a.z); d = mk3(a.w, b.x, b.y);
+                    }
+                }
+                if (have) {
+                    const float dd = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
+                    const float rinv = rsqrtApprox(dd);
+                    rdLen = dd * rinv;                            // |d|
+                    dn = mk3(d.x * rinv, d.y * rinv, d.z * rinv);
+                    invD = mk3(rcpApprox(d.x), rcpApprox(d.y), rcpApprox(d.z));
+                    dl = rdLen * 0.9999f;
+                    slack = 2e-5f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f);
+                    best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
+                    bestOrig = 0x7fffffff;
+                    sp = 0; node = 0; primCnt = 0; cand = -1;
+                    done = false;
+                }
+            }
+        }
+        if (__ballot_sync(0xffffffffu, !done) == 0u) {
+            if (drained) break;
+            continue;                                             // every lane idle: the next pass refills
+        }
+        // One pass = A, then B, then (when enough lanes wait) C, each a plain `if` the lanes reconverge
+        // after: a lane that pops a leaf in A prunes its first primitive in the same pass, and one that
+        // finds a candidate in B can take part in this pass's exact test.
+        // ---- A: one traversal step (lanes with nothing pending)
+        if (!done && cand < 0 && primCnt == 0) {
+            if (node < 0) {
+                if (sp == 0) {
+                    // the ray is finished: raw hit record out, lane idle
+                    p.hits.tn[idx] = make_float4(best.slot >= 0 ? best.t : -1.0f, best.a, best.b, best.c);
+                    p.hits.meta[idx] = best.slot >= 0 ? (best.slot | (best.outside << 30)) : -1;
+                    done = true;
+                } else {
+                    const int e = stack[--sp];
+                    if (e < 0) { const int enc = ~e; primRef = enc & 0x7ffffff; primCnt = enc >> 27; }
+                    else node = e;
+                }
+            }
+            if (node >= 0) {
+                float4 llo, lhi, rlo, rhi;
+                if (node < smemNodes) { llo = snodes[node].llo; lhi = snodes[node].lhi; rlo = snodes[node].rlo; rhi = snodes[node].rhi; }
+                else {
+                    const float4 *np = reinterpret_cast<const float4 *>(p.bvh + node);
+                    llo = __ldg(np); lhi = __ldg(np + 1); rlo = __ldg(np + 2); rhi = __ldg(np + 3);
+                }
+                float tl, tr;
+                // tNear * |d| (slackened) is a lower bound of the world distance of anything inside the box
+                const bool vl = __float_as_int(llo.w) >= 0 && slabNear(llo, lhi, o, invD, tl) && tl * dl - 1e-4f <= best.t;
+                const bool vr = __float_as_int(rlo.w) >= 0 && slabNear(rlo, rhi, o, invD, tr) && tr * dl - 1e-4f <= best.t;
+                // children as stack entries: interior -> node index (>= 0), leaf -> ~(ref | count << 27) (< 0)
+                const int cl = __float_as_int(lhi.w) > 0 ? ~(__float_as_int(llo.w) | (__float_as_int(lhi.w) << 27)) : __float_as_int(llo.w);
+                const int cr = __float_as_int(rhi.w) > 0 ? ~(__float_as_int(rlo.w) | (__float_as_int(rhi.w) << 27)) : __float_as_int(rlo.w);
+                int next = 0;
+                bool haveNext = true;
+                if (vl && vr) {
+                    const bool leftFirst = tl <= tr;
+                    next = leftFirst ? cl : cr;
+                    if (sp < 64) stack[sp++] = leftFirst ? cr : cl;
+                } else if (vl) next = cl;
+                else if (vr) next = cr;
+                else haveNext = false;
+                node = -1;
+                if (haveNext) {
+                    if (next < 0) { const int enc = ~next; primRef = enc & 0x7ffffff; primCnt = enc >> 27; }
+                    else node = next;
+                }
+            }
+        }
+        // ---- B: prune one primitive of the pending leaf
+        if (!done && cand < 0 && primCnt > 0) {
+            const int slot = primRef;
+            ++primRef; --primCnt;
+            const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + slot);
+            const int4 tag = __ldg(reinterpret_cast<const int4 *>(gp + 9));
+            const float4 b0 = __ldg(gp + 10), b1 = __ldg(gp + 11);
+            const bool isCube = tag.x == 1;
+            const float e = boundEntryRaw(isCube, b0, b1, o, invD, dn, rdLen);
+            if (e >= 0.0f && fmaf(e, 0.99998f, -slack) <= best.t) {
+                Affine inv;
+                inv.r0 = __ldg(gp); inv.r1 = __ldg(gp + 1); inv.r2 = __ldg(gp + 2);
+                qo = mulMVPoint(inv, o);
+                qu = mulMV(inv, d, 0.0f);
+                bool miss = boxSureMiss(qo, qu);
+                if (!isCube) miss = sphereSureMiss(qo, qu);
+                if (!miss) { cand = slot; candCube = isCube; }
+            }
+        }
+        // ---- C: the reference-exact test, entered by the waiting lanes together
+        const unsigned waiting = __ballot_sync(0xffffffffu, cand >= 0);
+        const unsigned working = __ballot_sync(0xffffffffu, cand < 0 && !done);
+        if (waiting && (!working || __popc(waiting) >= kExactLanes)) {
+            if (cand >= 0) {
+                const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + cand);
+                Affine fwd;
+                fwd.r0 = __ldg(gp + 3); fwd.r1 = __ldg(gp + 4); fwd.r2 = __ldg(gp + 5);
+                const int origIndex = __ldg(reinterpret_cast<const int *>(gp + 9) + 2);
+                int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
+                const float t = exactTestCore(candCube, fwd, o, qo, qu, outside, a, b, c);
+                const bool take = t > 0.0f && (best.t > t || (best.t == t && origIndex < bestOrig));   // src/pathtrace.cu:192 + index tie rule
+                if (take) { best.t = t; best.slot = cand; best.outside = outside; best.a = a; best.b = b; best.c = c; bestOrig = origIndex; }
+                cand = -1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // THE FAST PATH: one launch per bounce.  FIRST = bounce 0 (camera rays generated in registers, no
 // path-state read); USE_BVH selects the flat BVH over the brute-force shared-memory loop.
 //
@@ -564,12 +757,11 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
     __shared__ uint32_t sNextChunk, sOutCount;
 
     if (threadIdx.x == 0) { sNextChunk = 0u; sOutCount = 0u; }
-    const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
     const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
-    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);      // ends with __syncthreads
-    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
+    // USE_BVH: the closest hits were found by trace_bvh_kernel (raw hit records in p.hits); nothing to stage
+    if (USE_BVH) __syncthreads();
+    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);      // ends with __syncthreads
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
-    const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
 
     Control *ctrl = p.ctrl;
     CameraParams cam;
@@ -601,11 +793,12 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
 
         bool alive = false, valid;
         f3 o, d, c; uint32_t id = 0;
-        uint32_t pix = 0, slot = 0;
+        uint32_t pix = 0, slot = 0, hitIndex = 0;
         o = d = c = mk3(0.f, 0.f, 0.f);
         if (FIRST) {
             const uint32_t tile = blockIdx.x + (chunk / (kBlock / 32)) * gridDim.x;
             const uint32_t i = tile * kBlock + (chunk % (kBlock / 32)) * 32u + lane;
+            hitIndex = i;
             valid = i < total;
             if (valid) {
                 slot = i / p.numPixels;
@@ -626,7 +819,17 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
         Candidate best;
         const bool cached = FIRST && p.fbTn != nullptr;            // warp-uniform
         if (!USE_BVH && !cached) closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
-        if (USE_BVH && !cached) closestHitBvh(p, snodes, smemNodes, o, d, valid, best);
+        if (USE_BVH && !cached && valid) {
+            // BVH scenes: trace_bvh_kernel ran before this launch and left the raw hit record of every path
+            const uint32_t h = FIRST ? hitIndex : segBase + chunk * 32u + lane;
+            const int meta = p.hits.meta[h];
+            best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
+            if (meta >= 0) {
+                const float4 r = p.hits.tn[h];
+                best.t = r.x; best.a = r.y; best.b = r.z; best.c = r.w;
+                best.slot = meta & 0x3fffffff; best.outside = (meta >> 30) & 1;
+            }
+        }
         if (valid) {
             f3 n = mk3(0.f, 0.f, 0.f); int matId = 0;
             bool isHit;
