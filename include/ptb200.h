@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 1
+#define PTB_ABI_VERSION 2
 
 /* ---- POD mirrors of src/sceneStructs.h (byte-identical; matrices column-major like glm) ---- */
 typedef struct PtbGeom {            /* struct Geom, src/sceneStructs.h:20-29, 236 bytes */
@@ -94,10 +94,18 @@ typedef struct PtbOptions {
     int32_t firstBounceCache;       /* fused pipeline: 1 = cache the bounce-0 hit record of every pixel across iterations
                                        (INSTRUCTION.md:87-89); refilled after ptb_create / ptb_update_scene */
     int32_t useGraphs;              /* 1 = replay the per-batch launch sequence as a CUDA graph */
-    int32_t reserved0;
+    int32_t antialias;              /* 1 = stochastic antialiasing: the sample position is jittered uniformly inside the
+                                       pixel each iteration (the TODO of src/pathtrace.cu:118-120,134; INSTRUCTION.md:109-113) */
     void   *stream;                 /* cudaStream_t to launch on; NULL = library-owned stream */
     float  *externalAccum;          /* device pointer to W*H*3 floats to accumulate into; NULL = library-owned */
+    float   lensRadius;             /* > 0 = thin-lens depth of field (INSTRUCTION.md:107-108, PBRT 6.2.3) */
+    float   focalDistance;          /* distance of the plane in focus along camera.view (used when lensRadius > 0) */
 } PtbOptions;
+/* antialias / lensRadius make the camera rays depend on the iteration, so they cannot be combined with
+ * firstBounceCache (INSTRUCTION.md:113: "keep in mind how this influences the first-bounce cache"):
+ * ptb_create returns PTB_ERR_UNSUPPORTED.  Materials with REFL > 0 and SPECEX > 0 scatter into a Phong
+ * lobe around the mirror direction in PTB_BSDF_FULL mode (imperfect specular, INSTRUCTION.md:202-216);
+ * SPECEX 0 stays the perfect mirror.  Exact formulas: DESIGN.md section 8 and oracle/pt_oracle.c. */
 
 typedef struct PtbStats {
     int64_t iterations;             /* iterations traced since ptb_init */
@@ -164,8 +172,10 @@ int ptb_accum_device_ptr(PtbContext *ctx, float **devPtr);
 int ptb_resolve_rgb8(PtbContext *ctx, int samples, uint8_t *hostRgb8);
 
 /* ---- stage-level entry points (used by the parity tests; host arrays in, host arrays out) ---- */
-/* generateRayFromCamera (src/pathtrace.cu:122-143): origins/dirs = W*H*3 floats each */
+/* generateRayFromCamera (src/pathtrace.cu:122-143): origins/dirs = W*H*3 floats each.  With antialias /
+ * lensRadius set the rays depend on the iteration: ptb_stage_raygen is iteration 1. */
 int ptb_stage_raygen(PtbContext *ctx, float *origins, float *dirs);
+int ptb_stage_raygen_iter(PtbContext *ctx, int iter, float *origins, float *dirs);
 /* computeIntersections (src/pathtrace.cu:149-213) over n caller-supplied rays.
  * accel: PTB_ACCEL_BRUTE / PTB_ACCEL_BVH / PTB_ACCEL_AUTO.  hit = geom index or -1, t = -1 on miss. */
 int ptb_stage_intersect(PtbContext *ctx, int accel, const float *origins, const float *dirs, int n,

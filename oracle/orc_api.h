@@ -61,6 +61,18 @@ typedef struct OrcCamera {
 
 enum { ORC_MODE_GOLDEN_DIFFUSE = 0, ORC_MODE_FULL = 1 };
 
+/* Camera-ray extensions the reference leaves as TODOs in generateRayFromCamera
+ * (src/pathtrace.cu:118-120, 134; INSTRUCTION.md:109-113): stochastic antialiasing and a thin
+ * lens.  Semantics authored here; all zero = the reference's pinhole ray. */
+typedef struct OrcLens {
+    int   antialias;       /* 1: jitter the sample position uniformly inside the pixel */
+    float lensRadius;      /* > 0: thin-lens depth of field (PBRT 6.2.3) */
+    float focalDistance;   /* distance of the plane in focus, measured along cam.view */
+} OrcLens;
+/* depth key of the camera-ray engine: makeSeededRandomEngine(iter, index, ORC_RAYGEN_DEPTH_KEY).
+ * Bounce engines use depth 0 .. traceDepth-1 <= 63; the key field is 9 bits wide (src/pathtrace.cu:43). */
+#define ORC_RAYGEN_DEPTH_KEY 511
+
 /* "reference" or "port" */
 const char *orc_kind(void);
 
@@ -85,6 +97,9 @@ void  orc_rng_u01(int iter, int index, int depth, int n, float *out);
 
 /* generateRayFromCamera (src/pathtrace.cu:122-143): origins/dirs are P*3 floats */
 void  orc_generate_rays(const OrcCamera *cam, float *origins, float *dirs);
+
+/* the same with the OrcLens extensions, for iteration `iter` (lens may be NULL) */
+void  orc_generate_rays_lens(const OrcCamera *cam, const OrcLens *lens, int iter, float *origins, float *dirs);
 
 /* computeIntersections closest-hit loop (src/pathtrace.cu:162-211) over arbitrary rays.
  * hit[i] = geom index or -1; t[i] = t_min or -1; normal = 3 floats; outside = flag of the
@@ -116,6 +131,12 @@ long long orc_render(const OrcGeom *geoms, int ngeoms, const OrcMaterial *materi
                      const OrcCamera *cam, int traceDepth, int mode,
                      int iterBegin, int nIters, float *image, long long *alivePerDepth,
                      int nthreads);
+
+/* orc_render with the OrcLens camera extensions (lens == NULL: identical to orc_render) */
+long long orc_render_lens(const OrcGeom *geoms, int ngeoms, const OrcMaterial *materials, int nmaterials,
+                          const OrcCamera *cam, const OrcLens *lens, int traceDepth, int mode,
+                          int iterBegin, int nIters, float *image, long long *alivePerDepth,
+                          int nthreads);
 
 #ifdef __cplusplus
 }

@@ -642,6 +642,64 @@ static inline ORay cameraRay(const OrcCamera *cam, int x, int y) {
     return r;
 }
 
+/* Camera ray with the OrcLens extensions (orc_api.h; the reference's TODOs at src/pathtrace.cu:118-120,134).
+ * One engine per (iter, pixel) keyed by ORC_RAYGEN_DEPTH_KEY; draws, in order: jitter x, jitter y
+ * (antialias only), lens radius, lens angle (lensRadius > 0 only).
+ *   antialias : the sample position (x, y) becomes (x + u - 0.5, y + u' - 0.5) in src/pathtrace.cu:135-136
+ *   thin lens : PBRT 6.2.3 -- the point in focus is position + dir * focalDistance / dot(dir, view); the
+ *               origin moves to a uniformly sampled point of the lens disc spanned by right / up */
+static inline ORay cameraRayLens(const OrcCamera *cam, const OrcLens *lens, int x, int y, int iter) {
+    if (!lens || (!lens->antialias && !(lens->lensRadius > 0.0f))) return cameraRay(cam, x, y);
+    Rng rng = seededEngine(iter, x + y * cam->resolution[0], ORC_RAYGEN_DEPTH_KEY);
+    float sx = (float)x, sy = (float)y;
+    if (lens->antialias) {
+        sx = sx + (u01(&rng) - 0.5f);
+        sy = sy + (u01(&rng) - 0.5f);
+    }
+    const v3 right = V3(cam->right[0], cam->right[1], cam->right[2]);
+    const v3 up = V3(cam->up[0], cam->up[1], cam->up[2]);
+    const v3 view = V3(cam->view[0], cam->view[1], cam->view[2]);
+    ORay r;
+    r.o = V3(cam->position[0], cam->position[1], cam->position[2]);
+    v3 a = v3scale(v3scale(right, cam->pixelLength[0]), (sx - (float)cam->resolution[0] * 0.5f));
+    v3 b = v3scale(v3scale(up, cam->pixelLength[1]), (sy - (float)cam->resolution[1] * 0.5f));
+    r.d = v3normalize(v3sub(v3sub(view, a), b));
+    if (lens->lensRadius > 0.0f) {
+        float rad = lens->lensRadius * sqrtf(u01(&rng));
+        float phi = u01(&rng) * TWO_PI_F;
+        float lx = rad * cosf(phi), ly = rad * sinf(phi);
+        float ft = lens->focalDistance / v3dot(r.d, view);
+        v3 focus = v3add(r.o, v3scale(r.d, ft));
+        r.o = v3add(v3add(r.o, v3scale(right, lx)), v3scale(up, ly));
+        r.d = v3normalize(v3sub(focus, r.o));
+    }
+    return r;
+}
+
+/* the tangent frame and combination of src/interactions.h:21-41 for a given cos(theta) = up */
+static v3 lobeDirection(v3 normal, float up, float over, float around) {
+    v3 notNormal;
+    if (fabsf(normal.x) < SQRT_OF_ONE_THIRD_F) notNormal = V3(1, 0, 0);
+    else if (fabsf(normal.y) < SQRT_OF_ONE_THIRD_F) notNormal = V3(0, 1, 0);
+    else notNormal = V3(0, 0, 1);
+    v3 p1 = v3normalize(v3cross(normal, notNormal));
+    v3 p2 = v3normalize(v3cross(normal, p1));
+    v3 a = v3scale(normal, up);
+    v3 b = v3scale(p1, cosf(around) * over);
+    v3 c = v3scale(p2, sinf(around) * over);
+    return v3add(v3add(a, b), c);
+}
+
+/* Imperfect specular (INSTRUCTION.md:202-216; GPU Gems 3 ch. 20, eq. 7-9): a direction around `axis`
+ * (unit) with cos(theta) = u1^(1/(n+1)), phi = 2 pi u2 -- two draws, in that order. */
+static v3 phongLobe(v3 axis, float exponent, Rng *rng) {
+    float up = powf(u01(rng), 1.0f / (exponent + 1.0f));
+    float s = 1 - up * up;
+    float over = s > 0.0f ? sqrtf(s) : 0.0f;
+    float around = u01(rng) * TWO_PI_F;
+    return lobeDirection(axis, up, over, around);
+}
+
 /* src/interactions.h:10-42 */
 static v3 hemisphere(v3 normal, Rng *rng) {
     float up = sqrtf(u01(rng));
@@ -695,7 +753,14 @@ static void scatter(ORay *ray, v3 *color, float t, v3 n, int outside, const OrcM
             *color = v3mul(*color, V3(m->color[0], m->color[1], m->color[2]));
         }
     } else if (mode == ORC_MODE_FULL && m->hasReflective > 0.0f) {
-        ray->d = reflect3(ray->d, n);
+        v3 R = reflect3(ray->d, n);
+        if (m->specExponent > 0.0f) {
+            /* SPECEX n > 0: Phong lobe around the mirror direction; a sample that dips below the
+             * surface is mirrored back above it */
+            R = phongLobe(v3normalize(R), m->specExponent, rng);
+            if (v3dot(R, n) < 0.0f) R = reflect3(R, n);
+        }
+        ray->d = R;
         ray->o = P;
         *color = v3mul(*color, V3(m->specColor[0], m->specColor[1], m->specColor[2]));
     } else {
@@ -745,6 +810,18 @@ void orc_generate_rays(const OrcCamera *cam, float *origins, float *dirs) {
         }
 }
 
+void orc_generate_rays_lens(const OrcCamera *cam, const OrcLens *lens, int iter, float *origins, float *dirs) {
+    const int W = cam->resolution[0], H = cam->resolution[1];
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            ORay r = cameraRayLens(cam, lens, x, y, iter);
+            size_t i = (size_t)x + (size_t)y * (size_t)W;
+            st3(origins + 3 * i, r.o);
+            st3(dirs + 3 * i, r.d);
+        }
+}
+
 void orc_closest_hit(const OrcGeom *geoms, int ngeoms, const float *origins, const float *dirs,
                      int n, int *hit, float *t, float *normal, int *outside) {
 #pragma omp parallel for schedule(dynamic, 1024)
@@ -785,6 +862,14 @@ long long orc_render(const OrcGeom *geoms, int ngeoms, const OrcMaterial *materi
                      const OrcCamera *cam, int traceDepth, int mode,
                      int iterBegin, int nIters, float *image, long long *alivePerDepth,
                      int nthreads) {
+    return orc_render_lens(geoms, ngeoms, materials, nmaterials, cam, NULL, traceDepth, mode, iterBegin, nIters,
+                           image, alivePerDepth, nthreads);
+}
+
+long long orc_render_lens(const OrcGeom *geoms, int ngeoms, const OrcMaterial *materials, int nmaterials,
+                          const OrcCamera *cam, const OrcLens *lens, int traceDepth, int mode,
+                          int iterBegin, int nIters, float *image, long long *alivePerDepth,
+                          int nthreads) {
     (void)nmaterials;
     const int W = cam->resolution[0], H = cam->resolution[1];
     const int nd = traceDepth > 0 ? traceDepth : 1;
@@ -805,7 +890,7 @@ long long orc_render(const OrcGeom *geoms, int ngeoms, const OrcMaterial *materi
                 const int index = x + y * W;                          /* src/pathtrace.cu:128 */
                 for (int it = 0; it < nIters; it++) {
                     const int iter = iterBegin + it;
-                    ORay ray = cameraRay(cam, x, y);
+                    ORay ray = cameraRayLens(cam, lens, x, y, iter);
                     v3 color = V3(1.0f, 1.0f, 1.0f);                  /* src/pathtrace.cu:132 */
                     int remaining = traceDepth;                       /* src/pathtrace.cu:141 */
                     int depth = 0;

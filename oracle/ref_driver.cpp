@@ -105,6 +105,52 @@ static inline Ray cameraRay(const Camera &cam, int x, int y) {
     return r;
 }
 
+/* Camera ray with the OrcLens extensions (orc_api.h); same formulas as pt_oracle.c::cameraRayLens, written
+ * with the reference's glm / thrust calls. */
+static inline Ray cameraRayLens(const Camera &cam, const OrcLens *lens, int x, int y, int iter) {
+    if (!lens || (!lens->antialias && !(lens->lensRadius > 0.0f))) return cameraRay(cam, x, y);
+    thrust::default_random_engine rng = seededEngine(iter, x + y * cam.resolution.x, ORC_RAYGEN_DEPTH_KEY);
+    thrust::uniform_real_distribution<float> u01(0, 1);
+    float sx = (float)x, sy = (float)y;
+    if (lens->antialias) {
+        sx = sx + (u01(rng) - 0.5f);
+        sy = sy + (u01(rng) - 0.5f);
+    }
+    Ray r;
+    r.origin = cam.position;
+    r.direction = glm::normalize(cam.view
+        - cam.right * cam.pixelLength.x * (sx - (float)cam.resolution.x * 0.5f)
+        - cam.up * cam.pixelLength.y * (sy - (float)cam.resolution.y * 0.5f));
+    if (lens->lensRadius > 0.0f) {
+        float rad = lens->lensRadius * sqrtf(u01(rng));
+        float phi = u01(rng) * TWO_PI;
+        float lx = rad * cosf(phi), ly = rad * sinf(phi);
+        float ft = lens->focalDistance / glm::dot(r.direction, cam.view);
+        glm::vec3 focus = r.origin + r.direction * ft;
+        r.origin = r.origin + cam.right * lx + cam.up * ly;
+        r.direction = glm::normalize(focus - r.origin);
+    }
+    return r;
+}
+
+/* Imperfect specular lobe (INSTRUCTION.md:202-216; GPU Gems 3 ch. 20 eq. 7-9): the tangent frame and the
+ * combination are those of calculateRandomDirectionInHemisphere (src/interactions.h:21-41) with
+ * cos(theta) = u1^(1/(n+1)) in place of sqrt(u1). */
+static inline glm::vec3 phongLobe(const glm::vec3 &axis, float exponent, thrust::default_random_engine &rng) {
+    thrust::uniform_real_distribution<float> u01(0, 1);
+    float up = powf(u01(rng), 1.0f / (exponent + 1.0f));
+    float s = 1 - up * up;
+    float over = s > 0.0f ? sqrtf(s) : 0.0f;
+    float around = u01(rng) * TWO_PI;
+    glm::vec3 directionNotNormal;
+    if (abs(axis.x) < SQRT_OF_ONE_THIRD) directionNotNormal = glm::vec3(1, 0, 0);
+    else if (abs(axis.y) < SQRT_OF_ONE_THIRD) directionNotNormal = glm::vec3(0, 1, 0);
+    else directionNotNormal = glm::vec3(0, 0, 1);
+    glm::vec3 p1 = glm::normalize(glm::cross(axis, directionNotNormal));
+    glm::vec3 p2 = glm::normalize(glm::cross(axis, p1));
+    return up * axis + cos(around) * over * p1 + sin(around) * over * p2;
+}
+
 /* The scatterRay body the reference leaves empty (src/interactions.h:44-79), per SURVEY.md section 9.
  * Returns nothing; updates ray + colour in place.  `t` is the hit distance along `ray`. */
 static inline void scatter(Ray &ray, glm::vec3 &color, float t, const glm::vec3 &n, bool outside,
@@ -141,7 +187,12 @@ static inline void scatter(Ray &ray, glm::vec3 &color, float t, const glm::vec3 
             color *= m.color;
         }
     } else if (mode == ORC_MODE_FULL && m.hasReflective > 0.0f) {
-        ray.direction = glm::reflect(ray.direction, n);
+        glm::vec3 R = glm::reflect(ray.direction, n);
+        if (m.specular.exponent > 0.0f) {
+            R = phongLobe(glm::normalize(R), m.specular.exponent, rng);
+            if (glm::dot(R, n) < 0.0f) R = glm::reflect(R, n);
+        }
+        ray.direction = R;
         ray.origin = P;
         color *= m.specular.color;
     } else {
@@ -274,6 +325,20 @@ void orc_generate_rays(const OrcCamera *ocam, float *origins, float *dirs) {
         }
 }
 
+void orc_generate_rays_lens(const OrcCamera *ocam, const OrcLens *lens, int iter, float *origins, float *dirs) {
+    Camera cam;
+    memcpy(&cam, ocam, sizeof(Camera));
+    const int W = cam.resolution.x, H = cam.resolution.y;
+#pragma omp parallel for schedule(static)
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            Ray r = cameraRayLens(cam, lens, x, y, iter);
+            size_t i = (size_t)x + (size_t)y * W;
+            put3(origins + 3 * i, r.origin);
+            put3(dirs + 3 * i, r.direction);
+        }
+}
+
 void orc_closest_hit(const OrcGeom *ogeoms, int ngeoms, const float *origins, const float *dirs,
                      int n, int *hit, float *t, float *normal, int *outside) {
     const Geom *geoms = (const Geom *)ogeoms;
@@ -325,6 +390,14 @@ long long orc_render(const OrcGeom *ogeoms, int ngeoms, const OrcMaterial *omats
                      const OrcCamera *ocam, int traceDepth, int mode,
                      int iterBegin, int nIters, float *image, long long *alivePerDepth,
                      int nthreads) {
+    return orc_render_lens(ogeoms, ngeoms, omats, nmaterials, ocam, NULL, traceDepth, mode, iterBegin, nIters,
+                           image, alivePerDepth, nthreads);
+}
+
+long long orc_render_lens(const OrcGeom *ogeoms, int ngeoms, const OrcMaterial *omats, int nmaterials,
+                          const OrcCamera *ocam, const OrcLens *lens, int traceDepth, int mode,
+                          int iterBegin, int nIters, float *image, long long *alivePerDepth,
+                          int nthreads) {
     (void)nmaterials;
     const Geom *geoms = (const Geom *)ogeoms;
     const Material *materials = (const Material *)omats;
@@ -348,7 +421,7 @@ long long orc_render(const OrcGeom *ogeoms, int ngeoms, const OrcMaterial *omats
                 const int index = x + y * W;                       /* src/pathtrace.cu:128 */
                 for (int it = 0; it < nIters; it++) {
                     const int iter = iterBegin + it;
-                    Ray ray = cameraRay(cam, x, y);
+                    Ray ray = cameraRayLens(cam, lens, x, y, iter);
                     glm::vec3 color(1.0f, 1.0f, 1.0f);             /* src/pathtrace.cu:132 */
                     int remaining = traceDepth;                    /* src/pathtrace.cu:141 */
                     int depth = 0;

@@ -48,8 +48,9 @@ class PtbSceneDesc(C.Structure):
 class PtbOptions(C.Structure):
     _fields_ = [("device", C.c_int32), ("bsdfMode", C.c_int32), ("pipeline", C.c_int32), ("accel", C.c_int32),
                 ("batchIters", C.c_int32), ("compaction", C.c_int32), ("sortMaterials", C.c_int32),
-                ("firstBounceCache", C.c_int32), ("useGraphs", C.c_int32), ("reserved0", C.c_int32),
-                ("stream", C.c_void_p), ("externalAccum", C.c_void_p)]
+                ("firstBounceCache", C.c_int32), ("useGraphs", C.c_int32), ("antialias", C.c_int32),
+                ("stream", C.c_void_p), ("externalAccum", C.c_void_p),
+                ("lensRadius", C.c_float), ("focalDistance", C.c_float)]
 
 
 class PtbStats(C.Structure):
@@ -67,7 +68,7 @@ class PtbError(RuntimeError):
 ABI_SYMBOLS = [
     "ptb_default_options", "ptb_last_error", "ptb_abi_version", "ptb_create", "ptb_update_scene", "ptb_destroy",
     "ptb_pathtrace", "ptb_render", "ptb_download", "ptb_write_pbo", "ptb_reset", "ptb_sync",
-    "ptb_stats", "ptb_accum_device_ptr", "ptb_resolve_rgb8", "ptb_stage_raygen", "ptb_stage_intersect",
+    "ptb_stats", "ptb_accum_device_ptr", "ptb_resolve_rgb8", "ptb_stage_raygen", "ptb_stage_raygen_iter", "ptb_stage_intersect",
     "ptb_stage_shade", "ptb_stage_compact", "ptb_stage_sort_keys", "ptb_stage_rng", "ptb_stage_arith",
     "ptb_scene_load", "ptb_scene_counts", "ptb_scene_get", "ptb_scene_free", "ptb_camera_fixup",
     "ptb_save_png", "ptb_save_hdr",
@@ -98,6 +99,7 @@ def lib():
         L.ptb_accum_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
         L.ptb_resolve_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.ptb_stage_raygen.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ptb_stage_raygen_iter.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ptb_stage_intersect.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
         L.ptb_stage_shade.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 11
         L.ptb_stage_compact.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32)]
@@ -174,7 +176,7 @@ class Renderer:
 
     def __init__(self, scene, device=-1, bsdf=BSDF_FULL, pipeline=PIPELINE_FUSED, accel=ACCEL_AUTO,
                  batch_iters=0, compaction=1, sort_materials=0, first_bounce_cache=0, use_graphs=1,
-                 stream=None, external_accum=None, trace_depth=None):
+                 stream=None, external_accum=None, trace_depth=None, antialias=0, lens_radius=0.0, focal_distance=0.0):
         L = lib()
         self.scene = scene
         self.trace_depth = scene.traceDepth if trace_depth is None else int(trace_depth)
@@ -186,6 +188,7 @@ class Renderer:
         opt.firstBounceCache, opt.useGraphs = first_bounce_cache, use_graphs
         opt.stream = stream
         opt.externalAccum = external_accum
+        opt.antialias, opt.lensRadius, opt.focalDistance = int(antialias), float(lens_radius), float(focal_distance)
         self._h = C.c_void_p()
         _check(L.ptb_create(C.byref(self._h), C.byref(desc), C.byref(opt)))
 
@@ -271,10 +274,10 @@ class Renderer:
         return out
 
     # ---- stage-level entry points ----
-    def stage_raygen(self):
+    def stage_raygen(self, iteration=1):
         o = np.zeros((self.scene.pixels, 3), np.float32)
         d = np.zeros((self.scene.pixels, 3), np.float32)
-        _check(lib().ptb_stage_raygen(self._h, o.ctypes.data, d.ctypes.data))
+        _check(lib().ptb_stage_raygen_iter(self._h, int(iteration), o.ctypes.data, d.ctypes.data))
         return o, d
 
     def stage_intersect(self, origins, dirs, accel=ACCEL_AUTO):

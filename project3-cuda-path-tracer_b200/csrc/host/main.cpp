@@ -79,6 +79,9 @@ int main(int argc, char **argv) {
         else if (a == "--sort") opt.sortMaterials = 1;
         else if (a == "--no-compaction") opt.compaction = 0;
         else if (a == "--quiet") quiet = true;
+        else if (a == "--cache-first-bounce") opt.firstBounceCache = 1;
+        else if (a == "--aa") opt.antialias = 1;                                        // stochastic antialiasing
+        else if (a == "--lens") { opt.lensRadius = (float)atof(next()); opt.focalDistance = (float)atof(next()); }   // --lens RADIUS FOCAL_DISTANCE
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
     }
     opt.batchIters = perIteration ? 1 : batch;

@@ -65,6 +65,7 @@ struct PtbContext {
     int pixBits = 0;
     int batch = 1;                       // slots per wavefront
     bool useBvh = false;
+    bool ext = false;                    // camera / material extensions in use: the EXT kernel instantiations run
     std::vector<int> sceneMaterial;      // scene geom index -> material id
     std::vector<int> slotOfScene;
     DevBuf<GeomRec> geoms;
@@ -227,7 +228,14 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     const PtbCamera &cam = scene->camera;
     hdr->cam = CameraParams{cam.position[0], cam.position[1], cam.position[2], cam.view[0], cam.view[1], cam.view[2],
                             cam.up[0], cam.up[1], cam.up[2], cam.right[0], cam.right[1], cam.right[2],
-                            cam.pixelLength[0], cam.pixelLength[1], c->W, c->H};
+                            cam.pixelLength[0], cam.pixelLength[1], c->W, c->H,
+                            c->opt.antialias ? 1 : 0, c->opt.lensRadius > 0.0f ? c->opt.lensRadius : 0.0f, c->opt.focalDistance};
+    // the EXT instantiations are needed for a jittered / thin-lens camera and for imperfect-specular materials
+    bool ext = c->opt.antialias || c->opt.lensRadius > 0.0f;
+    if (c->opt.bsdfMode == PTB_BSDF_FULL)
+        for (int i = 0; i < M; ++i) ext = ext || (scene->materials[i].hasReflective > 0.0f && scene->materials[i].specularExponent > 0.0f);
+    if (ext != c->ext && c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }   // other kernels: re-capture
+    c->ext = ext;
     hdr->numNodes = c->numNodes; hdr->smemNodes = c->smemNodes;
 
     CU(cudaMemcpyAsync(c->geomsScene.p, bruteOrder, bytesGeoms, cudaMemcpyHostToDevice, c->stream));
@@ -242,7 +250,8 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
 
 // ---- launch sequences -------------------------------------------------------------------------
 // fused: traceDepth bounce kernels + the advance kernel.  Buffers ping-pong per bounce.
-int launchFusedBatch(PtbContext *c) {
+template <bool EXT>
+void launchFusedBounces(PtbContext *c) {
     const size_t smem = c->useBvh ? c->smemBvh : c->smemBrute;
     for (int d = 0; d < c->traceDepth; ++d) {
         // bounce d reads buffer (d-1)&1... bounce 0 reads nothing and writes buffer 0
@@ -251,18 +260,22 @@ int launchFusedBatch(PtbContext *c) {
             // closest hit first (persistent threads, dynamic ray fetch), then shade / scatter / compact
             const bool cached = d == 0 && p.fbTn != nullptr;
             if (!cached) {
-                if (d == 0) trace_bvh_kernel<true><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
-                else        trace_bvh_kernel<false><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+                if (d == 0) trace_bvh_kernel<true, EXT><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+                else        trace_bvh_kernel<false, false><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
                 c->launches++;
             }
-            if (d == 0) bounce_kernel<true, true><<<c->gridFused, kBlock, 0, c->stream>>>(p, d);
-            else        bounce_kernel<false, true><<<c->gridFused, kBlock, 0, c->stream>>>(p, d);
+            if (d == 0) bounce_kernel<true, true, EXT><<<c->gridFused, kBlock, 0, c->stream>>>(p, d);
+            else        bounce_kernel<false, true, EXT><<<c->gridFused, kBlock, 0, c->stream>>>(p, d);
         } else {
-            if (d == 0) bounce_kernel<true, false><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
-            else        bounce_kernel<false, false><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+            if (d == 0) bounce_kernel<true, false, EXT><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+            else        bounce_kernel<false, false, EXT><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
         }
         c->launches++;
     }
+}
+int launchFusedBatch(PtbContext *c) {
+    if (c->ext) launchFusedBounces<true>(c);
+    else        launchFusedBounces<false>(c);
     advance_kernel<<<1, 32, 0, c->stream>>>(c->ctrl.p, c->traceDepth, c->numPixels);
     c->launches++;
     cudaError_t e = cudaGetLastError();
@@ -416,6 +429,9 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     const int W = scene->camera.resolution[0], H = scene->camera.resolution[1];
     if (W <= 0 || H <= 0 || (int64_t)W * H > (1ll << 30)) return fail(PTB_ERR_INVALID, "ptb_create: bad resolution %dx%d", W, H);
     if (scene->traceDepth < 1 || scene->traceDepth > 64) return fail(PTB_ERR_INVALID, "ptb_create: traceDepth %d outside [1,64]", scene->traceDepth);
+    if (opt.firstBounceCache && (opt.antialias || opt.lensRadius > 0.0f))
+        return fail(PTB_ERR_UNSUPPORTED, "ptb_create: firstBounceCache cannot be combined with antialias / lensRadius (camera rays change every iteration)");
+    if (opt.lensRadius > 0.0f && !(opt.focalDistance > 0.0f)) return fail(PTB_ERR_INVALID, "ptb_create: lensRadius > 0 needs focalDistance > 0");
 
     int ndev = 0;
     CU(cudaGetDeviceCount(&ndev));
@@ -475,15 +491,16 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     c->smemBvh = (size_t)511 * sizeof(BvhNode);     // fixed: the node count may change in ptb_update_scene
     if (bruteBytes <= 200 * 1024) {                  // brute force is only launchable when the geoms fit in shared memory
         int rc = PTB_OK;
-        rc |= setSmem(bounce_kernel<true, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false>, c->smemBrute);
+        rc |= setSmem(bounce_kernel<true, false, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, false>, c->smemBrute);
+        rc |= setSmem(bounce_kernel<true, false, true>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, true>, c->smemBrute);
         rc |= setSmem(intersect_kernel<false>, c->smemBrute); rc |= setSmem(stage_intersect_kernel<false>, c->smemBrute);
         rc |= setSmem(fb_cache_kernel<false>, c->smemBrute);
         if (rc != PTB_OK) return bail(rc);
     }
     int occ = 0;
     const size_t smem = c->useBvh ? c->smemBvh : c->smemBrute;
-    if (c->useBvh) CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_bvh_kernel<false>, kBlock, smem));
-    else           CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, false>, kBlock, smem));
+    if (c->useBvh) CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_bvh_kernel<false, false>, kBlock, smem));
+    else           CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, false, false>, kBlock, smem));
     // 4 CTAs per resident slot: the CTA-owned segments cannot be rebalanced inside a launch, so a few
     // waves of smaller CTAs keep the tail short (measured: x1 142 us, x2 138, x4 134.5, x8 135.4, x16 142 per cornell iteration)
     int gridMult = 4;
@@ -651,13 +668,15 @@ int ptb_resolve_rgb8(PtbContext *c, int samples, uint8_t *hostRgb8) {
 }
 
 // ---- stage-level entry points ---------------------------------------------------------------------
-int ptb_stage_raygen(PtbContext *c, float *origins, float *dirs) {
+int ptb_stage_raygen(PtbContext *c, float *origins, float *dirs) { return ptb_stage_raygen_iter(c, 1, origins, dirs); }
+
+int ptb_stage_raygen_iter(PtbContext *c, int iter, float *origins, float *dirs) {
     if (!c || !origins || !dirs) return fail(PTB_ERR_INVALID, "ptb_stage_raygen: null argument");
     CU(cudaSetDevice(c->device));
     const size_t n = (size_t)c->numPixels * 3;
     DevBuf<float> o, d;
     CU(o.alloc(n)); CU(d.alloc(n));
-    stage_raygen_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(c->base, o.p, d.p);
+    stage_raygen_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(c->base, iter, o.p, d.p);
     c->launches++;
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(origins, o.p, n * 4, cudaMemcpyDeviceToHost, c->stream));

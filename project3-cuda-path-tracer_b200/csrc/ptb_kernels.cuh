@@ -60,6 +60,8 @@ struct CameraParams {
     float rx, ry, rz;            // right
     float plx, ply;              // pixelLength
     int   W, H;
+    int   aa;                    // PtbOptions::antialias
+    float lensRadius, focalDist; // PtbOptions::lensRadius / focalDistance (thin lens when lensRadius > 0)
 };
 
 struct SceneHeader {             // device-resident, rewritten by ptb_update_scene without touching launch parameters
@@ -104,6 +106,43 @@ PTB_DEV void cameraRay(const CameraParams &c, uint32_t pix, f3 &o, f3 &d) {
     f3 a = scale3(scale3(mk3(c.rx, c.ry, c.rz), c.plx), fx);
     f3 b = scale3(scale3(mk3(c.ux, c.uy, c.uz), c.ply), fy);
     d = normalize3(sub3(sub3(mk3(c.vx, c.vy, c.vz), a), b));
+}
+
+// Camera ray with the two raygen extensions the reference leaves as TODOs (src/pathtrace.cu:118-120, 134;
+// INSTRUCTION.md:109-113): stochastic antialiasing and a thin lens.  One engine per (iter, pixel), keyed by
+// kRaygenDepthKey in the depth field of makeSeededRandomEngine (bounces use 0 .. traceDepth-1 <= 63; the
+// field is 9 bits wide, src/pathtrace.cu:43).  Draws, in order: jitter x, jitter y (aa only), lens radius,
+// lens angle (lensRadius > 0 only).  Same formulas as oracle/pt_oracle.c::cameraRayLens.
+constexpr int kRaygenDepthKey = 511;
+template <bool EXT>
+PTB_DEV void cameraRayIter(const CameraParams &c, uint32_t pix, int iter, f3 &o, f3 &d) {
+    if (!EXT || (!c.aa && !(c.lensRadius > 0.0f))) { cameraRay(c, pix, o, d); return; }
+    const int y = (int)(pix / (uint32_t)c.W);
+    const int x = (int)(pix - (uint32_t)y * (uint32_t)c.W);
+    Rng rng = seedRng(iter, (int)pix, kRaygenDepthKey);
+    float sx = (float)x, sy = (float)y;
+    if (c.aa) {
+        sx = add(sx, sub(u01(rng), 0.5f));
+        sy = add(sy, sub(u01(rng), 0.5f));
+    }
+    const f3 right = mk3(c.rx, c.ry, c.rz), up = mk3(c.ux, c.uy, c.uz), view = mk3(c.vx, c.vy, c.vz);
+    o = mk3(c.px, c.py, c.pz);
+    const f3 a = scale3(scale3(right, c.plx), sub(sx, mul((float)c.W, 0.5f)));
+    const f3 b = scale3(scale3(up, c.ply), sub(sy, mul((float)c.H, 0.5f)));
+    d = normalize3(sub3(sub3(view, a), b));
+    if (c.lensRadius > 0.0f) {
+        // PBRT 6.2.3: the point in focus is o + d * focalDist / dot(d, view); the origin moves to a
+        // uniformly sampled point of the lens disc spanned by right / up
+        const float rad = mul(c.lensRadius, fsqrt(u01(rng)));
+        const float phi = mul(u01(rng), 6.2831853071795864769252867665590057683943f);
+        float sn, cs;
+        sincosf(phi, &sn, &cs);
+        const float lx = mul(rad, cs), ly = mul(rad, sn);
+        const float ft = fdiv(c.focalDist, dot3(d, view));
+        const f3 focus = add3(o, scale3(d, ft));
+        o = add3(add3(o, scale3(right, lx)), scale3(up, ly));
+        d = normalize3(sub3(focus, o));
+    }
 }
 
 struct Candidate {               // what must survive the geom loop to build the winner's normal
@@ -400,21 +439,18 @@ PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, const int sme
     }
 }
 
-struct Mat { f3 color; float emittance; f3 spec; float refl; float refr; float ior; };
+struct Mat { f3 color; float emittance; f3 spec; float refl; float refr; float ior; float specex; };
 PTB_DEV Mat loadMat(const float4 *mats, int id) {
     float4 a = __ldg(&mats[3 * id]), b = __ldg(&mats[3 * id + 1]), c = __ldg(&mats[3 * id + 2]);
     Mat m;
     m.color = mk3(a.x, a.y, a.z); m.emittance = a.w;
     m.spec = mk3(b.x, b.y, b.z); m.refl = b.w;
-    m.refr = c.x; m.ior = c.y;
+    m.refr = c.x; m.ior = c.y; m.specex = c.z;
     return m;
 }
 
-// calculateRandomDirectionInHemisphere, src/interactions.h:10-42
-PTB_DEV f3 hemisphere(f3 n, Rng &rng) {
-    float up = fsqrt(u01(rng));
-    float over = fsqrt(sub(1.0f, mul(up, up)));
-    float around = mul(u01(rng), 6.2831853071795864769252867665590057683943f);
+// the tangent frame and the combination of src/interactions.h:21-41 for a given cos(theta) = up
+PTB_DEV f3 lobeDirection(f3 n, float up, float over, float around) {
     f3 notNormal;
     if (fabsf(n.x) < 0.5773502691896257645091487805019574556476f) notNormal = mk3(1.f, 0.f, 0.f);
     else if (fabsf(n.y) < 0.5773502691896257645091487805019574556476f) notNormal = mk3(0.f, 1.f, 0.f);
@@ -425,12 +461,31 @@ PTB_DEV f3 hemisphere(f3 n, Rng &rng) {
     sincosf(around, &s, &c);      // full-precision libdevice path (no fast-math); ulp-level vs glibc
     return add3(add3(scale3(n, up), scale3(p1, mul(c, over))), scale3(p2, mul(s, over)));
 }
+// calculateRandomDirectionInHemisphere, src/interactions.h:10-42
+PTB_DEV f3 hemisphere(f3 n, Rng &rng) {
+    const float up = fsqrt(u01(rng));
+    const float over = fsqrt(sub(1.0f, mul(up, up)));
+    const float around = mul(u01(rng), 6.2831853071795864769252867665590057683943f);
+    return lobeDirection(n, up, over, around);
+}
+// Imperfect specular (INSTRUCTION.md:202-216; GPU Gems 3 ch. 20 eq. 7-9): a direction around the unit
+// `axis` with cos(theta) = u1^(1/(n+1)), phi = 2 pi u2 -- two draws, in that order (oracle: phongLobe).
+// powf is libdevice's full-precision path: ulp-level vs glibc, like sincosf above.
+PTB_DEV f3 phongLobe(f3 axis, float exponent, Rng &rng) {
+    const float up = powf(u01(rng), fdiv(1.0f, add(exponent, 1.0f)));
+    const float s = sub(1.0f, mul(up, up));
+    const float over = s > 0.0f ? fsqrt(s) : 0.0f;
+    const float around = mul(u01(rng), 6.2831853071795864769252867665590057683943f);
+    return lobeDirection(axis, up, over, around);
+}
 
 // glm::reflect, func_geometric.inl:176-179: I - N * dot(N, I) * 2
 PTB_DEV f3 reflect3(f3 I, f3 N) { return sub3(I, scale3(scale3(N, dot3(N, I)), 2.0f)); }
 
 // One shade step.  Returns true while the path stays alive; when it returns
 // false, `c` holds the radiance this path contributes (zero for a miss or an exhausted path).
+// EXT: the material extensions beyond the round-1 BSDF set are compiled in (imperfect specular, SPECEX > 0).
+template <bool EXT>
 PTB_DEV bool shadeStep(const Params &p, int depth, int iter, uint32_t pix, bool isHit, int matId,
                        float t, f3 n, int outside, f3 &o, f3 &d, f3 &c, int remainingBefore) {
     if (!isHit) { c = mk3(0.f, 0.f, 0.f); return false; }                 // src/pathtrace.cu:262-264
@@ -472,7 +527,14 @@ PTB_DEV bool shadeStep(const Params &p, int depth, int iter, uint32_t pix, bool 
             c = mul3(c, m.color);
         }
     } else if (p.bsdfMode == 1 && m.refl > 0.0f) {
-        d = reflect3(d, n);
+        f3 R = reflect3(d, n);
+        if (EXT && m.specex > 0.0f) {
+            // SPECEX n > 0: Phong lobe around the mirror direction; a sample that dips below the surface
+            // is mirrored back above it
+            R = phongLobe(normalize3(R), m.specex, rng);
+            if (dot3(R, n) < 0.0f) R = reflect3(R, n);
+        }
+        d = R;
         o = P;
         c = mul3(c, m.spec);
     } else {
@@ -568,7 +630,7 @@ constexpr int kRefillLanes = PTB_REFILL_LANES;
 #endif
 constexpr int kExactLanes = PTB_EXACT_LANES;                       // lanes that must wait before the exact test runs (unless nobody can work)
 
-template <bool FIRST>
+template <bool FIRST, bool EXT>
 __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const __grid_constant__ Params p, const int depth) {
     extern __shared__ float4 smem4[];
     __shared__ uint32_t sNextTicket;
@@ -578,6 +640,8 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const 
     const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
     CameraParams cam;
     if (FIRST) cam = p.hdr->cam;
+    int iterBase = 0, iterStride = 0;
+    if (FIRST && EXT) { iterBase = p.ctrl->iterBase; iterStride = p.ctrl->iterStride; }
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t laneBelow = (1u << lane) - 1u;
     const uint32_t segBase = blockIdx.x * p.segCap;
@@ -624,7 +688,10 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const 
                         const uint32_t tile = blockIdx.x + (k / kBlock) * gridDim.x;
                         idx = tile * kBlock + (k % kBlock);
                         have = idx < total;
-                        if (have) cameraRay(cam, idx % p.numPixels, o, d);
+                        if (have) {
+                            const uint32_t slot = idx / p.numPixels;
+                            cameraRayIter<EXT>(cam, idx - slot * p.numPixels, iterBase + (int)slot * iterStride, o, d);
+                        }
                     } else {
                         idx = segBase + k;
                         const float4 a = p.in.A[idx], b = p.in.B[idx];
@@ -751,7 +818,9 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const 
 // synchronises inside an iteration.  At bounce 0 tile t of 256 camera paths belongs to CTA t mod grid,
 // which gives every CTA a uniform sample of the image and keeps the segments balanced.
 // ------------------------------------------------------------------------------------------------
-template <bool FIRST, bool USE_BVH>
+// EXT compiles in the camera / material extensions (antialiasing, thin lens, imperfect specular); scenes
+// that use none of them run the EXT = false instantiation, which is the round-1 code path unchanged.
+template <bool FIRST, bool USE_BVH, bool EXT>
 __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __grid_constant__ Params p, const int depth) {
     extern __shared__ float4 smem4[];
     __shared__ uint32_t sNextChunk, sOutCount;
@@ -804,7 +873,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
                 slot = i / p.numPixels;
                 pix = i - slot * p.numPixels;
                 id = pix | (slot << p.pixBits);
-                cameraRay(cam, pix, o, d);
+                cameraRayIter<EXT>(cam, pix, iterBase + (int)slot * iterStride, o, d);
                 c = mk3(1.0f, 1.0f, 1.0f);                                // src/pathtrace.cu:132
             }
         } else {
@@ -857,7 +926,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
                 }
             }
             const int iter = iterBase + (int)slot * iterStride;
-            alive = shadeStep(p, depth, iter, pix, isHit, matId, best.t, n, best.outside, o, d, c, remainingBefore);
+            alive = shadeStep<EXT>(p, depth, iter, pix, isHit, matId, best.t, n, best.outside, o, d, c, remainingBefore);
             if (!alive) deposit(p, pix, c);                               // gather at termination
         }
         // CTA-local stream compaction: ballot + popc prefix, one shared-memory atomic per warp
@@ -934,7 +1003,7 @@ __global__ void __launch_bounds__(kBlock) raygen_kernel(const __grid_constant__ 
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
         const uint32_t slot = i / p.numPixels, pix = i - slot * p.numPixels;
         f3 o, d;
-        cameraRay(cam, pix, o, d);
+        cameraRayIter<true>(cam, pix, p.ctrl->iterBase + (int)slot * p.ctrl->iterStride, o, d);
         storePath(p.in, i, o, d, mk3(1.0f, 1.0f, 1.0f), pix | (slot << p.pixBits));
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) p.ctrl->counts[0] = n;
@@ -996,7 +1065,7 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(const __grid_constant__ P
             outside = (meta >> 30) & 1;
             matId = p.geoms[meta & 0x3fffffff].tag.y;
         }
-        const bool alive = shadeStep(p, depth, iterBase + (int)slot * iterStride, pix, isHit, matId, t, n, outside,
+        const bool alive = shadeStep<true>(p, depth, iterBase + (int)slot * iterStride, pix, isHit, matId, t, n, outside,
                                      o, d, c, p.traceDepth - depth);
         if (!alive) {
             if (depositAtTermination) deposit(p, pix, c);
@@ -1174,11 +1243,11 @@ __global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_co
     }
 }
 
-__global__ void __launch_bounds__(kBlock) stage_raygen_kernel(const __grid_constant__ Params p, float *origins, float *dirs) {
+__global__ void __launch_bounds__(kBlock) stage_raygen_kernel(const __grid_constant__ Params p, const int iter, float *origins, float *dirs) {
     const CameraParams cam = p.hdr->cam;
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < p.numPixels; i += gridDim.x * kBlock) {
         f3 o, d;
-        cameraRay(cam, i, o, d);
+        cameraRayIter<true>(cam, i, iter, o, d);
         origins[3 * (size_t)i] = o.x; origins[3 * (size_t)i + 1] = o.y; origins[3 * (size_t)i + 2] = o.z;
         dirs[3 * (size_t)i] = d.x; dirs[3 * (size_t)i + 1] = d.y; dirs[3 * (size_t)i + 2] = d.z;
     }
@@ -1195,7 +1264,7 @@ __global__ void __launch_bounds__(kBlock) stage_shade_kernel(const __grid_consta
         const f3 nn = mk3(normal[3 * (size_t)i], normal[3 * (size_t)i + 1], normal[3 * (size_t)i + 2]);
         const bool isHit = hit[i] >= 0;
         const int rem = remaining[i];
-        const bool alive = shadeStep(p, depth[i], iter[i], (uint32_t)pixelIndex[i], isHit, isHit ? sceneMat[hit[i]] : 0,
+        const bool alive = shadeStep<true>(p, depth[i], iter[i], (uint32_t)pixelIndex[i], isHit, isHit ? sceneMat[hit[i]] : 0,
                                      t[i], nn, outside[i], o, d, c, rem);
         // stage contract: miss / emissive -> remaining 0; scatter -> remaining - 1 (0 => colour 0)
         int newRem = 0;

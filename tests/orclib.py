@@ -21,6 +21,12 @@ CAMERA_DT = np.dtype([("resolution", "<i4", 2), ("position", "<f4", 3), ("lookAt
 assert GEOM_DT.itemsize == 236 and MATERIAL_DT.itemsize == 44 and CAMERA_DT.itemsize == 84
 
 MODE_GOLDEN_DIFFUSE, MODE_FULL = 0, 1
+RAYGEN_DEPTH_KEY = 511
+
+
+class OrcLens(C.Structure):
+    """orc_api.h OrcLens: stochastic antialiasing + thin lens"""
+    _fields_ = [("antialias", C.c_int), ("lensRadius", C.c_float), ("focalDistance", C.c_float)]
 
 _PATHS = {
     "port": os.path.join(ROOT, "oracle", "libptoracle.so"),
@@ -67,6 +73,10 @@ class Oracle:
         L.orc_render.restype = C.c_longlong
         L.orc_render.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_generate_rays_lens.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
+        L.orc_render_lens.restype = C.c_longlong
+        L.orc_render_lens.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         self.kind = L.orc_kind().decode()
 
     # ---- scene ----
@@ -112,6 +122,14 @@ class Oracle:
         self.lib.orc_generate_rays(cam.ctypes.data, o.ctypes.data, d.ctypes.data)
         return o, d
 
+    def generate_rays_lens(self, cam, iteration, antialias=0, lens_radius=0.0, focal_distance=0.0):
+        P = int(cam["resolution"][0][0]) * int(cam["resolution"][0][1])
+        o = np.zeros((P, 3), np.float32)
+        d = np.zeros((P, 3), np.float32)
+        lens = OrcLens(int(antialias), float(lens_radius), float(focal_distance))
+        self.lib.orc_generate_rays_lens(cam.ctypes.data, C.addressof(lens), int(iteration), o.ctypes.data, d.ctypes.data)
+        return o, d
+
     def closest_hit(self, geoms, o, d):
         o = np.ascontiguousarray(o, np.float32)
         d = np.ascontiguousarray(d, np.float32)
@@ -148,12 +166,19 @@ class Oracle:
                            c.ctypes.data, rem.ctypes.data)
         return o, d, c, rem
 
-    def render(self, scene, mode, iter_begin, n_iters, depth=None, image=None, nthreads=0):
+    def render(self, scene, mode, iter_begin, n_iters, depth=None, image=None, nthreads=0,
+               antialias=0, lens_radius=0.0, focal_distance=0.0):
         """Returns (image_sum[P,3] float32, alive_per_depth int64, segments)."""
         depth = scene.depth if depth is None else depth
         if image is None:
             image = np.zeros((scene.pixels, 3), np.float32)
         alive = np.zeros(max(depth, 1), np.int64)
+        if antialias or lens_radius > 0.0:
+            lens = OrcLens(int(antialias), float(lens_radius), float(focal_distance))
+            seg = self.lib.orc_render_lens(scene.geoms.ctypes.data, len(scene.geoms), scene.materials.ctypes.data,
+                                           len(scene.materials), scene.camera.ctypes.data, C.addressof(lens), depth, mode,
+                                           iter_begin, n_iters, image.ctypes.data, alive.ctypes.data, nthreads)
+            return image, alive, int(seg)
         seg = self.lib.orc_render(scene.geoms.ctypes.data, len(scene.geoms), scene.materials.ctypes.data,
                                   len(scene.materials), scene.camera.ctypes.data, depth, mode,
                                   iter_begin, n_iters, image.ctypes.data, alive.ctypes.data, nthreads)

@@ -71,6 +71,18 @@ def glass_text(**kw):
     return emit(mats, objs, name="glass", **kw)
 
 
+def glossy_text(**kw):
+    """cornell with imperfect-specular materials (REFL 1, SPECEX > 0; INSTRUCTION.md:202-216): a wide lobe
+    (SPECEX 8) on the sphere, a tight one (SPECEX 200) on a tilted box and on the back wall."""
+    mats = list(_CORNELL_MATERIALS) + [("Glossy wide", ".9 .9 .9", "8", ".9 .9 .9", "1", "0", "0", "0"),
+                                       ("Glossy tight", ".9 .8 .6", "200", ".9 .8 .6", "1", "0", "0", "0")]
+    objs = list(_CORNELL_OBJECTS)
+    objs[3] = ("Back wall", "cube", 6, "0 5 -5", "0 90 0", ".01 10 10")
+    objs[6] = ("Glossy sphere", "sphere", 5, "-1 4 -1", "0 0 0", "3 3 3")
+    objs.append(("Tilted glossy box", "cube", 6, "2.5 1.5 1", "0 30 0", "2 3 2"))
+    return emit(mats, objs, name="glossy", **kw)
+
+
 def synthetic_text(n_objects=100000, seed=565, res=(1920, 1080), depth=16, iterations=64):
     """BASELINE.json configs[4]: mixed SPHERE/CUBE scene, diffuse/REFL/REFR materials, one large
     ceiling light and a floor, horizontal -z view (the
@@ -105,7 +117,7 @@ def synthetic_text(n_objects=100000, seed=565, res=(1920, 1080), depth=16, itera
 
 def write_all(dirname, synthetic_objects=0):
     os.makedirs(dirname, exist_ok=True)
-    files = {"cornell.txt": cornell_text(), "sphere.txt": sphere_text(), "glass.txt": glass_text()}
+    files = {"cornell.txt": cornell_text(), "sphere.txt": sphere_text(), "glass.txt": glass_text(), "glossy.txt": glossy_text()}
     if synthetic_objects:
         files["synthetic.txt"] = synthetic_text(synthetic_objects)
     for name, text in files.items():

@@ -268,7 +268,9 @@ def test_first_bounce_cache_is_result_neutral(m, scene_dir, scene, accel):
     assert same_bits(out[0][0], out[1][0]) and out[0][1] == out[1][1]
     assert same_bits(out[0][2], out[1][2]) and out[0][3] == out[1][3]
     assert not same_bits(out[0][0] * (2.0 / 3.0), out[0][2])           # the moved camera really renders another image
-    assert out[1][4] == out[0][4] + 1                                   # one cache-fill launch
+    # one cache-fill launch; on BVH scenes the cached wavefronts also skip their bounce-0 trace_bvh_kernel
+    # (3 single-iteration wavefronts had run when the launch count was read)
+    assert out[1][4] == out[0][4] + 1 - (3 if accel == 2 else 0)
 
 
 def test_every_bounce_hits_bit_exact_on_gpu_rays(m, port, scene_dir):
