@@ -25,11 +25,11 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 2
+#define PTB_ABI_VERSION 3
 
 /* ---- POD mirrors of src/sceneStructs.h (byte-identical; matrices column-major like glm) ---- */
 typedef struct PtbGeom {            /* struct Geom, src/sceneStructs.h:20-29, 236 bytes */
-    int32_t type;                   /* enum GeomType: 0 = SPHERE, 1 = CUBE (src/sceneStructs.h:10-13) */
+    int32_t type;                   /* enum GeomType: 0 = SPHERE, 1 = CUBE (src/sceneStructs.h:10-13); 2 = MESH (extension, see PtbTriangle) */
     int32_t materialid;
     float   translation[3];
     float   rotation[3];
@@ -60,6 +60,13 @@ typedef struct PtbCamera {          /* struct Camera, src/sceneStructs.h:43-52, 
     float   pixelLength[2];
 } PtbCamera;
 
+/* Triangle meshes.  The scene format reserves the object type `mesh` (INSTRUCTION.md:291-293) and the
+ * assignment names glm::intersectRayTriangle for it (INSTRUCTION.md:123-127); the reference's loader and kernels
+ * implement neither.  A geom of type PTB_GEOM_MESH owns triangles[first .. first + count) of the scene's
+ * triangle array: object-space vertices under the geom's transform, counter-clockwise = front face. */
+#define PTB_GEOM_MESH 2
+typedef struct PtbTriangle { float v0[3], v1[3], v2[3]; } PtbTriangle;
+
 typedef struct PtbUchar4 { uint8_t x, y, z, w; } PtbUchar4;   /* CUDA uchar4 (the GL PBO texel) */
 
 /* What pathtraceInit reads from `Scene*` (src/pathtrace.cu:79-93): geoms, materials,
@@ -71,6 +78,10 @@ typedef struct PtbSceneDesc {
     int32_t            numMaterials;
     PtbCamera          camera;
     int32_t            traceDepth;
+    /* meshes (all three zero / NULL when no geom has type PTB_GEOM_MESH) */
+    int32_t            numTriangles;
+    const PtbTriangle *triangles;
+    const int32_t     *meshRanges;  /* 2 ints per geom: first triangle, triangle count (ignored for spheres / cubes) */
 } PtbSceneDesc;
 
 enum PtbBsdfMode {
@@ -206,6 +217,10 @@ int  ptb_scene_load(const char *path, void **sceneOut);
 int  ptb_scene_counts(void *scene, int32_t *numGeoms, int32_t *numMaterials);
 int  ptb_scene_get(void *scene, PtbGeom *geoms, PtbMaterial *materials, PtbCamera *camera,
                    int32_t *iterations, int32_t *traceDepth, char *imageName, int nameCap);
+/* triangles of the `mesh <file.obj>` objects of a loaded scene: count, then the array and the (first, count)
+ * pair of every geom (2 * numGeoms ints) */
+int  ptb_scene_mesh_counts(void *scene, int32_t *numTriangles);
+int  ptb_scene_get_meshes(void *scene, PtbTriangle *triangles, int32_t *meshRanges);
 void ptb_scene_free(void *scene);
 /* the camera rebuild main.cpp performs before the first frame (src/main.cpp:53-67, 102-120) */
 void ptb_camera_fixup(PtbCamera *camera);

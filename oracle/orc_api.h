@@ -69,6 +69,18 @@ typedef struct OrcLens {
     float lensRadius;      /* > 0: thin-lens depth of field (PBRT 6.2.3) */
     float focalDistance;   /* distance of the plane in focus, measured along cam.view */
 } OrcLens;
+/* Triangle meshes: the scene format reserves the object type `mesh` (INSTRUCTION.md:291-293) and the
+ * assignment names glm::intersectRayTriangle for it (INSTRUCTION.md:123-127); the reference's loader and
+ * kernels implement neither.  A geom with type ORC_MESH owns triangles[first .. first+count) of OrcMeshes
+ * (object-space vertices, counter-clockwise = front face), ranges = 2 ints (first, count) per geom. */
+#define ORC_MESH 2
+typedef struct OrcTriangle { float v0[3], v1[3], v2[3]; } OrcTriangle;
+typedef struct OrcMeshes {
+    const OrcTriangle *triangles;
+    int                ntriangles;
+    const int         *ranges;
+} OrcMeshes;
+
 /* depth key of the camera-ray engine: makeSeededRandomEngine(iter, index, ORC_RAYGEN_DEPTH_KEY).
  * Bounce engines use depth 0 .. traceDepth-1 <= 63; the key field is 9 bits wide (src/pathtrace.cu:43). */
 #define ORC_RAYGEN_DEPTH_KEY 511
@@ -132,11 +144,22 @@ long long orc_render(const OrcGeom *geoms, int ngeoms, const OrcMaterial *materi
                      int iterBegin, int nIters, float *image, long long *alivePerDepth,
                      int nthreads);
 
-/* orc_render with the OrcLens camera extensions (lens == NULL: identical to orc_render) */
-long long orc_render_lens(const OrcGeom *geoms, int ngeoms, const OrcMaterial *materials, int nmaterials,
-                          const OrcCamera *cam, const OrcLens *lens, int traceDepth, int mode,
-                          int iterBegin, int nIters, float *image, long long *alivePerDepth,
-                          int nthreads);
+/* orc_closest_hit over a scene with ORC_MESH geoms (meshes may be NULL when there are none).  The mesh test
+ * (authored) follows the structure of the reference's two tests: ray into object space,
+ * direction normalised there, glm::intersectRayTriangle per triangle (front winding, then the reversed
+ * winding for the back face), smallest object-space t > 0 wins with the lowest triangle index on ties,
+ * hit point = transform * getPointOnRay, normal = normalize(invTranspose * cross(e1, e2)) facing the incoming
+ * ray, returned t = world distance. */
+void  orc_closest_hit_mesh(const OrcGeom *geoms, int ngeoms, const OrcMeshes *meshes,
+                           const float *origins, const float *dirs, int n,
+                           int *hit, float *t, float *normal, int *outside);
+
+/* orc_render with the extensions: meshes and / or lens may be NULL (both NULL: identical to orc_render) */
+long long orc_render_ex(const OrcGeom *geoms, int ngeoms, const OrcMeshes *meshes,
+                        const OrcMaterial *materials, int nmaterials,
+                        const OrcCamera *cam, const OrcLens *lens, int traceDepth, int mode,
+                        int iterBegin, int nIters, float *image, long long *alivePerDepth,
+                        int nthreads);
 
 #ifdef __cplusplus
 }

@@ -611,8 +611,57 @@ static float sphereIntersectionTest(const OrcGeom *sphere, ORay r, v3 *normal, i
     return v3length(v3sub(r.o, P));
 }
 
+/* glm::intersectRayTriangle, glm/gtx/intersect.inl:29-66 of the vendored glm 0.9.6.3 (Moeller-Trumbore,
+ * back faces culled by `a < epsilon`); bary = (u, v, t) */
+static int intersectRayTriangle(v3 orig, v3 dir, v3 v0, v3 v1, v3 v2, v3 *bary) {
+    v3 e1 = v3sub(v1, v0);
+    v3 e2 = v3sub(v2, v0);
+    v3 p = v3cross(dir, e2);
+    float a = v3dot(e1, p);
+    if (a < FLT_EPSILON) return 0;
+    float f = 1.0f / a;
+    v3 s = v3sub(orig, v0);
+    bary->x = f * v3dot(s, p);
+    if (bary->x < 0.0f) return 0;
+    if (bary->x > 1.0f) return 0;
+    v3 q = v3cross(s, e1);
+    bary->y = f * v3dot(dir, q);
+    if (bary->y < 0.0f) return 0;
+    if (bary->y + bary->x > 1.0f) return 0;
+    bary->z = f * v3dot(e2, q);
+    return bary->z >= 0.0f;
+}
+
+/* The mesh test (authored, see orc_api.h), built like boxIntersectionTest / sphereIntersectionTest. */
+static float meshIntersectionTest(const OrcGeom *mesh, const OrcTriangle *tris, int count, ORay r, v3 *normal, int *outside) {
+    ORay q;
+    q.o = mulMV(mesh->inverseTransform, r.o, 1.0f);
+    q.d = v3normalize(mulMV(mesh->inverseTransform, r.d, 0.0f));
+    float tmin = FLT_MAX;
+    int best = -1, bestFront = 1;
+    for (int i = 0; i < count; i++) {
+        v3 v0 = V3(tris[i].v0[0], tris[i].v0[1], tris[i].v0[2]);
+        v3 v1 = V3(tris[i].v1[0], tris[i].v1[1], tris[i].v1[2]);
+        v3 v2 = V3(tris[i].v2[0], tris[i].v2[1], tris[i].v2[2]);
+        v3 bary = V3(0, 0, 0);
+        int front = 1;
+        int hit = intersectRayTriangle(q.o, q.d, v0, v1, v2, &bary);
+        if (!hit) { front = 0; hit = intersectRayTriangle(q.o, q.d, v0, v2, v1, &bary); }
+        if (hit && bary.z > 0.0f && bary.z < tmin) { tmin = bary.z; best = i; bestFront = front; }
+    }
+    if (best < 0) return -1;
+    v3 v0 = V3(tris[best].v0[0], tris[best].v0[1], tris[best].v0[2]);
+    v3 v1 = V3(tris[best].v1[0], tris[best].v1[1], tris[best].v1[2]);
+    v3 v2 = V3(tris[best].v2[0], tris[best].v2[1], tris[best].v2[2]);
+    v3 P = mulMV(mesh->transform, getPointOnRay(q, tmin), 1.0f);
+    v3 n = v3normalize(mulMV(mesh->invTranspose, v3cross(v3sub(v1, v0), v3sub(v2, v0)), 0.0f));
+    *normal = bestFront ? n : v3neg(n);
+    *outside = bestFront;
+    return v3length(v3sub(r.o, P));
+}
+
 /* src/pathtrace.cu:162-211: strictly smaller t wins => lowest index wins ties */
-static int closestHit(const OrcGeom *geoms, int ngeoms, ORay ray, float *tOut, v3 *nOut, int *outsideOut) {
+static int closestHit(const OrcGeom *geoms, int ngeoms, const OrcMeshes *meshes, ORay ray, float *tOut, v3 *nOut, int *outsideOut) {
     float t_min = FLT_MAX;
     int hit = -1, outside = 1, hitOutside = 1;
     v3 normal = V3(0, 0, 0), tmpN = V3(0, 0, 0);
@@ -620,6 +669,8 @@ static int closestHit(const OrcGeom *geoms, int ngeoms, ORay ray, float *tOut, v
         float t = -1.0f;
         if (geoms[i].type == 1) t = boxIntersectionTest(&geoms[i], ray, &tmpN, &outside);
         else if (geoms[i].type == 0) t = sphereIntersectionTest(&geoms[i], ray, &tmpN, &outside);
+        else if (geoms[i].type == ORC_MESH && meshes)
+            t = meshIntersectionTest(&geoms[i], meshes->triangles + meshes->ranges[2 * i], meshes->ranges[2 * i + 1], ray, &tmpN, &outside);
         if (t > 0.0f && t_min > t) {
             t_min = t; hit = i; normal = tmpN; hitOutside = outside;
         }
@@ -824,11 +875,17 @@ void orc_generate_rays_lens(const OrcCamera *cam, const OrcLens *lens, int iter,
 
 void orc_closest_hit(const OrcGeom *geoms, int ngeoms, const float *origins, const float *dirs,
                      int n, int *hit, float *t, float *normal, int *outside) {
+    orc_closest_hit_mesh(geoms, ngeoms, NULL, origins, dirs, n, hit, t, normal, outside);
+}
+
+void orc_closest_hit_mesh(const OrcGeom *geoms, int ngeoms, const OrcMeshes *meshes,
+                          const float *origins, const float *dirs, int n,
+                          int *hit, float *t, float *normal, int *outside) {
 #pragma omp parallel for schedule(dynamic, 1024)
     for (int i = 0; i < n; i++) {
         ORay r; r.o = ld3(origins + 3 * (size_t)i); r.d = ld3(dirs + 3 * (size_t)i);
         float tt; v3 nn; int oo;
-        hit[i] = closestHit(geoms, ngeoms, r, &tt, &nn, &oo);
+        hit[i] = closestHit(geoms, ngeoms, meshes, r, &tt, &nn, &oo);
         t[i] = tt; st3(normal + 3 * (size_t)i, nn); outside[i] = oo;
     }
 }
@@ -862,14 +919,15 @@ long long orc_render(const OrcGeom *geoms, int ngeoms, const OrcMaterial *materi
                      const OrcCamera *cam, int traceDepth, int mode,
                      int iterBegin, int nIters, float *image, long long *alivePerDepth,
                      int nthreads) {
-    return orc_render_lens(geoms, ngeoms, materials, nmaterials, cam, NULL, traceDepth, mode, iterBegin, nIters,
-                           image, alivePerDepth, nthreads);
+    return orc_render_ex(geoms, ngeoms, NULL, materials, nmaterials, cam, NULL, traceDepth, mode, iterBegin, nIters,
+                         image, alivePerDepth, nthreads);
 }
 
-long long orc_render_lens(const OrcGeom *geoms, int ngeoms, const OrcMaterial *materials, int nmaterials,
-                          const OrcCamera *cam, const OrcLens *lens, int traceDepth, int mode,
-                          int iterBegin, int nIters, float *image, long long *alivePerDepth,
-                          int nthreads) {
+long long orc_render_ex(const OrcGeom *geoms, int ngeoms, const OrcMeshes *meshes,
+                        const OrcMaterial *materials, int nmaterials,
+                        const OrcCamera *cam, const OrcLens *lens, int traceDepth, int mode,
+                        int iterBegin, int nIters, float *image, long long *alivePerDepth,
+                        int nthreads) {
     (void)nmaterials;
     const int W = cam->resolution[0], H = cam->resolution[1];
     const int nd = traceDepth > 0 ? traceDepth : 1;
@@ -898,7 +956,7 @@ long long orc_render_lens(const OrcGeom *geoms, int ngeoms, const OrcMaterial *m
                         myAlive[depth]++;
                         mySeg++;
                         float t; v3 n; int outside;
-                        int hit = closestHit(geoms, ngeoms, ray, &t, &n, &outside);
+                        int hit = closestHit(geoms, ngeoms, meshes, ray, &t, &n, &outside);
                         int mid = hit < 0 ? 0 : geoms[hit].materialid;
                         int go = shadeStep(materials, mode, hit, mid, t, n, outside, iter, index, depth,
                                            &ray, &color, &remaining);

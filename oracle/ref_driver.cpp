@@ -30,6 +30,7 @@
 #include "intersections.h"
 #include "interactions.h"
 #include <glm/gtc/matrix_inverse.hpp>
+#include <glm/gtx/intersect.hpp>    /* glm::intersectRayTriangle, the function INSTRUCTION.md:123-127 names for meshes */
 
 #include <cfloat>
 #include <cstring>
@@ -58,8 +59,35 @@ static thrust::default_random_engine seededEngine(int iter, int index, int depth
 static inline glm::vec3 v3(const float *p) { return glm::vec3(p[0], p[1], p[2]); }
 static inline void put3(float *p, const glm::vec3 &v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
 
+/* The mesh test (authored, see orc_api.h) written like the reference writes its two tests
+ * (src/intersections.h:48-144), on the vendored glm::intersectRayTriangle. */
+static float meshIntersectionTest(const Geom &mesh, const OrcTriangle *tris, int count, const Ray &r,
+                                  glm::vec3 &intersectionPoint, glm::vec3 &normal, bool &outside) {
+    Ray q;
+    q.origin = multiplyMV(mesh.inverseTransform, glm::vec4(r.origin, 1.0f));
+    q.direction = glm::normalize(multiplyMV(mesh.inverseTransform, glm::vec4(r.direction, 0.0f)));
+    float tmin = FLT_MAX;
+    int best = -1;
+    bool bestFront = true;
+    for (int i = 0; i < count; i++) {
+        glm::vec3 v0 = v3(tris[i].v0), v1 = v3(tris[i].v1), v2 = v3(tris[i].v2);
+        glm::vec3 bary(0.0f);
+        bool front = true;
+        bool hit = glm::intersectRayTriangle(q.origin, q.direction, v0, v1, v2, bary);
+        if (!hit) { front = false; hit = glm::intersectRayTriangle(q.origin, q.direction, v0, v2, v1, bary); }
+        if (hit && bary.z > 0.0f && bary.z < tmin) { tmin = bary.z; best = i; bestFront = front; }
+    }
+    if (best < 0) return -1;
+    glm::vec3 v0 = v3(tris[best].v0), v1 = v3(tris[best].v1), v2 = v3(tris[best].v2);
+    intersectionPoint = multiplyMV(mesh.transform, glm::vec4(getPointOnRay(q, tmin), 1.0f));
+    glm::vec3 n = glm::normalize(multiplyMV(mesh.invTranspose, glm::vec4(glm::cross(v1 - v0, v2 - v0), 0.0f)));
+    normal = bestFront ? n : -n;
+    outside = bestFront;
+    return glm::length(r.origin - intersectionPoint);
+}
+
 /* src/pathtrace.cu:162-211 */
-static int closestHit(const Geom *geoms, int ngeoms, const Ray &ray,
+static int closestHit(const Geom *geoms, int ngeoms, const OrcMeshes *meshes, const Ray &ray,
                       float &tOut, glm::vec3 &nOut, bool &outsideOut) {
     float t;
     glm::vec3 normal;
@@ -75,6 +103,9 @@ static int closestHit(const Geom *geoms, int ngeoms, const Ray &ray,
             t = boxIntersectionTest(geom, ray, tmp_intersect, tmp_normal, outside);
         } else if (geom.type == SPHERE) {
             t = sphereIntersectionTest(geom, ray, tmp_intersect, tmp_normal, outside);
+        } else if ((int)geom.type == ORC_MESH && meshes) {
+            t = meshIntersectionTest(geom, meshes->triangles + meshes->ranges[2 * i], meshes->ranges[2 * i + 1], ray,
+                                     tmp_intersect, tmp_normal, outside);
         }
         if (t > 0.0f && t_min > t) {
             t_min = t;
@@ -341,6 +372,12 @@ void orc_generate_rays_lens(const OrcCamera *ocam, const OrcLens *lens, int iter
 
 void orc_closest_hit(const OrcGeom *ogeoms, int ngeoms, const float *origins, const float *dirs,
                      int n, int *hit, float *t, float *normal, int *outside) {
+    orc_closest_hit_mesh(ogeoms, ngeoms, NULL, origins, dirs, n, hit, t, normal, outside);
+}
+
+void orc_closest_hit_mesh(const OrcGeom *ogeoms, int ngeoms, const OrcMeshes *meshes,
+                          const float *origins, const float *dirs, int n,
+                          int *hit, float *t, float *normal, int *outside) {
     const Geom *geoms = (const Geom *)ogeoms;
 #pragma omp parallel for schedule(dynamic, 1024)
     for (int i = 0; i < n; i++) {
@@ -348,7 +385,7 @@ void orc_closest_hit(const OrcGeom *ogeoms, int ngeoms, const float *origins, co
         r.origin = v3(origins + 3 * (size_t)i);
         r.direction = v3(dirs + 3 * (size_t)i);
         float tt; glm::vec3 nn; bool oo;
-        hit[i] = closestHit(geoms, ngeoms, r, tt, nn, oo);
+        hit[i] = closestHit(geoms, ngeoms, meshes, r, tt, nn, oo);
         t[i] = tt;
         put3(normal + 3 * (size_t)i, nn);
         outside[i] = oo ? 1 : 0;
@@ -390,14 +427,15 @@ long long orc_render(const OrcGeom *ogeoms, int ngeoms, const OrcMaterial *omats
                      const OrcCamera *ocam, int traceDepth, int mode,
                      int iterBegin, int nIters, float *image, long long *alivePerDepth,
                      int nthreads) {
-    return orc_render_lens(ogeoms, ngeoms, omats, nmaterials, ocam, NULL, traceDepth, mode, iterBegin, nIters,
-                           image, alivePerDepth, nthreads);
+    return orc_render_ex(ogeoms, ngeoms, NULL, omats, nmaterials, ocam, NULL, traceDepth, mode, iterBegin, nIters,
+                         image, alivePerDepth, nthreads);
 }
 
-long long orc_render_lens(const OrcGeom *ogeoms, int ngeoms, const OrcMaterial *omats, int nmaterials,
-                          const OrcCamera *ocam, const OrcLens *lens, int traceDepth, int mode,
-                          int iterBegin, int nIters, float *image, long long *alivePerDepth,
-                          int nthreads) {
+long long orc_render_ex(const OrcGeom *ogeoms, int ngeoms, const OrcMeshes *meshes,
+                        const OrcMaterial *omats, int nmaterials,
+                        const OrcCamera *ocam, const OrcLens *lens, int traceDepth, int mode,
+                        int iterBegin, int nIters, float *image, long long *alivePerDepth,
+                        int nthreads) {
     (void)nmaterials;
     const Geom *geoms = (const Geom *)ogeoms;
     const Material *materials = (const Material *)omats;
@@ -429,7 +467,7 @@ long long orc_render_lens(const OrcGeom *ogeoms, int ngeoms, const OrcMaterial *
                         myAlive[depth]++;
                         mySeg++;
                         float t; glm::vec3 n; bool outside;
-                        int hit = closestHit(geoms, ngeoms, ray, t, n, outside);
+                        int hit = closestHit(geoms, ngeoms, meshes, ray, t, n, outside);
                         int mid = hit < 0 ? 0 : geoms[hit].materialid;
                         bool go = shadeStep(materials, mode, hit, mid, t, n, outside,
                                             iter, index, depth, ray, color, remaining);

@@ -27,7 +27,9 @@ MATERIAL_DT = np.dtype([("color", "<f4", 3), ("specularExponent", "<f4"), ("spec
 CAMERA_DT = np.dtype([("resolution", "<i4", 2), ("position", "<f4", 3), ("lookAt", "<f4", 3),
                       ("view", "<f4", 3), ("up", "<f4", 3), ("right", "<f4", 3), ("fov", "<f4", 2),
                       ("pixelLength", "<f4", 2)])
-assert GEOM_DT.itemsize == 236 and MATERIAL_DT.itemsize == 44 and CAMERA_DT.itemsize == 84
+TRIANGLE_DT = np.dtype([("v0", "<f4", 3), ("v1", "<f4", 3), ("v2", "<f4", 3)])     # PtbTriangle: object-space vertices
+assert GEOM_DT.itemsize == 236 and MATERIAL_DT.itemsize == 44 and CAMERA_DT.itemsize == 84 and TRIANGLE_DT.itemsize == 36
+GEOM_SPHERE, GEOM_CUBE, GEOM_MESH = 0, 1, 2
 
 BSDF_GOLDEN_DIFFUSE, BSDF_FULL = 0, 1
 PIPELINE_FUSED, PIPELINE_STAGED = 0, 1
@@ -42,7 +44,8 @@ class PtbCamera(C.Structure):
 
 class PtbSceneDesc(C.Structure):
     _fields_ = [("geoms", C.c_void_p), ("numGeoms", C.c_int32), ("materials", C.c_void_p),
-                ("numMaterials", C.c_int32), ("camera", PtbCamera), ("traceDepth", C.c_int32)]
+                ("numMaterials", C.c_int32), ("camera", PtbCamera), ("traceDepth", C.c_int32),
+                ("numTriangles", C.c_int32), ("triangles", C.c_void_p), ("meshRanges", C.c_void_p)]
 
 
 class PtbOptions(C.Structure):
@@ -70,7 +73,7 @@ ABI_SYMBOLS = [
     "ptb_pathtrace", "ptb_render", "ptb_download", "ptb_write_pbo", "ptb_reset", "ptb_sync",
     "ptb_stats", "ptb_accum_device_ptr", "ptb_resolve_rgb8", "ptb_stage_raygen", "ptb_stage_raygen_iter", "ptb_stage_intersect",
     "ptb_stage_shade", "ptb_stage_compact", "ptb_stage_sort_keys", "ptb_stage_rng", "ptb_stage_arith",
-    "ptb_scene_load", "ptb_scene_counts", "ptb_scene_get", "ptb_scene_free", "ptb_camera_fixup",
+    "ptb_scene_load", "ptb_scene_counts", "ptb_scene_get", "ptb_scene_mesh_counts", "ptb_scene_get_meshes", "ptb_scene_free", "ptb_camera_fixup",
     "ptb_save_png", "ptb_save_hdr",
 ]
 
@@ -113,6 +116,8 @@ def lib():
             L.ptb_scene_get.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int32),
                                         C.POINTER(C.c_int32), C.c_char_p, C.c_int]
             L.ptb_scene_free.argtypes = [C.c_void_p]
+            L.ptb_scene_mesh_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int32)]
+            L.ptb_scene_get_meshes.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
             L.ptb_camera_fixup.argtypes = [C.c_void_p]
             L.ptb_save_png.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int]
             L.ptb_save_hdr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int]
@@ -128,8 +133,12 @@ def _check(rc):
 class Scene:
     """Mirror of the reference's `Scene` public members (src/scene.h:20-25): geoms, materials, state."""
 
-    def __init__(self, geoms, materials, camera, iterations=5000, trace_depth=8, image_name="image"):
+    def __init__(self, geoms, materials, camera, iterations=5000, trace_depth=8, image_name="image",
+                 triangles=None, mesh_ranges=None):
         self.geoms = np.ascontiguousarray(geoms, GEOM_DT)
+        # `mesh` objects (extension): (T, 9) object-space vertices and (G, 2) first / count per geom
+        self.triangles = np.ascontiguousarray(np.zeros((0, 9)) if triangles is None else triangles, np.float32).reshape(-1, 9)
+        self.mesh_ranges = np.ascontiguousarray(np.zeros((len(self.geoms), 2)) if mesh_ranges is None else mesh_ranges, np.int32).reshape(-1, 2)
         self.materials = np.ascontiguousarray(materials, MATERIAL_DT)
         self.camera = np.ascontiguousarray(camera, CAMERA_DT).reshape(1)
         self.iterations = int(iterations)
@@ -165,10 +174,15 @@ class Scene:
         it, dp = C.c_int32(), C.c_int32()
         name = C.create_string_buffer(256)
         L.ptb_scene_get(h, geoms.ctypes.data, mats.ctypes.data, cam.ctypes.data, C.byref(it), C.byref(dp), name, 256)
+        nt = C.c_int32()
+        L.ptb_scene_mesh_counts(h, C.byref(nt))
+        tris = np.zeros((nt.value, 9), np.float32)
+        ranges = np.zeros((ng.value, 2), np.int32)
+        L.ptb_scene_get_meshes(h, tris.ctypes.data, ranges.ctypes.data)
         L.ptb_scene_free(h)
         if fixup:
             L.ptb_camera_fixup(cam.ctypes.data)
-        return cls(geoms, mats, cam, it.value, dp.value, name.value.decode())
+        return cls(geoms, mats, cam, it.value, dp.value, name.value.decode(), tris, ranges)
 
 
 class Renderer:
@@ -193,8 +207,11 @@ class Renderer:
         _check(L.ptb_create(C.byref(self._h), C.byref(desc), C.byref(opt)))
 
     def _desc(self, scene):
-        self._keep = (scene.geoms, scene.materials)
+        self._keep = (scene.geoms, scene.materials, scene.triangles, scene.mesh_ranges)
         desc = PtbSceneDesc()
+        desc.numTriangles = len(scene.triangles)
+        desc.triangles = scene.triangles.ctypes.data if len(scene.triangles) else None
+        desc.meshRanges = scene.mesh_ranges.ctypes.data if len(scene.mesh_ranges) else None
         desc.geoms = scene.geoms.ctypes.data
         desc.numGeoms = len(scene.geoms)
         desc.materials = scene.materials.ctypes.data

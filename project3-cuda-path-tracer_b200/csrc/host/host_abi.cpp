@@ -35,6 +35,19 @@ int ptb_scene_get(void *scene, PtbGeom *geoms, PtbMaterial *materials, PtbCamera
     if (imageName && nameCap > 0) { strncpy(imageName, s->state.imageName.c_str(), (size_t)nameCap - 1); imageName[nameCap - 1] = 0; }
     return PTB_OK;
 }
+int ptb_scene_mesh_counts(void *scene, int32_t *numTriangles) {
+    if (!scene) return PTB_ERR_INVALID;
+    if (numTriangles) *numTriangles = (int32_t)static_cast<Scene *>(scene)->triangles.size();
+    return PTB_OK;
+}
+int ptb_scene_get_meshes(void *scene, PtbTriangle *triangles, int32_t *meshRanges) {
+    if (!scene) return PTB_ERR_INVALID;
+    Scene *s = static_cast<Scene *>(scene);
+    static_assert(sizeof(Triangle) == sizeof(PtbTriangle), "triangle layout");
+    if (triangles && !s->triangles.empty()) memcpy(triangles, s->triangles.data(), s->triangles.size() * sizeof(Triangle));
+    if (meshRanges && !s->meshRanges.empty()) memcpy(meshRanges, s->meshRanges.data(), s->meshRanges.size() * sizeof(int));
+    return PTB_OK;
+}
 void ptb_scene_free(void *scene) { delete static_cast<Scene *>(scene); }
 
 // The camera rebuild the app performs before the first frame: derive (zoom, phi, theta) from the

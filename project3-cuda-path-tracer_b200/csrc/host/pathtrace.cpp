@@ -37,6 +37,11 @@ void pathtraceInit(Scene *scene) {
     d.numMaterials = (int)scene->materials.size();
     memcpy(&d.camera, &scene->state.camera, sizeof(PtbCamera));
     d.traceDepth = scene->state.traceDepth;
+#ifdef PTB_SCENE_HAS_MESHES                                      // this repo's scene.h; the reference's Scene has no meshes
+    d.numTriangles = (int)scene->triangles.size();
+    d.triangles = reinterpret_cast<const PtbTriangle *>(scene->triangles.data());
+    d.meshRanges = scene->meshRanges.data();
+#endif
     PtbOptions o;
     if (g_haveOpts) o = g_opts; else ptb_default_options(&o);
     check(ptb_create(&g_ctx, &d, &o), "pathtraceInit");

@@ -3,6 +3,9 @@
 // of five fixed lines followed by EYE/LOOKAT/UP until a blank line, OBJECT blocks of a type line
 // (compared as a whole line), a material line and TRANS/ROTAT/SCALE until a blank line; ids must be
 // sequential; numbers go through atof -> float.
+// Extension: the type line `mesh <file.obj>` (the format reserves `mesh`, INSTRUCTION.md:291-293; the
+// reference's loader leaves the type uninitialised for it, src/scene.cpp:46-55) loads a Wavefront OBJ
+// (v / f records, polygons fanned into triangles) relative to the scene file's directory.
 #include "scene.h"
 #include <cstdlib>
 #include <cstring>
@@ -20,6 +23,8 @@ Scene::Scene(std::string filename, bool verbose_) : verbose(verbose_) {
     memset(&state.camera, 0, sizeof state.camera);
     state.iterations = 0; state.traceDepth = 0;
     if (verbose) std::cout << "Reading scene from " << filename << " ..." << std::endl;
+    const size_t slash = filename.find_last_of("/\\");
+    baseDir = slash == std::string::npos ? std::string() : filename.substr(0, slash + 1);
     fp_in.open(filename.c_str());
     if (!fp_in.is_open()) { if (verbose) std::cout << "Error reading from file - aborting!" << std::endl; return; }
     ok = true;
@@ -45,10 +50,22 @@ int Scene::loadGeom(std::string objectid) {                        // src/scene.
     g.type = SPHERE; g.materialid = 0;
     std::string line;
     safeGetline(fp_in, line);                                      // type line, matched whole (:46-55)
+    int firstTri = (int)triangles.size(), numTri = 0;
     if (!line.empty() && fp_in.good()) {
         if (line == "sphere") g.type = SPHERE;
         else if (line == "cube") g.type = CUBE;
+        else {
+            std::vector<std::string> tokens = tokenizeString(line);
+            if (tokens.size() > 1 && tokens[0] == "mesh") {
+                g.type = MESH;
+                const std::string path = (tokens[1][0] == '/') ? tokens[1] : baseDir + tokens[1];
+                numTri = loadObj(path, triangles);
+                if (numTri < 0) { ok = false; numTri = 0; if (verbose) std::cout << "Error reading mesh " << path << std::endl; }
+            }
+        }
     }
+    meshRanges.push_back(firstTri);
+    meshRanges.push_back(numTri);
     safeGetline(fp_in, line);                                      // "material N" (:58-63)
     if (!line.empty() && fp_in.good()) {
         std::vector<std::string> tokens = tokenizeString(line);
@@ -69,6 +86,39 @@ int Scene::loadGeom(std::string objectid) {                        // src/scene.
     g.invTranspose = glm::inverseTranspose(g.transform);
     geoms.push_back(g);
     return 1;
+}
+
+// Wavefront OBJ: `v x y z` and `f a b c ...` records (a = index, index/vt, index/vt/vn or index//vn;
+// 1-based, negative = relative to the vertices read so far); polygons become a fan around their first
+// vertex; everything else is ignored.  Returns the number of triangles appended, -1 if the file cannot be opened.
+int Scene::loadObj(const std::string &path, std::vector<Triangle> &out) {
+    std::ifstream f(path.c_str());
+    if (!f.is_open()) return -1;
+    std::vector<glm::vec3> verts;
+    int added = 0;
+    while (f.good()) {
+        std::string line;
+        safeGetline(f, line);
+        std::vector<std::string> tok = tokenizeString(line);
+        if (tok.empty()) continue;
+        if (tok[0] == "v" && tok.size() > 3) verts.push_back(vec3From(tok));
+        else if (tok[0] == "f" && tok.size() > 3) {
+            std::vector<int> idx;
+            for (size_t i = 1; i < tok.size(); ++i) {
+                int k = atoi(tok[i].c_str());                   // atoi stops at the first '/'
+                if (k < 0) k = (int)verts.size() + k; else k -= 1;
+                if (k < 0 || k >= (int)verts.size()) { idx.clear(); break; }
+                idx.push_back(k);
+            }
+            for (size_t i = 2; i < idx.size(); ++i) {
+                Triangle t;
+                t.v0 = verts[idx[0]]; t.v1 = verts[idx[i - 1]]; t.v2 = verts[idx[i]];
+                out.push_back(t);
+                ++added;
+            }
+        }
+    }
+    return added;
 }
 
 int Scene::loadCamera() {                                          // src/scene.cpp:92-151

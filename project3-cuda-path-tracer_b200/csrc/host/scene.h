@@ -13,12 +13,18 @@ private:
     int loadMaterial(std::string materialid);
     int loadGeom(std::string objectid);
     int loadCamera();
+    int loadObj(const std::string &path, std::vector<Triangle> &out);
+    std::string baseDir;      // directory of the scene file: `mesh <file.obj>` paths are relative to it
 public:
     explicit Scene(std::string filename, bool verbose = false);
     ~Scene() {}
 
     std::vector<Geom> geoms;
     std::vector<Material> materials;
+    // `mesh <file.obj>` objects (extension): all triangles, and (first, count) per geom
+#define PTB_SCENE_HAS_MESHES 1
+    std::vector<Triangle> triangles;
+    std::vector<int> meshRanges;
     RenderState state;
     bool ok = false;          // false when the file could not be opened (the reference aborts, src/scene.cpp:12-15)
     bool verbose = false;     // the reference prints 4+ lines per object (src/scene.cpp:41-62); quiet by default here

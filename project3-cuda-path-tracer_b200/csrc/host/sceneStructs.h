@@ -13,7 +13,9 @@ namespace glm = ptbglm;
 
 #define BACKGROUND_COLOR (glm::vec3(0.0f))
 
-enum GeomType { SPHERE, CUBE };
+enum GeomType { SPHERE, CUBE, MESH };      // MESH: extension (INSTRUCTION.md:291-293); the reference has SPHERE, CUBE
+
+struct Triangle { glm::vec3 v0, v1, v2; };  // object-space vertices of one mesh triangle (ptb200.h PtbTriangle)
 
 struct Ray { glm::vec3 origin; glm::vec3 direction; };
 

@@ -77,6 +77,8 @@ struct PtbContext {
     DevBuf<int> sceneMatDev;
     DevBuf<SceneHeader> hdr;
     int numGeoms = 0, numMats = 0;
+    int numTriangles = 0;                // triangles of PTB_GEOM_MESH geoms
+    int numPrims = 0;                    // BVH primitives: spheres + cubes + triangles
     uint8_t *pinned = nullptr;           // pinned staging for scene uploads (H2D from pinned memory)
     size_t pinnedBytes = 0;
     int64_t h2dBytes = 0;                // bytes copied host->device by the last ptb_create / ptb_update_scene
@@ -117,13 +119,14 @@ struct PtbContext {
 
 namespace {
 
-GeomRec packGeom(const PtbGeom &g, int sceneIndex) {
+GeomRec packGeom(const PtbGeom &g, int sceneIndex, int order = -1) {
     GeomRec r;
     auto row = [](const float *m, int k) { return make_float4(m[0 + k], m[4 + k], m[8 + k], m[12 + k]); };
     r.inv.r0 = row(g.inverseTransform, 0); r.inv.r1 = row(g.inverseTransform, 1); r.inv.r2 = row(g.inverseTransform, 2);
     r.fwd.r0 = row(g.transform, 0); r.fwd.r1 = row(g.transform, 1); r.fwd.r2 = row(g.transform, 2);
     r.nrm.r0 = row(g.invTranspose, 0); r.nrm.r1 = row(g.invTranspose, 1); r.nrm.r2 = row(g.invTranspose, 2);
-    r.tag = make_int4(g.type, g.materialid, sceneIndex, 0);
+    // tag.z = position in the scene's primitive order (tie rule), tag.w = scene geom index (what a hit reports)
+    r.tag = make_int4(g.type, g.materialid, order < 0 ? sceneIndex : order, sceneIndex);
     // conservative world-space pruning bound (phase 1 of the brute-force closest hit)
     if (g.type == 1) {
         float lo[3], hi[3];
@@ -136,6 +139,29 @@ GeomRec packGeom(const PtbGeom &g, int sceneIndex) {
         r.b0 = make_float4(c[0], c[1], c[2], r2);
         r.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
     }
+    return r;
+}
+// One mesh triangle as a BVH primitive: inv / fwd of the mesh geom, the object-space vertices and the world-space
+// normal in the nrm rows, the padded world box in b0 / b1.  The normal is normalize(invTranspose * cross(e1, e2))
+// in the oracle's (glm's) float operation order -- this TU's host code is built with -ffp-contract=off.
+GeomRec packTriangle(const PtbGeom &g, const PtbTriangle &t, int sceneIndex, int order) {
+    GeomRec r = packGeom(g, sceneIndex, order);
+    r.tag.x = PTB_GEOM_MESH;
+    const float e1[3] = {t.v1[0] - t.v0[0], t.v1[1] - t.v0[1], t.v1[2] - t.v0[2]};
+    const float e2[3] = {t.v2[0] - t.v0[0], t.v2[1] - t.v0[1], t.v2[2] - t.v0[2]};
+    const float cx = e1[1] * e2[2] - e2[1] * e1[2], cy = e1[2] * e2[0] - e2[2] * e1[0], cz = e1[0] * e2[1] - e2[0] * e1[1];   // glm::cross
+    const float *m = g.invTranspose;
+    float n[3];
+    for (int k = 0; k < 3; ++k) n[k] = (m[0 + k] * cx + m[4 + k] * cy) + (m[8 + k] * cz + m[12 + k] * 0.0f);            // mat4 * vec4(c, 0)
+    const float tx = n[0] * n[0], ty = n[1] * n[1], tz = n[2] * n[2];
+    const float inv = 1.0f / sqrtf(tx + ty + tz);                                                                        // glm::normalize
+    r.nrm.r0 = make_float4(t.v0[0], t.v0[1], t.v0[2], n[0] * inv);
+    r.nrm.r1 = make_float4(t.v1[0], t.v1[1], t.v1[2], n[1] * inv);
+    r.nrm.r2 = make_float4(t.v2[0], t.v2[1], t.v2[2], n[2] * inv);
+    float lo[3], hi[3];
+    triangleBounds(g, t, lo, hi);
+    r.b0 = make_float4(lo[0], lo[1], lo[2], 0.f);
+    r.b1 = make_float4(hi[0], hi[1], hi[2], 0.f);
     return r;
 }
 // brute-force table record: a cube's padded box as [lo, hi, lo] per axis in the nine words from tag.w on
@@ -170,7 +196,14 @@ int validateScene(const PtbSceneDesc *scene) {
     if (scene->numGeoms < 0 || scene->numMaterials <= 0 || (scene->numGeoms > 0 && !scene->geoms) || !scene->materials)
         return fail(PTB_ERR_INVALID, "scene needs geoms[%d] and materials[%d]", scene->numGeoms, scene->numMaterials);
     for (int i = 0; i < scene->numGeoms; ++i) {
-        if (scene->geoms[i].type != 0 && scene->geoms[i].type != 1) return fail(PTB_ERR_INVALID, "geom %d has unknown type %d", i, scene->geoms[i].type);
+        const int ty = scene->geoms[i].type;
+        if (ty != 0 && ty != 1 && ty != PTB_GEOM_MESH) return fail(PTB_ERR_INVALID, "geom %d has unknown type %d", i, ty);
+        if (ty == PTB_GEOM_MESH) {
+            if (!scene->meshRanges || (scene->numTriangles > 0 && !scene->triangles)) return fail(PTB_ERR_INVALID, "geom %d is a mesh but the scene has no triangle arrays", i);
+            const int64_t first = scene->meshRanges[2 * i], count = scene->meshRanges[2 * i + 1];
+            if (first < 0 || count < 0 || first + count > scene->numTriangles)
+                return fail(PTB_ERR_INVALID, "geom %d: triangle range [%lld, +%lld) outside the %d triangles", i, (long long)first, (long long)count, scene->numTriangles);
+        }
         if (scene->geoms[i].materialid < 0 || scene->geoms[i].materialid >= scene->numMaterials)
             return fail(PTB_ERR_INVALID, "geom %d references material %d of %d", i, scene->geoms[i].materialid, scene->numMaterials);
     }
@@ -181,9 +214,21 @@ int validateScene(const PtbSceneDesc *scene) {
 // device on the context's stream (src/pathtrace.cu:89-93 uploads the AoS structs instead).
 int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     const int G = scene->numGeoms, M = scene->numMaterials, Gp = std::max(1, G);
-    const size_t bytesGeoms = (size_t)Gp * sizeof(GeomRec), bytesNodes = (size_t)Gp * sizeof(BvhNode);
+    // BVH primitives in scene order, the triangles of a mesh expanded in place: (geom index, triangle index or -1)
+    std::vector<std::pair<int, int>> prims;
+    prims.reserve((size_t)G + (size_t)std::max(0, scene->numTriangles));
+    for (int i = 0; i < G; ++i) {
+        if (scene->geoms[i].type == PTB_GEOM_MESH)
+            for (int k = 0; k < scene->meshRanges[2 * i + 1]; ++k) prims.emplace_back(i, scene->meshRanges[2 * i] + k);
+        else prims.emplace_back(i, -1);
+    }
+    const int P = (int)prims.size(), Pp = std::max(1, P);
+    if (P != c->numPrims) return fail(PTB_ERR_INVALID, "scene has %d primitives, the context was created for %d", P, c->numPrims);
+    const bool hasMeshes = P != G || scene->numTriangles > 0;
+    const size_t bytesBrute = hasMeshes ? 0 : (size_t)Gp * sizeof(GeomRec);
+    const size_t bytesGeoms = (size_t)Pp * sizeof(GeomRec), bytesNodes = (size_t)Pp * sizeof(BvhNode);
     const size_t bytesMats = (size_t)M * 3 * sizeof(float4), bytesSm = (size_t)Gp * sizeof(int);
-    const size_t total = 2 * bytesGeoms + bytesNodes + bytesMats + bytesSm + sizeof(SceneHeader);
+    const size_t total = bytesBrute + bytesGeoms + bytesNodes + bytesMats + bytesSm + sizeof(SceneHeader);
     if (c->pinnedBytes < total) {
         if (c->pinned) cudaFreeHost(c->pinned);
         c->pinned = nullptr; c->pinnedBytes = 0;
@@ -191,7 +236,7 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
         c->pinnedBytes = total;
     }
     uint8_t *q = c->pinned;
-    GeomRec *bruteOrder = reinterpret_cast<GeomRec *>(q); q += bytesGeoms;
+    GeomRec *bruteOrder = reinterpret_cast<GeomRec *>(q); q += bytesBrute;
     GeomRec *leafOrder = reinterpret_cast<GeomRec *>(q); q += bytesGeoms;
     BvhNode *nodes = reinterpret_cast<BvhNode *>(q); q += bytesNodes;
     float4 *mats = reinterpret_cast<float4 *>(q); q += bytesMats;
@@ -203,8 +248,10 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     for (int i = 0; i < G; ++i) sceneMat[i] = c->sceneMaterial[i] = scene->geoms[i].materialid;
     // brute-force table: cubes first, then spheres, each in scene order (tag.z keeps the scene index for the tie rule)
     int numCubes = 0;
-    for (int i = 0; i < G; ++i) if (scene->geoms[i].type == 1) bruteOrder[numCubes++] = packGeomBrute(scene->geoms[i], i);
-    for (int i = 0, k = numCubes; i < G; ++i) if (scene->geoms[i].type != 1) bruteOrder[k++] = packGeomBrute(scene->geoms[i], i);
+    if (!hasMeshes) {
+        for (int i = 0; i < G; ++i) if (scene->geoms[i].type == 1) bruteOrder[numCubes++] = packGeomBrute(scene->geoms[i], i);
+        for (int i = 0, k = numCubes; i < G; ++i) if (scene->geoms[i].type != 1) bruteOrder[k++] = packGeomBrute(scene->geoms[i], i);
+    }
     c->numCubes = numCubes;
     hdr->numCubes = numCubes;
     // the BVH is always built so that ptb_stage_intersect can compare both traversals on any scene;
@@ -212,11 +259,24 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     HostBvh hb;
     int maxLeaf = 1;                     // one primitive per leaf: its padded bound IS the leaf box (measured: 4 -> 7.28, 2 -> 6.62, 1 -> 6.29 ms per iteration of the 100k-object scene)
     if (const char *e = getenv("PTB_BVH_LEAF")) maxLeaf = std::max(1, atoi(e));                       // tuning knob (experiments)
-    buildBvh(scene->geoms, G, maxLeaf, hb);
+    {
+        std::vector<float> lo((size_t)P * 3), hi((size_t)P * 3);
+        for (int k = 0; k < P; ++k) {
+            const PtbGeom &g = scene->geoms[prims[k].first];
+            if (prims[k].second >= 0) triangleBounds(g, scene->triangles[prims[k].second], &lo[3 * (size_t)k], &hi[3 * (size_t)k]);
+            else                      geomBounds(g, &lo[3 * (size_t)k], &hi[3 * (size_t)k]);
+        }
+        buildBvhBoxes(lo.data(), hi.data(), P, maxLeaf, hb);
+    }
     static_assert(sizeof(HostBvhNode) == sizeof(BvhNode), "bvh node");
-    if ((int)hb.nodes.size() > Gp) return fail(PTB_ERR_INVALID, "BVH has %zu nodes for %d geoms", hb.nodes.size(), G);
+    if ((int)hb.nodes.size() > Pp) return fail(PTB_ERR_INVALID, "BVH has %zu nodes for %d primitives", hb.nodes.size(), P);
     memcpy(nodes, hb.nodes.data(), hb.nodes.size() * sizeof(BvhNode));
-    for (int sIdx = 0; sIdx < G; ++sIdx) leafOrder[sIdx] = packGeom(scene->geoms[hb.order[sIdx]], hb.order[sIdx]);
+    for (int sIdx = 0; sIdx < P; ++sIdx) {
+        const int k = hb.order[sIdx];
+        const PtbGeom &g = scene->geoms[prims[k].first];
+        leafOrder[sIdx] = prims[k].second >= 0 ? packTriangle(g, scene->triangles[prims[k].second], prims[k].first, k)
+                                               : packGeom(g, prims[k].first, k);
+    }
     c->numNodes = (int)hb.nodes.size();
     c->smemNodes = std::min(c->numNodes, 511);
     for (int i = 0; i < M; ++i) {
@@ -238,7 +298,7 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     c->ext = ext;
     hdr->numNodes = c->numNodes; hdr->smemNodes = c->smemNodes;
 
-    CU(cudaMemcpyAsync(c->geomsScene.p, bruteOrder, bytesGeoms, cudaMemcpyHostToDevice, c->stream));
+    if (bytesBrute) CU(cudaMemcpyAsync(c->geomsScene.p, bruteOrder, bytesBrute, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->geoms.p, leafOrder, bytesGeoms, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->bvh.p, nodes, bytesNodes, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->mats.p, mats, bytesMats, cudaMemcpyHostToDevice, c->stream));
@@ -250,7 +310,7 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
 
 // ---- launch sequences -------------------------------------------------------------------------
 // fused: traceDepth bounce kernels + the advance kernel.  Buffers ping-pong per bounce.
-template <bool EXT>
+template <bool EXT, bool MESH>
 void launchFusedBounces(PtbContext *c) {
     const size_t smem = c->useBvh ? c->smemBvh : c->smemBrute;
     for (int d = 0; d < c->traceDepth; ++d) {
@@ -260,8 +320,8 @@ void launchFusedBounces(PtbContext *c) {
             // closest hit first (persistent threads, dynamic ray fetch), then shade / scatter / compact
             const bool cached = d == 0 && p.fbTn != nullptr;
             if (!cached) {
-                if (d == 0) trace_bvh_kernel<true, EXT><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
-                else        trace_bvh_kernel<false, false><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+                if (d == 0) trace_bvh_kernel<true, EXT, MESH><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+                else        trace_bvh_kernel<false, false, MESH><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
                 c->launches++;
             }
             if (d == 0) bounce_kernel<true, true, EXT><<<c->gridFused, kBlock, 0, c->stream>>>(p, d);
@@ -274,8 +334,9 @@ void launchFusedBounces(PtbContext *c) {
     }
 }
 int launchFusedBatch(PtbContext *c) {
-    if (c->ext) launchFusedBounces<true>(c);
-    else        launchFusedBounces<false>(c);
+    const bool mesh = c->numTriangles > 0;
+    if (c->ext) { if (mesh) launchFusedBounces<true, true>(c); else launchFusedBounces<true, false>(c); }
+    else        { if (mesh) launchFusedBounces<false, true>(c); else launchFusedBounces<false, false>(c); }
     advance_kernel<<<1, 32, 0, c->stream>>>(c->ctrl.p, c->traceDepth, c->numPixels);
     c->launches++;
     cudaError_t e = cudaGetLastError();
@@ -450,6 +511,13 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     c->W = W; c->H = H; c->traceDepth = scene->traceDepth;
     c->numPixels = (uint32_t)W * (uint32_t)H;
     c->numGeoms = scene->numGeoms; c->numMats = scene->numMaterials;
+    c->numTriangles = 0;
+    for (int i = 0; i < scene->numGeoms; ++i) if (scene->geoms[i].type == PTB_GEOM_MESH) c->numTriangles += scene->meshRanges[2 * i + 1];
+    c->numPrims = scene->numGeoms + c->numTriangles;
+    for (int i = 0; i < scene->numGeoms; ++i) if (scene->geoms[i].type == PTB_GEOM_MESH) c->numPrims--;   // a mesh geom is its triangles
+    const bool hasMeshes = c->numPrims != scene->numGeoms || c->numTriangles > 0;
+    if (c->numPrims >= (1 << 27)) { const int np = c->numPrims; delete c; return fail(PTB_ERR_UNSUPPORTED, "ptb_create: %d primitives (the BVH leaf encoding holds 2^27)", np); }
+    if (hasMeshes && opt.accel == PTB_ACCEL_BRUTE) { delete c; return fail(PTB_ERR_UNSUPPORTED, "ptb_create: scenes with meshes are traced through the BVH (accel = PTB_ACCEL_BRUTE refused)"); }
     int bits = 1;
     while ((1ull << bits) < c->numPixels) ++bits;
     c->pixBits = bits;
@@ -475,12 +543,12 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     else { CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->ownStream = true; }
 
     // ---- scene upload (src/pathtrace.cu:89-93) in the device layout ----
-    c->useBvh = opt.accel == PTB_ACCEL_BVH || (opt.accel == PTB_ACCEL_AUTO && scene->numGeoms > 64);
-    const size_t bruteBytes = (size_t)std::max(1, scene->numGeoms) * sizeof(GeomRec);
+    c->useBvh = hasMeshes || opt.accel == PTB_ACCEL_BVH || (opt.accel == PTB_ACCEL_AUTO && scene->numGeoms > 64);
+    const size_t bruteBytes = hasMeshes ? (size_t)201 * 1024 : (size_t)std::max(1, scene->numGeoms) * sizeof(GeomRec);   // meshes: no brute-force table
     if (!c->useBvh && bruteBytes > 200 * 1024) c->useBvh = true;
     {
-        const size_t Gp = (size_t)std::max(1, scene->numGeoms);
-        CUB(c->geomsScene.alloc(Gp)); CUB(c->geoms.alloc(Gp)); CUB(c->bvh.alloc(Gp)); CUB(c->sceneMatDev.alloc(Gp));
+        const size_t Gp = (size_t)std::max(1, scene->numGeoms), Pp = (size_t)std::max(1, c->numPrims);
+        CUB(c->geomsScene.alloc(hasMeshes ? 1 : Gp)); CUB(c->geoms.alloc(Pp)); CUB(c->bvh.alloc(Pp)); CUB(c->sceneMatDev.alloc(Gp));
         CUB(c->mats.alloc((size_t)scene->numMaterials * 3)); CUB(c->hdr.alloc(1));
         int urc = uploadScene(c, scene);
         if (urc != PTB_OK) return bail(urc);
@@ -499,7 +567,7 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     }
     int occ = 0;
     const size_t smem = c->useBvh ? c->smemBvh : c->smemBrute;
-    if (c->useBvh) CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_bvh_kernel<false, false>, kBlock, smem));
+    if (c->useBvh) CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_bvh_kernel<false, false, false>, kBlock, smem));
     else           CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, false, false>, kBlock, smem));
     // 4 CTAs per resident slot: the CTA-owned segments cannot be rebalanced inside a launch, so a few
     // waves of smaller CTAs keep the tail short (measured: x1 142 us, x2 138, x4 134.5, x8 135.4, x16 142 per cornell iteration)
@@ -557,6 +625,9 @@ int ptb_update_scene(PtbContext *c, const PtbSceneDesc *scene) {
     if (!c || !scene) return fail(PTB_ERR_INVALID, "ptb_update_scene: null argument");
     int rc = validateScene(scene);
     if (rc != PTB_OK) return rc;
+    int tris = 0;
+    for (int i = 0; i < scene->numGeoms; ++i) if (scene->geoms[i].type == PTB_GEOM_MESH) tris += scene->meshRanges[2 * i + 1];
+    if (tris != c->numTriangles) return fail(PTB_ERR_INVALID, "ptb_update_scene: %d mesh triangles, the context was created with %d", tris, c->numTriangles);
     if (scene->numGeoms != c->numGeoms || scene->numMaterials != c->numMats || scene->camera.resolution[0] != c->W ||
         scene->camera.resolution[1] != c->H || scene->traceDepth != c->traceDepth)
         return fail(PTB_ERR_INVALID, "ptb_update_scene: geometry/material counts, resolution and depth must match ptb_create");
@@ -691,6 +762,7 @@ int ptb_stage_intersect(PtbContext *c, int accel, const float *origins, const fl
     if (!c || !origins || !dirs || !hit || !t || !normal || !outside || n < 0) return fail(PTB_ERR_INVALID, "ptb_stage_intersect: bad argument");
     CU(cudaSetDevice(c->device));
     bool bvh = accel == PTB_ACCEL_BVH || (accel == PTB_ACCEL_AUTO && c->useBvh);
+    if (!bvh && c->numPrims != c->numGeoms) return fail(PTB_ERR_UNSUPPORTED, "ptb_stage_intersect: scenes with meshes have no brute-force table");
     if (!bvh && c->smemBrute > 200 * 1024) return fail(PTB_ERR_UNSUPPORTED, "brute force needs %zu B of shared memory", c->smemBrute);
     DevBuf<float> o, d, dt, dn; DevBuf<int> dh, dout;
     CU(o.alloc((size_t)n * 3)); CU(d.alloc((size_t)n * 3)); CU(dt.alloc(n)); CU(dn.alloc((size_t)n * 3)); CU(dh.alloc(n)); CU(dout.alloc(n));

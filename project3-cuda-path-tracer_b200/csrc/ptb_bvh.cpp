@@ -50,6 +50,28 @@ void sphereBounds(const PtbGeom &g, float centre[3], float *radius2) {
     *radius2 = (float)(R * R * (1.0 + 1e-6));
 }
 
+// A mesh triangle: the reported hit point is transform * (a point 1e-4 object units short of the triangle's
+// plane along the ray), computed in float.  Pad like geomBounds: the fall-short mapped through the transform
+// (<= 1e-4 * sum|row|), rounding of the object-space round trip (relative to the object- and world-space
+// magnitudes involved) and the pruning slab test.
+void triangleBounds(const PtbGeom &g, const PtbTriangle &t, float lo[3], float hi[3]) {
+    const float *m = g.transform;                       // column-major
+    const float *v[3] = {t.v0, t.v1, t.v2};
+    double vmax = 0;
+    for (int k = 0; k < 3; ++k) for (int a = 0; a < 3; ++a) vmax = std::max(vmax, std::fabs((double)v[k][a]));
+    for (int r = 0; r < 3; ++r) {
+        double wlo = DBL_MAX, whi = -DBL_MAX;
+        for (int k = 0; k < 3; ++k) {
+            const double w = (double)m[0 + r] * v[k][0] + (double)m[4 + r] * v[k][1] + (double)m[8 + r] * v[k][2] + (double)m[12 + r];
+            wlo = std::min(wlo, w); whi = std::max(whi, w);
+        }
+        const double rowAbs = std::fabs((double)m[0 + r]) + std::fabs((double)m[4 + r]) + std::fabs((double)m[8 + r]);
+        const double pad = 4e-4 * rowAbs + 1e-3 + 2e-5 * std::max(std::fabs(wlo), std::fabs(whi)) + 2e-6 * rowAbs * vmax;
+        lo[r] = (float)(wlo - pad);
+        hi[r] = (float)(whi + pad);
+    }
+}
+
 namespace {
 struct Box {
     float lo[3], hi[3];
@@ -136,12 +158,20 @@ struct Builder {
 } // namespace
 
 void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out) {
+    std::vector<float> lo((size_t)n * 3), hi((size_t)n * 3);
+    for (int i = 0; i < n; ++i) geomBounds(geoms[i], &lo[3 * (size_t)i], &hi[3 * (size_t)i]);
+    buildBvhBoxes(lo.data(), hi.data(), n, maxLeaf, out);
+}
+
+void buildBvhBoxes(const float *lo, const float *hi, int n, int maxLeaf, HostBvh &out) {
     Builder b;
     b.maxLeaf = std::max(1, std::min(maxLeaf, 8));
     b.prims.resize(n);
     for (int i = 0; i < n; ++i) {
-        geomBounds(geoms[i], b.prims[i].box.lo, b.prims[i].box.hi);
-        for (int a = 0; a < 3; ++a) b.prims[i].cen[a] = 0.5f * (b.prims[i].box.lo[a] + b.prims[i].box.hi[a]);
+        for (int a = 0; a < 3; ++a) {
+            b.prims[i].box.lo[a] = lo[3 * (size_t)i + a]; b.prims[i].box.hi[a] = hi[3 * (size_t)i + a];
+            b.prims[i].cen[a] = 0.5f * (b.prims[i].box.lo[a] + b.prims[i].box.hi[a]);
+        }
         b.prims[i].index = i;
     }
     out.nodes.clear(); out.order.clear();

@@ -25,7 +25,12 @@ void geomBounds(const PtbGeom &g, float lo[3], float hi[3]);
 // Padded world-space bounding sphere of a SPHERE geom: centre and squared radius.
 void sphereBounds(const PtbGeom &g, float centre[3], float *radius2);
 
+// Padded world-space box of one mesh triangle (object-space vertices under the mesh geom's transform).
+void triangleBounds(const PtbGeom &mesh, const PtbTriangle &tri, float lo[3], float hi[3]);
+
 // Binned-SAH top-down build; leaves hold at most `maxLeaf` geoms.
 void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out);
+// The same over caller-supplied primitive boxes (lo / hi: n x 3 floats); order[slot] = primitive index.
+void buildBvhBoxes(const float *lo, const float *hi, int n, int maxLeaf, HostBvh &out);
 
 } // namespace ptb

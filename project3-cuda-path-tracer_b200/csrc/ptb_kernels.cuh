@@ -328,6 +328,28 @@ PTB_DEV GeomRec loadGeom(const GeomRec *gp) {
     return g;
 }
 
+// Stage C of the BVH searches: the reference-exact test of primitive `cand` (leaf-order table) and the
+// closest-hit rule.  type 2 = mesh triangle (its vertices are the record's nrm rows).
+// MESH = false compiles the triangle path out (scenes without meshes run the round-1 code).
+template <bool MESH>
+PTB_DEV void exactCandidate(const GeomRec *geoms, int cand, int candType, f3 o, f3 qo, f3 qu, Candidate &best, int &bestOrig) {
+    const float4 *gp = reinterpret_cast<const float4 *>(geoms + cand);
+    Affine fwd, vtx;
+    fwd.r0 = __ldg(gp + 3); fwd.r1 = __ldg(gp + 4); fwd.r2 = __ldg(gp + 5);
+    vtx.r0 = vtx.r1 = vtx.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int2 ord = __ldg(reinterpret_cast<const int2 *>(gp + 9) + 1);          // tag.z = scene order, tag.w = object index
+    bool sameMesh = false;
+    if (MESH && candType == 2) {
+        vtx.r0 = __ldg(gp + 6); vtx.r1 = __ldg(gp + 7); vtx.r2 = __ldg(gp + 8);
+        if (best.slot >= 0) sameMesh = __ldg(reinterpret_cast<const int *>(geoms + best.slot) + 39) == ord.y;   // word 39 = tag.w
+    }
+    int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
+    const float t = exactTestCore<MESH>(candType, fwd, vtx, o, qo, qu, outside, a, b, c);
+    if (takesOver(sameMesh, t, a, ord.x, best.t, best.a, bestOrig)) {            // src/pathtrace.cu:192 + index tie rule
+        best.t = t; best.slot = cand; best.outside = outside; best.a = a; best.b = b; best.c = c; bestOrig = ord.x;
+    }
+}
+
 // Closest hit through the flat BVH.  Warp-collective (all 32 lanes call it; `valid` = the lane carries a
 // ray).  Three kinds of work alternate, and the expensive one is entered by the lanes TOGETHER:
 //   A. traversal steps: fetch a 64-byte node (shared memory for the top levels), slab-test both child
@@ -361,7 +383,7 @@ PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, const int sme
     int primRef = 0, primCnt = 0;                                 // pending leaf: geoms[primRef .. primRef + primCnt)
     int cand = -1;                                                // primitive waiting for the exact test
     f3 qo = mk3(0.f, 0.f, 0.f), qu = qo;
-    bool candCube = false;
+    int candType = 0;
     // One warp-uniform loop; the votes at its head make the lanes reconverge EVERY step (a per-lane
     // `while` with early exits lets divergent groups drift apart for the whole traversal).
     for (;;) {
@@ -371,14 +393,7 @@ PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, const int sme
         if (waiting && (!working || __popc(waiting) >= 8)) {
             if (cand >= 0) {
                 // ---- C: the reference-exact test
-                const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + cand);
-                Affine fwd;
-                fwd.r0 = __ldg(gp + 3); fwd.r1 = __ldg(gp + 4); fwd.r2 = __ldg(gp + 5);
-                const int origIndex = __ldg(reinterpret_cast<const int *>(gp + 9) + 2);
-                int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
-                const float t = exactTestCore(candCube, fwd, o, qo, qu, outside, a, b, c);
-                const bool take = t > 0.0f && (best.t > t || (best.t == t && origIndex < bestOrig));   // src/pathtrace.cu:192 + index tie rule
-                if (take) { best.t = t; best.slot = cand; best.outside = outside; best.a = a; best.b = b; best.c = c; bestOrig = origIndex; }
+                exactCandidate<true>(p.geoms, cand, candType, o, qo, qu, best, bestOrig);
                 cand = -1;
             }
             continue;
@@ -392,13 +407,13 @@ PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, const int sme
             const int4 tag = __ldg(reinterpret_cast<const int4 *>(gp + 9));
             const float4 b0 = __ldg(gp + 10), b1 = __ldg(gp + 11);
             const bool isCube = tag.x == 1;
-            const float e = boundEntryRaw(isCube, b0, b1, o, invD, dn, rdLen);
+            const float e = boundEntryRaw(tag.x != 0, b0, b1, o, invD, dn, rdLen);       // cubes and triangles: padded world box
             if (e >= 0.0f && fmaf(e, 0.99998f, -slack) <= best.t) {
                 Affine inv;
                 inv.r0 = __ldg(gp); inv.r1 = __ldg(gp + 1); inv.r2 = __ldg(gp + 2);
                 qo = mulMVPoint(inv, o);
                 qu = mulMV(inv, d, 0.0f);
-                if (!sureMissT(isCube, qo, qu)) { cand = slot; candCube = isCube; }
+                if (tag.x == 2 || !sureMissT(isCube, qo, qu)) { cand = slot; candType = tag.x; }
             }
             continue;
         }
@@ -630,7 +645,7 @@ constexpr int kRefillLanes = PTB_REFILL_LANES;
 #endif
 constexpr int kExactLanes = PTB_EXACT_LANES;                       // lanes that must wait before the exact test runs (unless nobody can work)
 
-template <bool FIRST, bool EXT>
+template <bool FIRST, bool EXT, bool MESH>
 __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const __grid_constant__ Params p, const int depth) {
     extern __shared__ float4 smem4[];
     __shared__ uint32_t sNextTicket;
@@ -666,7 +681,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const 
     int primRef = 0, primCnt = 0;                                 // pending leaf: geoms[primRef .. primRef + primCnt)
     int cand = -1;                                                // primitive waiting for the exact test
     f3 qo = o, qu = o;
-    bool candCube = false;
+    int candType = 0;
     bool done = true;                                             // the lane holds no ray
     bool drained = false;                                         // warp-uniform: the CTA's queue is empty
     uint32_t idx = 0;                                             // hit-record index of the lane's ray
@@ -772,7 +787,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const 
             const int4 tag = __ldg(reinterpret_cast<const int4 *>(gp + 9));
             const float4 b0 = __ldg(gp + 10), b1 = __ldg(gp + 11);
             const bool isCube = tag.x == 1;
-            const float e = boundEntryRaw(isCube, b0, b1, o, invD, dn, rdLen);
+            const float e = boundEntryRaw(tag.x != 0, b0, b1, o, invD, dn, rdLen);       // cubes and triangles: padded world box
             if (e >= 0.0f && fmaf(e, 0.99998f, -slack) <= best.t) {
                 Affine inv;
                 inv.r0 = __ldg(gp); inv.r1 = __ldg(gp + 1); inv.r2 = __ldg(gp + 2);
@@ -780,7 +795,8 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const 
                 qu = mulMV(inv, d, 0.0f);
                 bool miss = boxSureMiss(qo, qu);
                 if (!isCube) miss = sphereSureMiss(qo, qu);
-                if (!miss) { cand = slot; candCube = isCube; }
+                if (MESH && tag.x == 2) miss = false;                                     // triangles go straight to the exact test
+                if (!miss) { cand = slot; candType = tag.x; }
             }
         }
         // ---- C: the reference-exact test, entered by the waiting lanes together
@@ -788,14 +804,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const 
         const unsigned working = __ballot_sync(0xffffffffu, cand < 0 && !done);
         if (waiting && (!working || __popc(waiting) >= kExactLanes)) {
             if (cand >= 0) {
-                const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + cand);
-                Affine fwd;
-                fwd.r0 = __ldg(gp + 3); fwd.r1 = __ldg(gp + 4); fwd.r2 = __ldg(gp + 5);
-                const int origIndex = __ldg(reinterpret_cast<const int *>(gp + 9) + 2);
-                int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
-                const float t = exactTestCore(candCube, fwd, o, qo, qu, outside, a, b, c);
-                const bool take = t > 0.0f && (best.t > t || (best.t == t && origIndex < bestOrig));   // src/pathtrace.cu:192 + index tie rule
-                if (take) { best.t = t; best.slot = cand; best.outside = outside; best.a = a; best.b = b; best.c = c; bestOrig = origIndex; }
+                exactCandidate<MESH>(p.geoms, cand, candType, o, qo, qu, best, bestOrig);
                 cand = -1;
             }
         }
@@ -1237,7 +1246,7 @@ __global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_co
         } else {
             const GeomRec &g = USE_BVH ? p.geoms[best.slot] : sgeoms[best.slot];
             const f3 nn = candidateNormal(g, best);
-            hit[i] = g.tag.z; t[i] = best.t; outside[i] = best.outside;
+            hit[i] = USE_BVH ? g.tag.w : g.tag.z; t[i] = best.t; outside[i] = best.outside;       // scene geom (object) index
             normal[3 * (size_t)i] = nn.x; normal[3 * (size_t)i + 1] = nn.y; normal[3 * (size_t)i + 2] = nn.z;
         }
     }

@@ -65,3 +65,12 @@ def rel_err_lit(img, ref):
     lit = (ref.max(1) > 0) | (img.max(1) > 0)
     denom = np.maximum(np.maximum(ref.max(1), img.max(1)), 1e-12)
     return np.abs(img - ref).max(1)[lit] / denom[lit], lit
+
+
+def to_oracle_scene(ms):
+    """A product-side Scene (pkg().Scene, loaded by the host C++ loader) as an orclib.Scene for the CPU checkers:
+    the POD arrays are byte-identical (src/sceneStructs.h), only the numpy field names differ."""
+    import orclib
+    return orclib.Scene(ms.geoms.view(orclib.GEOM_DT), ms.materials.view(orclib.MATERIAL_DT), ms.camera.view(orclib.CAMERA_DT),
+                        ms.iterations, ms.traceDepth, ms.imageName,
+                        ms.triangles if len(ms.triangles) else None, ms.mesh_ranges if len(ms.triangles) else None)

@@ -41,6 +41,16 @@ def main():
         out["img_%s" % tag], out["alive_%s" % tag] = img, alive
     img, alive, seg = ref.render(sc["glossy"], orclib.MODE_FULL, 1, 2)
     out["img_glossy"], out["alive_glossy"] = img, alive
+    # ---- triangle meshes: glm::intersectRayTriangle of the vendored glm, called by the
+    # reference-linked build; the scene (OBJ files included) is parsed by the product's host loader
+    from common import pkg, to_oracle_scene
+    ms = to_oracle_scene(pkg().Scene.load(scenes.mesh_scene_files(os.path.join(d, "mesh"), res=RES)))
+    o, dd = ref.generate_rays(ms.camera)
+    hit, t, n, outside = ref.closest_hit(ms.geoms, o, dd, ms)
+    out["mesh_triangles"], out["mesh_ranges"] = ms.triangles, ms.mesh_ranges
+    out["mesh_hit"], out["mesh_t"], out["mesh_n"], out["mesh_outside"] = hit.astype(np.int8), t, n, outside.astype(np.int8)
+    img, alive, seg = ref.render(ms, orclib.MODE_FULL, 1, 2)
+    out["img_mesh"], out["alive_mesh"] = img, alive
     np.savez_compressed(os.path.join(HERE, "extension_vectors.npz"), **out)
     print("wrote", os.path.join(HERE, "extension_vectors.npz"), os.path.getsize(os.path.join(HERE, "extension_vectors.npz")), "bytes")
 

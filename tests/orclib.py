@@ -24,6 +24,27 @@ MODE_GOLDEN_DIFFUSE, MODE_FULL = 0, 1
 RAYGEN_DEPTH_KEY = 511
 
 
+MESH = 2            # orc_api.h ORC_MESH
+TRIANGLE_DT = np.dtype([("v0", "<f4", 3), ("v1", "<f4", 3), ("v2", "<f4", 3)])
+
+
+class OrcMeshes(C.Structure):
+    """orc_api.h OrcMeshes: triangles + (first, count) per geom"""
+    _fields_ = [("triangles", C.c_void_p), ("ntriangles", C.c_int), ("ranges", C.c_void_p)]
+
+
+def _meshes(scene_or_pair):
+    """-> (OrcMeshes or None, keepalive): accepts a Scene with .triangles / .mesh_ranges or a (triangles, ranges) pair"""
+    if scene_or_pair is None:
+        return None, None
+    tri, rng = scene_or_pair if isinstance(scene_or_pair, tuple) else (getattr(scene_or_pair, "triangles", None), getattr(scene_or_pair, "mesh_ranges", None))
+    if tri is None or len(tri) == 0:
+        return None, None
+    tri = np.ascontiguousarray(tri, np.float32).reshape(-1, 9)
+    rng = np.ascontiguousarray(rng, np.int32).reshape(-1, 2)
+    return OrcMeshes(tri.ctypes.data, len(tri), rng.ctypes.data), (tri, rng)
+
+
 class OrcLens(C.Structure):
     """orc_api.h OrcLens: stochastic antialiasing + thin lens"""
     _fields_ = [("antialias", C.c_int), ("lensRadius", C.c_float), ("focalDistance", C.c_float)]
@@ -36,9 +57,12 @@ _PATHS = {
 
 
 class Scene:
-    def __init__(self, geoms, materials, camera, iterations, depth, name):
+    def __init__(self, geoms, materials, camera, iterations, depth, name, triangles=None, mesh_ranges=None):
         self.geoms, self.materials, self.camera = geoms, materials, camera
         self.iterations, self.depth, self.name = iterations, depth, name
+        # triangle meshes (geoms of type MESH): (T, 9) object-space vertices and (G, 2) first / count per geom
+        self.triangles = None if triangles is None else np.ascontiguousarray(triangles, np.float32).reshape(-1, 9)
+        self.mesh_ranges = None if mesh_ranges is None else np.ascontiguousarray(mesh_ranges, np.int32).reshape(-1, 2)
 
     @property
     def width(self):
@@ -74,9 +98,10 @@ class Oracle:
         L.orc_render.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                  C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_generate_rays_lens.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
-        L.orc_render_lens.restype = C.c_longlong
-        L.orc_render_lens.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
-                                      C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_render_ex.restype = C.c_longlong
+        L.orc_render_ex.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+        L.orc_closest_hit_mesh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
         self.kind = L.orc_kind().decode()
 
     # ---- scene ----
@@ -130,7 +155,8 @@ class Oracle:
         self.lib.orc_generate_rays_lens(cam.ctypes.data, C.addressof(lens), int(iteration), o.ctypes.data, d.ctypes.data)
         return o, d
 
-    def closest_hit(self, geoms, o, d):
+    def closest_hit(self, geoms, o, d, meshes=None):
+        """meshes: None, a Scene carrying .triangles / .mesh_ranges, or a (triangles, ranges) pair"""
         o = np.ascontiguousarray(o, np.float32)
         d = np.ascontiguousarray(d, np.float32)
         n = o.shape[0]
@@ -138,8 +164,9 @@ class Oracle:
         t = np.zeros(n, np.float32)
         nrm = np.zeros((n, 3), np.float32)
         outside = np.zeros(n, np.int32)
-        self.lib.orc_closest_hit(geoms.ctypes.data, len(geoms), o.ctypes.data, d.ctypes.data, n,
-                                 hit.ctypes.data, t.ctypes.data, nrm.ctypes.data, outside.ctypes.data)
+        ms, keep = _meshes(meshes)
+        self.lib.orc_closest_hit_mesh(geoms.ctypes.data, len(geoms), C.addressof(ms) if ms else None, o.ctypes.data, d.ctypes.data, n,
+                                      hit.ctypes.data, t.ctypes.data, nrm.ctypes.data, outside.ctypes.data)
         return hit, t, nrm, outside
 
     def hemisphere(self, normals, it, index, depth):
@@ -173,11 +200,13 @@ class Oracle:
         if image is None:
             image = np.zeros((scene.pixels, 3), np.float32)
         alive = np.zeros(max(depth, 1), np.int64)
-        if antialias or lens_radius > 0.0:
+        ms, keep = _meshes(scene)
+        if antialias or lens_radius > 0.0 or ms is not None:
             lens = OrcLens(int(antialias), float(lens_radius), float(focal_distance))
-            seg = self.lib.orc_render_lens(scene.geoms.ctypes.data, len(scene.geoms), scene.materials.ctypes.data,
-                                           len(scene.materials), scene.camera.ctypes.data, C.addressof(lens), depth, mode,
-                                           iter_begin, n_iters, image.ctypes.data, alive.ctypes.data, nthreads)
+            seg = self.lib.orc_render_ex(scene.geoms.ctypes.data, len(scene.geoms), C.addressof(ms) if ms else None,
+                                         scene.materials.ctypes.data, len(scene.materials), scene.camera.ctypes.data,
+                                         C.addressof(lens), depth, mode,
+                                         iter_begin, n_iters, image.ctypes.data, alive.ctypes.data, nthreads)
             return image, alive, int(seg)
         seg = self.lib.orc_render(scene.geoms.ctypes.data, len(scene.geoms), scene.materials.ctypes.data,
                                   len(scene.materials), scene.camera.ctypes.data, depth, mode,

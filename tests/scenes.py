@@ -83,6 +83,90 @@ def glossy_text(**kw):
     return emit(mats, objs, name="glossy", **kw)
 
 
+# ---- triangle meshes (`mesh <file.obj>` objects; extension of the scene format, INSTRUCTION.md:291-293) ----
+def icosphere(subdiv=1, radius=0.5):
+    """Unit-diameter icosphere: 20 * 4^subdiv counter-clockwise (outward-facing) triangles."""
+    t = (1.0 + 5.0 ** 0.5) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+         (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6),
+         (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    v = [np.array(p, np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(subdiv):
+        mid, nf = {}, []
+        def m(a, b):
+            k = (min(a, b), max(a, b))
+            if k not in mid:
+                p = v[a] + v[b]
+                v.append(p / np.linalg.norm(p))
+                mid[k] = len(v) - 1
+            return mid[k]
+        for a, b, c in f:
+            ab, bc, ca = m(a, b), m(b, c), m(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    return np.array(v) * radius, f
+
+
+def box_quads():
+    """The unit cube of the `cube` primitive (+-0.5) as six outward-facing quads (the OBJ reader fans them)."""
+    v = [(x, y, z) for x in (-.5, .5) for y in (-.5, .5) for z in (-.5, .5)]
+    f = [(0, 1, 3, 2), (4, 6, 7, 5), (0, 4, 5, 1), (2, 3, 7, 6), (0, 2, 6, 4), (1, 5, 7, 3)]
+    return np.array(v, np.float64), f
+
+
+def obj_text(verts, faces, slashes=False, negative=False):
+    """Wavefront OBJ text; `slashes` writes v/vt/vn style references, `negative` relative (negative) indices."""
+    out = ["# generated by tests/scenes.py", "o mesh"]
+    out += ["v %.7f %.7f %.7f" % tuple(p) for p in verts]
+    if slashes:
+        out += ["vt 0 0", "vn 0 0 1"]
+    n = len(verts)
+    for face in faces:
+        ref = [(i - n) if negative else (i + 1) for i in face]
+        out.append("f " + " ".join(("%d/1/1" % r) if slashes else str(r) for r in ref))
+    return "\n".join(out) + "\n"
+
+
+def parse_obj(text):
+    """Independent (test-side) OBJ reader: -> (T, 9) float32 triangles, polygons fanned around their first vertex."""
+    verts, tris = [], []
+    for line in text.splitlines():
+        tok = line.split()
+        if not tok:
+            continue
+        if tok[0] == "v":
+            verts.append([np.float32(float(x)) for x in tok[1:4]])
+        elif tok[0] == "f":
+            idx = [int(t.split("/")[0]) for t in tok[1:]]
+            idx = [len(verts) + i if i < 0 else i - 1 for i in idx]
+            for k in range(2, len(idx)):
+                tris.append(verts[idx[0]] + verts[idx[k - 1]] + verts[idx[k]])
+    return np.array(tris, np.float32).reshape(-1, 9)
+
+
+def mesh_scene_files(dirname, res=(800, 800), subdiv=1, name="meshes"):
+    """cornell with the sphere replaced by an icosphere MESH (mirror), a glass-like diffuse box mesh made of quads
+    (rotated, non-uniformly scaled) and a small diffuse icosphere; writes the OBJ files next to the scene file and
+    returns the scene path."""
+    os.makedirs(dirname, exist_ok=True)
+    v, f = icosphere(subdiv)
+    open(os.path.join(dirname, "ico.obj"), "w").write(obj_text(v, f))
+    bv, bf = box_quads()
+    open(os.path.join(dirname, "box.obj"), "w").write(obj_text(bv, bf, slashes=True))
+    v0, f0 = icosphere(0)
+    open(os.path.join(dirname, "ico0.obj"), "w").write(obj_text(v0, f0, negative=True))
+    mats = list(_CORNELL_MATERIALS) + [("Glass", ".98 .98 .98", "0", ".98 .98 .98", "0", "1", "1.5", "0")]
+    objs = list(_CORNELL_OBJECTS)
+    objs[6] = ("Mirror icosphere", "mesh ico.obj", 4, "-1 4 -1", "10 20 30", "3 3 3")
+    objs.append(("Box mesh", "mesh box.obj", 2, "2.5 1.5 1", "20 35 10", "1.5 3 1.5"))
+    objs.append(("Glass icosahedron", "mesh ico0.obj", 5, "-3 1.2 2.5", "0 15 0", "2.2 2.2 2.2"))
+    objs.append(("Small sphere", "sphere", 3, "3 6 -2", "0 0 0", "1.5 1.5 1.5"))
+    path = os.path.join(dirname, name + ".txt")
+    open(path, "w").write(emit(mats, objs, res=res, name=name))
+    return path
+
+
 def synthetic_text(n_objects=100000, seed=565, res=(1920, 1080), depth=16, iterations=64):
     """BASELINE.json configs[4]: mixed SPHERE/CUBE scene, diffuse/REFL/REFR materials, one large
     ceiling light and a floor, horizontal -z view (the
