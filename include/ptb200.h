@@ -211,6 +211,11 @@ int ptb_stage_rng(PtbContext *ctx, int iter, int index, int depth, int n, float 
  * rounded host arithmetic (the glm operations of src/intersections.h:48-144 are built from exactly these) */
 int ptb_stage_arith(PtbContext *ctx, int n, const float *a, const float *b, float *quot, float *root, float *normY);
 
+/* sin / cos as the hemisphere and lens samplers compute them on the device (src/interactions.h:38-39:
+ * `cos(around)`, `sin(around)` -- the host build of the reference calls glibc's sinf / cosf; the device
+ * function restates that algorithm in double precision and is bit-identical to it on [0, 2 pi]) */
+int ptb_stage_sincos(PtbContext *ctx, int n, const float *angles, float *sinOut, float *cosOut);
+
 /* ---- host-side pieces of the drop-in surface (C++ in csrc/host/, reachable over the C ABI) ---- */
 /* new Scene(filename) (src/scene.cpp:7-33); PTB_ERR_IO when the file cannot be opened */
 int  ptb_scene_load(const char *path, void **sceneOut);

@@ -161,6 +161,13 @@ long long orc_render_ex(const OrcGeom *geoms, int ngeoms, const OrcMeshes *meshe
                         int iterBegin, int nIters, float *image, long long *alivePerDepth,
                         int nthreads);
 
+/* ---- plain-C restatement only (libptoracle.so) ----
+ * sin / cos of the samplers: restated = 0 -> libm's sinf / cosf (what the loops above call); restated = 1 ->
+ * the double-precision restatement of glibc's algorithm that the CUDA path mirrors.  orc_sincos_exhaustive
+ * counts the floats with bit pattern in [loBits, hiBits] on which the two disagree. */
+void  orc_sincos(const float *y, int n, int restated, float *sn, float *cs);
+long long orc_sincos_exhaustive(unsigned loBits, unsigned hiBits, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

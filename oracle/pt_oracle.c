@@ -20,6 +20,7 @@
 #include <float.h>
 #include <stdio.h>
 #include <stdlib.h>
+#include <stdint.h>
 #include <string.h>
 #ifdef _OPENMP
 #include <omp.h>
@@ -980,4 +981,54 @@ long long orc_render_ex(const OrcGeom *geoms, int ngeoms, const OrcMeshes *meshe
         for (int d = 0; d < traceDepth; d++) alivePerDepth[d] += alive[d];
     free(alive);
     return segments;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * sin / cos restated.  The loop above calls libm's sinf / cosf, as the host build of the reference does
+ * (src/interactions.h:38-39 resolve to the float overloads).  The CUDA path cannot call libm, so it
+ * carries a restatement of glibc's algorithm (sysdeps/ieee754/flt-32/s_sincosf.h: double-precision
+ * reduction by pi/2 and two double polynomials, one rounding to float).  The same restatement is kept
+ * here so that it can be checked against THIS machine's libm over every float the samplers can produce
+ * (orc_sincos_exhaustive) and used as the bit-exact expectation of the device function.
+ * ------------------------------------------------------------------------------------------------ */
+static void sincosRestated(float y, float *sn, float *cs) {
+    const double x = (double)y;
+    const int n = ((int)(x * 0x1.45F306DC9C883p+23) + 0x800000) >> 24;     /* reduce_fast, s_sincosf.h */
+    const double r = x - (double)n * 0x1.921FB54442D18p0;
+    const double r2 = r * r, r3 = r2 * r, r4 = r2 * r2;
+    const double c2 = -0x1.6c087e89a359dp-10 + r2 * 0x1.99343027bf8c3p-16;
+    const double s1 = 0x1.1107605230bc4p-7 + r2 * -0x1.994eb3774cf24p-13;
+    const double c1 = 1.0 + r2 * -0x1.ffffffd0c621cp-2;
+    const double r5 = r3 * r2, r6 = r4 * r2;
+    const double s = r + r3 * -0x1.555545995a603p-3;
+    const double c = c1 + r4 * 0x1.55553e1068f19p-5;
+    float S = (float)(s + r5 * s1), C = (float)(c + r6 * c2);
+    if (n & 1) { const float t = S; S = C; C = -t; }
+    if (n & 2) { S = -S; C = -C; }
+    uint32_t u;
+    memcpy(&u, &y, 4);
+    const int tiny = ((u >> 20) & 0x7ffu) < 0x398u;                          /* |y| < 2^-12 */
+    *sn = tiny ? y : S;
+    *cs = tiny ? 1.0f : C;
+}
+void orc_sincos(const float *y, int n, int restated, float *sn, float *cs) {
+    for (int i = 0; i < n; ++i) {
+        if (restated) sincosRestated(y[i], &sn[i], &cs[i]);
+        else { sn[i] = sinf(y[i]); cs[i] = cosf(y[i]); }
+    }
+}
+/* number of floats with bit pattern in [loBits, hiBits] for which the restatement and libm disagree */
+long long orc_sincos_exhaustive(unsigned loBits, unsigned hiBits, int nthreads) {
+    long long bad = 0;
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#pragma omp parallel for schedule(static) reduction(+ : bad)
+    for (long long b = (long long)loBits; b <= (long long)hiBits; ++b) {
+        const uint32_t u = (uint32_t)b;
+        float y, s, c;
+        memcpy(&y, &u, 4);
+        sincosRestated(y, &s, &c);
+        const float ls = sinf(y), lc = cosf(y);
+        bad += memcmp(&s, &ls, 4) != 0 || memcmp(&c, &lc, 4) != 0;
+    }
+    return bad;
 }

@@ -72,7 +72,7 @@ ABI_SYMBOLS = [
     "ptb_default_options", "ptb_last_error", "ptb_abi_version", "ptb_create", "ptb_update_scene", "ptb_destroy",
     "ptb_pathtrace", "ptb_render", "ptb_download", "ptb_write_pbo", "ptb_reset", "ptb_sync",
     "ptb_stats", "ptb_accum_device_ptr", "ptb_resolve_rgb8", "ptb_stage_raygen", "ptb_stage_raygen_iter", "ptb_stage_intersect",
-    "ptb_stage_shade", "ptb_stage_compact", "ptb_stage_sort_keys", "ptb_stage_rng", "ptb_stage_arith",
+    "ptb_stage_shade", "ptb_stage_compact", "ptb_stage_sort_keys", "ptb_stage_rng", "ptb_stage_arith", "ptb_stage_sincos",
     "ptb_scene_load", "ptb_scene_counts", "ptb_scene_get", "ptb_scene_mesh_counts", "ptb_scene_get_meshes", "ptb_scene_free", "ptb_camera_fixup",
     "ptb_save_png", "ptb_save_hdr",
 ]
@@ -109,6 +109,7 @@ def lib():
         L.ptb_stage_sort_keys.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.ptb_stage_rng.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ptb_stage_arith.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.ptb_stage_sincos.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
         if hasattr(L, "ptb_scene_load"):
             L.ptb_scene_load.restype = C.c_int
             L.ptb_scene_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
@@ -343,6 +344,12 @@ class Renderer:
         q, r, ny = np.zeros_like(a), np.zeros_like(a), np.zeros_like(a)
         _check(lib().ptb_stage_arith(self._h, len(a), a.ctypes.data, b.ctypes.data, q.ctypes.data, r.ctypes.data, ny.ctypes.data))
         return q, r, ny
+
+    def stage_sincos(self, angles):
+        a = np.ascontiguousarray(angles, np.float32)
+        sn, cs = np.zeros_like(a), np.zeros_like(a)
+        _check(lib().ptb_stage_sincos(self._h, len(a), a.ctypes.data, sn.ctypes.data, cs.ctypes.data))
+        return sn, cs
 
     def stage_rng(self, it, index, depth, n):
         out = np.zeros(n, np.float32)

@@ -875,6 +875,24 @@ int ptb_stage_arith(PtbContext *c, int n, const float *a, const float *b, float 
     return PTB_OK;
 }
 
+int ptb_stage_sincos(PtbContext *c, int n, const float *angles, float *sinOut, float *cosOut) {
+    if (!c || n < 0 || !angles || !sinOut || !cosOut) return fail(PTB_ERR_INVALID, "ptb_stage_sincos: bad argument");
+    CU(cudaSetDevice(c->device));
+    DevBuf<float> da, ds, dc;
+    CU(da.alloc(n)); CU(ds.alloc(n)); CU(dc.alloc(n));
+    if (n) {
+        CU(cudaMemcpyAsync(da.p, angles, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
+        stage_sincos_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(n, da.p, ds.p, dc.p);
+        c->launches++;
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(sinOut, ds.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaMemcpyAsync(cosOut, dc.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(cudaStreamSynchronize(c->stream));
+    da.release(); ds.release(); dc.release();
+    return PTB_OK;
+}
+
 int ptb_stage_rng(PtbContext *c, int iter, int index, int depth, int n, float *out) {
     if (!c || n < 0 || !out) return fail(PTB_ERR_INVALID, "ptb_stage_rng: bad argument");
     CU(cudaSetDevice(c->device));

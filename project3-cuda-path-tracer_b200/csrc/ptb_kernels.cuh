@@ -136,7 +136,7 @@ PTB_DEV void cameraRayIter(const CameraParams &c, uint32_t pix, int iter, f3 &o,
         const float rad = mul(c.lensRadius, fsqrt(u01(rng)));
         const float phi = mul(u01(rng), 6.2831853071795864769252867665590057683943f);
         float sn, cs;
-        sincosf(phi, &sn, &cs);
+        sincosExact(phi, sn, cs);
         const float lx = mul(rad, cs), ly = mul(rad, sn);
         const float ft = fdiv(c.focalDist, dot3(d, view));
         const f3 focus = add3(o, scale3(d, ft));
@@ -473,7 +473,7 @@ PTB_DEV f3 lobeDirection(f3 n, float up, float over, float around) {
     f3 p1 = normalize3(cross3(n, notNormal));
     f3 p2 = normalize3(cross3(n, p1));
     float s, c;
-    sincosf(around, &s, &c);      // full-precision libdevice path (no fast-math); ulp-level vs glibc
+    sincosExact(around, s, c);    // glibc's sinf / cosf bit for bit (ptb_math.cuh)
     return add3(add3(scale3(n, up), scale3(p1, mul(c, over))), scale3(p2, mul(s, over)));
 }
 // calculateRandomDirectionInHemisphere, src/interactions.h:10-42
@@ -1309,6 +1309,11 @@ __global__ void __launch_bounds__(kBlock) stage_arith_kernel(int n, const float 
         ninv[i] = fdiv(v.y, y);        // not compared bit-for-bit by the test; keeps normalize3 alive
         if (y != 0.0f) ninv[i] = v.y;
     }
+}
+
+// sincosExact (ptb_math.cuh) on caller-supplied angles
+__global__ void __launch_bounds__(kBlock) stage_sincos_kernel(int n, const float *y, float *sn, float *cs) {
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) sincosExact(y[i], sn[i], cs[i]);
 }
 
 __global__ void stage_rng_kernel(int iter, int index, int depth, int n, float *out) {

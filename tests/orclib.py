@@ -103,6 +103,21 @@ class Oracle:
                                     C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
         L.orc_closest_hit_mesh.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 4
         self.kind = L.orc_kind().decode()
+        if hasattr(L, "orc_sincos"):           # plain-C restatement only
+            L.orc_sincos.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+            L.orc_sincos_exhaustive.restype = C.c_longlong
+            L.orc_sincos_exhaustive.argtypes = [C.c_uint, C.c_uint, C.c_int]
+
+    def sincos(self, angles, restated):
+        """(sin, cos) per angle: libm's sinf / cosf (restated=False, what the oracle loops call) or the
+        double-precision restatement the CUDA path mirrors (restated=True)."""
+        a = np.ascontiguousarray(angles, np.float32)
+        sn, cs = np.zeros_like(a), np.zeros_like(a)
+        self.lib.orc_sincos(a.ctypes.data, len(a), int(bool(restated)), sn.ctypes.data, cs.ctypes.data)
+        return sn, cs
+
+    def sincos_mismatches(self, lo_bits, hi_bits, nthreads=0):
+        return int(self.lib.orc_sincos_exhaustive(int(lo_bits), int(hi_bits), nthreads))
 
     # ---- scene ----
     def load_scene(self, path, fixup=True):

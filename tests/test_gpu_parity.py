@@ -4,9 +4,12 @@ through size-independent properties.
 
 Tolerances (BASELINE.json north_star):
   * first-bounce hit indices, t, normals and compacted path counts: BIT-EXACT
-  * later bounces: per-pixel radiance within 1e-4 relative at a fixed spp.  The only non-IEEE step in
-    the path is sinf/cosf inside the hemisphere sampler (src/interactions.h:40-41), so hits are still
-    checked bit-exactly at every bounce by re-running the oracle on the GPU's own rays.
+  * later bounces: per-pixel radiance within 1e-4 relative at a fixed spp.  The bar is met with room to
+    spare: the only non-IEEE step of the loop, sinf / cosf inside the hemisphere sampler
+    (src/interactions.h:38-39), is computed on the device by a restatement of glibc's algorithm that is
+    bit-identical to it on the sampler's whole range (test_sincos_bit_exact), so every bounce -- compacted
+    counts, hits, radiance -- is asserted BIT-EXACT against the oracle and the golden fixtures; the 1e-4
+    check is kept as the stated acceptance bar.
 """
 import numpy as np
 import pytest
@@ -18,7 +21,7 @@ from common import pkg, golden, crc, bits, same_bits, densify, rel_err_lit
 pytestmark = pytest.mark.gpu
 
 RADIANCE_RTOL = 1e-4      # north_star: later bounces within 1e-4 relative error per pixel
-DIR_ATOL = 4e-7           # scattered directions: 1-2 ulp of sinf/cosf between CUDA and glibc
+DIR_ATOL = 4e-7           # scattered directions: the tolerance a libdevice sinf/cosf would need; the device restatement meets 0
 
 
 @pytest.fixture(scope="module")
@@ -79,6 +82,27 @@ def test_ieee_helpers_bit_exact(m, cornell):
     assert np.array_equal(bits(root), bits(wr))
     ok = (b != 0) & ~np.isnan(wn)
     assert np.array_equal(bits(ny)[ok], bits(wn)[ok])
+
+
+def test_sincos_bit_exact(m, port, cornell):
+    """sin / cos of the samplers: the device function equals libm's sinf / cosf (what the host build of the
+    reference calls, src/interactions.h:38-39) bit for bit -- 4 M random angles in [0, 2 pi], every u01 grid point
+    `x / 2^31 * TWO_PI` the RNG can emit near the quadrant boundaries, and the special values."""
+    rs = np.random.RandomState(5)
+    two_pi = np.float32(6.2831853071795864769252867665590057683943)
+    a = (rs.randint(0, 1 << 31, 1 << 22).astype(np.float32) * np.float32(4.656612873077392578125e-10) * two_pi).astype(np.float32)
+    edges = np.float32([0.0, 1e-45, 2.0 ** -126, 2.0 ** -13, 2.0 ** -12, 0.75, 0.785398, 0.7853982, 1.5707963, 1.5707964,
+                        3.1415925, 3.1415927, 4.712389, 6.2831845, 6.283185, two_pi])
+    near = np.concatenate([np.nextafter(edges, np.float32(10)).astype(np.float32), edges])
+    q = np.concatenate([(np.float32(k) * np.float32(0.5) * np.float32(np.pi) + np.arange(-2000, 2000).astype(np.float32) * np.float32(1e-7)).astype(np.float32)
+                        for k in range(1, 5)])
+    a = np.concatenate([a, near.astype(np.float32), np.clip(q, 0, two_pi)])
+    with m.Renderer(cornell, device=0) as r:
+        sn, cs = r.stage_sincos(a)
+    wsn, wcs = port.sincos(a, False)
+    assert same_bits(sn, wsn) and same_bits(cs, wcs)
+    rsn, rcs = port.sincos(a, True)
+    assert same_bits(sn, rsn) and same_bits(cs, rcs)
 
 
 # --------------------------------------------------------------------------------- raygen + bounce 0
@@ -202,19 +226,17 @@ def test_iteration_1_against_golden(m, scene_dir, tag, scene, mode, cfg):
     want_alive = g["loop_%s_alive" % tag]
     alive = np.array(st["alive_per_depth"])
     if cfg[0] != "staged_nocompact":
-        # compacted path counts: bit-exact for the first bounce (and the one it feeds);
-        # deeper counts can move by a few paths when sinf/cosf differ by an ulp
-        assert list(alive[:2]) == list(want_alive[:2])
-        assert np.all(np.abs(alive - want_alive) <= np.maximum(8, want_alive // 5000)), (alive, want_alive)
+        # compacted path counts: bit-exact at every depth
+        assert list(alive) == list(want_alive), (alive, want_alive)
         assert st["segments"] == alive.sum()
     else:
         assert np.all(alive == s.pixels)
     want = densify(g["loop_%s_idx" % tag], g["loop_%s_rgb" % tag], s.pixels)
     rel, lit = rel_err_lit(img, want)
     frac = float((rel <= RADIANCE_RTOL).mean())
-    # pixels whose path took a different branch after an ulp-level difference are counted, not hidden
-    assert frac >= (0.9995 if scene == "cornell" else 0.998), "%s: only %.5f of lit pixels within 1e-4" % (cfg[0], frac)
-    assert np.allclose(img.astype(np.float64).sum(0), g["loop_%s_sum" % tag], rtol=3e-3)
+    assert frac == 1.0, "%s: only %.5f of lit pixels within 1e-4" % (cfg[0], frac)       # the stated bar ...
+    assert same_bits(img, want), "%s: %d pixels differ" % (cfg[0], int((bits(img) != bits(want)).any(1).sum()))   # ... and what holds
+    assert np.allclose(img.astype(np.float64).sum(0), g["loop_%s_sum" % tag], rtol=1e-6)
 
 
 def test_pipelines_agree_bit_for_bit(m, scene_dir):
@@ -275,7 +297,7 @@ def test_first_bounce_cache_is_result_neutral(m, scene_dir, scene, accel):
 
 def test_every_bounce_hits_bit_exact_on_gpu_rays(m, port, scene_dir):
     """Drive the staged stages by hand for 8 bounces; at EVERY bounce the oracle, fed the GPU's own
-    rays, must return bit-identical hit records, and the scattered state must match to ulps."""
+    rays, must return bit-identical hit records and bit-identical scattered state."""
     s = m.Scene.load(scene_dir + "/glass.txt")
     os_ = port.load_scene(scene_dir + "/glass.txt")
     P = s.pixels
@@ -297,7 +319,7 @@ def test_every_bounce_hits_bit_exact_on_gpu_rays(m, port, scene_dir):
             assert np.array_equal(grem, wrem) and same_bits(gc, wc)
             keep = grem > 0
             assert same_bits(go[keep], wo[keep])
-            assert not keep.any() or np.abs(gd[keep] - wd[keep]).max() <= DIR_ATOL
+            assert not keep.any() or (np.abs(gd[keep] - wd[keep]).max() <= DIR_ATOL and same_bits(gd[keep], wd[keep]))
             ids, cnt = r.stage_compact(np.arange(len(pix), dtype=np.int32), keep.astype(np.int32))
             assert cnt == int(keep.sum())
             ids = np.sort(ids)
@@ -381,6 +403,6 @@ def test_empty_scene_ragged_resolution_and_depth_1(m, port, tmp_path):
         with m.Renderer(s2, device=0, bsdf=1, **kw) as r:
             r.render(1, 2)
             img = r.download()
-            assert r.stats()["alive_per_depth"][:2] == list(walive[:2])
+            assert r.stats()["alive_per_depth"] == list(walive)
         rel, _ = rel_err_lit(img, want)
-        assert (rel <= RADIANCE_RTOL).mean() > 0.999
+        assert (rel <= RADIANCE_RTOL).all() and same_bits(img, want)      # two deposits per pixel: a + b == b + a

@@ -90,6 +90,18 @@ def test_first_bounce_pins(port, scene_dir):
     assert int((hit < 0).sum()) == 628376 and int((hit == 0).sum()) == 11624
 
 
+def test_sincos_restatement_exhaustive(port):
+    """The double-precision restatement of glibc's sinf / cosf that the CUDA path mirrors
+    (csrc/ptb_math.cuh::sincosExact, oracle/pt_oracle.c::sincosRestated) against THIS machine's libm on every
+    float in [0, 2 pi] -- the whole range `around = u * TWO_PI`, u in [0, 1] (src/interactions.h:19) and the lens
+    angle can take: 1 086 918 620 arguments, zero disagreements (about 2 s on 8 cores)."""
+    two_pi = np.float32(6.2831853071795864769252867665590057683943)
+    assert port.sincos_mismatches(0, int(two_pi.view(np.uint32))) == 0
+    # and a little beyond the sampler range (reduce_fast is valid below 120)
+    a = np.float32([7.0, 31.4, 100.0, 119.9])
+    assert same_bits(np.stack(port.sincos(a, True)), np.stack(port.sincos(a, False)))
+
+
 def test_hemisphere_vectors(port):
     g = golden()
     seed = g["hemi_seed"]
