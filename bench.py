@@ -134,7 +134,7 @@ def cpu_reference_run(scene_path, iters_per_sample, repeats, nthreads=0):
     return total_seg / total_t, orc.kind, cores, sample, total_t, seg / iters_per_sample
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, out):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -155,11 +155,23 @@ def run_reference_arm(args):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    out.write(json.dumps(line) + "\n")
+    out.flush()
     return 0
 
 
+def claim_stdout():
+    """The driver reads ONE JSON line from stdout.  Libraries loaded later write there too (NCCL prints its
+    version banner to fd 1 under torchrun), so fd 1 is pointed at stderr for the whole run and the JSON line
+    goes to the saved descriptor."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
+
+
 def main():
+    out = claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -170,7 +182,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, out)
     args.warmup = max(args.warmup, 3)
 
     import numpy as np
@@ -336,10 +348,13 @@ def main():
         achieved = alg_bytes / (ms * 1e-3) / 1e9 / world             # per GPU
         bounce_launches = launches_all / world
         traffic = None
-        prof = os.path.join(ROOT, "profiles", "r01_bounce_traffic.json")
-        if os.path.exists(prof):
+        import glob
+        profs = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_bounce_traffic.json")))    # newest ncu --set full capture
+        traffic_src = None
+        if profs:
             try:
-                traffic = json.load(open(prof)).get("dram_bytes_per_launch")
+                traffic = json.load(open(profs[-1])).get("dram_bytes_per_launch")
+                traffic_src = os.path.relpath(profs[-1], ROOT)
             except Exception:
                 traffic = None
         line = {
@@ -360,7 +375,7 @@ def main():
             "first_bounce_cache": {"value": seg_fbc / (ms_fbc * 1e-3), "unit": UNIT, "iters_per_s": iters_fbc / (ms_fbc * 1e-3),
                                    "note": "PtbOptions.firstBounceCache = 1: bounce-0 hit records reused across iterations (bit-identical images)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "ptb::bounce_kernel",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "ptb::bounce_kernel",
                          "algorithmic_bytes": "88 B/segment + 24 B/pixel/iteration (SURVEY.md 8(d))",
                          "launches_in_timed_region_per_gpu": bounce_launches,
                          "avg_launch_us": ms * 1e3 / max(1.0, bounce_launches),
@@ -374,7 +389,8 @@ def main():
                 line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "seconds": secs}
             except Exception as ex:                                     # the checker is optional for the bench line
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
-        print(json.dumps(line))
+        out.write(json.dumps(line) + "\n")
+        out.flush()
     r.close()
     if world > 1:
         dist.barrier()
