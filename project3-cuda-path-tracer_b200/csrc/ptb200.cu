@@ -164,15 +164,15 @@ GeomRec packTriangle(const PtbGeom &g, const PtbTriangle &t, int sceneIndex, int
     r.b1 = make_float4(hi[0], hi[1], hi[2], 0.f);
     return r;
 }
-// brute-force table record: a cube's padded box as [lo, hi, lo] per axis in the nine words from tag.w on
-// (sign-selected near / far plane loads in closestHitBrute)
+// brute-force table record: a cube's padded box as [lo, hi, hi, lo] per axis in its (otherwise unused) nrm rows
+// (sign-selected 64-bit (near, far) pair loads in closestHitBrute)
 GeomRec packGeomBrute(const PtbGeom &g, int sceneIndex) {
     GeomRec r = packGeom(g, sceneIndex);
     if (g.type == 1) {
-        static_assert(offsetof(GeomRec, tag) + 12 == kPruneWord0 * 4 && sizeof(GeomRec) == (kPruneWord0 + 9) * 4, "prune words");
+        static_assert(offsetof(GeomRec, nrm) == kPrunePair0 * 8 && sizeof(Affine) == 12 * 4, "prune pairs");
         const float lo[3] = {r.b0.x, r.b0.y, r.b0.z}, hi[3] = {r.b1.x, r.b1.y, r.b1.z};
-        float *w = reinterpret_cast<float *>(&r) + kPruneWord0;
-        for (int ax = 0; ax < 3; ++ax) { w[3 * ax] = lo[ax]; w[3 * ax + 1] = hi[ax]; w[3 * ax + 2] = lo[ax]; }
+        float *w = reinterpret_cast<float *>(&r.nrm);
+        for (int ax = 0; ax < 3; ++ax) { w[4 * ax] = lo[ax]; w[4 * ax + 1] = hi[ax]; w[4 * ax + 2] = hi[ax]; w[4 * ax + 3] = lo[ax]; }
     }
     return r;
 }

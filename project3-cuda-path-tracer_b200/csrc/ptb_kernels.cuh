@@ -181,26 +181,26 @@ PTB_DEV f3 candidateNormal(const GeomRec &g, const Candidate &c) { return exactN
 //      "reachable" for the world-space bound), so that the lanes of a warp arrive TOGETHER at the one
 //      copy of the exact test; the walk stops as soon as the next lower bound exceeds the exact
 //      distance found so far.
-// When more than three primitives are reachable and the third bound did not end the walk (rare), the
-// same two phases run again over the keys above the last one consumed.
+// When all three keys were walked and the third bound did not end the walk (rare), the same two phases
+// run again over the keys above the last one consumed (they find nothing when only three were reachable).
 // Phase 1 only prunes and orders; every output value comes from the exact test.
 //
 // The phase-1 loop is bound by the ALU pipe (min/max, compares, selects: one warp instruction per two
 // cycles), not by the FMA pipe, so it is laid out to need as few of those as possible:
 //   * the brute-force geom table is ordered cubes first (Params::numCubes of them), then spheres, so
 //     each type has its own branch-free loop (the scene index for the tie rule lives in tag.z);
-//   * a cube's padded world box is stored as [lo, hi, lo] per axis (GeomRec::pruneWords): a lane reads
-//     its NEAR plane at word s and its FAR plane at word s + 1, s = sign bit of the direction
-//     component, so the six per-axis min/max of a slab test disappear (two distinct words of one
-//     geom per load: different banks, one shared-memory wavefront);
+//   * a cube's padded world box is stored as [lo, hi, hi, lo] per axis (kPrunePair0): a lane reads its
+//     (NEAR, FAR) planes as one 64-bit pair at pair s, s = sign bit of the direction component, so the
+//     six per-axis min/max of a slab test disappear, and the pair goes through ONE packed subtract and
+//     ONE packed multiply (FADD2 / FMUL2 with the scalar broadcast): 9 instructions per cube where
+//     scalar code needs 18;
 //   * entry = max3, exit = min3 (FMNMX3).
 constexpr uint32_t kNoCand = 0xffffffffu;
 constexpr uint32_t kMissKey = 0x7f800000u;                        // bits(+inf): every key at or above it is "not reachable"
 
 struct BruteRay {                                                 // per-lane constants of phase 1
-    f3 o, invD, dn;
-    float rdLen, slack;
-    uint32_t sx, sy, sz;                                          // sign bits of the direction components
+    f3 o, d, invD;                                                // o, d alias the ray's own registers
+    float rinv, rdLen, slack;                                     // 1 / |d| (approximate), |d|
 };
 
 // sorted insert of `key` into (k0 <= k1 <= k2); the largest of the four falls out
@@ -211,39 +211,41 @@ PTB_DEV void insertKey(uint32_t key, uint32_t &k0, uint32_t &k1, uint32_t &k2) {
 }
 // lower-bound key of one primitive: e = entry distance (world units) or +inf for a sure miss (`reach` false)
 template <bool RESCAN>
-PTB_DEV void pushBound(float e, bool reach, int idx, const BruteRay &r, uint32_t floorKey, uint32_t &k0, uint32_t &k1, uint32_t &k2, int &nAbove) {
+PTB_DEV void pushBound(float e, bool reach, int idx, const BruteRay &r, uint32_t floorKey, uint32_t &k0, uint32_t &k1, uint32_t &k2) {
     const float lo = fmaxf(fmaf(e, 0.99998f, -r.slack), 0.0f);    // inf stays inf
     uint32_t key = (__float_as_uint(lo) & ~31u) | (uint32_t)idx;
     if (RESCAN) { reach = reach && key >= floorKey; key = reach ? key : kNoCand; }
-    if (reach) ++nAbove;
     insertKey(key, k0, k1, k2);
 }
 template <bool RESCAN>
 PTB_DEV void boundsPhase(const GeomRec *sg, int g0, int c1, int g1, const BruteRay &r, uint32_t floorKey,
-                         uint32_t &k0, uint32_t &k1, uint32_t &k2, int &nAbove) {
+                         uint32_t &k0, uint32_t &k1, uint32_t &k2) {
     const float inf = __uint_as_float(kMissKey);
-    constexpr int kStride = (int)(sizeof(GeomRec) / 4);
-    // cubes [g0, c1): sign-selected near / far planes
-    const float *wx = reinterpret_cast<const float *>(sg + g0) + kPruneWord0 + r.sx;
-    const float *wy = reinterpret_cast<const float *>(sg + g0) + kPruneWord0 + 3 + r.sy;
-    const float *wz = reinterpret_cast<const float *>(sg + g0) + kPruneWord0 + 6 + r.sz;
+    // cubes [g0, c1): sign-selected (near, far) plane pairs, one 64-bit load and two packed operations per axis
+    constexpr int kStride2 = (int)(sizeof(GeomRec) / 8);
+    // s = sign bit of the direction component (recomputed here rather than kept in registers across the walk)
+    const f2 *wx = reinterpret_cast<const f2 *>(sg + g0) + kPrunePair0 + (__float_as_uint(r.d.x) >> 31);
+    const f2 *wy = reinterpret_cast<const f2 *>(sg + g0) + kPrunePair0 + 2 + (__float_as_uint(r.d.y) >> 31);
+    const f2 *wz = reinterpret_cast<const f2 *>(sg + g0) + kPrunePair0 + 4 + (__float_as_uint(r.d.z) >> 31);
 #pragma unroll 2
-    for (int i = 0; i < c1 - g0; ++i, wx += kStride, wy += kStride, wz += kStride) {
-        const float nx = (wx[0] - r.o.x) * r.invD.x, fx = (wx[1] - r.o.x) * r.invD.x;
-        const float ny = (wy[0] - r.o.y) * r.invD.y, fy = (wy[1] - r.o.y) * r.invD.y;
-        const float nz = (wz[0] - r.o.z) * r.invD.z, fz = (wz[1] - r.o.z) * r.invD.z;
+    for (int i = 0; i < c1 - g0; ++i, wx += kStride2, wy += kStride2, wz += kStride2) {
+        float nx, fx, ny, fy, nz, fz;
+        upk2(mul2(add2(wx[0], bc2(-r.o.x)), bc2(r.invD.x)), nx, fx);
+        upk2(mul2(add2(wy[0], bc2(-r.o.y)), bc2(r.invD.y)), ny, fy);
+        upk2(mul2(add2(wz[0], bc2(-r.o.z)), bc2(r.invD.z)), nz, fz);
         // fminf / fmaxf drop the NaN of 0 * inf (origin exactly on a padded plane, direction component 0):
         // that errs towards "reachable"
         const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
         const float tf = fminf(fminf(fx, fy), fz);
         const bool reach = tn <= fmaf(tf, 1.00002f, 1e-6f);
-        pushBound<RESCAN>(reach ? tn * r.rdLen : inf, reach, i, r, floorKey, k0, k1, k2, nAbove);
+        pushBound<RESCAN>(reach ? tn * r.rdLen : inf, reach, i, r, floorKey, k0, k1, k2);
     }
     // spheres [max(g0, c1), g1): padded bounding sphere
+    const f3 dn = mk3(r.d.x * r.rinv, r.d.y * r.rinv, r.d.z * r.rinv);
 #pragma unroll 1
     for (int g = max(g0, c1); g < g1; ++g) {
-        const float e = boundEntryRaw(false, sg[g].b0, sg[g].b1, r.o, r.invD, r.dn, r.rdLen);
-        pushBound<RESCAN>(e >= 0.0f ? e : inf, e >= 0.0f, g - g0, r, floorKey, k0, k1, k2, nAbove);
+        const float e = boundEntryRaw(false, sg[g].b0, sg[g].b1, r.o, r.invD, dn, r.rdLen);
+        pushBound<RESCAN>(e >= 0.0f ? e : inf, e >= 0.0f, g - g0, r, floorKey, k0, k1, k2);
     }
 }
 
@@ -253,12 +255,10 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
     int orig = 0x7fffffff;
     BruteRay r;
     const float dd = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
-    const float rinv = rsqrtApprox(dd);
-    r.o = o;
-    r.rdLen = dd * rinv;
-    r.dn = mk3(d.x * rinv, d.y * rinv, d.z * rinv);
+    r.rinv = rsqrtApprox(dd);
+    r.o = o; r.d = d;
+    r.rdLen = dd * r.rinv;
     r.invD = mk3(rcpApprox(d.x), rcpApprox(d.y), rcpApprox(d.z));
-    r.sx = __float_as_uint(d.x) >> 31; r.sy = __float_as_uint(d.y) >> 31; r.sz = __float_as_uint(d.z) >> 31;
     // slack on every lower bound: rounding of the bound itself plus the deviation of the exact hit
     // point from the ideal ray (a few ulp of the coordinates involved)
     r.slack = 2e-5f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f);
@@ -268,9 +268,9 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
         uint32_t floorKey = 0u;                                   // keys below it were consumed by an earlier round
         for (;;) {
             uint32_t k0 = kNoCand, k1 = kNoCand, k2 = kNoCand;
-            int nAbove = 0;
-            if (floorKey == 0u) boundsPhase<false>(sg, g0, c1, g1, r, 0u, k0, k1, k2, nAbove);
-            else                boundsPhase<true>(sg, g0, c1, g1, r, floorKey, k0, k1, k2, nAbove);
+            int taken = 0;                                        // keys consumed this round
+            if (floorKey == 0u) boundsPhase<false>(sg, g0, c1, g1, r, 0u, k0, k1, k2);
+            else                boundsPhase<true>(sg, g0, c1, g1, r, floorKey, k0, k1, k2);
             if (!valid) k0 = kNoCand;
             uint32_t lastKey = 0u;
             bool exhausted = true;                                // all three keys consumed without the bound ending the walk
@@ -281,7 +281,7 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
                     const float lo = __uint_as_float(k0 & ~31u);
                     if (!(lo <= best.t)) { exhausted = false; k0 = kNoCand; break; }   // sorted: nothing further can win (+inf = miss keys too)
                     const int cand = g0 + (int)(k0 & 31u);
-                    lastKey = k0;
+                    lastKey = k0; ++taken;
                     k0 = k1; k1 = k2; k2 = kNoCand;
                     objectRay(sg[cand], o, d, qo, qu);
                     // The cube filter runs for every lane and the sphere filter overrides it inside a plain `if`
@@ -298,7 +298,7 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
                 const float t = exactTestQ(sg[g], o, qo, qu, outside, a, b, c);
                 acceptHit(sg[g], g, t, outside, a, b, c, best, orig);
             }
-            if (!(valid && exhausted && nAbove > 3)) break;
+            if (!(valid && exhausted && taken == 3)) break;       // all three keys walked and the bound never ended the walk: look for more
             floorKey = lastKey + 1u;
         }
     }
@@ -575,6 +575,18 @@ PTB_DEV void loadPath(const PathPlanes &s, uint32_t i, f3 &o, f3 &d, f3 &c, uint
     const float4 a = s.A[i], b = s.B[i];
     const float2 e = s.C[i];
     o = mk3(a.x, a.y, a.z); d = mk3(a.w, b.x, b.y); c = mk3(b.z, b.w, e.x); id = __float_as_uint(e.y);
+}
+// the two halves of loadPath: the ray before the closest-hit search, throughput and id after it (four
+// registers fewer live across the search)
+PTB_DEV void loadPathRay(const PathPlanes &s, uint32_t i, f3 &o, f3 &d) {
+    const float4 a = s.A[i];
+    const float2 b = *reinterpret_cast<const float2 *>(&s.B[i]);
+    o = mk3(a.x, a.y, a.z); d = mk3(a.w, b.x, b.y);
+}
+PTB_DEV void loadPathTail(const PathPlanes &s, uint32_t i, f3 &c, uint32_t &id) {
+    const float2 b = reinterpret_cast<const float2 *>(&s.B[i])[1];
+    const float2 e = s.C[i];
+    c = mk3(b.x, b.y, e.x); id = __float_as_uint(e.y);
 }
 PTB_DEV void storePath(const PathPlanes &s, uint32_t i, f3 o, f3 d, f3 c, uint32_t id) {
     s.A[i] = make_float4(o.x, o.y, o.z, d.x);
@@ -881,18 +893,12 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
             if (valid) {
                 slot = i / p.numPixels;
                 pix = i - slot * p.numPixels;
-                id = pix | (slot << p.pixBits);
                 cameraRayIter<EXT>(cam, pix, iterBase + (int)slot * iterStride, o, d);
-                c = mk3(1.0f, 1.0f, 1.0f);                                // src/pathtrace.cu:132
             }
         } else {
             const uint32_t k = chunk * 32u + lane;
             valid = k < total;
-            if (valid) {
-                loadPath(p.in, segBase + k, o, d, c, id);
-                pix = id & pixMask;
-                slot = (id & ~kDeadBit) >> p.pixBits;
-            }
+            if (valid) loadPathRay(p.in, segBase + k, o, d);           // throughput and id follow after the search
         }
         Candidate best;
         const bool cached = FIRST && p.fbTn != nullptr;            // warp-uniform
@@ -909,6 +915,14 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
             }
         }
         if (valid) {
+            if (FIRST) {
+                id = pix | (slot << p.pixBits);
+                c = mk3(1.0f, 1.0f, 1.0f);                                    // src/pathtrace.cu:132
+            } else {
+                loadPathTail(p.in, segBase + chunk * 32u + lane, c, id);
+                pix = id & pixMask;
+                slot = (id & ~kDeadBit) >> p.pixBits;
+            }
             f3 n = mk3(0.f, 0.f, 0.f); int matId = 0;
             bool isHit;
             if (cached) {

@@ -6,6 +6,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as g
 import scenes
 m = g.load_package()
+if os.environ.get("PTB_SO"): m.LIB_PATH = os.path.join(ROOT, os.environ["PTB_SO"])
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 name = sys.argv[2] if len(sys.argv) > 2 else "cornell.txt"
 B = int(sys.argv[3]) if len(sys.argv) > 3 else 16
