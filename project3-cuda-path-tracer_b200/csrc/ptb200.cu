@@ -94,6 +94,7 @@ struct PtbContext {
     DevBuf<int> hitMeta, sortKeys, sortOrder;
     DevBuf<uint32_t> sortHist, segCounts;
     uint32_t segCap = 0;
+    bool loopBounces = false;      // fused pipeline, brute force: one launch for bounces 1 .. traceDepth-1
     DevBuf<Control> ctrl;
     DevBuf<uint8_t> rgb8;
 
@@ -328,6 +329,12 @@ void launchFusedBounces(PtbContext *c) {
             else        bounce_kernel<false, true, EXT><<<c->gridFused, kBlock, 0, c->stream>>>(p, d);
         } else {
             if (d == 0) bounce_kernel<true, false, EXT><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+            else if (c->loopBounces) {
+                // bounces 1 .. traceDepth-1 in one launch: every CTA walks its own segment through them
+                bounce_loop_kernel<EXT><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+                c->launches++;
+                break;
+            }
             else        bounce_kernel<false, false, EXT><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
         }
         c->launches++;
@@ -401,6 +408,7 @@ int kernelsPerBatch(const PtbContext *c) {
         return 1 + per * c->traceDepth + (c->opt.compaction ? 0 : 1) + 1;
     }
     if (c->useBvh) return 2 * c->traceDepth + 1 - (c->opt.firstBounceCache ? 1 : 0);   // trace + bounce per depth
+    if (c->loopBounces) return (c->traceDepth > 1 ? 2 : 1) + 1;                         // bounce 0, bounces 1.., advance
     return c->traceDepth + 1;
 }
 
@@ -561,6 +569,7 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
         int rc = PTB_OK;
         rc |= setSmem(bounce_kernel<true, false, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, false>, c->smemBrute);
         rc |= setSmem(bounce_kernel<true, false, true>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, true>, c->smemBrute);
+        rc |= setSmem(bounce_loop_kernel<false>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true>, c->smemBrute);
         rc |= setSmem(intersect_kernel<false>, c->smemBrute); rc |= setSmem(stage_intersect_kernel<false>, c->smemBrute);
         rc |= setSmem(fb_cache_kernel<false>, c->smemBrute);
         if (rc != PTB_OK) return bail(rc);
@@ -569,9 +578,15 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     const size_t smem = c->useBvh ? c->smemBvh : c->smemBrute;
     if (c->useBvh) CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_bvh_kernel<false, false, false>, kBlock, smem));
     else           CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, false, false>, kBlock, smem));
-    // 4 CTAs per resident slot: the CTA-owned segments cannot be rebalanced inside a launch, so a few
-    // waves of smaller CTAs keep the tail short (measured: x1 142 us, x2 138, x4 134.5, x8 135.4, x16 142 per cornell iteration)
-    int gridMult = 4;
+    // brute-force scenes: bounces 1.. in one launch (bounce_loop_kernel), every CTA walking its own segment through them
+    c->loopBounces = !c->useBvh;
+    if (const char *e = getenv("PTB_LOOP_BOUNCES")) c->loopBounces = c->loopBounces && atoi(e) != 0;   // tuning knob (experiments)
+    // Several CTAs per resident slot: the CTA-owned segments cannot be rebalanced inside a launch, so a few waves of
+    // smaller CTAs keep the tail short.  Measured per cornell iteration, one launch per bounce: x1 142 us, x2 138, x4 134.5,
+    // x8 135.4, x16 142 (round 1, first build); with the one-launch bounce loop the per-CTA set-up is paid once per
+    // wavefront and x8 wins: x2 119.0, x4 114.8, x8 112.9, x16 112.7 (profiles/r01n_loop_ab.txt)
+    const size_t wavefrontTiles = ((size_t)c->numPixels * c->batch + kBlock - 1) / kBlock;
+    int gridMult = (c->loopBounces && wavefrontTiles >= (size_t)c->numSMs * std::max(1, occ) * 8 * 4) ? 8 : 4;   // >= 4 tiles per CTA
     if (const char *e = getenv("PTB_GRID_MULT")) gridMult = std::max(1, atoi(e));           // tuning knob (experiments)
     c->gridFused = c->numSMs * std::max(1, occ) * gridMult;
     c->gridStaged = c->numSMs * 8;

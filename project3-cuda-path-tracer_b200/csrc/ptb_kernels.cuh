@@ -841,43 +841,20 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const 
 // ------------------------------------------------------------------------------------------------
 // EXT compiles in the camera / material extensions (antialiasing, thin lens, imperfect specular); scenes
 // that use none of them run the EXT = false instantiation, which is the round-1 code path unchanged.
+// One bounce of one CTA's segment: the warps of the CTA pull 32-path chunks from *sNextChunk until the
+// segment's `total` paths (FIRST: nChunks chunks of the CTA's camera-path tiles) are done, and pack the
+// survivors at the front of the CTA's segment of `pout`; *sOutCount ends up holding their number.
 template <bool FIRST, bool USE_BVH, bool EXT>
-__global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __grid_constant__ Params p, const int depth) {
-    extern __shared__ float4 smem4[];
-    __shared__ uint32_t sNextChunk, sOutCount;
-
-    if (threadIdx.x == 0) { sNextChunk = 0u; sOutCount = 0u; }
-    const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
-    // USE_BVH: the closest hits were found by trace_bvh_kernel (raw hit records in p.hits); nothing to stage
-    if (USE_BVH) __syncthreads();
-    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);      // ends with __syncthreads
-    const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
-
-    Control *ctrl = p.ctrl;
-    CameraParams cam;
-    if (FIRST) cam = p.hdr->cam;
-    const int iterBase = ctrl->iterBase, iterStride = ctrl->iterStride;
+PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPlanes &pout, const int depth, const GeomRec *sgeoms,
+                           const int numCubes, const CameraParams &cam, const int iterBase, const int iterStride,
+                           const uint32_t total, const uint32_t nChunks, uint32_t *sNextChunk, uint32_t *sOutCount) {
     const int remainingBefore = p.traceDepth - depth;
     const uint32_t pixMask = (1u << p.pixBits) - 1u;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t segBase = blockIdx.x * p.segCap;
-    const uint32_t *segIn = p.segCounts + ((depth + 1) & 1) * gridDim.x;
-    uint32_t *segOut = p.segCounts + (depth & 1) * gridDim.x;
-
-    uint32_t total = 0, nChunks;
-    if (FIRST) {
-        total = p.numPixels * (uint32_t)ctrl->batch;
-        const uint32_t tiles = (total + kBlock - 1) / kBlock;
-        const uint32_t myTiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
-        nChunks = myTiles * (kBlock / 32);
-    } else {
-        total = segIn[blockIdx.x];
-        nChunks = (total + 31u) / 32u;
-    }
-
     for (;;) {
         uint32_t chunk = 0;
-        if (lane == 0) chunk = atomicAdd(&sNextChunk, 1u);
+        if (lane == 0) chunk = atomicAdd(sNextChunk, 1u);
         chunk = __shfl_sync(0xffffffffu, chunk, 0);
         if (chunk >= nChunks) break;
 
@@ -898,7 +875,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
         } else {
             const uint32_t k = chunk * 32u + lane;
             valid = k < total;
-            if (valid) loadPathRay(p.in, segBase + k, o, d);           // throughput and id follow after the search
+            if (valid) loadPathRay(pin, segBase + k, o, d);           // throughput and id follow after the search
         }
         Candidate best;
         const bool cached = FIRST && p.fbTn != nullptr;            // warp-uniform
@@ -919,7 +896,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
                 id = pix | (slot << p.pixBits);
                 c = mk3(1.0f, 1.0f, 1.0f);                                    // src/pathtrace.cu:132
             } else {
-                loadPathTail(p.in, segBase + chunk * 32u + lane, c, id);
+                loadPathTail(pin, segBase + chunk * 32u + lane, c, id);
                 pix = id & pixMask;
                 slot = (id & ~kDeadBit) >> p.pixBits;
             }
@@ -956,16 +933,83 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
         const unsigned ballot = __ballot_sync(0xffffffffu, alive);
         if (ballot) {
             uint32_t off = 0;
-            if (lane == 0) off = atomicAdd(&sOutCount, (uint32_t)__popc(ballot));
+            if (lane == 0) off = atomicAdd(sOutCount, (uint32_t)__popc(ballot));
             off = __shfl_sync(0xffffffffu, off, 0);
-            if (alive) storePath(p.out, segBase + off + (uint32_t)__popc(ballot & ((1u << lane) - 1u)), o, d, c, id);
+            if (alive) storePath(pout, segBase + off + (uint32_t)__popc(ballot & ((1u << lane) - 1u)), o, d, c, id);
         }
     }
+}
+
+template <bool FIRST, bool USE_BVH, bool EXT>
+__global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __grid_constant__ Params p, const int depth) {
+    extern __shared__ float4 smem4[];
+    __shared__ uint32_t sNextChunk, sOutCount;
+
+    if (threadIdx.x == 0) { sNextChunk = 0u; sOutCount = 0u; }
+    const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
+    // USE_BVH: the closest hits were found by trace_bvh_kernel (raw hit records in p.hits); nothing to stage
+    if (USE_BVH) __syncthreads();
+    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);      // ends with __syncthreads
+    const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
+
+    Control *ctrl = p.ctrl;
+    CameraParams cam;
+    if (FIRST) cam = p.hdr->cam;
+    const int iterBase = ctrl->iterBase, iterStride = ctrl->iterStride;
+    const uint32_t *segIn = p.segCounts + ((depth + 1) & 1) * gridDim.x;
+    uint32_t *segOut = p.segCounts + (depth & 1) * gridDim.x;
+
+    uint32_t total = 0, nChunks;
+    if (FIRST) {
+        total = p.numPixels * (uint32_t)ctrl->batch;
+        const uint32_t tiles = (total + kBlock - 1) / kBlock;
+        const uint32_t myTiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+        nChunks = myTiles * (kBlock / 32);
+    } else {
+        total = segIn[blockIdx.x];
+        nChunks = (total + 31u) / 32u;
+    }
+    bounceSegment<FIRST, USE_BVH, EXT>(p, p.in, p.out, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, nChunks, &sNextChunk, &sOutCount);
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t n = sOutCount;
         segOut[blockIdx.x] = n;
         if (n) atomicAdd(&ctrl->counts[depth + 1], n);
+    }
+}
+
+// Bounces depthBegin .. traceDepth - 1 of a brute-force scene in ONE launch.  A CTA only ever reads the
+// segment it wrote itself at the previous bounce, so nothing orders the CTAs of consecutive bounces
+// against each other: each CTA walks through the remaining bounces of its own segment (ping-ponging
+// between the two path buffers, a __syncthreads between bounces) and the grid never waits for its
+// slowest CTA until the wavefront is finished -- one launch tail per wavefront instead of one per
+// bounce, and the geoms are staged once.  Per path the arithmetic is bounce_kernel's, so the results are
+// identical; counts[d + 1] still receives one atomic per CTA and bounce.
+template <bool EXT>
+__global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_loop_kernel(const __grid_constant__ Params p, const int depthBegin) {
+    extern __shared__ float4 smem4[];
+    __shared__ uint32_t sNextChunk, sOutCount;
+
+    if (threadIdx.x == 0) { sNextChunk = 0u; sOutCount = 0u; }
+    const int numCubes = p.hdr->numCubes;
+    stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);      // ends with __syncthreads
+    const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
+    Control *ctrl = p.ctrl;
+    CameraParams cam;                                                  // never read: no camera rays after bounce 0
+    const int iterBase = ctrl->iterBase, iterStride = ctrl->iterStride;
+    uint32_t total = p.segCounts[((depthBegin + 1) & 1) * gridDim.x + blockIdx.x];
+    PathPlanes pin = p.in, pout = p.out;
+    for (int depth = depthBegin; depth < p.traceDepth && total > 0u; ++depth) {
+        bounceSegment<false, false, EXT>(p, pin, pout, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, (total + 31u) / 32u, &sNextChunk, &sOutCount);
+        __syncthreads();                                               // the survivors are written and counted
+        total = sOutCount;
+        const PathPlanes t = pin; pin = pout; pout = t;
+        __syncthreads();                                               // everyone has read the count ...
+        if (threadIdx.x == 0) {                                        // ... before it is cleared for the next bounce
+            if (total) atomicAdd(&ctrl->counts[depth + 1], total);
+            sNextChunk = 0u; sOutCount = 0u;
+        }
+        __syncthreads();
     }
 }
 
