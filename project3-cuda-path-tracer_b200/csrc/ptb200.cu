@@ -132,8 +132,8 @@ GeomRec packGeom(const PtbGeom &g, int sceneIndex, int order = -1) {
     if (g.type == 1) {
         float lo[3], hi[3];
         geomBounds(g, lo, hi);
-        r.b0 = make_float4(lo[0], lo[1], lo[2], 0.f);
-        r.b1 = make_float4(hi[0], hi[1], hi[2], 0.f);
+        r.b0 = make_float4(lo[0], hi[0], lo[1], hi[1]);          // (lo, hi) pairs per axis: operands of the packed slab test
+        r.b1 = make_float4(lo[2], hi[2], 0.f, 0.f);
     } else {
         float c[3], r2;
         sphereBounds(g, c, &r2);
@@ -161,8 +161,8 @@ GeomRec packTriangle(const PtbGeom &g, const PtbTriangle &t, int sceneIndex, int
     r.nrm.r2 = make_float4(t.v2[0], t.v2[1], t.v2[2], n[2] * inv);
     float lo[3], hi[3];
     triangleBounds(g, t, lo, hi);
-    r.b0 = make_float4(lo[0], lo[1], lo[2], 0.f);
-    r.b1 = make_float4(hi[0], hi[1], hi[2], 0.f);
+    r.b0 = make_float4(lo[0], hi[0], lo[1], hi[1]);
+    r.b1 = make_float4(lo[2], hi[2], 0.f, 0.f);
     return r;
 }
 // brute-force table record: a cube's padded box as [lo, hi, hi, lo] per axis in its (otherwise unused) nrm rows
@@ -171,7 +171,7 @@ GeomRec packGeomBrute(const PtbGeom &g, int sceneIndex) {
     GeomRec r = packGeom(g, sceneIndex);
     if (g.type == 1) {
         static_assert(offsetof(GeomRec, nrm) == kPrunePair0 * 8 && sizeof(Affine) == 12 * 4, "prune pairs");
-        const float lo[3] = {r.b0.x, r.b0.y, r.b0.z}, hi[3] = {r.b1.x, r.b1.y, r.b1.z};
+        const float lo[3] = {r.b0.x, r.b0.z, r.b1.x}, hi[3] = {r.b0.y, r.b0.w, r.b1.y};
         float *w = reinterpret_cast<float *>(&r.nrm);
         for (int ax = 0; ax < 3; ++ax) { w[4 * ax] = lo[ax]; w[4 * ax + 1] = hi[ax]; w[4 * ax + 2] = hi[ax]; w[4 * ax + 3] = lo[ax]; }
     }
@@ -271,7 +271,14 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     }
     static_assert(sizeof(HostBvhNode) == sizeof(BvhNode), "bvh node");
     if ((int)hb.nodes.size() > Pp) return fail(PTB_ERR_INVALID, "BVH has %zu nodes for %d primitives", hb.nodes.size(), P);
-    memcpy(nodes, hb.nodes.data(), hb.nodes.size() * sizeof(BvhNode));
+    // device node layout: the planes of BOTH children paired per axis (operands of the packed slab test), then the links
+    for (size_t i = 0; i < hb.nodes.size(); ++i) {
+        const HostBvhNode &h = hb.nodes[i];
+        nodes[i].x = make_float4(h.llo[0], h.rlo[0], h.lhi[0], h.rhi[0]);
+        nodes[i].y = make_float4(h.llo[1], h.rlo[1], h.lhi[1], h.rhi[1]);
+        nodes[i].z = make_float4(h.llo[2], h.rlo[2], h.lhi[2], h.rhi[2]);
+        nodes[i].m = make_int4(h.lref, h.rref, h.lcount, h.rcount);
+    }
     for (int sIdx = 0; sIdx < P; ++sIdx) {
         const int k = hb.order[sIdx];
         const PtbGeom &g = scene->geoms[prims[k].first];

@@ -30,9 +30,9 @@ namespace ptb {
 constexpr int kBlock = PTB_BLOCK;
 constexpr uint32_t kDeadBit = 0x80000000u;
 
-struct BvhNode {                 // 64 B = four 128-bit loads: a binary node holding BOTH child boxes
-    float4 llo, lhi;             // left  child: min.xyz | ref (int bits), max.xyz | count (int bits)
-    float4 rlo, rhi;             // right child: same.  count > 0: leaf, ref = first geom slot;
+struct BvhNode {                 // 64 B = four 128-bit loads: a binary node holding BOTH child boxes, the planes of the
+    float4 x, y, z;              // two children paired per axis: x = (left.lo.x, right.lo.x, left.hi.x, right.hi.x), ...
+    int4   m;                    // left ref, right ref, left count, right count.  count > 0: leaf, ref = first geom slot;
 };                               //              count == 0: interior, ref = node index; ref < 0: empty
 
 struct PathPlanes { float4 *A; float4 *B; float2 *C; };
@@ -304,18 +304,54 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
     }
 }
 
-// Conservative ray/AABB test for pruning only.  The boxes are padded on the host (ptb_bvh.cpp) to cover
-// the reference's rounding and its 1e-4 fall-short (src/intersections.h:27-29); tNear is the entry
-// parameter along the ray in units of |d|.  fminf/fmaxf drop the NaNs that 0*inf produces when the
-// origin lies on a slab plane, which errs on the side of visiting.
-PTB_DEV bool slabNear(float4 lo, float4 hi, f3 o, f3 inv, float &tNear) {
-    float tx0 = (lo.x - o.x) * inv.x, tx1 = (hi.x - o.x) * inv.x;
-    float ty0 = (lo.y - o.y) * inv.y, ty1 = (hi.y - o.y) * inv.y;
-    float tz0 = (lo.z - o.z) * inv.z, tz1 = (hi.z - o.z) * inv.z;
-    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
-    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
-    tNear = tn;
-    return tn <= tf * 1.00001f + 1e-5f;
+// Conservative ray/AABB test of BOTH child boxes of a node, for pruning only.  The boxes are padded on the host
+// (ptb_bvh.cpp) to cover the reference's rounding and its 1e-4 fall-short (src/intersections.h:27-29); tl / tr are
+// the entry parameters along the ray in units of |d|.  The lo planes of the two children on one axis go through one
+// packed subtract and one packed multiply, the hi planes through another (12 packed operations per node where the
+// scalar test needs 24).  fminf/fmaxf drop the NaNs that 0*inf produces when the origin lies on a slab plane, which
+// errs on the side of visiting.
+PTB_DEV void slabNearPair(float4 X, float4 Y, float4 Z, f3 o, f3 inv, float &tl, float &tr, bool &hl, bool &hr) {
+    float lx0, rx0, lx1, rx1, ly0, ry0, ly1, ry1, lz0, rz0, lz1, rz1;
+    upk2(mul2(add2(pk2(X.x, X.y), bc2(-o.x)), bc2(inv.x)), lx0, rx0);
+    upk2(mul2(add2(pk2(X.z, X.w), bc2(-o.x)), bc2(inv.x)), lx1, rx1);
+    upk2(mul2(add2(pk2(Y.x, Y.y), bc2(-o.y)), bc2(inv.y)), ly0, ry0);
+    upk2(mul2(add2(pk2(Y.z, Y.w), bc2(-o.y)), bc2(inv.y)), ly1, ry1);
+    upk2(mul2(add2(pk2(Z.x, Z.y), bc2(-o.z)), bc2(inv.z)), lz0, rz0);
+    upk2(mul2(add2(pk2(Z.z, Z.w), bc2(-o.z)), bc2(inv.z)), lz1, rz1);
+    tl = fmaxf(fmaxf(fminf(lx0, lx1), fminf(ly0, ly1)), fmaxf(fminf(lz0, lz1), 0.0f));
+    tr = fmaxf(fmaxf(fminf(rx0, rx1), fminf(ry0, ry1)), fmaxf(fminf(rz0, rz1), 0.0f));
+    const float fl = fminf(fminf(fmaxf(lx0, lx1), fmaxf(ly0, ly1)), fmaxf(lz0, lz1));
+    const float fr = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1));
+    hl = tl <= fl * 1.00001f + 1e-5f;
+    hr = tr <= fr * 1.00001f + 1e-5f;
+}
+
+// One traversal step at `node`: slab-test both child boxes against the best distance so far; returns the children to
+// visit as stack entries (interior -> node index (>= 0), leaf -> ~(ref | count << 27) (< 0)): `next` (haveNext) is
+// the nearer one, `far` (haveFar) the other.
+PTB_DEV void bvhNodeStep(const BvhNode *snodes, int smemNodes, const BvhNode *gnodes, int node, f3 o, f3 invD, float dl, float bestT,
+                         int &next, bool &haveNext, int &far, bool &haveFar) {
+    float4 X, Y, Z; int4 m;
+    if (node < smemNodes) { X = snodes[node].x; Y = snodes[node].y; Z = snodes[node].z; m = snodes[node].m; }
+    else {
+        const float4 *np = reinterpret_cast<const float4 *>(gnodes + node);
+        X = __ldg(np); Y = __ldg(np + 1); Z = __ldg(np + 2); m = __ldg(reinterpret_cast<const int4 *>(np + 3));
+    }
+    float tl, tr; bool hl, hr;
+    slabNearPair(X, Y, Z, o, invD, tl, tr, hl, hr);
+    // tNear * |d| (slackened) is a lower bound of the world distance of anything inside the box
+    const bool vl = m.x >= 0 && hl && tl * dl - 1e-4f <= bestT;
+    const bool vr = m.y >= 0 && hr && tr * dl - 1e-4f <= bestT;
+    const int cl = m.z > 0 ? ~(m.x | (m.z << 27)) : m.x;
+    const int cr = m.w > 0 ? ~(m.y | (m.w << 27)) : m.y;
+    haveNext = true; haveFar = false; next = 0; far = 0;
+    if (vl && vr) {
+        const bool leftFirst = tl <= tr;
+        next = leftFirst ? cl : cr;
+        far = leftFirst ? cr : cl; haveFar = true;
+    } else if (vl) next = cl;
+    else if (vr) next = cr;
+    else haveNext = false;
 }
 
 PTB_DEV GeomRec loadGeom(const GeomRec *gp) {
@@ -424,28 +460,9 @@ PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, const int sme
             if (e < 0) { const int enc = ~e; primRef = enc & 0x7ffffff; primCnt = enc >> 27; continue; }
             node = e;
         }
-        float4 llo, lhi, rlo, rhi;
-        if (node < smemNodes) { llo = snodes[node].llo; lhi = snodes[node].lhi; rlo = snodes[node].rlo; rhi = snodes[node].rhi; }
-        else {
-            const float4 *np = reinterpret_cast<const float4 *>(p.bvh + node);
-            llo = __ldg(np); lhi = __ldg(np + 1); rlo = __ldg(np + 2); rhi = __ldg(np + 3);
-        }
-        float tl, tr;
-        // tNear * |d| (slackened) is a lower bound of the world distance of anything inside the box
-        const bool vl = __float_as_int(llo.w) >= 0 && slabNear(llo, lhi, o, invD, tl) && tl * dl - 1e-4f <= best.t;
-        const bool vr = __float_as_int(rlo.w) >= 0 && slabNear(rlo, rhi, o, invD, tr) && tr * dl - 1e-4f <= best.t;
-        // children as stack entries: interior -> node index (>= 0), leaf -> ~(ref | count << 27) (< 0)
-        const int cl = __float_as_int(lhi.w) > 0 ? ~(__float_as_int(llo.w) | (__float_as_int(lhi.w) << 27)) : __float_as_int(llo.w);
-        const int cr = __float_as_int(rhi.w) > 0 ? ~(__float_as_int(rlo.w) | (__float_as_int(rhi.w) << 27)) : __float_as_int(rlo.w);
-        int next = 0;
-        bool haveNext = true;
-        if (vl && vr) {
-            const bool leftFirst = tl <= tr;
-            next = leftFirst ? cl : cr;
-            if (sp < 64) stack[sp++] = leftFirst ? cr : cl;
-        } else if (vl) next = cl;
-        else if (vr) next = cr;
-        else haveNext = false;
+        int next, far; bool haveNext, haveFar;
+        bvhNodeStep(snodes, smemNodes, p.bvh, node, o, invD, dl, best.t, next, haveNext, far, haveFar);
+        if (haveFar && sp < 64) stack[sp++] = far;
         node = -1;
         if (haveNext) {
             if (next < 0) { const int enc = ~next; primRef = enc & 0x7ffffff; primCnt = enc >> 27; }
@@ -762,28 +779,9 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const 
                 }
             }
             if (node >= 0) {
-                float4 llo, lhi, rlo, rhi;
-                if (node < smemNodes) { llo = snodes[node].llo; lhi = snodes[node].lhi; rlo = snodes[node].rlo; rhi = snodes[node].rhi; }
-                else {
-                    const float4 *np = reinterpret_cast<const float4 *>(p.bvh + node);
-                    llo = __ldg(np); lhi = __ldg(np + 1); rlo = __ldg(np + 2); rhi = __ldg(np + 3);
-                }
-                float tl, tr;
-                // tNear * |d| (slackened) is a lower bound of the world distance of anything inside the box
-                const bool vl = __float_as_int(llo.w) >= 0 && slabNear(llo, lhi, o, invD, tl) && tl * dl - 1e-4f <= best.t;
-                const bool vr = __float_as_int(rlo.w) >= 0 && slabNear(rlo, rhi, o, invD, tr) && tr * dl - 1e-4f <= best.t;
-                // children as stack entries: interior -> node index (>= 0), leaf -> ~(ref | count << 27) (< 0)
-                const int cl = __float_as_int(lhi.w) > 0 ? ~(__float_as_int(llo.w) | (__float_as_int(lhi.w) << 27)) : __float_as_int(llo.w);
-                const int cr = __float_as_int(rhi.w) > 0 ? ~(__float_as_int(rlo.w) | (__float_as_int(rhi.w) << 27)) : __float_as_int(rlo.w);
-                int next = 0;
-                bool haveNext = true;
-                if (vl && vr) {
-                    const bool leftFirst = tl <= tr;
-                    next = leftFirst ? cl : cr;
-                    if (sp < 64) stack[sp++] = leftFirst ? cr : cl;
-                } else if (vl) next = cl;
-                else if (vr) next = cr;
-                else haveNext = false;
+                int next, far; bool haveNext, haveFar;
+                bvhNodeStep(snodes, smemNodes, p.bvh, node, o, invD, dl, best.t, next, haveNext, far, haveFar);
+                if (haveFar && sp < 64) stack[sp++] = far;
                 node = -1;
                 if (haveNext) {
                     if (next < 0) { const int enc = ~next; primRef = enc & 0x7ffffff; primCnt = enc >> 27; }

@@ -254,6 +254,24 @@ def test_pipelines_agree_bit_for_bit(m, scene_dir):
         assert same_bits(im, imgs[0][1]), tag
 
 
+def test_bounce_loop_launch_matches_one_launch_per_bounce(m, scene_dir, monkeypatch):
+    """Brute-force scenes run bounces 1.. in one launch (bounce_loop_kernel: each CTA walks its own path segment
+    through the remaining bounces).  Same per-path arithmetic as one bounce_kernel launch per bounce: identical
+    images bit for bit (B = 1: one writer per pixel), identical per-depth counts, fewer launches."""
+    for name in ("cornell", "glass"):
+        s = m.Scene.load(scene_dir + "/%s.txt" % name)
+        out = {}
+        for loop in ("0", "1"):
+            monkeypatch.setenv("PTB_LOOP_BOUNCES", loop)          # read by ptb_create (tuning knob)
+            with m.Renderer(s, device=0, bsdf=1, batch_iters=1) as r:
+                r.render(1, 3)
+                out[loop] = (r.download(), r.stats())
+        monkeypatch.delenv("PTB_LOOP_BOUNCES")
+        assert same_bits(out["0"][0], out["1"][0]), name
+        assert out["0"][1]["alive_per_depth"] == out["1"][1]["alive_per_depth"], name
+        assert out["1"][1]["kernel_launches"] < out["0"][1]["kernel_launches"], name
+
+
 def test_batched_wavefront_matches_sequential(m, scene_dir):
     """B iterations per wavefront deposit with float atomics: same sums up to addition order."""
     s = m.Scene.load(scene_dir + "/cornell.txt")
