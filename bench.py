@@ -346,7 +346,9 @@ def main():
         hbm_peak, peak_src, sm_max = load_peaks()
         alg_bytes = BYTES_PER_SEGMENT * seg_all + BYTES_PER_PIXEL_ITER * P * iters_all
         achieved = alg_bytes / (ms * 1e-3) / 1e9 / world             # per GPU
-        bounce_launches = launches_all / world
+        # per GPU: every batch is `bounce launches` + one advance_kernel, every ptb_render call one set_control_kernel
+        batches = iters_all / world / st1["batch_iters"]
+        bounce_launches = max(1.0, launches_all / world - batches - args.steps)
         traffic = None
         import glob
         profs = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_bounce_traffic.json")))    # newest ncu --set full capture
@@ -377,7 +379,7 @@ def main():
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "ptb::bounce_kernel (bounce 0) + ptb::bounce_loop_kernel (bounces 1..)",
                          "algorithmic_bytes": "88 B/segment + 24 B/pixel/iteration (SURVEY.md 8(d))",
-                         "launches_in_timed_region_per_gpu": bounce_launches,
+                         "bounce_launches_in_timed_region_per_gpu": bounce_launches,
                          "avg_launch_us": ms * 1e3 / max(1.0, bounce_launches),
                          "fp32": {"achieved_tflops": FLOP_PER_SEGMENT * seg_all / (ms * 1e-3) / 1e12 / world,
                                   "peak_tflops": 148 * 128 * 2 * sm_max * 1e6 / 1e12, "flop_per_segment": FLOP_PER_SEGMENT,
