@@ -932,3 +932,14 @@ int ptb_stage_rng(PtbContext *c, int iter, int index, int depth, int n, float *o
 }
 
 } // extern "C"
+
+#ifdef PTB_WALK_STATS
+// tuning builds only: read and clear the candidate-walk histogram (ptb_kernels.cuh, PTB_WALK_COUNT)
+extern "C" int ptb_debug_walk_stats(unsigned long long *out) {
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(out, ptb::g_walkStats, sizeof(unsigned long long) * 128) != cudaSuccess) return 1;
+    static unsigned long long zeros[128];
+    return cudaMemcpyToSymbol(ptb::g_walkStats, zeros, sizeof zeros) != cudaSuccess;
+}
+#endif
+

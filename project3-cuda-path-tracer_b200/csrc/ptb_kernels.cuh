@@ -249,6 +249,15 @@ PTB_DEV void boundsPhase(const GeomRec *sg, int g0, int c1, int g1, const BruteR
     }
 }
 
+#ifdef PTB_WALK_STATS
+// tuning builds only (tools/build_variant.sh -DPTB_WALK_STATS): histogram of the candidate walk,
+// [walk iteration of the lane, capped at 4][candidate slot < 8][0 filtered, 1 exact miss, 2 exact hit accepted, 3 exact hit rejected]
+__device__ unsigned long long g_walkStats[4 * 8 * 4];
+#define PTB_WALK_COUNT(it, cand, what) atomicAdd(&g_walkStats[(min((it), 4) - 1) * 32 + ((cand) & 7) * 4 + (what)], 1ull)
+#else
+#define PTB_WALK_COUNT(it, cand, what)
+#endif
+
 // `valid` = this lane carries a ray (callers keep their loops warp-uniform).
 PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o, f3 d, bool valid, Candidate &best) {
     best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
@@ -291,12 +300,19 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
                     // the whole exact test as a separate pass.
                     bool miss = boxSureMiss(qo, qu);
                     if (sg[cand].tag.x != 1) miss = sphereSureMiss(qo, qu);
+                    if (miss) PTB_WALK_COUNT(taken, cand, 0);
                     if (!miss) { g = cand; break; }
                 }
                 if (g < 0) break;
                 int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
                 const float t = exactTestQ(sg[g], o, qo, qu, outside, a, b, c);
+#ifdef PTB_WALK_STATS
+                const float before = best.t;
+#endif
                 acceptHit(sg[g], g, t, outside, a, b, c, best, orig);
+#ifdef PTB_WALK_STATS
+                PTB_WALK_COUNT(taken, g, !(t > 0.0f) ? 1 : (best.t != before ? 2 : 3));
+#endif
             }
             if (!(valid && exhausted && taken == 3)) break;       // all three keys walked and the bound never ended the walk: look for more
             floorKey = lastKey + 1u;

@@ -6,7 +6,8 @@ One process per GPU:
 Rank r renders iterations r+1, r+1+N, ... (spp_split.rank_iterations) into its private buffer; the frame is the
 NCCL sum-reduce to rank 0.  Time: CUDA events on the launching stream around render + reduce, max over ranks.
 --check: rank 0 afterwards renders ALL the iterations alone and compares the reduced frame with it (the float
-summation order differs between the two, SURVEY.md 8(e) caveat; the bar is 1e-5 relative per pixel channel of the mean).
+summation order differs between the two, SURVEY.md 8(e) caveat; the bar is the recursive-summation bound, iterations * 2^-24
+relative per pixel channel of the mean -- pixels whose samples are all equal reach 5e-5 at 5000 spp).
 One JSON line per config on rank 0."""
 import json, os, sys, tempfile, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -95,7 +96,8 @@ for name in which:
         out["max_abs_diff_of_mean"] = float((a - bb).abs().max().item())
         out["max_rel_diff_of_mean"] = float(((a - bb).abs() / bb.abs().clamp_min(1e-3)).max().item())
         out["frame_mean"] = float(a.mean().item())
-        out["check_ok"] = bool(out["max_rel_diff_of_mean"] <= 1e-5)
+        out["check_bar"] = total * 2.0 ** -24                  # recursive float32 summation of `total` samples
+        out["check_ok"] = bool(out["max_rel_diff_of_mean"] <= out["check_bar"])
     if rank == 0:
         print(json.dumps(out), flush=True)
     barrier()
