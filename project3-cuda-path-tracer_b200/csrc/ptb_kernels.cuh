@@ -293,13 +293,20 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
                     lastKey = k0; ++taken;
                     k0 = k1; k1 = k2; k2 = kNoCand;
                     objectRay(sg[cand], o, d, qo, qu);
-                    // The cube filter runs for every lane and the sphere filter overrides it inside a plain `if`
-                    // (no break / continue in either arm), so the lanes reconverge right here.  With the filters
-                    // in the two arms of a type branch that both lead to the loop exits, the lanes holding a
-                    // sphere candidate (2 of 32 on the cornell box, in two warps out of three) went through
-                    // the whole exact test as a separate pass.
                     bool miss = boxSureMiss(qo, qu);
-                    if (sg[cand].tag.x != 1) miss = sphereSureMiss(qo, qu);
+                    // The cube filter runs for every lane; the sphere filter runs for ALL the lanes of this walk step as
+                    // soon as one of them holds a sphere (a vote among the lanes converged here) and a select keeps each
+                    // lane's own answer -- there is no divergent arm, so the lanes arrive together at the loop exits.
+                    // History: with the filters in the two arms of a type branch the sphere lanes (2 of 32 on the
+                    // cornell box) went through the whole exact test as a separate pass; with the sphere filter as a
+                    // plain `if` overriding the cube result they still left that arm on their own and ran the rest of
+                    // the walk alone -- 2.61 object-ray + filter passes per warp where 2 are needed (ncu source
+                    // counters, profiles/r01p_loop_regions.txt); the vote + select brought 112.9 -> 110.7 us/iteration.
+                    const bool sph = sg[cand].tag.x != 1;
+                    if (__any_sync(__activemask(), sph)) {
+                        const bool sm = sphereSureMiss(qo, qu);
+                        miss = sph ? sm : miss;
+                    }
                     if (miss) PTB_WALK_COUNT(taken, cand, 0);
                     if (!miss) { g = cand; break; }
                 }
