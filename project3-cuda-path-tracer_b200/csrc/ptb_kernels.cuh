@@ -862,22 +862,22 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const 
 // ------------------------------------------------------------------------------------------------
 // EXT compiles in the camera / material extensions (antialiasing, thin lens, imperfect specular); scenes
 // that use none of them run the EXT = false instantiation, which is the round-1 code path unchanged.
-// One bounce of one CTA's segment: the warps of the CTA pull 32-path chunks from *sNextChunk until the
-// segment's `total` paths (FIRST: nChunks chunks of the CTA's camera-path tiles) are done, and pack the
+// One bounce of one CTA's segment: warp w of the CTA takes the 32-path chunks w, w + 8, ... of the segment's
+// `total` paths (FIRST: nChunks chunks of the CTA's camera-path tiles), and the warps pack the
 // survivors at the front of the CTA's segment of `pout`; *sOutCount ends up holding their number.
 template <bool FIRST, bool USE_BVH, bool EXT>
 PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPlanes &pout, const int depth, const GeomRec *sgeoms,
                            const int numCubes, const CameraParams &cam, const int iterBase, const int iterStride,
-                           const uint32_t total, const uint32_t nChunks, uint32_t *sNextChunk, uint32_t *sOutCount) {
+                           const uint32_t total, const uint32_t nChunks, uint32_t *sOutCount) {
     const int remainingBefore = p.traceDepth - depth;
     const uint32_t pixMask = (1u << p.pixBits) - 1u;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t segBase = blockIdx.x * p.segCap;
-    for (;;) {
-        uint32_t chunk = 0;
-        if (lane == 0) chunk = atomicAdd(sNextChunk, 1u);
-        chunk = __shfl_sync(0xffffffffu, chunk, 0);
-        if (chunk >= nChunks) break;
+    // Warp w of the CTA takes chunks w, w + 8, ... of the segment.  (A shared-memory ticket per chunk balanced the
+    // warps no better -- the other resident CTAs fill an SM whose CTA is in its tail -- and cost 14 single-lane
+    // instructions per chunk: ptxas wraps every one-lane shared atomic, inline PTX included, in its warp-aggregation
+    // sequence.  Static assignment: 110.6 -> 108.6 us per cornell iteration, profiles/r01w_static_chunks_ab.txt.)
+    for (uint32_t chunk = threadIdx.x >> 5; chunk < nChunks; chunk += kBlock / 32) {
 
         bool alive = false, valid;
         f3 o, d, c; uint32_t id = 0;
@@ -897,6 +897,21 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
             const uint32_t k = chunk * 32u + lane;
             valid = k < total;
             if (valid) loadPathRay(pin, segBase + k, o, d);           // throughput and id follow after the search
+#ifdef PTB_PREFETCH
+            // the warp's next chunk (static assignment: chunk + 8) on its way while this one is traced
+            const uint32_t kn = k + kBlock;
+            if (kn < total) {
+#if PTB_PREFETCH == 1
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(pin.A + segBase + kn));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(pin.B + segBase + kn));
+                asm volatile("prefetch.global.L2 [%0];" :: "l"(pin.C + segBase + kn));
+#else
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(pin.A + segBase + kn));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(pin.B + segBase + kn));
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(pin.C + segBase + kn));
+#endif
+            }
+#endif
         }
         Candidate best;
         const bool cached = FIRST && p.fbTn != nullptr;            // warp-uniform
@@ -964,9 +979,9 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
 template <bool FIRST, bool USE_BVH, bool EXT>
 __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __grid_constant__ Params p, const int depth) {
     extern __shared__ float4 smem4[];
-    __shared__ uint32_t sNextChunk, sOutCount;
+    __shared__ uint32_t sOutCount;
 
-    if (threadIdx.x == 0) { sNextChunk = 0u; sOutCount = 0u; }
+    if (threadIdx.x == 0) sOutCount = 0u;
     const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
     // USE_BVH: the closest hits were found by trace_bvh_kernel (raw hit records in p.hits); nothing to stage
     if (USE_BVH) __syncthreads();
@@ -990,7 +1005,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
         total = segIn[blockIdx.x];
         nChunks = (total + 31u) / 32u;
     }
-    bounceSegment<FIRST, USE_BVH, EXT>(p, p.in, p.out, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, nChunks, &sNextChunk, &sOutCount);
+    bounceSegment<FIRST, USE_BVH, EXT>(p, p.in, p.out, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, nChunks, &sOutCount);
     __syncthreads();
     if (threadIdx.x == 0) {
         const uint32_t n = sOutCount;
@@ -1009,9 +1024,9 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
 template <bool EXT>
 __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_loop_kernel(const __grid_constant__ Params p, const int depthBegin) {
     extern __shared__ float4 smem4[];
-    __shared__ uint32_t sNextChunk, sOutCount;
+    __shared__ uint32_t sOutCount;
 
-    if (threadIdx.x == 0) { sNextChunk = 0u; sOutCount = 0u; }
+    if (threadIdx.x == 0) sOutCount = 0u;
     const int numCubes = p.hdr->numCubes;
     stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);      // ends with __syncthreads
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
@@ -1021,14 +1036,14 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_loop_kernel(cons
     uint32_t total = p.segCounts[((depthBegin + 1) & 1) * gridDim.x + blockIdx.x];
     PathPlanes pin = p.in, pout = p.out;
     for (int depth = depthBegin; depth < p.traceDepth && total > 0u; ++depth) {
-        bounceSegment<false, false, EXT>(p, pin, pout, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, (total + 31u) / 32u, &sNextChunk, &sOutCount);
+        bounceSegment<false, false, EXT>(p, pin, pout, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, (total + 31u) / 32u, &sOutCount);
         __syncthreads();                                               // the survivors are written and counted
         total = sOutCount;
         const PathPlanes t = pin; pin = pout; pout = t;
         __syncthreads();                                               // everyone has read the count ...
         if (threadIdx.x == 0) {                                        // ... before it is cleared for the next bounce
             if (total) atomicAdd(&ctrl->counts[depth + 1], total);
-            sNextChunk = 0u; sOutCount = 0u;
+            sOutCount = 0u;
         }
         __syncthreads();
     }
