@@ -634,6 +634,18 @@ PTB_DEV void storePath(const PathPlanes &s, uint32_t i, f3 o, f3 d, f3 c, uint32
     s.C[i] = make_float2(c.z, __uint_as_float(id));
 }
 
+// The staged scene table's base as a VALUE held in a register.  Every shared-memory access through a pointer
+// needs the CTA's shared-window base ((cluster CTA rank << 24) + 0x400 + offset: S2UR SR_CgaCtaId, UMOV, UIADD3, ULEA);
+// left alone, ptxas rematerialises those four instructions in front of every block that touches the table (14 sites
+// in the loop kernel, 10 executed per 32-path chunk; held: 5 sites, cornell 108.7 -> 107.2 us/iteration).  Used by the
+// brute-force bounce kernels only: in trace_bvh_kernel the extra live register spills (synthetic scene +0.9 %).
+template <typename T>
+PTB_DEV const T *heldSharedBase(const void *smem) {
+    uint32_t a = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("mov.u32 %0, %0;" : "+r"(a));
+    return reinterpret_cast<const T *>(__cvta_shared_to_generic((size_t)a));
+}
+
 // cooperative copy of the scene tables into shared memory (geoms for brute force, BVH top levels)
 PTB_DEV void stageShared(float4 *dst, const float4 *src, int nFloat4) {
     for (int i = threadIdx.x; i < nFloat4; i += blockDim.x) dst[i] = __ldg(src + i);
@@ -897,21 +909,6 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
             const uint32_t k = chunk * 32u + lane;
             valid = k < total;
             if (valid) loadPathRay(pin, segBase + k, o, d);           // throughput and id follow after the search
-#ifdef PTB_PREFETCH
-            // the warp's next chunk (static assignment: chunk + 8) on its way while this one is traced
-            const uint32_t kn = k + kBlock;
-            if (kn < total) {
-#if PTB_PREFETCH == 1
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(pin.A + segBase + kn));
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(pin.B + segBase + kn));
-                asm volatile("prefetch.global.L2 [%0];" :: "l"(pin.C + segBase + kn));
-#else
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(pin.A + segBase + kn));
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(pin.B + segBase + kn));
-                asm volatile("prefetch.global.L1 [%0];" :: "l"(pin.C + segBase + kn));
-#endif
-            }
-#endif
         }
         Candidate best;
         const bool cached = FIRST && p.fbTn != nullptr;            // warp-uniform
@@ -986,7 +983,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
     // USE_BVH: the closest hits were found by trace_bvh_kernel (raw hit records in p.hits); nothing to stage
     if (USE_BVH) __syncthreads();
     else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);      // ends with __syncthreads
-    const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
+    const GeomRec *sgeoms = heldSharedBase<GeomRec>(smem4);
 
     Control *ctrl = p.ctrl;
     CameraParams cam;
@@ -1029,7 +1026,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_loop_kernel(cons
     if (threadIdx.x == 0) sOutCount = 0u;
     const int numCubes = p.hdr->numCubes;
     stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);      // ends with __syncthreads
-    const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
+    const GeomRec *sgeoms = heldSharedBase<GeomRec>(smem4);
     Control *ctrl = p.ctrl;
     CameraParams cam;                                                  // never read: no camera rays after bounce 0
     const int iterBase = ctrl->iterBase, iterStride = ctrl->iterStride;
