@@ -704,10 +704,20 @@ PTB_DEV uint32_t compactSlot(bool keep, uint32_t *counter, int *warpTotals, uint
 #define PTB_REFILL_LANES 8
 #endif
 constexpr int kRefillLanes = PTB_REFILL_LANES;
-#ifndef PTB_EXACT_LANES
-#define PTB_EXACT_LANES 8
+// Stage thresholds of the state machine below, tuned on the synthetic 100 k-object scene (profiles/r02_bvh_state_machine_ab.txt:
+// 5 994 -> 4 442 us per iteration):
+#ifndef PTB_BVH_STEPS
+#define PTB_BVH_STEPS 8
 #endif
-constexpr int kExactLanes = PTB_EXACT_LANES;                       // lanes that must wait before the exact test runs (unless nobody can work)
+constexpr int kStepsPerPass = PTB_BVH_STEPS;                       // traversal steps (stage A) per pass
+#ifndef PTB_PRUNE_LANES
+#define PTB_PRUNE_LANES 8
+#endif
+constexpr int kPruneLanes = PTB_PRUNE_LANES;                       // lanes with a pending leaf that gather before stage B runs
+#ifndef PTB_EXACT_LANES
+#define PTB_EXACT_LANES 1
+#endif
+constexpr int kExactLanes = PTB_EXACT_LANES;                       // lanes with a candidate that gather before stage C runs
 
 template <bool FIRST, bool EXT, bool MESH>
 __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const __grid_constant__ Params p, const int depth) {
@@ -796,10 +806,13 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const 
             if (drained) break;
             continue;                                             // every lane idle: the next pass refills
         }
-        // One pass = A, then B, then (when enough lanes wait) C, each a plain `if` the lanes reconverge
-        // after: a lane that pops a leaf in A prunes its first primitive in the same pass, and one that
-        // finds a candidate in B can take part in this pass's exact test.
-        // ---- A: one traversal step (lanes with nothing pending)
+        // One pass = kStepsPerPass x A, then B (when kPruneLanes lanes hold a pending leaf, or nobody can step), then C
+        // (when kExactLanes lanes hold a candidate, or nobody else can work), each a plain `if` the lanes reconverge
+        // after: a lane whose leaf survives B can take part in this pass's exact test.
+        // ---- A: traversal steps (lanes with nothing pending); kStepsPerPass of them per pass, because a pass costs
+        // ~40 instructions of votes and branches whatever its lanes do and most passes are traversal only
+#pragma unroll 1
+        for (int rep = 0; rep < kStepsPerPass; ++rep)
         if (!done && cand < 0 && primCnt == 0) {
             if (node < 0) {
                 if (sp == 0) {
@@ -824,8 +837,12 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const 
                 }
             }
         }
-        // ---- B: prune one primitive of the pending leaf
-        if (!done && cand < 0 && primCnt > 0) {
+        // ---- B: prune one primitive of the pending leaf, entered by kPruneLanes lanes together (or when no lane has
+        // traversal work left): with every lane pruning on its own this stage ran with 2 of 32 lanes active
+        const bool pending = !done && cand < 0 && primCnt > 0;
+        const unsigned pend = __ballot_sync(0xffffffffu, pending);
+        const unsigned canStep = __ballot_sync(0xffffffffu, !done && cand < 0 && primCnt == 0);
+        if (pend && ((int)__popc(pend) >= kPruneLanes || !canStep) && pending) {
             const int slot = primRef;
             ++primRef; --primCnt;
             const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + slot);
