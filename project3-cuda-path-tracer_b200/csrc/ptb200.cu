@@ -14,6 +14,9 @@
 #include <string>
 #include <vector>
 
+#ifndef PTB_SMEM_NODES
+#define PTB_SMEM_NODES 511          // leading BVH nodes (BFS order = top levels) staged in shared memory by the BVH kernels
+#endif
 using namespace ptb;
 
 namespace {
@@ -286,7 +289,7 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
                                                : packGeom(g, prims[k].first, k);
     }
     c->numNodes = (int)hb.nodes.size();
-    c->smemNodes = std::min(c->numNodes, 511);
+    c->smemNodes = std::min(c->numNodes, PTB_SMEM_NODES);
     for (int i = 0; i < M; ++i) {
         const PtbMaterial &m = scene->materials[i];
         mats[3 * i + 0] = make_float4(m.color[0], m.color[1], m.color[2], m.emittance);
@@ -571,7 +574,7 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
 
     // ---- launch geometry ----
     c->smemBrute = bruteBytes;
-    c->smemBvh = (size_t)511 * sizeof(BvhNode);     // fixed: the node count may change in ptb_update_scene
+    c->smemBvh = (size_t)PTB_SMEM_NODES * sizeof(BvhNode);     // fixed: the node count may change in ptb_update_scene
     if (bruteBytes <= 200 * 1024) {                  // brute force is only launchable when the geoms fit in shared memory
         int rc = PTB_OK;
         rc |= setSmem(bounce_kernel<true, false, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, false>, c->smemBrute);

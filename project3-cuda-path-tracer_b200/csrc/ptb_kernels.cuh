@@ -719,8 +719,11 @@ constexpr int kPruneLanes = PTB_PRUNE_LANES;                       // lanes with
 #endif
 constexpr int kExactLanes = PTB_EXACT_LANES;                       // lanes with a candidate that gather before stage C runs
 
+#ifndef PTB_BVH_MINBLOCKS
+#define PTB_BVH_MINBLOCKS PTB_MINBLOCKS
+#endif
 template <bool FIRST, bool EXT, bool MESH>
-__global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) trace_bvh_kernel(const __grid_constant__ Params p, const int depth) {
+__global__ void __launch_bounds__(kBlock, PTB_BVH_MINBLOCKS) trace_bvh_kernel(const __grid_constant__ Params p, const int depth) {
     extern __shared__ float4 smem4[];
     __shared__ uint32_t sNextTicket;
     if (threadIdx.x == 0) sNextTicket = 0u;
