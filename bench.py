@@ -118,9 +118,14 @@ def cpu_reference_run(scene_path, iters_per_sample, repeats, nthreads=0):
     if orc is None:
         raise RuntimeError("neither oracle/_ref/libptref.so nor oracle/libptoracle.so is built")
     scene = orc.load_scene(scene_path)
-    cores = os.cpu_count() or 1
-    if nthreads:
-        cores = nthreads
+    # the thread count is passed explicitly (omp_set_num_threads in the oracle): torchrun exports OMP_NUM_THREADS=1 to
+    # its workers, which would silently turn the all-cores baseline of an N > 1 launch into a one-core run
+    if not nthreads:
+        try:
+            nthreads = len(os.sched_getaffinity(0))
+        except (AttributeError, OSError):
+            nthreads = os.cpu_count() or 1
+    cores = nthreads
     best = None
     total_seg, total_t = 0, 0.0
     for _ in range(repeats):
