@@ -35,7 +35,7 @@ WORKLOAD = "scenes/cornell.txt 800x800 traceDepth 8 (BASELINE.json configs[2] sc
 METRIC = "path_segments_per_s"
 UNIT = "segments/s"
 SPP_PER_STEP = 256            # iterations per step (frame)
-BATCH_ITERS = 64              # iterations per wavefront: 40.96 M paths, 2 x 1.64 GB of path state (>> 126 MB L2)
+BATCH_ITERS = 128             # iterations per wavefront: 81.92 M paths, 2 x 3.28 GB of path state (>> 126 MB L2); 32: 109.3, 64: 107.2, 128: 106.1, 256: 105.5 us/iteration
 CPU_ITERS = 16                # BASELINE.json configs[0]: 16 iterations through the reference's host functions
 FLOP_PER_SEGMENT = 700        # ~7 ray-primitive tests + scatter, FMA counted as 2
 BYTES_PER_SEGMENT = 88        # 44 B read + 44 B write of path state

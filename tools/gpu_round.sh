@@ -18,7 +18,7 @@ if [ -x oracle/_ref/skeleton_bench ]; then
 fi
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --spp-per-step 16 --no-cpu-baseline > gpurun_out/${TAG}_bench_under_ncu.log 2>&1
-# one full capture of the two bounce launches (bounce 0, bounces 1..) of the timed step's 64-iteration wavefront
+# one full capture of the two bounce launches (bounce 0, bounces 1..) of the timed step's 128-iteration wavefront (bench.py BATCH_ITERS)
 ncu --set full --clock-control none --import-source on -k regex:bounce -s 6 -c 2 -f -o gpurun_out/${TAG}_bounce \
-    python bench.py --steps 1 --warmup 3 --spp-per-step 64 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
+    python bench.py --steps 1 --warmup 3 --spp-per-step 128 --no-cpu-baseline > gpurun_out/${TAG}_ncu_full.log 2>&1
 ls -la gpurun_out
