@@ -98,6 +98,26 @@ def test_synthetic_100k_full_size_properties(m, port, synthetic):
         assert same_bits(whole, r.download())
 
 
+def test_far_sphere_hit_the_reference_reports_outside_the_sphere(m, port, synthetic):
+    """Regression for the BVH leaf boxes: at ~240 object units from the origin of a thin ellipsoid the reference's sphere
+    test (src/intersections.h:102-144) loses |ro|^2 - 0.25 against (ro . rd)^2 and reports a hit for a ray that passes just
+    OUTSIDE the sphere; a box hugging the ellipsoid dropped that hit (iteration 14, pixel 1041646, depth 9 of the synthetic
+    scene: profiles/r03_bvh_pathdiff.txt).  The BVH must return what the reference's brute-force loop returns."""
+    s = m.Scene.load(synthetic)
+    os_ = port.load_scene(synthetic)
+    o = np.array([[26.248161, 22.502022, -8.040187]], np.float32)
+    d = np.array([[0.16347983, 0.02360658, -0.9862642]], np.float32)
+    # neighbours of the ray as well: the same geometry a few ulps away
+    rs = np.random.RandomState(14)
+    o = np.concatenate([o, o + rs.uniform(-2e-5, 2e-5, (4095, 3)).astype(np.float32)])
+    d = np.concatenate([d, d + rs.uniform(-2e-7, 2e-7, (4095, 3)).astype(np.float32)])
+    want = port.closest_hit(os_.geoms, o, d)
+    assert want[0][0] == 31153 and (want[0] == 31153).sum() > 100 and (want[0] != 31153).sum() > 100      # the grazing band
+    with m.Renderer(s, device=0, bsdf=1, batch_iters=1) as r:
+        hit, t, n, outside = r.stage_intersect(o, d, m.ACCEL_BVH)
+    assert np.array_equal(hit, want[0]) and same_bits(t, want[1]) and same_bits(n, want[2]) and np.array_equal(outside, want[3])
+
+
 def test_4k_cornell_properties(m):
     """configs[3] resolution (3840x2160): linearity of the accumulation and interleaved spp split."""
     import tempfile, os
