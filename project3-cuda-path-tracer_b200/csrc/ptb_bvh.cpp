@@ -32,7 +32,8 @@ void geomBounds(const PtbGeom &g, float lo[3], float hi[3]) {
         const bool tight = [] { const char *e = getenv("PTB_BVH_TIGHT_SPHERES"); return e ? atoi(e) != 0 : PTB_BVH_TIGHT_SPHERES != 0; }();   // knob for A/B runs
         const double e = (tight && g.type == 0) ? 0.5 * std::sqrt((double)m[0 + r] * m[0 + r] + (double)m[4 + r] * m[4 + r] + (double)m[8 + r] * m[8 + r]) * (1.0 + 1e-6)
                                      : 0.5 * rowAbs;
-        const double pad = 4e-4 * rowAbs + 1e-3 + 2e-5 * (std::fabs(c) + e);
+        const double extra = [] { const char *x = getenv("PTB_BVH_EXTRA_PAD"); return x ? atof(x) : 0.0; }();   // validation runs: tools/gpu_bvh_pathdiff.py
+        const double pad = 4e-4 * rowAbs + 1e-3 + 2e-5 * (std::fabs(c) + e) + extra;
         lo[r] = (float)(c - e - pad);
         hi[r] = (float)(c + e + pad);
     }

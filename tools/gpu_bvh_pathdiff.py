@@ -1,7 +1,9 @@
 """Which of two BVH builds is right where they differ: walk the REAL paths of the synthetic 100k-object scene bounce by
 bounce (stage_raygen / stage_intersect / stage_shade, the render's own RNG) through both BVHs and send every ray on which
 they disagree to the CPU oracle's brute-force loop over all the geoms.
-   python tools/gpu_bvh_pathdiff.py [first_iter] [n_iters]"""
+   python tools/gpu_bvh_pathdiff.py [first_iter] [n_iters]
+OLD_ALL_AXES / NEW_ALL_AXES / NEW_TIGHT / NEW_EXTRA_PAD choose the two builds; OLD_ALL_AXES=1 NEW_EXTRA_PAD=0.3 asks whether the
+shipped leaf boxes lose a hit that boxes 0.3 world units fatter would find."""
 import os, sys, tempfile
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -21,8 +23,9 @@ def make(env):
     return m.Renderer(scene, device=0, bsdf=1, batch_iters=1)
 
 
-r_old = make({"PTB_BVH_ALL_AXES": "0", "PTB_BVH_TIGHT_SPHERES": "0"})
-r_new = make({"PTB_BVH_ALL_AXES": os.environ.get("NEW_ALL_AXES", "1"), "PTB_BVH_TIGHT_SPHERES": os.environ.get("NEW_TIGHT", "0")})
+r_old = make({"PTB_BVH_ALL_AXES": os.environ.get("OLD_ALL_AXES", "0"), "PTB_BVH_TIGHT_SPHERES": "0", "PTB_BVH_EXTRA_PAD": "0"})
+r_new = make({"PTB_BVH_ALL_AXES": os.environ.get("NEW_ALL_AXES", "1"), "PTB_BVH_TIGHT_SPHERES": os.environ.get("NEW_TIGHT", "0"),
+              "PTB_BVH_EXTRA_PAD": os.environ.get("NEW_EXTRA_PAD", "0")})
 bits = lambda a: np.ascontiguousarray(a).view(np.uint32)
 tot_rays = tot_diff = wrong_old = wrong_new = 0
 for it in range(first, first + n_it):
