@@ -138,10 +138,10 @@ GeomRec packGeom(const PtbGeom &g, int sceneIndex, int order = -1) {
         r.b0 = make_float4(lo[0], hi[0], lo[1], hi[1]);          // (lo, hi) pairs per axis: operands of the packed slab test
         r.b1 = make_float4(lo[2], hi[2], 0.f, 0.f);
     } else {
-        float c[3], r2;
-        sphereBounds(g, c, &r2);
+        float c[3], r2, errK;
+        sphereBounds(g, c, &r2, &errK);
         r.b0 = make_float4(c[0], c[1], c[2], r2);
-        r.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
+        r.b1 = make_float4(errK, 0.f, 0.f, 0.f);
     }
     return r;
 }

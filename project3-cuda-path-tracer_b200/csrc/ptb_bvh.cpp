@@ -42,7 +42,7 @@ void geomBounds(const PtbGeom &g, float lo[3], float hi[3]) {
 // The unit-radius-0.5 sphere under the linear part A of Geom::transform lies inside the ball of radius
 // 0.5 * sigma_max(A) around the translation; sigma_max by power iteration on A^T A (3x3, double).
 // Padded like geomBounds for the 1e-4 fall-short and float rounding of the reference's hit point.
-void sphereBounds(const PtbGeom &g, float centre[3], float *radius2) {
+void sphereBounds(const PtbGeom &g, float centre[3], float *radius2, float *errK) {
     const float *m = g.transform;
     double A[3][3];
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) A[r][c] = m[4 * c + r];
@@ -64,6 +64,30 @@ void sphereBounds(const PtbGeom &g, float centre[3], float *radius2) {
     const double R = 0.5 * sigma * (1.0 + 1e-4) + 4e-4 * sigma + 1e-3 + 2e-5 * (cmag + sigma);
     centre[0] = m[12]; centre[1] = m[13]; centre[2] = m[14];
     *radius2 = (float)(R * R * (1.0 + 1e-6));
+    // Relative slack of the pruning discriminant (ptb_math.cuh, boundEntryRaw: err = errK * (|oc|^2 + b^2)).  The
+    // reference's test accepts a ray whose OBJECT-space distance from the centre is up to sqrt(0.25 + c u |ro|^2)
+    // (it cancels |ro|^2 - 0.25 against (ro . rd)^2 in float; c ~ 10 rounding errors, u = 2^-24, |ro| the object-space
+    // distance of the ray origin).  In world space that is a slack of c u |oc|^2 (sigma_max / sigma_min)^2 on the squared
+    // distance between the centre and the ray: isotropic spheres are covered by the 2e-6 that also absorbs the rounding
+    // of the bound itself, thin ellipsoids need more.  sigma_min = 1 / sigma_max(A^-1), same power iteration.
+    double Ai[3][3];
+    const float *mi = g.inverseTransform;
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) Ai[r][c] = mi[4 * c + r];
+    double Si[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { Si[i][j] = 0; for (int k = 0; k < 3; ++k) Si[i][j] += Ai[k][i] * Ai[k][j]; }
+    double vi[3] = {0.577, 0.577, 0.577}, lambdaInv = 0;
+    for (int it = 0; it < 64; ++it) {
+        double w[3] = {0, 0, 0};
+        for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) w[i] += Si[i][j] * vi[j];
+        const double n = std::sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
+        if (!(n > 0)) break;
+        lambdaInv = n;
+        for (int i = 0; i < 3; ++i) vi[i] = w[i] / n;
+    }
+    const double frobInv = std::sqrt(Si[0][0] + Si[1][1] + Si[2][2]);
+    const double sigmaInvMax = std::min(frobInv, std::sqrt(lambdaInv) * 1.001);     // = 1 / sigma_min, from above
+    const double ratio = sigma * sigmaInvMax;
+    if (errK) *errK = (float)std::max(2e-6, 16.0 * 5.9604644775390625e-08 * ratio * ratio * 1.5 + 1e-6);
 }
 
 // A mesh triangle: the reported hit point is transform * (a point 1e-4 object units short of the triangle's
