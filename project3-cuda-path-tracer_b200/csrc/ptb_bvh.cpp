@@ -22,15 +22,26 @@ namespace ptb {
 // of the surface (getPointOnRay, src/intersections.h:27-29), so the point can lie slightly outside
 // the exact world box of the primitive.  The pad covers that shortfall mapped through the transform
 // (<= 1e-4 * sum|column|), float rounding of the object-space round trip, and the pruning slab test.
-void geomBounds(const PtbGeom &g, float lo[3], float hi[3]) {
+void geomBounds(const PtbGeom &g, float lo[3], float hi[3], double sceneDiameter) {
     const float *m = g.transform;                       // column-major
+    // Spheres, rigorous part: the reference's test accepts a ray that passes up to c u |ro|^2 object units outside the sphere
+    // (see sphereBounds), |ro| <= sceneDiameter / sigma_min for any ray that starts inside the scene, so the hit point it reports
+    // can lie sigma_max c u (D / sigma_min)^2 outside the ellipsoid.  The box is the cube's box or the ellipsoid's own extent plus
+    // that distance, whichever is larger.
+    double farPad = 0.0;
+    if (g.type == 0 && sceneDiameter > 0.0) {
+        float cc[3], r2; double smax = 1.0, smin = 1.0;
+        sphereBounds(g, cc, &r2, nullptr, &smax, &smin);
+        farPad = smax * 16.0 * 5.9604644775390625e-08 * 1.5 * (sceneDiameter / smin) * (sceneDiameter / smin);
+    }
     for (int r = 0; r < 3; ++r) {
         const double c = m[12 + r];
         const double rowAbs = std::fabs((double)m[0 + r]) + std::fabs((double)m[4 + r]) + std::fabs((double)m[8 + r]);
         // half extent along world axis r: the unit cube reaches 0.5 * |row|_1, the radius-0.5 sphere only 0.5 * |row|_2
         // (an ellipsoid's box is up to sqrt(3) x tighter per axis than the box of the cube around it)
         const bool tight = [] { const char *e = getenv("PTB_BVH_TIGHT_SPHERES"); return e ? atoi(e) != 0 : PTB_BVH_TIGHT_SPHERES != 0; }();   // knob for A/B runs
-        const double e = (tight && g.type == 0) ? 0.5 * std::sqrt((double)m[0 + r] * m[0 + r] + (double)m[4 + r] * m[4 + r] + (double)m[8 + r] * m[8 + r]) * (1.0 + 1e-6)
+        const double eTight = 0.5 * std::sqrt((double)m[0 + r] * m[0 + r] + (double)m[4 + r] * m[4 + r] + (double)m[8 + r] * m[8 + r]);
+        const double e = (g.type == 0 && farPad > 0.0 && !tight) ? std::max(0.5 * rowAbs, eTight + farPad) : (tight && g.type == 0) ? 0.5 * std::sqrt((double)m[0 + r] * m[0 + r] + (double)m[4 + r] * m[4 + r] + (double)m[8 + r] * m[8 + r]) * (1.0 + 1e-6)
                                      : 0.5 * rowAbs;
         const double extra = [] { const char *x = getenv("PTB_BVH_EXTRA_PAD"); return x ? atof(x) : 0.0; }();   // validation runs: tools/gpu_bvh_pathdiff.py
         const double pad = 4e-4 * rowAbs + 1e-3 + 2e-5 * (std::fabs(c) + e) + extra;
@@ -42,7 +53,7 @@ void geomBounds(const PtbGeom &g, float lo[3], float hi[3]) {
 // The unit-radius-0.5 sphere under the linear part A of Geom::transform lies inside the ball of radius
 // 0.5 * sigma_max(A) around the translation; sigma_max by power iteration on A^T A (3x3, double).
 // Padded like geomBounds for the 1e-4 fall-short and float rounding of the reference's hit point.
-void sphereBounds(const PtbGeom &g, float centre[3], float *radius2, float *errK) {
+void sphereBounds(const PtbGeom &g, float centre[3], float *radius2, float *errK, double *sigmaMaxOut, double *sigmaMinOut) {
     const float *m = g.transform;
     double A[3][3];
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) A[r][c] = m[4 * c + r];
@@ -88,6 +99,8 @@ void sphereBounds(const PtbGeom &g, float centre[3], float *radius2, float *errK
     const double sigmaInvMax = std::min(frobInv, std::sqrt(lambdaInv) * 1.001);     // = 1 / sigma_min, from above
     const double ratio = sigma * sigmaInvMax;
     if (errK) *errK = (float)std::max(2e-6, 16.0 * 5.9604644775390625e-08 * ratio * ratio * 1.5 + 1e-6);
+    if (sigmaMaxOut) *sigmaMaxOut = sigma;
+    if (sigmaMinOut) *sigmaMinOut = 1.0 / sigmaInvMax;
 }
 
 // A mesh triangle: the reported hit point is transform * (a point 1e-4 object units short of the triangle's
@@ -212,7 +225,7 @@ struct Builder {
 
 void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out) {
     std::vector<float> lo((size_t)n * 3), hi((size_t)n * 3);
-    for (int i = 0; i < n; ++i) geomBounds(geoms[i], &lo[3 * (size_t)i], &hi[3 * (size_t)i]);
+    for (int i = 0; i < n; ++i) geomBounds(geoms[i], &lo[3 * (size_t)i], &hi[3 * (size_t)i], 0.0);
     buildBvhBoxes(lo.data(), hi.data(), n, maxLeaf, out);
 }
 

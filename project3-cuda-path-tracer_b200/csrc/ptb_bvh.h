@@ -21,10 +21,12 @@ struct HostBvh {
 };
 
 // Padded world-space box of one geom (unit cube / sphere under Geom::transform).
-void geomBounds(const PtbGeom &g, float lo[3], float hi[3]);
+// sceneDiameter > 0: sphere boxes additionally cover the hits the reference's test reports for rays that pass outside the sphere
+// (they grow with the square of the distance of the ray origin; see ptb_bvh.cpp).
+void geomBounds(const PtbGeom &g, float lo[3], float hi[3], double sceneDiameter = 0.0);
 // Padded world-space bounding sphere of a SPHERE geom: centre, squared radius and the relative slack errK of the pruning
 // discriminant (grows with the anisotropy of the ellipsoid, see ptb_bvh.cpp).
-void sphereBounds(const PtbGeom &g, float centre[3], float *radius2, float *errK = nullptr);
+void sphereBounds(const PtbGeom &g, float centre[3], float *radius2, float *errK = nullptr, double *sigmaMax = nullptr, double *sigmaMin = nullptr);
 
 // Padded world-space box of one mesh triangle (object-space vertices under the mesh geom's transform).
 void triangleBounds(const PtbGeom &mesh, const PtbTriangle &tri, float lo[3], float hi[3]);
