@@ -235,6 +235,16 @@ void ptb_camera_fixup(PtbCamera *camera);
 int  ptb_save_png(const char *baseFilename, int w, int h, const float *sum, float samples, int flipX);
 int  ptb_save_hdr(const char *baseFilename, int w, int h, const float *sum, float samples, int flipX);
 
+/* The flat BVH the library builds for large scenes (csrc/ptb_bvh.cpp; the reference's loop is brute force,
+ * src/pathtrace.cu:176-199, a hierarchical structure is an assignment ask, INSTRUCTION.md:123-140), built on the host
+ * over SPHERE / CUBE geoms exactly as ptb_create builds it (maxLeaf = 1 is what the render path uses).  No CUDA call.
+ * nodes: nodeCap x 16 words, one 64-byte record per interior node in breadth-first order --
+ *   left lo[3], left ref (int32), left hi[3], left count (int32), then the same four fields of the right child;
+ *   count > 0: a leaf holding slots [ref, ref + count) of `order`; count == 0: ref = index of the child node; ref < 0: no child.
+ * order: numGeoms ints, order[slot] = geom index.  nodes / order may be NULL to query *numNodes (<= max(numGeoms, 1)) first. */
+int  ptb_bvh_build_host(const PtbGeom *geoms, int32_t numGeoms, int32_t maxLeaf, float *nodes, int32_t nodeCap,
+                        int32_t *order, int32_t *numNodes, int32_t *maxDepth);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "ptb_stats", "ptb_accum_device_ptr", "ptb_resolve_rgb8", "ptb_stage_raygen", "ptb_stage_raygen_iter", "ptb_stage_intersect",
     "ptb_stage_shade", "ptb_stage_compact", "ptb_stage_sort_keys", "ptb_stage_rng", "ptb_stage_arith", "ptb_stage_sincos",
     "ptb_scene_load", "ptb_scene_counts", "ptb_scene_get", "ptb_scene_mesh_counts", "ptb_scene_get_meshes", "ptb_scene_free", "ptb_camera_fixup",
-    "ptb_save_png", "ptb_save_hdr",
+    "ptb_save_png", "ptb_save_hdr", "ptb_bvh_build_host",
 ]
 
 _lib = None
@@ -122,6 +122,8 @@ def lib():
             L.ptb_camera_fixup.argtypes = [C.c_void_p]
             L.ptb_save_png.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int]
             L.ptb_save_hdr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int]
+            L.ptb_bvh_build_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+                                             C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _lib = L
     return _lib
 
@@ -395,3 +397,19 @@ def save_png(filename_base, width, height, image_sum, samples, flip_x=True):
     """saveImage + image::savePNG (src/main.cpp:78-99, src/image.cpp:22-39): writes <base>.png"""
     img = np.ascontiguousarray(image_sum, np.float32)
     _check(lib().ptb_save_png(os.fsencode(filename_base), width, height, img.ctypes.data, float(samples), int(flip_x)))
+
+
+BVH_NODE_DT = np.dtype([("llo", "<f4", 3), ("lref", "<i4"), ("lhi", "<f4", 3), ("lcount", "<i4"),
+                        ("rlo", "<f4", 3), ("rref", "<i4"), ("rhi", "<f4", 3), ("rcount", "<i4")])   # csrc/ptb_bvh.h HostBvhNode
+
+
+def bvh_build_host(geoms, max_leaf=1):
+    """The flat BVH ptb_create builds over SPHERE / CUBE geoms (csrc/ptb_bvh.cpp), on the host: (nodes, order, max_depth)."""
+    geoms = np.ascontiguousarray(geoms, GEOM_DT)
+    n, depth = C.c_int32(0), C.c_int32(0)
+    _check(lib().ptb_bvh_build_host(geoms.ctypes.data, len(geoms), int(max_leaf), None, 0, None, C.byref(n), None))
+    nodes = np.zeros(n.value, BVH_NODE_DT)
+    order = np.zeros(len(geoms), np.int32)
+    _check(lib().ptb_bvh_build_host(geoms.ctypes.data, len(geoms), int(max_leaf), nodes.ctypes.data, len(nodes), order.ctypes.data,
+                                    C.byref(n), C.byref(depth)))
+    return nodes, order, depth.value

@@ -290,3 +290,21 @@ void buildBvhBoxes(const float *lo, const float *hi, int n, int maxLeaf, HostBvh
 }
 
 } // namespace ptb
+
+// Host-only entry point of the C ABI (include/ptb200.h): the flat BVH ptb_create builds over the SPHERE / CUBE geoms of a scene
+// (same bounds, same builder, same PTB_BVH_* knobs), returned as HostBvhNode records.  No CUDA call.
+extern "C" int ptb_bvh_build_host(const PtbGeom *geoms, int32_t numGeoms, int32_t maxLeaf, float *nodes, int32_t nodeCap,
+                                  int32_t *order, int32_t *numNodes, int32_t *maxDepth) {
+    if (numGeoms < 0 || (numGeoms > 0 && !geoms) || !numNodes) return PTB_ERR_INVALID;
+    for (int i = 0; i < numGeoms; ++i) if (geoms[i].type != 0 && geoms[i].type != 1) return PTB_ERR_INVALID;
+    ptb::HostBvh hb;
+    ptb::buildBvh(geoms, numGeoms, maxLeaf, hb);
+    *numNodes = (int32_t)hb.nodes.size();
+    if (maxDepth) *maxDepth = hb.maxDepth;
+    if (nodes) {
+        if (nodeCap < (int32_t)hb.nodes.size()) return PTB_ERR_INVALID;
+        std::copy(hb.nodes.begin(), hb.nodes.end(), reinterpret_cast<ptb::HostBvhNode *>(nodes));
+    }
+    if (order) std::copy(hb.order.begin(), hb.order.end(), order);
+    return PTB_OK;
+}

@@ -1,0 +1,227 @@
+"""CPU tests of the host-side BVH builder (csrc/ptb_bvh.cpp) through the C ABI (ptb_bvh_build_host; no compute call).
+
+The reference's closest-hit loop is brute force (src/pathtrace.cu:176-199); the BVH only prunes it, so what must hold is
+(1) the flat tree is well formed -- every primitive in exactly one leaf, breadth-first links, child boxes enclosing what
+hangs below them, depth within the traversal stack -- and (2) the padded boxes are CONSERVATIVE for the reference's own
+tests: for every ray the oracle (tests/orclib.py, the CPU restatement of src/intersections.h) reports a hit for, every
+box on the way from the root to the leaf of the hit primitive passes the slab test the traversal kernel applies
+(ptb_kernels.cuh slabNearPair / bvhNodeStep), so the traversal cannot lose the hit.
+"""
+import numpy as np
+import pytest
+
+import orclib
+import scenes
+from common import pkg, to_oracle_scene
+
+F = np.float32
+
+
+@pytest.fixture(scope="module")
+def port():
+    return orclib.load("port")
+
+
+@pytest.fixture(scope="module")
+def synth(tmp_path_factory):
+    m = pkg()
+    d = tmp_path_factory.mktemp("bvh")
+    path = str(d / "synthetic.txt")
+    with open(path, "w") as f:
+        f.write(scenes.synthetic_text(n_objects=3000, res=(400, 225), depth=4, iterations=1))
+    return m.Scene.load(path)
+
+
+def children(nodes, i):
+    """(lo, hi, ref, count) of the two children of interior node i"""
+    n = nodes[i]
+    return ((n["llo"], n["lhi"], int(n["lref"]), int(n["lcount"])), (n["rlo"], n["rhi"], int(n["rref"]), int(n["rcount"])))
+
+
+def walk(nodes):
+    """parent link of every interior node and of every leaf slot: (parentNode, side)"""
+    nodeParent = {0: None}
+    slotParent = {}
+    for i in range(len(nodes)):
+        for side, (lo, hi, ref, count) in enumerate(children(nodes, i)):
+            if ref < 0:
+                continue
+            if count > 0:
+                for s in range(ref, ref + count):
+                    assert s not in slotParent, "slot %d sits in two leaves" % s
+                    slotParent[s] = (i, side)
+            else:
+                assert ref not in nodeParent, "node %d has two parents" % ref
+                assert ref > i, "breadth-first order: child %d of node %d" % (ref, i)
+                nodeParent[ref] = (i, side)
+    return nodeParent, slotParent
+
+
+@pytest.mark.parametrize("max_leaf", [1, 4])
+def test_tree_is_well_formed(synth, max_leaf):
+    m = pkg()
+    nodes, order, depth = m.bvh_build_host(synth.geoms, max_leaf)
+    n = len(synth.geoms)
+    assert sorted(order.tolist()) == list(range(n)), "order is a permutation of the geoms"
+    nodeParent, slotParent = walk(nodes)
+    assert sorted(nodeParent) == list(range(len(nodes))), "every interior node hangs off exactly one parent"
+    assert sorted(slotParent) == list(range(n)), "every primitive sits in exactly one leaf"
+    assert 0 < depth < 60, "the traversal stack holds 64 entries"
+    assert len(nodes) <= max(n, 1)
+    for i in range(len(nodes)):
+        for lo, hi, ref, count in children(nodes, i):
+            if ref < 0:
+                continue
+            assert np.all(lo <= hi)
+            assert count <= 8                                      # 27-bit ref | count << 27 stack entries, leaves of at most 8
+            if max_leaf == 1:
+                assert count <= 1
+            if count == 0:
+                # the box of an interior child is the union of the two boxes stored in its own node
+                (alo, ahi, _, _), (blo, bhi, bref, _) = children(nodes, ref)
+                ulo, uhi = (np.minimum(alo, blo), np.maximum(ahi, bhi)) if bref >= 0 else (alo, ahi)
+                assert np.array_equal(lo, ulo) and np.array_equal(hi, uhi)
+            else:
+                # scene order inside a leaf (keeps the reference's first-index tie rule, src/pathtrace.cu:190)
+                assert np.all(np.diff(order[ref:ref + count]) > 0)
+    # deterministic: the same scene builds the same bytes
+    nodes2, order2, _ = m.bvh_build_host(synth.geoms, max_leaf)
+    assert nodes.tobytes() == nodes2.tobytes() and np.array_equal(order, order2)
+
+
+def test_leaf_boxes_contain_their_primitive(synth):
+    m = pkg()
+    nodes, order, _ = m.bvh_build_host(synth.geoms, 1)
+    _, slotParent = walk(nodes)
+    g = synth.geoms
+    corners = np.array([[x, y, z, 1.0] for x in (-.5, .5) for y in (-.5, .5) for z in (-.5, .5)])
+    rs = np.random.RandomState(3)
+    u = rs.normal(size=(64, 3))
+    u = 0.5 * u / np.linalg.norm(u, axis=1, keepdims=True)
+    surf = np.concatenate([u, np.ones((64, 1))], 1)
+    for slot in range(0, len(g), 7):
+        i, side = slotParent[slot]
+        lo, hi, _, _ = children(nodes, i)[side]
+        geom = g[order[slot]]
+        T = geom["transform"].reshape(4, 4).T.astype(np.float64)        # column-major mat4
+        pts = (corners if geom["type"] == 1 else surf) @ T.T
+        assert np.all(pts[:, :3] >= lo) and np.all(pts[:, :3] <= hi)
+
+
+def slab(lo, hi, o, inv):
+    """slabNearPair (ptb_kernels.cuh) for one child box and n rays, in float32"""
+    with np.errstate(invalid="ignore", over="ignore"):
+        t0 = (lo[None, :] - o) * inv
+        t1 = (hi[None, :] - o) * inv
+    near = np.fmax(np.fmax(np.fmin(t0[:, 0], t1[:, 0]), np.fmin(t0[:, 1], t1[:, 1])), np.fmax(np.fmin(t0[:, 2], t1[:, 2]), F(0)))
+    far = np.fmin(np.fmin(np.fmax(t0[:, 0], t1[:, 0]), np.fmax(t0[:, 1], t1[:, 1])), np.fmax(t0[:, 2], t1[:, 2]))
+    return near, near <= far * F(1.00001) + F(1e-5)
+
+
+def rays_of(port, scene, n_bounce, seed):
+    """camera rays plus rays leaving their hit points in random directions (origins ON surfaces, like bounce rays)"""
+    os_ = to_oracle_scene(scene)
+    o, d = port.generate_rays(os_.camera)
+    hit, t, nrm, _ = port.closest_hit(os_.geoms, o, d)
+    rs = np.random.RandomState(seed)
+    k = np.flatnonzero(hit >= 0)
+    k = k[rs.permutation(len(k))[:n_bounce]]
+    dn = d[k] / np.linalg.norm(d[k], axis=1, keepdims=True)
+    o2 = (o[k] + dn * (t[k, None] - F(1e-4))).astype(F)
+    d2 = rs.normal(size=(len(k), 3)).astype(F)
+    d2[::40, 0] = 0.0                                              # axis-parallel directions: 1 / 0 in the slab test
+    d2[::55, 1] = 0.0
+    d2 /= np.linalg.norm(d2, axis=1, keepdims=True).astype(F)
+    return np.concatenate([o, o2]), np.concatenate([d, d2]), os_
+
+
+def pruned_hits(nodes, order, o, d, hit, t):
+    """Rays whose oracle hit the traversal would lose: some box between the root and the leaf of the hit primitive fails
+    bvhNodeStep's visit rule with best.t = the hit's own distance (best.t is never smaller during a traversal).
+    Returns (lost rays, number of (ray, box) pairs checked)."""
+    nodeParent, slotParent = walk(nodes)
+    slotOf = np.empty(len(order), np.int64)
+    slotOf[order] = np.arange(len(order))
+    with np.errstate(divide="ignore"):
+        inv = (F(1) / d).astype(F)
+    dl = (np.sqrt((d * d).sum(1, dtype=F)) * F(0.9999)).astype(F)
+    todo = {}                                                      # (node, side) -> rays, over the whole root-to-leaf chain
+    for r in np.flatnonzero(hit >= 0):
+        link = slotParent[int(slotOf[hit[r]])]
+        while link is not None:
+            todo.setdefault(link, []).append(r)
+            link = nodeParent[link[0]]
+    lost, checked = set(), 0
+    for (i, side), rr in todo.items():
+        rr = np.asarray(rr)
+        lo, hi, _, _ = children(nodes, i)[side]
+        near, inside = slab(lo, hi, o[rr], inv[rr])
+        visit = inside & (near * dl[rr] - F(1e-4) <= t[rr])
+        lost.update(rr[~visit].tolist())
+        checked += len(rr)
+    return sorted(lost), checked
+
+
+@pytest.mark.parametrize("max_leaf", [1, 4])
+def test_boxes_are_conservative_for_the_reference_tests(port, synth, max_leaf):
+    m = pkg()
+    nodes, order, _ = m.bvh_build_host(synth.geoms, max_leaf)
+    o, d, os_ = rays_of(port, synth, 40000, 11)
+    hit, t, _, _ = port.closest_hit(os_.geoms, o, d)
+    assert (hit >= 0).sum() > 40000
+    lost, checked = pruned_hits(nodes, order, o, d, hit, t)
+    assert not lost, "the boxes prune the oracle's hit of rays %s" % lost[:8]
+    assert checked > 150000
+
+
+def test_far_sphere_hit_the_reference_reports_outside_the_sphere(port, tmp_path, monkeypatch):
+    """CPU side of tests/test_gpu_scale.py's regression of the same name, on the full 100 k-object scene of BASELINE.json
+    configs[4]: ~240 object units from the origin of a thin ellipsoid the reference's sphere test (src/intersections.h:102-144)
+    cancels |ro|^2 - 0.25 against (ro . rd)^2 and reports hits for rays that pass just OUTSIDE sphere 31153.  The shipped leaf
+    boxes keep every one of those hits; boxes hugging the ellipsoid (PTB_BVH_TIGHT_SPHERES=1, withdrawn) lose some --
+    which also shows that this check can fail."""
+    m = pkg()
+    path = str(tmp_path / "synthetic.txt")
+    with open(path, "w") as f:
+        f.write(scenes.synthetic_text())
+    s = m.Scene.load(path)
+    assert len(s.geoms) == 100000
+    o = np.array([[26.248161, 22.502022, -8.040187]], F)
+    d = np.array([[0.16347983, 0.02360658, -0.9862642]], F)
+    rs = np.random.RandomState(14)
+    o = np.concatenate([o, o + rs.uniform(-2e-5, 2e-5, (4095, 3)).astype(F)])
+    d = np.concatenate([d, d + rs.uniform(-2e-7, 2e-7, (4095, 3)).astype(F)])
+    hit, t, _, _ = port.closest_hit(to_oracle_scene(s).geoms, o, d)
+    assert hit[0] == 31153 and (hit == 31153).sum() > 100 and (hit != 31153).sum() > 100      # the grazing band
+    monkeypatch.delenv("PTB_BVH_TIGHT_SPHERES", raising=False)
+    nodes, order, depth = m.bvh_build_host(s.geoms, 1)
+    assert depth < 60
+    lost, checked = pruned_hits(nodes, order, o, d, hit, t)
+    assert not lost and checked > 4096 * 10
+    monkeypatch.setenv("PTB_BVH_TIGHT_SPHERES", "1")
+    tight, order2, _ = m.bvh_build_host(s.geoms, 1)
+    lost, _ = pruned_hits(tight, order2, o, d, hit, t)
+    assert lost and np.all(hit[lost] == 31153)
+
+
+def test_degenerate_scenes():
+    m = pkg()
+    nodes, order, depth = m.bvh_build_host(np.zeros(0, m.GEOM_DT))
+    assert len(nodes) == 1 and len(order) == 0 and nodes[0]["lref"] == -1 and nodes[0]["rref"] == -1
+    g = np.zeros(1, m.GEOM_DT)
+    g["type"] = 1
+    g["transform"][0] = np.eye(4, dtype=F).ravel()
+    g["inverseTransform"][0] = np.eye(4, dtype=F).ravel()
+    nodes, order, depth = m.bvh_build_host(g)
+    assert len(nodes) == 1 and order.tolist() == [0]
+    assert nodes[0]["lref"] == 0 and nodes[0]["lcount"] == 1 and nodes[0]["rref"] == -1
+    assert np.all(nodes[0]["llo"] < -0.5) and np.all(nodes[0]["lhi"] > 0.5) and np.all(nodes[0]["lhi"] < 0.51)
+    # coincident primitives cannot be split by any plane: the builder still terminates with one primitive per leaf slot
+    g = np.repeat(g, 40)
+    nodes, order, depth = m.bvh_build_host(g)
+    _, slotParent = walk(nodes)
+    assert sorted(slotParent) == list(range(40)) and depth < 60
+    # a mesh geom (type 2) has no box of its own: triangles are boxed one by one inside ptb_create
+    g["type"][3] = 2
+    with pytest.raises(m.PtbError):
+        m.bvh_build_host(g)
