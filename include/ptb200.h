@@ -238,11 +238,14 @@ int  ptb_save_hdr(const char *baseFilename, int w, int h, const float *sum, floa
 /* The flat BVH the library builds for large scenes (csrc/ptb_bvh.cpp; the reference's loop is brute force,
  * src/pathtrace.cu:176-199, a hierarchical structure is an assignment ask, INSTRUCTION.md:123-140), built on the host
  * over SPHERE / CUBE geoms exactly as ptb_create builds it (maxLeaf = 1 is what the render path uses).  No CUDA call.
+ * farPadDiameter > 0: sphere boxes also cover the hits the reference's sphere test (src/intersections.h:102-144) reports for rays
+ *   that pass outside the sphere, for ray origins up to that many world units away; 0: none; < 0: the library's own choice, the
+ *   diameter of the geoms' boxes (ptb_create adds the camera position), or none when PTB_BVH_FAR_PAD=0 is set in the environment.
  * nodes: nodeCap x 16 words, one 64-byte record per interior node in breadth-first order --
  *   left lo[3], left ref (int32), left hi[3], left count (int32), then the same four fields of the right child;
  *   count > 0: a leaf holding slots [ref, ref + count) of `order`; count == 0: ref = index of the child node; ref < 0: no child.
  * order: numGeoms ints, order[slot] = geom index.  nodes / order may be NULL to query *numNodes (<= max(numGeoms, 1)) first. */
-int  ptb_bvh_build_host(const PtbGeom *geoms, int32_t numGeoms, int32_t maxLeaf, float *nodes, int32_t nodeCap,
+int  ptb_bvh_build_host(const PtbGeom *geoms, int32_t numGeoms, int32_t maxLeaf, double farPadDiameter, float *nodes, int32_t nodeCap,
                         int32_t *order, int32_t *numNodes, int32_t *maxDepth);
 
 #ifdef __cplusplus

@@ -122,7 +122,7 @@ def lib():
             L.ptb_camera_fixup.argtypes = [C.c_void_p]
             L.ptb_save_png.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int]
             L.ptb_save_hdr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int]
-            L.ptb_bvh_build_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p,
+            L.ptb_bvh_build_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_int32, C.c_void_p,
                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
         _lib = L
     return _lib
@@ -403,13 +403,15 @@ BVH_NODE_DT = np.dtype([("llo", "<f4", 3), ("lref", "<i4"), ("lhi", "<f4", 3), (
                         ("rlo", "<f4", 3), ("rref", "<i4"), ("rhi", "<f4", 3), ("rcount", "<i4")])   # csrc/ptb_bvh.h HostBvhNode
 
 
-def bvh_build_host(geoms, max_leaf=1):
-    """The flat BVH ptb_create builds over SPHERE / CUBE geoms (csrc/ptb_bvh.cpp), on the host: (nodes, order, max_depth)."""
+def bvh_build_host(geoms, max_leaf=1, far_pad_diameter=-1.0):
+    """The flat BVH ptb_create builds over SPHERE / CUBE geoms (csrc/ptb_bvh.cpp), on the host: (nodes, order, max_depth).
+    far_pad_diameter > 0: the rigorous sphere boxes for ray origins up to that far away (csrc/ptb_bvh.cpp geomBounds); 0: none;
+    < 0: what ptb_create uses (the diameter of the scene, or none under PTB_BVH_FAR_PAD=0)."""
     geoms = np.ascontiguousarray(geoms, GEOM_DT)
     n, depth = C.c_int32(0), C.c_int32(0)
-    _check(lib().ptb_bvh_build_host(geoms.ctypes.data, len(geoms), int(max_leaf), None, 0, None, C.byref(n), None))
+    _check(lib().ptb_bvh_build_host(geoms.ctypes.data, len(geoms), int(max_leaf), float(far_pad_diameter), None, 0, None, C.byref(n), None))
     nodes = np.zeros(n.value, BVH_NODE_DT)
     order = np.zeros(len(geoms), np.int32)
-    _check(lib().ptb_bvh_build_host(geoms.ctypes.data, len(geoms), int(max_leaf), nodes.ctypes.data, len(nodes), order.ctypes.data,
+    _check(lib().ptb_bvh_build_host(geoms.ctypes.data, len(geoms), int(max_leaf), float(far_pad_diameter), nodes.ctypes.data, len(nodes), order.ctypes.data,
                                     C.byref(n), C.byref(depth)))
     return nodes, order, depth.value

@@ -264,17 +264,9 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     int maxLeaf = 1;                     // one primitive per leaf: its padded bound IS the leaf box (measured: 4 -> 7.28, 2 -> 6.62, 1 -> 6.29 ms per iteration of the 100k-object scene)
     if (const char *e = getenv("PTB_BVH_LEAF")) maxLeaf = std::max(1, atoi(e));                       // tuning knob (experiments)
     {
-        // diameter of everything a ray can start from: the camera and every geom's world box
-        double slo[3] = {scene->camera.position[0], scene->camera.position[1], scene->camera.position[2]}, shi[3] = {slo[0], slo[1], slo[2]};
-        for (int i = 0; i < G; ++i) {
-            float l[3], h[3];
-            geomBounds(scene->geoms[i], l, h);
-            for (int a = 0; a < 3; ++a) { slo[a] = std::min(slo[a], (double)l[a]); shi[a] = std::max(shi[a], (double)h[a]); }
-        }
-        double sceneDiameter = std::sqrt((shi[0] - slo[0]) * (shi[0] - slo[0]) + (shi[1] - slo[1]) * (shi[1] - slo[1]) + (shi[2] - slo[2]) * (shi[2] - slo[2]));
-        // The rigorous far pad costs 19 % on the 100 k-object scene (4 006 -> 4 781 us/iteration) for a failure that the cube's box
-        // has not shown on any ray tested (227 M real paths against boxes 0.3 fatter, profiles/r03_bvh_pathdiff.txt): opt-in.
-        { const char *e = getenv("PTB_BVH_FAR_PAD"); if (!e || atoi(e) == 0) sceneDiameter = 0.0; }
+        // Sphere boxes also cover the hits the reference's sphere test reports for rays passing OUTSIDE the sphere, for every ray that
+        // starts inside the scene (ptb_bvh.cpp geomBounds / defaultFarPadDiameter; PTB_BVH_FAR_PAD=0 opts out).
+        const double sceneDiameter = defaultFarPadDiameter(scene->geoms, G, scene->camera.position);
         std::vector<float> lo((size_t)P * 3), hi((size_t)P * 3);
         for (int k = 0; k < P; ++k) {
             const PtbGeom &g = scene->geoms[prims[k].first];

@@ -223,9 +223,27 @@ struct Builder {
 };
 } // namespace
 
-void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out) {
+// Diameter of everything a ray can start from -- the camera (when given) and every geom's world box -- which is the argument the
+// rigorous sphere boxes of geomBounds need.  0 (no far pad) when PTB_BVH_FAR_PAD=0 asks for the round-1 boxes: those are 19 % faster on the
+// 100 k-object scene (4 006 against 4 781 us per iteration, profiles/r03_bvh_pathdiff.txt) and lose reference hits of rays that graze a thin
+// ellipsoid from more than ~100 world units away (5-21 of 1.2 M silhouette rays, tools/cpu_bvh_grazing_fuzz.py --dist 160 230; none of the
+// 2.3e8 real paths of that scene).
+double defaultFarPadDiameter(const PtbGeom *geoms, int n, const float *cameraPosition) {
+    if (const char *e = getenv("PTB_BVH_FAR_PAD")) if (atoi(e) == 0) return 0.0;
+    double slo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, shi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
+    if (cameraPosition) for (int a = 0; a < 3; ++a) slo[a] = shi[a] = cameraPosition[a];
+    for (int i = 0; i < n; ++i) {
+        float l[3], h[3];
+        geomBounds(geoms[i], l, h);
+        for (int a = 0; a < 3; ++a) { slo[a] = std::min(slo[a], (double)l[a]); shi[a] = std::max(shi[a], (double)h[a]); }
+    }
+    if (!(shi[0] >= slo[0])) return 0.0;                  // nothing to bound
+    return std::sqrt((shi[0] - slo[0]) * (shi[0] - slo[0]) + (shi[1] - slo[1]) * (shi[1] - slo[1]) + (shi[2] - slo[2]) * (shi[2] - slo[2]));
+}
+
+void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out, double sceneDiameter) {
     std::vector<float> lo((size_t)n * 3), hi((size_t)n * 3);
-    for (int i = 0; i < n; ++i) geomBounds(geoms[i], &lo[3 * (size_t)i], &hi[3 * (size_t)i], 0.0);
+    for (int i = 0; i < n; ++i) geomBounds(geoms[i], &lo[3 * (size_t)i], &hi[3 * (size_t)i], sceneDiameter);
     buildBvhBoxes(lo.data(), hi.data(), n, maxLeaf, out);
 }
 
@@ -293,12 +311,13 @@ void buildBvhBoxes(const float *lo, const float *hi, int n, int maxLeaf, HostBvh
 
 // Host-only entry point of the C ABI (include/ptb200.h): the flat BVH ptb_create builds over the SPHERE / CUBE geoms of a scene
 // (same bounds, same builder, same PTB_BVH_* knobs), returned as HostBvhNode records.  No CUDA call.
-extern "C" int ptb_bvh_build_host(const PtbGeom *geoms, int32_t numGeoms, int32_t maxLeaf, float *nodes, int32_t nodeCap,
+extern "C" int ptb_bvh_build_host(const PtbGeom *geoms, int32_t numGeoms, int32_t maxLeaf, double farPadDiameter, float *nodes, int32_t nodeCap,
                                   int32_t *order, int32_t *numNodes, int32_t *maxDepth) {
     if (numGeoms < 0 || (numGeoms > 0 && !geoms) || !numNodes) return PTB_ERR_INVALID;
     for (int i = 0; i < numGeoms; ++i) if (geoms[i].type != 0 && geoms[i].type != 1) return PTB_ERR_INVALID;
     ptb::HostBvh hb;
-    ptb::buildBvh(geoms, numGeoms, maxLeaf, hb);
+    if (farPadDiameter < 0.0) farPadDiameter = ptb::defaultFarPadDiameter(geoms, numGeoms, nullptr);
+    ptb::buildBvh(geoms, numGeoms, maxLeaf, hb, farPadDiameter);
     *numNodes = (int32_t)hb.nodes.size();
     if (maxDepth) *maxDepth = hb.maxDepth;
     if (nodes) {

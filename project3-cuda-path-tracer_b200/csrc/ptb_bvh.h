@@ -31,8 +31,12 @@ void sphereBounds(const PtbGeom &g, float centre[3], float *radius2, float *errK
 // Padded world-space box of one mesh triangle (object-space vertices under the mesh geom's transform).
 void triangleBounds(const PtbGeom &mesh, const PtbTriangle &tri, float lo[3], float hi[3]);
 
-// Binned-SAH top-down build; leaves hold at most `maxLeaf` geoms.
-void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out);
+// The sceneDiameter ptb_create hands to geomBounds: diameter of the geoms' boxes and the camera position (may be NULL); 0 when
+// PTB_BVH_FAR_PAD=0 opts out of the rigorous sphere boxes.
+double defaultFarPadDiameter(const PtbGeom *geoms, int n, const float *cameraPosition);
+
+// Binned-SAH top-down build; leaves hold at most `maxLeaf` geoms.  sceneDiameter: see geomBounds.
+void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out, double sceneDiameter = 0.0);
 // The same over caller-supplied primitive boxes (lo / hi: n x 3 floats); order[slot] = primitive index.
 void buildBvhBoxes(const float *lo, const float *hi, int n, int maxLeaf, HostBvh &out);
 

@@ -204,6 +204,80 @@ def test_far_sphere_hit_the_reference_reports_outside_the_sphere(port, tmp_path,
     assert lost and np.all(hit[lost] == 31153)
 
 
+def random_spheres(orc, rs, n, scale_lo, scale_hi):
+    """SPHERE geoms placed like the synthetic scene's (tests/scenes.py synthetic_text): ellipsoids with per-axis scales"""
+    g = np.zeros(n, orclib.GEOM_DT)
+    g["type"] = 0
+    g["materialid"] = 1
+    t = np.stack([rs.uniform(-50, 50, n), rs.uniform(0, 100, n), rs.uniform(-100, 0, n)], 1).astype(F)
+    r = rs.uniform(0, 360, (n, 3)).astype(F)
+    s = rs.uniform(scale_lo, scale_hi, (n, 3)).astype(F)
+    for i in range(n):
+        g["translation"][i], g["rotation"][i], g["scale"][i] = t[i], r[i], s[i]
+        g["transform"][i], g["inverseTransform"][i], g["invTranspose"][i] = orc.build_transform(t[i], r[i], s[i])
+    return g
+
+
+def grazing_band(orc, g, rs, origins, band, dist, scale_hi, in_scene=False):
+    """Rays aimed at the silhouette of every sphere of g from `origins` far points each: the edge is found by bisection on the
+    oracle's own answer, then `band` rays sweep from 2e-3 world units inside it to 2e-2 outside (log-spaced: the spurious hits of
+    the reference's cancellation-prone sphere test live just outside).  Returns (o, d, owner sphere of every ray)."""
+    K, Q = len(g), origins
+    c = np.repeat(g["translation"].astype(np.float64), Q, 0)
+    owner = np.repeat(np.arange(K), Q)
+    u = rs.normal(size=(K * Q, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+    org = c + u * rs.uniform(dist[0], dist[1], (K * Q, 1))
+    if in_scene:                                                   # origins next to OTHER spheres, like bounce rays
+        org = g["translation"].astype(np.float64)[rs.randint(0, K, K * Q)] + 2.0 * scale_hi * u
+        u = org - c; u /= np.linalg.norm(u, axis=1, keepdims=True)
+    w = np.cross(u, rs.normal(size=(K * Q, 3))); w /= np.linalg.norm(w, axis=1, keepdims=True)
+
+    def rays(c, org, w, sv):                                       # target = centre + w * s
+        d = c + w * sv[:, None] - org
+        return org.astype(F), (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(F)
+
+    lo = np.zeros(K * Q); hi = np.full(K * Q, 2.0 * scale_hi)
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        inside = orc.closest_hit(g, *rays(c, org, w, mid))[0] == owner
+        lo = np.where(inside, mid, lo); hi = np.where(inside, hi, mid)
+    offs = np.concatenate([-np.geomspace(2e-3, 1e-7, band // 4), np.geomspace(1e-7, 2e-2, band - band // 4)])
+    sv = (0.5 * (lo + hi)[:, None] + offs[None, :]).ravel()
+    rep = lambda x: np.repeat(x, len(offs), 0)
+    o, d = rays(rep(c), rep(org), rep(w), sv)
+    return o, d, rep(owner)
+
+
+def test_far_grazing_hits_need_the_rigorous_sphere_boxes(port, monkeypatch):
+    """From 160-230 world units away -- distances the 100 k-object scene of BASELINE.json configs[4] has room for -- the reference's
+    sphere test reports hits up to ~0.1 object units OUTSIDE a thin ellipsoid.  The boxes ptb_create builds (far pad over the
+    diameter of everything a ray can start from) keep every one of them; the round-1 boxes (PTB_BVH_FAR_PAD=0) lose a few."""
+    m = pkg()
+    rs = np.random.RandomState(1)
+    g = random_spheres(port, rs, 300, 0.3, 1.2)
+    o, d, owner = grazing_band(port, g, rs, 8, 512, (160.0, 230.0), 1.2)
+    hit, t, _, _ = port.closest_hit(g, o, d)
+    assert (hit == owner).sum() > 300000
+    gm = g.view(m.GEOM_DT)
+    pts = np.concatenate([o.astype(np.float64), g["translation"] + 2.4, g["translation"] - 2.4])
+    diameter = float(np.linalg.norm(pts.max(0) - pts.min(0)))
+    nodes, order, _ = m.bvh_build_host(gm, 1, diameter)
+    lost, checked = pruned_hits(nodes, order, o, d, hit, t)
+    assert not lost and checked > 3000000
+    nodes0, order0, _ = m.bvh_build_host(gm, 1, 0.0)
+    lost0, _ = pruned_hits(nodes0, order0, o, d, hit, t)
+    assert lost0 and np.all(hit[lost0] == owner[lost0])             # the failing control
+    # the library's own choice (far_pad_diameter < 0, what ptb_create does): the diameter of the scene's boxes, unless opted out
+    monkeypatch.delenv("PTB_BVH_FAR_PAD", raising=False)
+    root = nodes0[0]
+    scene = float(np.linalg.norm(np.maximum(root["lhi"], root["rhi"]).astype(np.float64) - np.minimum(root["llo"], root["rlo"])))
+    auto = m.bvh_build_host(gm, 1, -1.0)
+    want = m.bvh_build_host(gm, 1, scene)
+    assert auto[0].tobytes() == want[0].tobytes() and auto[0].tobytes() != nodes0.tobytes()
+    monkeypatch.setenv("PTB_BVH_FAR_PAD", "0")
+    assert m.bvh_build_host(gm, 1, -1.0)[0].tobytes() == nodes0.tobytes()
+
+
 def test_degenerate_scenes():
     m = pkg()
     nodes, order, depth = m.bvh_build_host(np.zeros(0, m.GEOM_DT))
