@@ -239,8 +239,9 @@ int  ptb_save_hdr(const char *baseFilename, int w, int h, const float *sum, floa
  * src/pathtrace.cu:176-199, a hierarchical structure is an assignment ask, INSTRUCTION.md:123-140), built on the host
  * over SPHERE / CUBE geoms exactly as ptb_create builds it (maxLeaf = 1 is what the render path uses).  No CUDA call.
  * farPadDiameter > 0: sphere boxes also cover the hits the reference's sphere test (src/intersections.h:102-144) reports for rays
- *   that pass outside the sphere, for ray origins up to that many world units away; 0: none; < 0: the library's own choice, the
- *   diameter of the geoms' boxes (ptb_create adds the camera position), or none when PTB_BVH_FAR_PAD=0 is set in the environment.
+ *   that pass outside the sphere, for ray origins up to that many world units from the sphere's centre; 0: none; < 0: the library's
+ *   own choice -- per sphere, the distance to the farthest corner of the box around all geoms (ptb_create adds the camera position) --
+ *   or none when PTB_BVH_FAR_PAD=0 is set in the environment.
  * nodes: nodeCap x 16 words, one 64-byte record per interior node in breadth-first order --
  *   left lo[3], left ref (int32), left hi[3], left count (int32), then the same four fields of the right child;
  *   count > 0: a leaf holding slots [ref, ref + count) of `order`; count == 0: ref = index of the child node; ref < 0: no child.

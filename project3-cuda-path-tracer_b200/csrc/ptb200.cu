@@ -265,13 +265,13 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     if (const char *e = getenv("PTB_BVH_LEAF")) maxLeaf = std::max(1, atoi(e));                       // tuning knob (experiments)
     {
         // Sphere boxes also cover the hits the reference's sphere test reports for rays passing OUTSIDE the sphere, for every ray that
-        // starts inside the scene (ptb_bvh.cpp geomBounds / defaultFarPadDiameter; PTB_BVH_FAR_PAD=0 opts out).
-        const double sceneDiameter = defaultFarPadDiameter(scene->geoms, G, scene->camera.position);
+        // starts inside the scene (ptb_bvh.cpp geomBounds / defaultFarPadScene; PTB_BVH_FAR_PAD=0 opts out).
+        const FarPadScene farPad = defaultFarPadScene(scene->geoms, G, scene->camera.position);
         std::vector<float> lo((size_t)P * 3), hi((size_t)P * 3);
         for (int k = 0; k < P; ++k) {
             const PtbGeom &g = scene->geoms[prims[k].first];
             if (prims[k].second >= 0) triangleBounds(g, scene->triangles[prims[k].second], &lo[3 * (size_t)k], &hi[3 * (size_t)k]);
-            else                      geomBounds(g, &lo[3 * (size_t)k], &hi[3 * (size_t)k], sceneDiameter);
+            else                      geomBounds(g, &lo[3 * (size_t)k], &hi[3 * (size_t)k], farPadReach(g, farPad));
         }
         buildBvhBoxes(lo.data(), hi.data(), P, maxLeaf, hb);
     }

@@ -22,17 +22,17 @@ namespace ptb {
 // of the surface (getPointOnRay, src/intersections.h:27-29), so the point can lie slightly outside
 // the exact world box of the primitive.  The pad covers that shortfall mapped through the transform
 // (<= 1e-4 * sum|column|), float rounding of the object-space round trip, and the pruning slab test.
-void geomBounds(const PtbGeom &g, float lo[3], float hi[3], double sceneDiameter) {
+void geomBounds(const PtbGeom &g, float lo[3], float hi[3], double reach) {
     const float *m = g.transform;                       // column-major
     // Spheres, rigorous part: the reference's test accepts a ray that passes up to c u |ro|^2 object units outside the sphere
-    // (see sphereBounds), |ro| <= sceneDiameter / sigma_min for any ray that starts inside the scene, so the hit point it reports
-    // can lie sigma_max c u (D / sigma_min)^2 outside the ellipsoid.  The box is the cube's box or the ellipsoid's own extent plus
+    // (see sphereBounds), |ro| <= reach / sigma_min for any ray that starts within `reach` world units of the sphere's centre, so the
+    // hit point it reports can lie sigma_max c u (reach / sigma_min)^2 outside the ellipsoid.  The box is the cube's box or the ellipsoid's own extent plus
     // that distance, whichever is larger.
     double farPad = 0.0;
-    if (g.type == 0 && sceneDiameter > 0.0) {
+    if (g.type == 0 && reach > 0.0) {
         float cc[3], r2; double smax = 1.0, smin = 1.0;
         sphereBounds(g, cc, &r2, nullptr, &smax, &smin);
-        farPad = smax * 16.0 * 5.9604644775390625e-08 * 1.5 * (sceneDiameter / smin) * (sceneDiameter / smin);
+        farPad = smax * 16.0 * 5.9604644775390625e-08 * 1.5 * (reach / smin) * (reach / smin);
     }
     for (int r = 0; r < 3; ++r) {
         const double c = m[12 + r];
@@ -223,27 +223,51 @@ struct Builder {
 };
 } // namespace
 
-// Diameter of everything a ray can start from -- the camera (when given) and every geom's world box -- which is the argument the
-// rigorous sphere boxes of geomBounds need.  0 (no far pad) when PTB_BVH_FAR_PAD=0 asks for the round-1 boxes: those are 19 % faster on the
-// 100 k-object scene (4 006 against 4 781 us per iteration, profiles/r03_bvh_pathdiff.txt) and lose reference hits of rays that graze a thin
-// ellipsoid from more than ~100 world units away (5-21 of 1.2 M silhouette rays, tools/cpu_bvh_grazing_fuzz.py --dist 160 230; none of the
-// 2.3e8 real paths of that scene).
-double defaultFarPadDiameter(const PtbGeom *geoms, int n, const float *cameraPosition) {
-    if (const char *e = getenv("PTB_BVH_FAR_PAD")) if (atoi(e) == 0) return 0.0;
-    double slo[3] = {DBL_MAX, DBL_MAX, DBL_MAX}, shi[3] = {-DBL_MAX, -DBL_MAX, -DBL_MAX};
-    if (cameraPosition) for (int a = 0; a < 3; ++a) slo[a] = shi[a] = cameraPosition[a];
+// The box of everything a ray can start from -- the camera (when given) and every geom's world box -- from which the rigorous sphere
+// boxes of geomBounds take their `reach`: the distance from the sphere's centre to the farthest corner of that box.  Off when
+// PTB_BVH_FAR_PAD=0 asks for the round-1 boxes: those are 19 % faster on the 100 k-object scene (4 006 against 4 781 us per iteration with a
+// uniform reach = the scene diameter, profiles/r03_bvh_pathdiff.txt) and lose reference hits of rays that graze a thin ellipsoid from more
+// than ~100 world units away (5-21 of 1.2 M silhouette rays, tools/cpu_bvh_grazing_fuzz.py --dist 160 230; none of the 2.3e8 real paths
+// of that scene).
+FarPadScene defaultFarPadScene(const PtbGeom *geoms, int n, const float *cameraPosition) {
+    FarPadScene s;
+    if (const char *e = getenv("PTB_BVH_FAR_PAD")) if (atoi(e) == 0) return s;
+    for (int a = 0; a < 3; ++a) { s.lo[a] = DBL_MAX; s.hi[a] = -DBL_MAX; }
+    if (cameraPosition) for (int a = 0; a < 3; ++a) s.lo[a] = s.hi[a] = cameraPosition[a];
     for (int i = 0; i < n; ++i) {
         float l[3], h[3];
         geomBounds(geoms[i], l, h);
-        for (int a = 0; a < 3; ++a) { slo[a] = std::min(slo[a], (double)l[a]); shi[a] = std::max(shi[a], (double)h[a]); }
+        for (int a = 0; a < 3; ++a) { s.lo[a] = std::min(s.lo[a], (double)l[a]); s.hi[a] = std::max(s.hi[a], (double)h[a]); }
     }
-    if (!(shi[0] >= slo[0])) return 0.0;                  // nothing to bound
-    return std::sqrt((shi[0] - slo[0]) * (shi[0] - slo[0]) + (shi[1] - slo[1]) * (shi[1] - slo[1]) + (shi[2] - slo[2]) * (shi[2] - slo[2]));
+    if (!(s.hi[0] >= s.lo[0])) return s;                  // nothing to bound
+    s.on = true;
+    // A hit the far pad exists for lies OUTSIDE the round-1 box of its sphere, and the next ray of that path starts there: grow the box
+    // by the largest pad it implies (one fixed-point step; what is left is second order in pad / diameter, inside the 24u budget).
+    double maxPad = 0.0;
+    for (int i = 0; i < n; ++i) if (geoms[i].type == 0) {
+        float l0[3], h0[3], l1[3], h1[3];
+        geomBounds(geoms[i], l0, h0);
+        geomBounds(geoms[i], l1, h1, farPadReach(geoms[i], s));
+        for (int a = 0; a < 3; ++a) maxPad = std::max(maxPad, std::max((double)l0[a] - l1[a], (double)h1[a] - h0[a]));
+    }
+    for (int a = 0; a < 3; ++a) { s.lo[a] -= maxPad; s.hi[a] += maxPad; }
+    return s;
 }
 
-void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out, double sceneDiameter) {
+double farPadReach(const PtbGeom &g, const FarPadScene &s) {
+    if (!s.on) return 0.0;
+    double d2 = 0.0;
+    for (int a = 0; a < 3; ++a) {
+        const double c = g.transform[12 + a];
+        const double d = std::max(std::fabs(c - s.lo[a]), std::fabs(s.hi[a] - c));
+        d2 += d * d;
+    }
+    return std::sqrt(d2);
+}
+
+void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out, double reach, const FarPadScene *scene) {
     std::vector<float> lo((size_t)n * 3), hi((size_t)n * 3);
-    for (int i = 0; i < n; ++i) geomBounds(geoms[i], &lo[3 * (size_t)i], &hi[3 * (size_t)i], sceneDiameter);
+    for (int i = 0; i < n; ++i) geomBounds(geoms[i], &lo[3 * (size_t)i], &hi[3 * (size_t)i], scene ? farPadReach(geoms[i], *scene) : reach);
     buildBvhBoxes(lo.data(), hi.data(), n, maxLeaf, out);
 }
 
@@ -316,8 +340,10 @@ extern "C" int ptb_bvh_build_host(const PtbGeom *geoms, int32_t numGeoms, int32_
     if (numGeoms < 0 || (numGeoms > 0 && !geoms) || !numNodes) return PTB_ERR_INVALID;
     for (int i = 0; i < numGeoms; ++i) if (geoms[i].type != 0 && geoms[i].type != 1) return PTB_ERR_INVALID;
     ptb::HostBvh hb;
-    if (farPadDiameter < 0.0) farPadDiameter = ptb::defaultFarPadDiameter(geoms, numGeoms, nullptr);
-    ptb::buildBvh(geoms, numGeoms, maxLeaf, hb, farPadDiameter);
+    if (farPadDiameter < 0.0) {
+        const ptb::FarPadScene scene = ptb::defaultFarPadScene(geoms, numGeoms, nullptr);
+        ptb::buildBvh(geoms, numGeoms, maxLeaf, hb, 0.0, &scene);
+    } else ptb::buildBvh(geoms, numGeoms, maxLeaf, hb, farPadDiameter);
     *numNodes = (int32_t)hb.nodes.size();
     if (maxDepth) *maxDepth = hb.maxDepth;
     if (nodes) {

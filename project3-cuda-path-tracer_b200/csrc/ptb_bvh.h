@@ -21,9 +21,9 @@ struct HostBvh {
 };
 
 // Padded world-space box of one geom (unit cube / sphere under Geom::transform).
-// sceneDiameter > 0: sphere boxes additionally cover the hits the reference's test reports for rays that pass outside the sphere
+// reach > 0: sphere boxes additionally cover the hits the reference's test reports for rays that pass outside the sphere
 // (they grow with the square of the distance of the ray origin; see ptb_bvh.cpp).
-void geomBounds(const PtbGeom &g, float lo[3], float hi[3], double sceneDiameter = 0.0);
+void geomBounds(const PtbGeom &g, float lo[3], float hi[3], double reach = 0.0);
 // Padded world-space bounding sphere of a SPHERE geom: centre, squared radius and the relative slack errK of the pruning
 // discriminant (grows with the anisotropy of the ellipsoid, see ptb_bvh.cpp).
 void sphereBounds(const PtbGeom &g, float centre[3], float *radius2, float *errK = nullptr, double *sigmaMax = nullptr, double *sigmaMin = nullptr);
@@ -31,12 +31,15 @@ void sphereBounds(const PtbGeom &g, float centre[3], float *radius2, float *errK
 // Padded world-space box of one mesh triangle (object-space vertices under the mesh geom's transform).
 void triangleBounds(const PtbGeom &mesh, const PtbTriangle &tri, float lo[3], float hi[3]);
 
-// The sceneDiameter ptb_create hands to geomBounds: diameter of the geoms' boxes and the camera position (may be NULL); 0 when
+// The box of everything a ray can start from (geoms' boxes and the camera position, which may be NULL), and the `reach` of geomBounds it
+// implies for one sphere: the distance from the sphere's centre to the farthest corner of that box.  on = false (reach 0) when
 // PTB_BVH_FAR_PAD=0 opts out of the rigorous sphere boxes.
-double defaultFarPadDiameter(const PtbGeom *geoms, int n, const float *cameraPosition);
+struct FarPadScene { bool on = false; double lo[3] = {0, 0, 0}, hi[3] = {0, 0, 0}; };
+FarPadScene defaultFarPadScene(const PtbGeom *geoms, int n, const float *cameraPosition);
+double farPadReach(const PtbGeom &g, const FarPadScene &scene);
 
-// Binned-SAH top-down build; leaves hold at most `maxLeaf` geoms.  sceneDiameter: see geomBounds.
-void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out, double sceneDiameter = 0.0);
+// Binned-SAH top-down build; leaves hold at most `maxLeaf` geoms.  Sphere boxes: per-geom reach from `scene` when given, else `reach` for all.
+void buildBvh(const PtbGeom *geoms, int n, int maxLeaf, HostBvh &out, double reach = 0.0, const FarPadScene *scene = nullptr);
 // The same over caller-supplied primitive boxes (lo / hi: n x 3 floats); order[slot] = primitive index.
 void buildBvhBoxes(const float *lo, const float *hi, int n, int maxLeaf, HostBvh &out);
 

@@ -204,10 +204,10 @@ def test_far_sphere_hit_the_reference_reports_outside_the_sphere(port, tmp_path,
     assert lost and np.all(hit[lost] == 31153)
 
 
-def random_spheres(orc, rs, n, scale_lo, scale_hi):
-    """SPHERE geoms placed like the synthetic scene's (tests/scenes.py synthetic_text): ellipsoids with per-axis scales"""
+def random_spheres(orc, rs, n, scale_lo, scale_hi, kind=0):
+    """SPHERE (kind 0) or CUBE (kind 1) geoms placed like the synthetic scene's (tests/scenes.py synthetic_text), per-axis scales"""
     g = np.zeros(n, orclib.GEOM_DT)
-    g["type"] = 0
+    g["type"] = kind
     g["materialid"] = 1
     t = np.stack([rs.uniform(-50, 50, n), rs.uniform(0, 100, n), rs.uniform(-100, 0, n)], 1).astype(F)
     r = rs.uniform(0, 360, (n, 3)).astype(F)
@@ -248,34 +248,52 @@ def grazing_band(orc, g, rs, origins, band, dist, scale_hi, in_scene=False):
     return o, d, rep(owner)
 
 
+def leaf_boxes(nodes, order):
+    """(lo, hi) of the leaf box of every geom, indexed by geom (one primitive per leaf)"""
+    _, slotParent = walk(nodes)
+    lo = np.zeros((len(order), 3), F); hi = np.zeros((len(order), 3), F)
+    for slot, (i, side) in slotParent.items():
+        lo[order[slot]], hi[order[slot]] = children(nodes, i)[side][:2]
+    return lo, hi
+
+
 def test_far_grazing_hits_need_the_rigorous_sphere_boxes(port, monkeypatch):
     """From 160-230 world units away -- distances the 100 k-object scene of BASELINE.json configs[4] has room for -- the reference's
     sphere test reports hits up to ~0.1 object units OUTSIDE a thin ellipsoid.  The boxes ptb_create builds (far pad over the
-    diameter of everything a ray can start from) keep every one of them; the round-1 boxes (PTB_BVH_FAR_PAD=0) lose a few."""
+    reach of every sphere inside the box of everything a ray can start from) keep every one of them; the round-1 boxes
+    (PTB_BVH_FAR_PAD=0) lose a few."""
     m = pkg()
     rs = np.random.RandomState(1)
     g = random_spheres(port, rs, 300, 0.3, 1.2)
     o, d, owner = grazing_band(port, g, rs, 8, 512, (160.0, 230.0), 1.2)
+    # two anchor cubes put every ray origin inside the scene's box, as the origins of real paths are
+    anchors = random_spheres(port, rs, 2, 1.0, 1.0, kind=1)
+    for k, t in enumerate(([-290.0, -240.0, -340.0], [290.0, 340.0, 240.0])):
+        anchors["translation"][k] = t
+        anchors["transform"][k], anchors["inverseTransform"][k], anchors["invTranspose"][k] = \
+            port.build_transform(np.float32(t), anchors["rotation"][k], anchors["scale"][k])
+    g = np.concatenate([g, anchors])
+    assert np.all(o >= anchors["translation"][0]) and np.all(o <= anchors["translation"][1])
     hit, t, _, _ = port.closest_hit(g, o, d)
     assert (hit == owner).sum() > 300000
     gm = g.view(m.GEOM_DT)
-    pts = np.concatenate([o.astype(np.float64), g["translation"] + 2.4, g["translation"] - 2.4])
-    diameter = float(np.linalg.norm(pts.max(0) - pts.min(0)))
-    nodes, order, _ = m.bvh_build_host(gm, 1, diameter)
+    monkeypatch.delenv("PTB_BVH_FAR_PAD", raising=False)
+    nodes, order, _ = m.bvh_build_host(gm, 1)                       # the library's own choice: what ptb_create builds
     lost, checked = pruned_hits(nodes, order, o, d, hit, t)
     assert not lost and checked > 3000000
-    nodes0, order0, _ = m.bvh_build_host(gm, 1, 0.0)
+    nodes0, order0, _ = m.bvh_build_host(gm, 1, 0.0)                # the round-1 boxes: the failing control
     lost0, _ = pruned_hits(nodes0, order0, o, d, hit, t)
-    assert lost0 and np.all(hit[lost0] == owner[lost0])             # the failing control
-    # the library's own choice (far_pad_diameter < 0, what ptb_create does): the diameter of the scene's boxes, unless opted out
-    monkeypatch.delenv("PTB_BVH_FAR_PAD", raising=False)
-    root = nodes0[0]
-    scene = float(np.linalg.norm(np.maximum(root["lhi"], root["rhi"]).astype(np.float64) - np.minimum(root["llo"], root["rlo"])))
-    auto = m.bvh_build_host(gm, 1, -1.0)
-    want = m.bvh_build_host(gm, 1, scene)
-    assert auto[0].tobytes() == want[0].tobytes() and auto[0].tobytes() != nodes0.tobytes()
+    assert lost0 and np.all(hit[lost0] == owner[lost0])
+    # the rigorous boxes contain the round-1 boxes (so every hit those found is still found) and are no larger than the
+    # uniform worst case over the diameter of the whole scene
+    lo, hi = leaf_boxes(nodes, order)
+    lo0, hi0 = leaf_boxes(nodes0, order0)
+    assert np.all(lo <= lo0) and np.all(hi >= hi0) and np.any(lo < lo0)
+    span = anchors["translation"][1].astype(np.float64) - anchors["translation"][0] + 4.0
+    loU, hiU = leaf_boxes(*m.bvh_build_host(gm, 1, 1.05 * float(np.linalg.norm(span)))[:2])
+    assert np.all(lo >= loU) and np.all(hi <= hiU) and np.any(lo > loU)
     monkeypatch.setenv("PTB_BVH_FAR_PAD", "0")
-    assert m.bvh_build_host(gm, 1, -1.0)[0].tobytes() == nodes0.tobytes()
+    assert m.bvh_build_host(gm, 1)[0].tobytes() == nodes0.tobytes()
 
 
 def test_degenerate_scenes():

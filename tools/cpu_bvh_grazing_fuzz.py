@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--scale-hi", type=float, default=1.2)
     ap.add_argument("--dist", type=float, nargs=2, default=(50.0, 300.0))
     ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--cubes", type=int, default=0, help="1: CUBE primitives instead of SPHERE (the 'outside the sphere' line is then meaningless)")
     ap.add_argument("--far-pad", type=int, default=0, help="1: rigorous sphere boxes (geomBounds with the diameter of origins + spheres)")
     ap.add_argument("--in-scene", type=int, default=0, help="1: ray origins next to OTHER spheres of the scene (bounce rays), far pad diameter = "
                     "the diameter of the scene's own boxes, as ptb_create computes it; --dist is ignored")
@@ -42,7 +43,7 @@ def main():
     orc = orclib.load("port")
     m = pkg()
     rs = np.random.RandomState(a.seed)
-    g = random_spheres(orc, rs, a.spheres, a.scale_lo, a.scale_hi)
+    g = random_spheres(orc, rs, a.spheres, a.scale_lo, a.scale_hi, 1 if a.cubes else 0)
     K, Q = a.spheres, a.origins
     o, d, owner_b = grazing_band(orc, g, rs, a.origins, a.band, a.dist, a.scale_hi, bool(a.in_scene))
     hit, t, _, _ = orc.closest_hit(g, o, d)
