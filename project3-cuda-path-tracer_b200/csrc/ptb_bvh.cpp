@@ -33,6 +33,9 @@ void geomBounds(const PtbGeom &g, float lo[3], float hi[3], double reach) {
         float cc[3], r2; double smax = 1.0, smin = 1.0;
         sphereBounds(g, cc, &r2, nullptr, &smax, &smin);
         farPad = smax * 16.0 * 5.9604644775390625e-08 * 1.5 * (reach / smin) * (reach / smin);
+        // a box of 4 x reach around the centre already covers everything a ray can start from several times over; the cap also takes
+        // the inf / NaN of a singular transform (a SCALE of 0: glm::inverse returns non-finite entries, src/scene.cpp:82-85)
+        if (!(farPad <= 4.0 * reach)) farPad = 4.0 * reach;
     }
     for (int r = 0; r < 3; ++r) {
         const double c = m[12 + r];

@@ -313,6 +313,18 @@ def test_degenerate_scenes():
     nodes, order, depth = m.bvh_build_host(g)
     _, slotParent = walk(nodes)
     assert sorted(slotParent) == list(range(40)) and depth < 60
+    # a singular transform (SCALE 0 on one axis: the inverse is not finite) still gets finite boxes
+    port = orclib.load("port")
+    g2 = random_spheres(port, np.random.RandomState(2), 20, 0.3, 1.2)
+    g2["scale"][5] = [1.0, 0.0, 1.0]
+    with np.errstate(all="ignore"):
+        g2["transform"][5], g2["inverseTransform"][5], g2["invTranspose"][5] = port.build_transform(g2["translation"][5], g2["rotation"][5], g2["scale"][5])
+    assert not np.isfinite(g2["inverseTransform"][5]).all()
+    nodes, order, depth = m.bvh_build_host(g2.view(m.GEOM_DT))
+    _, slotParent = walk(nodes)
+    assert sorted(slotParent) == list(range(20))
+    for name in ("llo", "lhi", "rlo", "rhi"):
+        assert np.isfinite(nodes[name]).all()
     # a mesh geom (type 2) has no box of its own: triangles are boxed one by one inside ptb_create
     g["type"][3] = 2
     with pytest.raises(m.PtbError):
