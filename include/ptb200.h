@@ -249,6 +249,11 @@ int  ptb_save_hdr(const char *baseFilename, int w, int h, const float *sum, floa
 int  ptb_bvh_build_host(const PtbGeom *geoms, int32_t numGeoms, int32_t maxLeaf, double farPadDiameter, float *nodes, int32_t nodeCap,
                         int32_t *order, int32_t *numNodes, int32_t *maxDepth);
 
+/* The conservative pruning bounds of one SPHERE / CUBE geom as the kernels receive them (csrc/ptb_bvh.cpp geomBounds / sphereBounds):
+ * the padded world box (reach: see farPadDiameter above, <= 0 for none) and, for a sphere, the padded bounding sphere
+ * (centre, squared radius) with the relative slack errK of its discriminant (centre / radius2 / errK may be NULL).  No CUDA call. */
+int  ptb_geom_bounds_host(const PtbGeom *geom, double reach, float lo[3], float hi[3], float centre[3], float *radius2, float *errK);
+
 #ifdef __cplusplus
 }
 #endif

@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "ptb_stats", "ptb_accum_device_ptr", "ptb_resolve_rgb8", "ptb_stage_raygen", "ptb_stage_raygen_iter", "ptb_stage_intersect",
     "ptb_stage_shade", "ptb_stage_compact", "ptb_stage_sort_keys", "ptb_stage_rng", "ptb_stage_arith", "ptb_stage_sincos",
     "ptb_scene_load", "ptb_scene_counts", "ptb_scene_get", "ptb_scene_mesh_counts", "ptb_scene_get_meshes", "ptb_scene_free", "ptb_camera_fixup",
-    "ptb_save_png", "ptb_save_hdr", "ptb_bvh_build_host",
+    "ptb_save_png", "ptb_save_hdr", "ptb_bvh_build_host", "ptb_geom_bounds_host",
 ]
 
 _lib = None
@@ -124,6 +124,7 @@ def lib():
             L.ptb_save_hdr.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_void_p, C.c_float, C.c_int]
             L.ptb_bvh_build_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_double, C.c_void_p, C.c_int32, C.c_void_p,
                                              C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+            L.ptb_geom_bounds_host.argtypes = [C.c_void_p, C.c_double] + [C.c_void_p] * 5
         _lib = L
     return _lib
 
@@ -415,3 +416,16 @@ def bvh_build_host(geoms, max_leaf=1, far_pad_diameter=-1.0):
     _check(lib().ptb_bvh_build_host(geoms.ctypes.data, len(geoms), int(max_leaf), float(far_pad_diameter), nodes.ctypes.data, len(nodes), order.ctypes.data,
                                     C.byref(n), C.byref(depth)))
     return nodes, order, depth.value
+
+
+def geom_bounds_host(geoms, reach=0.0):
+    """Pruning bounds of SPHERE / CUBE geoms as the kernels receive them (csrc/ptb_bvh.cpp): (lo, hi, centre, radius2, errK);
+    the last three are zero for cubes."""
+    geoms = np.ascontiguousarray(geoms, GEOM_DT)
+    n = len(geoms)
+    lo, hi, c = (np.zeros((n, 3), np.float32) for _ in range(3))
+    r2, ek = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    for i in range(n):
+        _check(lib().ptb_geom_bounds_host(geoms[i:i + 1].ctypes.data, float(reach), lo[i:].ctypes.data, hi[i:].ctypes.data,
+                                          c[i:].ctypes.data, r2[i:].ctypes.data, ek[i:].ctypes.data))
+    return lo, hi, c, r2, ek

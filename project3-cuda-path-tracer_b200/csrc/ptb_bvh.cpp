@@ -356,3 +356,12 @@ extern "C" int ptb_bvh_build_host(const PtbGeom *geoms, int32_t numGeoms, int32_
     if (order) std::copy(hb.order.begin(), hb.order.end(), order);
     return PTB_OK;
 }
+
+// Host-only: the pruning bounds of one SPHERE / CUBE geom as ptb_create packs them for the kernels (ptb200.cu packGeom: the padded
+// world box of geomBounds with the given reach, and for spheres the bounding sphere and discriminant slack of sphereBounds).
+extern "C" int ptb_geom_bounds_host(const PtbGeom *geom, double reach, float lo[3], float hi[3], float centre[3], float *radius2, float *errK) {
+    if (!geom || !lo || !hi || (geom->type != 0 && geom->type != 1)) return PTB_ERR_INVALID;
+    ptb::geomBounds(*geom, lo, hi, reach > 0.0 ? reach : 0.0);
+    if (geom->type == 0 && centre && radius2) ptb::sphereBounds(*geom, centre, radius2, errK);
+    return PTB_OK;
+}

@@ -172,6 +172,7 @@ def test_boxes_are_conservative_for_the_reference_tests(port, synth, max_leaf):
     lost, checked = pruned_hits(nodes, order, o, d, hit, t)
     assert not lost, "the boxes prune the oracle's hit of rays %s" % lost[:8]
     assert checked > 150000
+    assert len(stage_b_rejects(m, os_.geoms, o, d, hit, t)) == 0
 
 
 def test_far_sphere_hit_the_reference_reports_outside_the_sphere(port, tmp_path, monkeypatch):
@@ -248,6 +249,35 @@ def grazing_band(orc, g, rs, origins, band, dist, scale_hi, in_scene=False):
     return o, d, rep(owner)
 
 
+def stage_b_rejects(m, g, o, d, hit, t):
+    """Oracle hits that the per-primitive pruning of the closest-hit searches would throw away: boundEntryRaw (ptb_math.cuh) of the
+    HIT primitive restated in float32 -- padded world box for cubes, padded bounding sphere with the errK slack for spheres --
+    followed by the searches' acceptance rule `e >= 0 && e * 0.99998 - slack <= best.t` (ptb_kernels.cuh stage B, best.t >= t)."""
+    lo, hi, c, r2, ek = m.geom_bounds_host(g.view(m.GEOM_DT))
+    k = np.flatnonzero(hit >= 0)
+    j = hit[k]
+    ok_, dk, tk = o[k], d[k], t[k]
+    rd = np.sqrt((dk * dk).sum(1, dtype=F)).astype(F)
+    dn = (dk / rd[:, None]).astype(F)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        inv = (F(1) / dk).astype(F)
+        t0 = (lo[j] - ok_) * inv
+        t1 = (hi[j] - ok_) * inv
+    tn = np.fmax(np.fmax(np.fmin(t0[:, 0], t1[:, 0]), np.fmin(t0[:, 1], t1[:, 1])), np.fmax(np.fmin(t0[:, 2], t1[:, 2]), F(0)))
+    tf = np.fmin(np.fmin(np.fmax(t0[:, 0], t1[:, 0]), np.fmax(t0[:, 1], t1[:, 1])), np.fmax(t0[:, 2], t1[:, 2]))
+    e_cube = np.where(tn <= tf * F(1.00002) + F(1e-6), tn * rd, F(-1)).astype(F)
+    oc = (c[j] - ok_).astype(F)
+    oc2 = (oc * oc).sum(1, dtype=F)
+    bq = (oc * dn).sum(1, dtype=F)
+    det = (bq * bq + (r2[j] - oc2) + ek[j] * (oc2 + bq * bq)).astype(F)
+    sq = np.sqrt(np.maximum(det, F(0))).astype(F)
+    e_sph = np.where((det < 0) | (bq + sq * F(1.000001) < 0), F(-1), np.fmax(bq - sq * F(1.000001) - F(1e-6) * np.abs(bq), F(0))).astype(F)
+    e = np.where(g["type"][j] == 1, e_cube, e_sph)
+    slack = F(2e-5) * (np.abs(ok_).sum(1, dtype=F) + F(1))
+    keep = (e >= 0) & (e * F(0.99998) - slack <= tk)
+    return k[~keep]
+
+
 def leaf_boxes(nodes, order):
     """(lo, hi) of the leaf box of every geom, indexed by geom (one primitive per leaf)"""
     _, slotParent = walk(nodes)
@@ -281,6 +311,7 @@ def test_far_grazing_hits_need_the_rigorous_sphere_boxes(port, monkeypatch):
     nodes, order, _ = m.bvh_build_host(gm, 1)                       # the library's own choice: what ptb_create builds
     lost, checked = pruned_hits(nodes, order, o, d, hit, t)
     assert not lost and checked > 3000000
+    assert len(stage_b_rejects(m, g, o, d, hit, t)) == 0            # the per-primitive bounds carry their own slack (errK)
     nodes0, order0, _ = m.bvh_build_host(gm, 1, 0.0)                # the round-1 boxes: the failing control
     lost0, _ = pruned_hits(nodes0, order0, o, d, hit, t)
     assert lost0 and np.all(hit[lost0] == owner[lost0])
@@ -294,6 +325,27 @@ def test_far_grazing_hits_need_the_rigorous_sphere_boxes(port, monkeypatch):
     assert np.all(lo >= loU) and np.all(hi <= hiU) and np.any(lo > loU)
     monkeypatch.setenv("PTB_BVH_FAR_PAD", "0")
     assert m.bvh_build_host(gm, 1)[0].tobytes() == nodes0.tobytes()
+
+
+def test_sphere_pruning_bound_carries_the_anisotropy_slack(port, monkeypatch):
+    """The per-primitive bounding-sphere test (stage B of the BVH search, phase 1 of the brute-force one) must keep the hits the
+    reference reports for rays passing outside a thin ellipsoid: the slack of its discriminant grows with (sigma_max / sigma_min)^2
+    (ptb_bvh.cpp sphereBounds).  With the 2e-6 constant that only covers near-isotropic spheres the same rays are rejected."""
+    m = pkg()
+    rs = np.random.RandomState(5)
+    g = random_spheres(port, rs, 150, 0.05, 2.0)
+    o, d, owner = grazing_band(port, g, rs, 4, 256, (100.0, 250.0), 2.0)
+    hit, t, _, _ = port.closest_hit(g, o, d)
+    assert (hit == owner).sum() > 30000
+    assert len(stage_b_rejects(m, g, o, d, hit, t)) == 0
+    shipped = m.geom_bounds_host
+
+    def isotropic_only(geoms, reach=0.0):
+        lo, hi, c, r2, ek = shipped(geoms, reach)
+        assert ek.max() > 1e-4                                      # thin ellipsoids ask for far more than the constant
+        return lo, hi, c, r2, np.full_like(ek, 2e-6)
+    monkeypatch.setattr(m, "geom_bounds_host", isotropic_only)
+    assert len(stage_b_rejects(m, g, o, d, hit, t)) > 100
 
 
 def test_degenerate_scenes():

@@ -21,7 +21,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 import orclib                                   # noqa: E402
 from common import pkg                          # noqa: E402
-from test_bvh_host import pruned_hits, random_spheres, grazing_band           # noqa: E402
+from test_bvh_host import pruned_hits, random_spheres, grazing_band, stage_b_rejects           # noqa: E402
 
 F = np.float32
 
@@ -67,9 +67,13 @@ def main():
           % (outside.sum(), (perp[outside] - 0.5).max() if outside.any() else 0.0,
              np.linalg.norm(qo[outside][np.argmax(perp[outside])]) if outside.any() else 0.0))
     print("far pad diameter %.1f; BVH depth %d, %d (ray, box) pairs checked, hits a box on the way prunes: %d" % (diameter, depth, checked, len(lost)))
+    rej = stage_b_rejects(m, g, o, d, hit, t)
+    print("per-primitive pruning bound (stage B / brute-force phase 1) rejects the oracle's hit: %d" % len(rej))
+    for r in rej[:5]:
+        print("  rejected: ray %d geom %d t %.6f o %s d %s" % (r, hit[r], t[r], o[r].tolist(), d[r].tolist()))
     for r in lost[:10]:
         print("  lost: ray %d sphere %d t %.6f o %s d %s" % (r, hit[r], t[r], o[r].tolist(), d[r].tolist()))
-    return 1 if lost else 0
+    return 1 if lost or len(rej) else 0
 
 
 if __name__ == "__main__":
