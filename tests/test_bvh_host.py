@@ -173,6 +173,7 @@ def test_boxes_are_conservative_for_the_reference_tests(port, synth, max_leaf):
     assert not lost, "the boxes prune the oracle's hit of rays %s" % lost[:8]
     assert checked > 150000
     assert len(stage_b_rejects(m, os_.geoms, o, d, hit, t)) == 0
+    assert len(sure_miss_rejects(os_.geoms, o, d, hit)) == 0
 
 
 def test_far_sphere_hit_the_reference_reports_outside_the_sphere(port, tmp_path, monkeypatch):
@@ -278,6 +279,39 @@ def stage_b_rejects(m, g, o, d, hit, t):
     return k[~keep]
 
 
+def sure_miss_rejects(g, o, d, hit):
+    """Oracle hits the object-space sure-miss filters (ptb_math.cuh boxSureMiss / sphereSureMiss, run on the hit primitive before the
+    reference-exact test in every closest-hit search) would call a miss.  float32 restatement; the filters' margins (4e-6 / 2e-5
+    relative) are far above the ulp-level differences between this and the device's approximate reciprocals."""
+    k = np.flatnonzero(hit >= 0)
+    j = hit[k]
+    M = g["inverseTransform"].reshape(-1, 4, 4).transpose(0, 2, 1)[j].astype(F)         # row-major 4x4 of every hit primitive
+    ok_, dk = o[k], d[k]
+    row = lambda r, v, w: ((M[:, r, 0] * v[:, 0] + M[:, r, 1] * v[:, 1]) + (M[:, r, 2] * v[:, 2] + M[:, r, 3] * F(w))).astype(F)
+    qo = np.stack([row(r, ok_, 1) for r in range(3)], 1)
+    qu = np.stack([row(r, dk, 0) for r in range(3)], 1)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        # boxSureMiss
+        usable = (np.abs(qu) > F(1e-30)).all(1)
+        inv = (F(1) / qu).astype(F)
+        a1 = (F(-0.5) - qo) * inv
+        a2 = (F(0.5) - qo) * inv
+        ta, tb = np.fmin(a1, a2), np.fmax(a1, a2)
+        tmin = np.where(ta > 0, ta, F(-1e38)).max(1)
+        tmax = np.fmin(tb.min(1), F(1e38))
+        mag = np.abs(tmax) + np.abs(tmin)
+        box_miss = usable & ((tmax - tmin < F(-4e-6) * mag) | (tmax < 0))
+        # sphereSureMiss
+        uu = (qu * qu).sum(1, dtype=F)
+        ok2 = (uu > F(1e-30)) & (uu < F(1e30))
+        b = ((qo * qu).sum(1, dtype=F) / np.sqrt(uu)).astype(F)
+        oo = (qo * qo).sum(1, dtype=F)
+        cc = oo - F(0.25)
+        mg = b * b + (oo + F(0.25))
+        sph_miss = ok2 & ((b * b - cc < F(-2e-5) * mg) | ((b > 0) & (b * b > F(1e-6) * mg) & (cc > F(2e-5) * mg)))
+    return k[np.where(g["type"][j] == 1, box_miss, sph_miss)]
+
+
 def leaf_boxes(nodes, order):
     """(lo, hi) of the leaf box of every geom, indexed by geom (one primitive per leaf)"""
     _, slotParent = walk(nodes)
@@ -312,6 +346,7 @@ def test_far_grazing_hits_need_the_rigorous_sphere_boxes(port, monkeypatch):
     lost, checked = pruned_hits(nodes, order, o, d, hit, t)
     assert not lost and checked > 3000000
     assert len(stage_b_rejects(m, g, o, d, hit, t)) == 0            # the per-primitive bounds carry their own slack (errK)
+    assert len(sure_miss_rejects(g, o, d, hit)) == 0                # and so do the object-space sure-miss filters
     nodes0, order0, _ = m.bvh_build_host(gm, 1, 0.0)                # the round-1 boxes: the failing control
     lost0, _ = pruned_hits(nodes0, order0, o, d, hit, t)
     assert lost0 and np.all(hit[lost0] == owner[lost0])
@@ -338,6 +373,7 @@ def test_sphere_pruning_bound_carries_the_anisotropy_slack(port, monkeypatch):
     hit, t, _, _ = port.closest_hit(g, o, d)
     assert (hit == owner).sum() > 30000
     assert len(stage_b_rejects(m, g, o, d, hit, t)) == 0
+    assert len(sure_miss_rejects(g, o, d, hit)) == 0
     shipped = m.geom_bounds_host
 
     def isotropic_only(geoms, reach=0.0):
@@ -346,6 +382,23 @@ def test_sphere_pruning_bound_carries_the_anisotropy_slack(port, monkeypatch):
         return lo, hi, c, r2, np.full_like(ek, 2e-6)
     monkeypatch.setattr(m, "geom_bounds_host", isotropic_only)
     assert len(stage_b_rejects(m, g, o, d, hit, t)) > 100
+
+
+def test_sure_miss_filters_prove_misses_and_keep_hits(port):
+    """The restated object-space filters are not vacuous: they prove nearly every miss of random (ray, primitive) pairs and never
+    call a primitive the oracle hits a miss."""
+    rs = np.random.RandomState(5)
+    n = 100000
+    o = np.stack([rs.uniform(-50, 50, n), rs.uniform(0, 100, n), rs.uniform(-100, 0, n)], 1).astype(F)
+    d = rs.normal(size=(n, 3)).astype(F)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    for kind in (0, 1):
+        g = random_spheres(port, rs, 100, 0.3, 1.2, kind)
+        hit = port.closest_hit(g, o, d)[0]
+        other = rs.randint(0, 100, n).astype(np.int32)
+        other[hit == other] = -1
+        assert len(sure_miss_rejects(g, o, d, other)) > 0.99 * (other >= 0).sum()
+        assert (hit >= 0).sum() > 100 and len(sure_miss_rejects(g, o, d, hit)) == 0
 
 
 def test_degenerate_scenes():

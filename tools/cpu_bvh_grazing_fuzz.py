@@ -21,7 +21,7 @@ for p in (ROOT, os.path.join(ROOT, "tests")):
 
 import orclib                                   # noqa: E402
 from common import pkg                          # noqa: E402
-from test_bvh_host import pruned_hits, random_spheres, grazing_band, stage_b_rejects           # noqa: E402
+from test_bvh_host import pruned_hits, random_spheres, grazing_band, stage_b_rejects, sure_miss_rejects           # noqa: E402
 
 F = np.float32
 
@@ -69,6 +69,9 @@ def main():
     print("far pad diameter %.1f; BVH depth %d, %d (ray, box) pairs checked, hits a box on the way prunes: %d" % (diameter, depth, checked, len(lost)))
     rej = stage_b_rejects(m, g, o, d, hit, t)
     print("per-primitive pruning bound (stage B / brute-force phase 1) rejects the oracle's hit: %d" % len(rej))
+    sm = sure_miss_rejects(g, o, d, hit)
+    print("object-space sure-miss filter calls the oracle's hit a miss: %d" % len(sm))
+    rej = np.concatenate([rej, sm])
     for r in rej[:5]:
         print("  rejected: ray %d geom %d t %.6f o %s d %s" % (r, hit[r], t[r], o[r].tolist(), d[r].tolist()))
     for r in lost[:10]:
