@@ -37,16 +37,17 @@ void geomBounds(const PtbGeom &g, float lo[3], float hi[3], double reach) {
         // the inf / NaN of a singular transform (a SCALE of 0: glm::inverse returns non-finite entries, src/scene.cpp:82-85)
         if (!(farPad <= 4.0 * reach)) farPad = 4.0 * reach;
     }
+    // knobs of A/B and validation runs (tools/gpu_bvh_pathdiff.py); read per call, the tests flip them between builds
+    const bool tight = [] { const char *e = getenv("PTB_BVH_TIGHT_SPHERES"); return e ? atoi(e) != 0 : PTB_BVH_TIGHT_SPHERES != 0; }();
+    const double extra = [] { const char *x = getenv("PTB_BVH_EXTRA_PAD"); return x ? atof(x) : 0.0; }();
     for (int r = 0; r < 3; ++r) {
         const double c = m[12 + r];
         const double rowAbs = std::fabs((double)m[0 + r]) + std::fabs((double)m[4 + r]) + std::fabs((double)m[8 + r]);
         // half extent along world axis r: the unit cube reaches 0.5 * |row|_1, the radius-0.5 sphere only 0.5 * |row|_2
         // (an ellipsoid's box is up to sqrt(3) x tighter per axis than the box of the cube around it)
-        const bool tight = [] { const char *e = getenv("PTB_BVH_TIGHT_SPHERES"); return e ? atoi(e) != 0 : PTB_BVH_TIGHT_SPHERES != 0; }();   // knob for A/B runs
         const double eTight = 0.5 * std::sqrt((double)m[0 + r] * m[0 + r] + (double)m[4 + r] * m[4 + r] + (double)m[8 + r] * m[8 + r]);
         const double e = (g.type == 0 && farPad > 0.0 && !tight) ? std::max(0.5 * rowAbs, eTight + farPad) : (tight && g.type == 0) ? 0.5 * std::sqrt((double)m[0 + r] * m[0 + r] + (double)m[4 + r] * m[4 + r] + (double)m[8 + r] * m[8 + r]) * (1.0 + 1e-6)
                                      : 0.5 * rowAbs;
-        const double extra = [] { const char *x = getenv("PTB_BVH_EXTRA_PAD"); return x ? atof(x) : 0.0; }();   // validation runs: tools/gpu_bvh_pathdiff.py
         const double pad = 4e-4 * rowAbs + 1e-3 + 2e-5 * (std::fabs(c) + e) + extra;
         lo[r] = (float)(c - e - pad);
         hi[r] = (float)(c + e + pad);
