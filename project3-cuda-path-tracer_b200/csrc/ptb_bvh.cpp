@@ -26,16 +26,18 @@ void geomBounds(const PtbGeom &g, float lo[3], float hi[3], double reach) {
     const float *m = g.transform;                       // column-major
     // Spheres, rigorous part: the reference's test accepts a ray that passes up to c u |ro|^2 object units outside the sphere
     // (see sphereBounds), |ro| <= reach / sigma_min for any ray that starts within `reach` world units of the sphere's centre, so the
-    // hit point it reports can lie sigma_max c u (reach / sigma_min)^2 outside the ellipsoid.  The box is the cube's box or the ellipsoid's own extent plus
+    // hit point it reports can lie sigma_max (sqrt(0.25 + c u (reach / sigma_min)^2) - 0.5) outside the ellipsoid.  The box is the cube's box or the ellipsoid's own extent plus
     // that distance, whichever is larger.
     double farPad = 0.0;
     if (g.type == 0 && reach > 0.0) {
         float cc[3], r2; double smax = 1.0, smin = 1.0;
         sphereBounds(g, cc, &r2, nullptr, &smax, &smin);
-        farPad = smax * 16.0 * 5.9604644775390625e-08 * 1.5 * (reach / smin) * (reach / smin);
-        // a box of 4 x reach around the centre already covers everything a ray can start from several times over; the cap also takes
-        // the inf / NaN of a singular transform (a SCALE of 0: glm::inverse returns non-finite entries, src/scene.cpp:82-85)
-        if (!(farPad <= 4.0 * reach)) farPad = 4.0 * reach;
+        // accepted: |closest approach|^2 <= 0.25 + E object units^2, E = c u |ro|^2 (c budgeted at 24)  =>  excess sqrt(0.25 + E) - 0.5
+        const double E = 16.0 * 5.9604644775390625e-08 * 1.5 * (reach / smin) * (reach / smin);
+        farPad = smax * (std::sqrt(0.25 + E) - 0.5);
+        // a singular transform (a SCALE of 0: glm::inverse returns non-finite entries, src/scene.cpp:82-85) has no finite bound; a box of
+        // 4 x reach around the centre covers everything a ray can start from several times over
+        if (!std::isfinite(farPad)) farPad = 4.0 * reach;
     }
     // knobs of A/B and validation runs (tools/gpu_bvh_pathdiff.py); read per call, the tests flip them between builds
     const bool tight = [] { const char *e = getenv("PTB_BVH_TIGHT_SPHERES"); return e ? atoi(e) != 0 : PTB_BVH_TIGHT_SPHERES != 0; }();
