@@ -266,12 +266,19 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     {
         // Sphere boxes also cover the hits the reference's sphere test reports for rays passing OUTSIDE the sphere, for every ray that
         // starts inside the scene (ptb_bvh.cpp geomBounds / defaultFarPadScene; PTB_BVH_FAR_PAD=0 opts out).
-        const FarPadScene farPad = defaultFarPadScene(scene->geoms, G, scene->camera.position);
+        FarPadScene farPad = defaultFarPadScene(scene->geoms, G, scene->camera.position);
         std::vector<float> lo((size_t)P * 3), hi((size_t)P * 3);
-        for (int k = 0; k < P; ++k) {
+        // triangles first: a mesh reaches as far as its vertices do, not as far as the unit cube under its transform, and rays start there too
+        for (int k = 0; k < P; ++k) if (prims[k].second >= 0) {
+            triangleBounds(scene->geoms[prims[k].first], scene->triangles[prims[k].second], &lo[3 * (size_t)k], &hi[3 * (size_t)k]);
+            if (farPad.on) for (int a = 0; a < 3; ++a) {
+                farPad.lo[a] = std::min(farPad.lo[a], (double)lo[3 * (size_t)k + a]);
+                farPad.hi[a] = std::max(farPad.hi[a], (double)hi[3 * (size_t)k + a]);
+            }
+        }
+        for (int k = 0; k < P; ++k) if (prims[k].second < 0) {
             const PtbGeom &g = scene->geoms[prims[k].first];
-            if (prims[k].second >= 0) triangleBounds(g, scene->triangles[prims[k].second], &lo[3 * (size_t)k], &hi[3 * (size_t)k]);
-            else                      geomBounds(g, &lo[3 * (size_t)k], &hi[3 * (size_t)k], farPadReach(g, farPad));
+            geomBounds(g, &lo[3 * (size_t)k], &hi[3 * (size_t)k], farPadReach(g, farPad));
         }
         buildBvhBoxes(lo.data(), hi.data(), P, maxLeaf, hb);
     }
