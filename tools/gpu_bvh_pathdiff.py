@@ -23,9 +23,10 @@ def make(env):
     return m.Renderer(scene, device=0, bsdf=1, batch_iters=1)
 
 
-r_old = make({"PTB_BVH_ALL_AXES": os.environ.get("OLD_ALL_AXES", "0"), "PTB_BVH_TIGHT_SPHERES": "0", "PTB_BVH_EXTRA_PAD": "0"})
+r_old = make({"PTB_BVH_ALL_AXES": os.environ.get("OLD_ALL_AXES", "0"), "PTB_BVH_TIGHT_SPHERES": "0", "PTB_BVH_EXTRA_PAD": "0",
+              "PTB_BVH_FAR_PAD": os.environ.get("OLD_FAR_PAD", "1")})
 r_new = make({"PTB_BVH_ALL_AXES": os.environ.get("NEW_ALL_AXES", "1"), "PTB_BVH_TIGHT_SPHERES": os.environ.get("NEW_TIGHT", "0"),
-              "PTB_BVH_EXTRA_PAD": os.environ.get("NEW_EXTRA_PAD", "0")})
+              "PTB_BVH_EXTRA_PAD": os.environ.get("NEW_EXTRA_PAD", "0"), "PTB_BVH_FAR_PAD": os.environ.get("NEW_FAR_PAD", "1")})
 bits = lambda a: np.ascontiguousarray(a).view(np.uint32)
 tot_rays = tot_diff = wrong_old = wrong_new = 0
 for it in range(first, first + n_it):
