@@ -175,6 +175,95 @@ def claim_stdout():
     return os.fdopen(saved, "w")
 
 
+def skeleton_gpu_baseline(scene_path, iters=1000, warm=50):
+    """The reference skeleton's own CUDA loop (unmodified src/pathtrace.cu rebuilt for sm_100 behind oracle/skeleton_main.cpp,
+    built by oracle/Makefile where /root/reference exists; the binary travels in oracle/_ref/): the denominator of
+    BASELINE.json's ">= 10x" target.  Runs on this box's GPU OUTSIDE every timed region.  None when the binary is absent."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "skeleton_bench")
+    if not os.path.exists(exe):
+        return None
+    try:
+        r = subprocess.run([exe, scene_path, str(iters), str(warm)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=300)
+        for line in r.stdout.splitlines():
+            if line.startswith("{"):
+                return json.loads(line)
+    except Exception:
+        return None
+    return None
+
+
+def roofline_of(seg, iters, pixels, ms, hbm_peak, sm_max):
+    """algorithmic bytes = 88 B per path segment + 24 B per pixel per iteration; flops = 700 per segment."""
+    alg = BYTES_PER_SEGMENT * seg + BYTES_PER_PIXEL_ITER * pixels * iters
+    gbs = alg / (ms * 1e-3) / 1e9
+    tf = FLOP_PER_SEGMENT * seg / (ms * 1e-3) / 1e12
+    return {"algorithmic_gbs": gbs, "hbm_frac": gbs / hbm_peak, "fp32_tflops": tf, "fp32_frac": tf / (148 * 128 * 2 * sm_max * 1e6 / 1e12)}
+
+
+def timed_render(torch, stream, r, first, count, reps=1):
+    """count iterations starting at `first`, timed with CUDA events on the launching stream; best of reps -> (ms, stats delta)"""
+    best = None
+    for _ in range(reps):
+        r.sync()
+        s0 = r.stats()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        r.render(first, count)
+        e1.record(stream)
+        r.sync()
+        ms = e0.elapsed_time(e1)
+        s1 = r.stats()
+        if best is None or ms < best[0]:
+            best = (ms, s1["segments"] - s0["segments"], s1["iterations"] - s0["iterations"])
+        first += count
+    return best
+
+
+def extra_configs(m, torch, stream, local, tmp, hbm_peak, sm_max):
+    """BASELINE.json configs[1], [3] (one GPU, short) and [4] beside the headline line: us/iteration, segments/s, roofline fractions.
+    Single-GPU only (world == 1); everything is timed with CUDA events after a warm-up run of the same length."""
+    import scenes
+    out = {}
+    specs = [
+        ("configs[1] sphere.txt 800x800 depth 8", scenes.sphere_text(), dict(batch_iters=128), 1024),
+        ("configs[3] cornell.txt 3840x2160 depth 8 (one GPU, 64 of the 5000 spp)", scenes.cornell_text(res=(3840, 2160)), dict(), 64),
+        ("configs[4] synthetic 100k SPHERE/CUBE 1920x1080 depth 16 (flat BVH)", scenes.synthetic_text(100000), dict(), 32),
+    ]
+    for name, text, kw, n in specs:
+        path = os.path.join(tmp, "extra.txt")
+        with open(path, "w") as f:
+            f.write(text)
+        sc = m.Scene.load(path)
+        with m.Renderer(sc, device=local, bsdf=m.BSDF_FULL, stream=stream.cuda_stream, **kw) as r:
+            r.render(1, n)                                              # warm-up (graph capture, first-touch)
+            ms, seg, its = timed_render(torch, stream, r, 1 + n, n, reps=2)
+            st = r.stats()
+        d = {"us_per_iteration": ms * 1e3 / its, "segments_per_s": seg / (ms * 1e-3), "iters_per_s": its / (ms * 1e-3),
+             "segments_per_iter": seg / its, "iterations_timed": its, "batch_iters": st["batch_iters"], "bvh_nodes": st["bvh_nodes"]}
+        d.update(roofline_of(seg, its, sc.pixels, ms, hbm_peak, sm_max))
+        out[name] = d
+    return out
+
+
+def golden_image_error(m, torch, stream, local, scene):
+    """north_star: the converged cornell image within relative RMSE 1e-2 of img/REFERENCE_cornell.5000samp.png (committed as
+    tests/golden/reference_cornell_5000samp.npz).  Same metric as tests/test_gpu_scale.py: 16x16 block means, golden-diffuse mode."""
+    import numpy as np
+    gp = os.path.join(ROOT, "tests", "golden", "reference_cornell_5000samp.npz")
+    if not os.path.exists(gp):
+        return None
+    gold = np.load(gp)["rgb8"].astype(np.float64) / 255.0
+    with m.Renderer(scene, device=local, bsdf=m.BSDF_GOLDEN_DIFFUSE, batch_iters=64, stream=stream.cuda_stream) as r:
+        r.render(1, 5000)
+        ours = r.resolve_rgb8(5000).astype(np.float64) / 255.0
+    rms = np.sqrt((gold ** 2).mean())
+    blk = lambda a: a.reshape(50, 16, 50, 16, 3).mean((1, 3))
+    return {"rel_rmse_16x16_blocks": float(np.sqrt(((blk(ours) - blk(gold)) ** 2).mean()) / rms),
+            "rel_rmse_per_pixel": float(np.sqrt(((ours - gold) ** 2).mean()) / rms),
+            "mean_ratio_rgb": [float(x) for x in ours.mean((0, 1)) / gold.mean((0, 1))], "spp": 5000, "bound": 1e-2,
+            "note": "golden-diffuse mode vs img/REFERENCE_cornell.5000samp.png; per-pixel floor between two 5000-spp renders is ~0.086"}
+
+
 def main():
     out = claim_stdout()
     ap = argparse.ArgumentParser()
@@ -185,6 +274,8 @@ def main():
     ap.add_argument("--spp-per-step", type=int, default=SPP_PER_STEP)
     ap.add_argument("--batch-iters", type=int, default=BATCH_ITERS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="headline line only: no extra configs, skeleton, golden image, strong-scaling leg")
+    ap.add_argument("--strong-spp", type=int, default=5000, help="samples per pixel of the configs[3] strong-scaling frame")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args, out)
@@ -214,15 +305,21 @@ def main():
     scene = m.Scene.load(scene_path)
     P = scene.pixels
     spp = args.spp_per_step
-    # a dedicated (non-default) stream: the library launches on it, torch's events are recorded on it and
-    # NCCL orders against it, so CUDA-event timing sees exactly the work of the step
+    # a dedicated (non-default) stream: the library launches on it (kernels AND its own NCCL reduce), torch's events are recorded
+    # on it, so CUDA-event timing sees exactly the work of the step
     stream = torch.cuda.Stream(dev)
     torch.cuda.set_stream(stream)
-    accum = torch.zeros(P * 3, dtype=torch.float32, device=dev)        # private partial sums of this rank
-    frame = torch.zeros_like(accum)                                     # reduced frame (meaningful on rank 0)
     host_frame = torch.empty(P * 3, dtype=torch.float32, pin_memory=True)
-    r = m.Renderer(scene, device=local, bsdf=m.BSDF_FULL, pipeline=m.PIPELINE_FUSED, batch_iters=args.batch_iters,
-                   stream=stream.cuda_stream, external_accum=accum.data_ptr())
+
+    def make_renderer(sc, **kw):
+        r = m.Renderer(sc, device=local, bsdf=m.BSDF_FULL, pipeline=m.PIPELINE_FUSED, stream=stream.cuda_stream, **kw)
+        if world > 1:
+            # the frame collective is the LIBRARY's: ncclCommInitRank + ncclReduce inside libptb200.so (include/ptb200.h
+            # ptb_comm_*); torch.distributed only carries the 128-byte ncclUniqueId, the barriers and the max over ranks
+            split.init_library_comm(r, rank, world, m)
+        return r
+
+    r = make_renderer(scene, batch_iters=args.batch_iters)
 
     def barrier():
         if world > 1:
@@ -236,7 +333,7 @@ def main():
         b, c, s = split.rank_iterations(first, spp * world, rank, world)
         r.render(b, c, s)
         if world > 1:
-            split.reduce_frame(accum, frame)
+            split.reduce_frame_library(r, 0)                           # ONE ncclReduce(sum) of 3*W*H floats per frame
         step_counter[0] += 1
 
     def e2e_step():
@@ -244,12 +341,11 @@ def main():
         b, c, s = split.rank_iterations(1, spp * world, rank, world)
         r.render(b, c, s)
         if world > 1:
-            split.reduce_frame(accum, frame)
-            if rank == 0:
-                host_frame.copy_(frame, non_blocking=True)
-                stream.synchronize()
+            split.reduce_frame_library(r, 0)
+        if rank == 0:
+            r.frame_download_to(host_frame.data_ptr())                 # D2H of the (reduced) frame into pinned host memory + sync
         else:
-            r.download_to(host_frame.data_ptr())                       # D2H into pinned host memory + sync
+            r.sync()
 
     # ------------------------------------------------------------------ device-resident timing (`value`)
     for _ in range(args.warmup):
@@ -294,44 +390,55 @@ def main():
     for _ in range(2):
         e2e_step()
     barrier()
-    se0 = r.stats()
     t0 = time.perf_counter()
-    g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    g0.record(stream)
     e2e_steps = max(3, args.steps // 2)
     seg_e2e = 0
     for _ in range(e2e_steps):
         e2e_step()
         seg_e2e += r.stats()["segments"]                                # stats reset with every scene upload
-    g1.record(stream)
     barrier()
     e2e_s = allmax(time.perf_counter() - t0)
     seg_e2e_all = allsum(seg_e2e)
     h2d = r.stats()["scene_upload_bytes"]
     d2h = P * 3 * 4 if rank == 0 else 0
 
-    # per-iteration drop-in semantic (pathtrace(pbo, frame, iter) + D2H every call), N = 1 only, reported as an extra
+    # ------------------------------------------------------------------ the reference's own call: pathtrace(pbo, frame, iter), N = 1
+    # strict = the host image is valid on return every iteration (src/pathtrace.cu:389-390); lazy = PtbOptions.lazyImage: the copy
+    # of iteration i overlaps iteration i + 1 on a copy stream, valid after ptb_sync.  One iteration per wavefront in both.
     dropin = None
     if world == 1:
-        r.reset()
-        img = np.empty((P, 3), np.float32)
+        dropin = {}
         hp = host_frame.data_ptr()
-        for it in range(1, 4):
-            m._check(m.lib().ptb_pathtrace(r._h, None, 0, it, hp))
-        t0 = time.perf_counter()
-        n_it = 32
-        for it in range(4, 4 + n_it):
-            m._check(m.lib().ptb_pathtrace(r._h, None, 0, it, hp))
-        dt = time.perf_counter() - t0
-        sdi = r.stats()
-        dropin = {"iters_per_s": n_it / dt, "segments_per_s": sdi["segments"] / sdi["iterations"] * n_it / dt,
-                  "d2h_bytes_per_iter": P * 12, "note": "ptb_pathtrace with a host image every iteration (src/pathtrace.cu:389-390 semantic)"}
+        for mode, lazy in (("strict", 0), ("lazy_image", 1)):
+            with m.Renderer(scene, device=local, bsdf=m.BSDF_FULL, batch_iters=1, lazy_image=lazy) as rd:
+                for it in range(1, 9):
+                    m._check(m.lib().ptb_pathtrace(rd._h, None, 0, it, hp))
+                rd.sync()
+                n_it = 256
+                t0 = time.perf_counter()
+                for it in range(9, 9 + n_it):
+                    m._check(m.lib().ptb_pathtrace(rd._h, None, 0, it, hp))
+                rd.sync()
+                dt = time.perf_counter() - t0
+                sdi = rd.stats()
+            dropin[mode] = {"iters_per_s": n_it / dt, "us_per_call": dt / n_it * 1e6,
+                            "segments_per_s": sdi["segments"] / sdi["iterations"] * n_it / dt, "d2h_bytes_per_iter": P * 12}
+        # the PCIe floor of the strict semantic: 7.68 MB device->host per call at the measured pinned D2H rate
+        src = torch.empty(P * 3, dtype=torch.float32, device=dev)
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        host_frame.copy_(src, non_blocking=True); stream.synchronize()
+        c0.record(stream)
+        for _ in range(20):
+            host_frame.copy_(src, non_blocking=True)
+        c1.record(stream); stream.synchronize()
+        d2h_ms = c0.elapsed_time(c1) / 20
+        dropin["pcie_floor"] = {"d2h_gbs_pinned": P * 12 / (d2h_ms * 1e-3) / 1e9, "us_per_7.68MB_copy": d2h_ms * 1e3,
+                                "note": "ptb_pathtrace with a host image every iteration cannot run faster than this copy (src/pathtrace.cu:389-390 semantic)"}
 
     # the same device-resident loop with the first-bounce cache on (INSTRUCTION.md:87-89; result-neutral,
     # tests/test_gpu_parity.py::test_first_bounce_cache_is_result_neutral) -- reported beside `value`, not as `value`
     r.close()
-    r = m.Renderer(scene, device=local, bsdf=m.BSDF_FULL, pipeline=m.PIPELINE_FUSED, batch_iters=args.batch_iters,
-                   stream=stream.cuda_stream, external_accum=accum.data_ptr(), first_bounce_cache=1)
+    r = make_renderer(scene, batch_iters=args.batch_iters, first_bounce_cache=1)
     for _ in range(args.warmup):
         device_step()
     barrier()
@@ -346,14 +453,56 @@ def main():
     sc1 = r.stats()
     seg_fbc = allsum(sc1["segments"] - sc0["segments"])
     iters_fbc = allsum(sc1["iterations"] - sc0["iterations"])
+    r.close()
+
+    # ------------------------------------------------------------------ strong scaling: BASELINE.json configs[3]
+    # cornell.txt at 3840 x 2160, depth 8, a FIXED number of samples per pixel split over the N GPUs, one NCCL reduce of the
+    # 99.5 MB accumulation buffer per frame (inside the library), the frame copied to the host on rank 0.
+    strong = None
+    if not args.no_extras:
+        import scenes
+        p4 = os.path.join(tmp, "cornell4k.txt")
+        with open(p4, "w") as f:
+            f.write(scenes.cornell_text(res=(3840, 2160)))
+        s4 = m.Scene.load(p4)
+        r4 = make_renderer(s4)
+        host4 = torch.empty(s4.pixels * 3, dtype=torch.float32, pin_memory=True) if rank == 0 else None
+        b, c, s = split.rank_iterations(1, args.strong_spp, rank, world)
+        r4.render(b, min(c, 32), s)                                    # warm-up: graph capture, NCCL connection set-up
+        if world > 1:
+            split.reduce_frame_library(r4, 0)
+        r4.reset()
+        barrier()
+        q0, q1, q2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        q0.record(stream)
+        r4.render(b, c, s)
+        q1.record(stream)
+        if world > 1:
+            split.reduce_frame_library(r4, 0)
+        q2.record(stream)
+        if rank == 0:
+            r4.frame_download_to(host4.data_ptr())
+        barrier()
+        ms_frame = allmax(q0.elapsed_time(q2))
+        ms_reduce = q1.elapsed_time(q2)
+        st4 = r4.stats()
+        seg4 = allsum(st4["segments"])
+        if rank == 0:
+            strong = {"workload": "scenes/cornell.txt 3840x2160 depth 8, %d spp per frame split over %d GPU(s) (BASELINE.json configs[3])" % (args.strong_spp, world),
+                      "scaling": "strong", "ms_per_frame": ms_frame, "segments_per_s": seg4 / (ms_frame * 1e-3),
+                      "reduce_ms_rank0": ms_reduce if world > 1 else 0.0, "reduce_bytes": s4.pixels * 12 if world > 1 else 0,
+                      "iterations_per_gpu": c, "batch_iters": st4["batch_iters"],
+                      "frame_mean": float(host4.mean().item()) / args.strong_spp}
+        r4.close()
 
     if rank == 0:
         hbm_peak, peak_src, sm_max = load_peaks()
         alg_bytes = BYTES_PER_SEGMENT * seg_all + BYTES_PER_PIXEL_ITER * P * iters_all
         achieved = alg_bytes / (ms * 1e-3) / 1e9 / world             # per GPU
-        # per GPU: every batch is `bounce launches` + one advance_kernel, every ptb_render call one set_control_kernel
+        # launches of the timed region per GPU, from the library's own counter: per wavefront bounce 0 + the bounce loop + the ordered-deposit
+        # reduce + advance, per ptb_render call one set_control
         batches = iters_all / world / st1["batch_iters"]
-        bounce_launches = max(1.0, launches_all / world - batches - args.steps)
+        bounce_launches = max(1.0, 2.0 * batches)
         traffic = None
         import glob
         profs = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_bounce_traffic.json")))    # newest ncu --set full capture
@@ -369,7 +518,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "reference cornell scene regenerated from tests/scenes.py; no external data",
             "config": {"workload": WORKLOAD, "bsdf": "full", "iterations_per_step_per_gpu": spp, "batch_iters": st1["batch_iters"],
-                       "pipeline": "fused bounce kernels + CUDA graph", "parallelism": "spp split x%d, 1 NCCL reduce/frame" % world,
+                       "deposit": "ordered (bit-identical to one iteration per wavefront; tests/test_gpu_parity.py::test_bench_configuration_against_the_oracle)",
+                       "pipeline": "fused bounce kernels + CUDA graph", "parallelism": "spp split x%d, 1 ncclReduce/frame inside libptb200.so" % world,
                        "l2": "inputs larger than L2: %.0f MB of path state per wavefront vs 126 MB L2" % (st1["path_state_bytes"] / 2 / 1e6)},
             "iters_per_s": iters_all / (ms * 1e-3),
             "segments_per_iter": seg_all / iters_all,
@@ -381,6 +531,7 @@ def main():
             "e2e_per_iteration_dropin": dropin,
             "first_bounce_cache": {"value": seg_fbc / (ms_fbc * 1e-3), "unit": UNIT, "iters_per_s": iters_fbc / (ms_fbc * 1e-3),
                                    "note": "PtbOptions.firstBounceCache = 1: bounce-0 hit records reused across iterations (bit-identical images)"},
+            "strong_scaling": strong,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "ptb::bounce_kernel (bounce 0) + ptb::bounce_loop_kernel (bounces 1..)",
                          "algorithmic_bytes": "88 B/segment + 24 B/pixel/iteration (SURVEY.md 8(d))",
@@ -390,6 +541,30 @@ def main():
                                   "peak_tflops": 148 * 128 * 2 * sm_max * 1e6 / 1e12, "flop_per_segment": FLOP_PER_SEGMENT,
                                   "note": "the bounce kernel is instruction-issue bound, not HBM bound: bit-exact parity forbids FFMA in the exact tests (DESIGN.md 4.4)"}},
         }
+        if world == 1 and not args.no_extras:
+            # beside the headline: the other BASELINE.json configs on one GPU, the reference skeleton's own CUDA loop on this
+            # GPU (the ">= 10x" denominator) and the converged-image error -- all outside the timed regions above
+            try:
+                line["configs"] = extra_configs(m, torch, stream, local, tmp, hbm_peak, sm_max)
+            except Exception as ex:
+                line["configs"] = {"error": str(ex)}
+            try:
+                line["golden_image"] = golden_image_error(m, torch, stream, local, scene)
+            except Exception as ex:
+                line["golden_image"] = {"error": str(ex)}
+            sk = skeleton_gpu_baseline(scene_path)
+            if sk:
+                ours_it, ours_seg = line["iters_per_s"], line["value"]
+                line["skeleton_gpu_baseline"] = {
+                    "impl": "unmodified reference src/pathtrace.cu rebuilt for sm_100 (oracle/_ref/skeleton_bench), one bounce per iteration, D2H of the image every iteration",
+                    "iters_per_s": sk["iters_per_s"], "segments_per_s": sk["segments_per_s"],
+                    "ours_over_skeleton": {
+                        "batched_api": {"segments_per_s": ours_seg / sk["segments_per_s"], "iters_per_s": ours_it / sk["iters_per_s"]},
+                        "pathtrace_call_strict": {"segments_per_s": dropin["strict"]["segments_per_s"] / sk["segments_per_s"],
+                                                  "iters_per_s": dropin["strict"]["iters_per_s"] / sk["iters_per_s"]},
+                        "pathtrace_call_lazy_image": {"segments_per_s": dropin["lazy_image"]["segments_per_s"] / sk["segments_per_s"],
+                                                      "iters_per_s": dropin["lazy_image"]["iters_per_s"] / sk["iters_per_s"]}},
+                    "target": "BASELINE.json north_star: >= 10x the skeleton's own CUDA loop on cornell 800x800 depth 8"}
         if not args.no_cpu_baseline and world == 1:
             try:
                 val, kind, cores, sample, secs, _ = cpu_reference_run(scene_path, CPU_ITERS, 8)     # ~10 s of CPU work
@@ -398,7 +573,6 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(ex)}
         out.write(json.dumps(line) + "\n")
         out.flush()
-    r.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

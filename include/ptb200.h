@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 3
+#define PTB_ABI_VERSION 4
 
 /* ---- POD mirrors of src/sceneStructs.h (byte-identical; matrices column-major like glm) ---- */
 typedef struct PtbGeom {            /* struct Geom, src/sceneStructs.h:20-29, 236 bytes */
@@ -93,6 +93,13 @@ enum PtbPipeline {
     PTB_PIPELINE_STAGED = 1         /* the reference's stage structure: raygen, intersect, [sort], shade, [compact], gather */
 };
 enum PtbAccel { PTB_ACCEL_AUTO = 0, PTB_ACCEL_BRUTE = 1, PTB_ACCEL_BVH = 2 };
+enum PtbDepositMode {
+    PTB_DEPOSIT_ORDERED = 0,        /* default: every slot of a wavefront deposits into its own partial image and the partial images
+                                       are added to image[] in iteration order -- bit for bit the sum the reference's loop builds one
+                                       iteration at a time (src/pathtrace.cu:269-278), reproducible run to run, for any batchIters */
+    PTB_DEPOSIT_ATOMIC  = 1         /* float atomicAdd straight into image[]: the order of the additions inside one wavefront, and so
+                                       the last bits of the sum, vary run to run (|error| <= batchIters * 2^-24 relative) */
+};
 
 typedef struct PtbOptions {
     int32_t device;                 /* CUDA ordinal; -1 = current device */
@@ -111,12 +118,35 @@ typedef struct PtbOptions {
     float  *externalAccum;          /* device pointer to W*H*3 floats to accumulate into; NULL = library-owned */
     float   lensRadius;             /* > 0 = thin-lens depth of field (INSTRUCTION.md:107-108, PBRT 6.2.3) */
     float   focalDistance;          /* distance of the plane in focus along camera.view (used when lensRadius > 0) */
+    int32_t launchPerBounce;        /* fused pipeline, brute-force scenes: 1 = one bounce_kernel launch per bounce instead of the
+                                       one-launch bounce loop (a timing toggle: same arithmetic per path, identical images) */
+    int32_t depositMode;            /* PtbDepositMode: how the iterations of one wavefront (batchIters > 1) reach image[] */
+    int32_t timeStages;             /* 1 = CUDA-event timers around every kernel launch, summed per stage into PtbStats.stageUs
+                                       (launches go out one by one instead of as a CUDA graph; INSTRUCTION.md:339-355 analysis) */
+    int32_t lazyImage;              /* ptb_pathtrace only: 1 = the host image copy of iteration i is queued on a copy stream and
+                                       overlaps iteration i+1; the host image is valid after ptb_sync (or the next call's return
+                                       for the previous iteration).  0 = the reference's semantic: valid on return (src/pathtrace.cu:389-390) */
 } PtbOptions;
 /* antialias / lensRadius make the camera rays depend on the iteration, so they cannot be combined with
  * firstBounceCache (INSTRUCTION.md:113: "keep in mind how this influences the first-bounce cache"):
  * ptb_create returns PTB_ERR_UNSUPPORTED.  Materials with REFL > 0 and SPECEX > 0 scatter into a Phong
  * lobe around the mirror direction in PTB_BSDF_FULL mode (imperfect specular, INSTRUCTION.md:202-216);
  * SPECEX 0 stays the perfect mirror.  Exact formulas: DESIGN.md section 8 and oracle/pt_oracle.c. */
+
+/* stages of the per-bounce loop as PtbStats.stageUs indexes them (the reference's kernels: src/pathtrace.cu:122, :149, :224, :269;
+ * compaction and material sort: INSTRUCTION.md:78-86, 183-185) */
+enum PtbStage {
+    PTB_STAGE_RAYGEN = 0,           /* raygen_kernel (staged pipeline) */
+    PTB_STAGE_INTERSECT = 1,        /* intersect_kernel (staged) / trace_bvh_kernel (fused, BVH scenes) */
+    PTB_STAGE_SORT = 2,             /* sort_keys / hist / scan / scatter */
+    PTB_STAGE_SHADE = 3,            /* shade_kernel (staged) / bounce_kernel<USE_BVH> (fused, BVH scenes: shade + compact) */
+    PTB_STAGE_COMPACT = 4,          /* compact_kernel / carry_count_kernel */
+    PTB_STAGE_GATHER = 5,           /* gather_kernel / the ordered-deposit reduce */
+    PTB_STAGE_FUSED_BOUNCE0 = 6,    /* bounce_kernel<FIRST>: raygen + intersect + shade + compact of bounce 0 in one launch */
+    PTB_STAGE_FUSED_BOUNCES = 7,    /* bounce_loop_kernel / bounce_kernel: the same for bounces 1.. */
+    PTB_STAGE_CONTROL = 8,          /* advance / set_control kernels */
+    PTB_NUM_STAGES = 12
+};
 
 typedef struct PtbStats {
     int64_t iterations;             /* iterations traced since ptb_init */
@@ -129,6 +159,9 @@ typedef struct PtbStats {
     int32_t batchIters;
     int64_t pathStateBytes;         /* bytes of path state resident in HBM */
     int64_t sceneUploadBytes;       /* host->device bytes of the last ptb_create / ptb_update_scene */
+    /* PtbOptions.timeStages = 1: device time (CUDA events) and launch count per stage since ptb_create / ptb_reset */
+    double  stageUs[PTB_NUM_STAGES];
+    int64_t stageLaunches[PTB_NUM_STAGES];
 } PtbStats;
 
 enum PtbError {
@@ -181,6 +214,40 @@ int ptb_accum_device_ptr(PtbContext *ctx, float **devPtr);
 /* (sum / samples) -> clamp[0,1]*255 -> truncate -> RGB8 with the horizontal flip of saveImage
  * (src/main.cpp:83-89, src/image.cpp:27-30) computed on the device; `hostRgb8` = W*H*3 bytes. */
 int ptb_resolve_rgb8(PtbContext *ctx, int samples, uint8_t *hostRgb8);
+
+/* ---- several GPUs: samples-per-pixel split + ONE NCCL sum-reduce of the accumulation buffer per frame -------------------
+ * Iterations are independent (the RNG is keyed by (iter, pixelIndex, depth), src/pathtrace.cu:41-45) and the only state they
+ * share is the additive accumulation buffer (src/pathtrace.cu:276), so GPU g of G renders iterations g+1, g+1+G, ... into a
+ * private buffer and ncclReduce(sum, float32, 3*W*H) brings the frame to the root (the reference is single-GPU:
+ * src/preview.cpp:106-111 pins device 0).  NCCL (libnccl.so.2) is loaded on first use; single-GPU use never touches it.
+ * The reduced frame lives in a second W*H*3 buffer on the root, so the private partial sums keep accumulating across frames.
+ *
+ * (1) One process per GPU (torchrun / MPI): every rank creates its own context, rank 0 makes an id, the launcher broadcasts it. */
+#define PTB_COMM_ID_BYTES 128
+int ptb_comm_unique_id(uint8_t id[PTB_COMM_ID_BYTES]);                         /* ncclGetUniqueId */
+int ptb_comm_init_rank(PtbContext *ctx, const uint8_t id[PTB_COMM_ID_BYTES], int rank, int nranks);   /* ncclCommInitRank; collective */
+/* ncclReduce of this rank's accumulation buffer into the root's frame buffer, on the context's stream (asynchronous; collective) */
+int ptb_comm_reduce(PtbContext *ctx, int root);
+/* the reduced frame on the root: device pointer / copy of the SUM to the host / saveImage + savePNG pixels computed on the device
+ * (sum / samples -> clamp -> * 255 -> truncate, x-flipped: src/main.cpp:83-89, src/image.cpp:27-30) fused after the reduce.
+ * Without a communicator (or after ptb_comm_reduce on a 1-rank communicator) the frame is the context's own accumulation. */
+int ptb_frame_device_ptr(PtbContext *ctx, float **devPtr);
+int ptb_frame_download(PtbContext *ctx, float *hostImage);
+int ptb_frame_resolve_rgb8(PtbContext *ctx, int samples, uint8_t *hostRgb8);
+
+/* (2) One process, several devices: n contexts + ncclCommInitAll behind one handle (what `ptb200_headless --gpus G` uses). */
+typedef struct PtbMulti PtbMulti;
+/* devices: CUDA ordinals (NULL = 0 .. numDevices-1); opts->device / stream / externalAccum are ignored */
+int ptb_multi_create(PtbMulti **multi, const PtbSceneDesc *scene, const PtbOptions *opts, const int32_t *devices, int32_t numDevices);
+int ptb_multi_destroy(PtbMulti *multi);
+int ptb_multi_reset(PtbMulti *multi);
+/* iterations iterBegin .. iterBegin+count-1, interleaved over the devices; asynchronous on every device */
+int ptb_multi_render(PtbMulti *multi, int iterBegin, int count);
+/* one frame: grouped ncclReduce to device 0, then (each optional) the SUM to hostImage and / or the RGB8 pixels to hostRgb8;
+ * milliseconds the reduce took on the root's stream go to *reduceMs when non-NULL.  Synchronises. */
+int ptb_multi_frame(PtbMulti *multi, int samples, float *hostImage, uint8_t *hostRgb8, float *reduceMs);
+int ptb_multi_stats(PtbMulti *multi, PtbStats *sum);                           /* summed over the devices; synchronises */
+int ptb_multi_context(PtbMulti *multi, int index, PtbContext **ctx);           /* borrow device `index`'s context (tests) */
 
 /* ---- stage-level entry points (used by the parity tests; host arrays in, host arrays out) ---- */
 /* generateRayFromCamera (src/pathtrace.cu:122-143): origins/dirs = W*H*3 floats each.  With antialias /

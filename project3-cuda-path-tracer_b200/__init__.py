@@ -34,6 +34,9 @@ GEOM_SPHERE, GEOM_CUBE, GEOM_MESH = 0, 1, 2
 BSDF_GOLDEN_DIFFUSE, BSDF_FULL = 0, 1
 PIPELINE_FUSED, PIPELINE_STAGED = 0, 1
 ACCEL_AUTO, ACCEL_BRUTE, ACCEL_BVH = 0, 1, 2
+DEPOSIT_ORDERED, DEPOSIT_ATOMIC = 0, 1
+NUM_STAGES = 12
+STAGE_NAMES = ["raygen", "intersect", "sort", "shade", "compact", "gather", "fused_bounce0", "fused_bounces", "control"]
 
 
 class PtbCamera(C.Structure):
@@ -53,14 +56,15 @@ class PtbOptions(C.Structure):
                 ("batchIters", C.c_int32), ("compaction", C.c_int32), ("sortMaterials", C.c_int32),
                 ("firstBounceCache", C.c_int32), ("useGraphs", C.c_int32), ("antialias", C.c_int32),
                 ("stream", C.c_void_p), ("externalAccum", C.c_void_p),
-                ("lensRadius", C.c_float), ("focalDistance", C.c_float)]
+                ("lensRadius", C.c_float), ("focalDistance", C.c_float),
+                ("launchPerBounce", C.c_int32), ("depositMode", C.c_int32), ("timeStages", C.c_int32), ("lazyImage", C.c_int32)]
 
 
 class PtbStats(C.Structure):
     _fields_ = [("iterations", C.c_int64), ("segments", C.c_int64), ("kernelLaunches", C.c_int64),
                 ("alivePerDepth", C.c_int64 * 64), ("traceDepth", C.c_int32), ("numGeoms", C.c_int32),
                 ("bvhNodes", C.c_int32), ("batchIters", C.c_int32), ("pathStateBytes", C.c_int64),
-                ("sceneUploadBytes", C.c_int64)]
+                ("sceneUploadBytes", C.c_int64), ("stageUs", C.c_double * NUM_STAGES), ("stageLaunches", C.c_int64 * NUM_STAGES)]
 
 
 class PtbError(RuntimeError):
@@ -75,7 +79,10 @@ ABI_SYMBOLS = [
     "ptb_stage_shade", "ptb_stage_compact", "ptb_stage_sort_keys", "ptb_stage_rng", "ptb_stage_arith", "ptb_stage_sincos",
     "ptb_scene_load", "ptb_scene_counts", "ptb_scene_get", "ptb_scene_mesh_counts", "ptb_scene_get_meshes", "ptb_scene_free", "ptb_camera_fixup",
     "ptb_save_png", "ptb_save_hdr", "ptb_bvh_build_host", "ptb_geom_bounds_host",
+    "ptb_comm_unique_id", "ptb_comm_init_rank", "ptb_comm_reduce", "ptb_frame_device_ptr", "ptb_frame_download", "ptb_frame_resolve_rgb8",
+    "ptb_multi_create", "ptb_multi_destroy", "ptb_multi_reset", "ptb_multi_render", "ptb_multi_frame", "ptb_multi_stats", "ptb_multi_context",
 ]
+COMM_ID_BYTES = 128
 
 _lib = None
 
@@ -110,6 +117,19 @@ def lib():
         L.ptb_stage_rng.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.ptb_stage_arith.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
         L.ptb_stage_sincos.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 3
+        L.ptb_comm_unique_id.argtypes = [C.c_void_p]
+        L.ptb_comm_init_rank.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.ptb_comm_reduce.argtypes = [C.c_void_p, C.c_int]
+        L.ptb_frame_device_ptr.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+        L.ptb_frame_download.argtypes = [C.c_void_p, C.c_void_p]
+        L.ptb_frame_resolve_rgb8.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.ptb_multi_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(PtbSceneDesc), C.POINTER(PtbOptions), C.c_void_p, C.c_int32]
+        L.ptb_multi_destroy.argtypes = [C.c_void_p]
+        L.ptb_multi_reset.argtypes = [C.c_void_p]
+        L.ptb_multi_render.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.ptb_multi_frame.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        L.ptb_multi_stats.argtypes = [C.c_void_p, C.POINTER(PtbStats)]
+        L.ptb_multi_context.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
         if hasattr(L, "ptb_scene_load"):
             L.ptb_scene_load.restype = C.c_int
             L.ptb_scene_load.argtypes = [C.c_char_p, C.POINTER(C.c_void_p)]
@@ -194,7 +214,8 @@ class Renderer:
 
     def __init__(self, scene, device=-1, bsdf=BSDF_FULL, pipeline=PIPELINE_FUSED, accel=ACCEL_AUTO,
                  batch_iters=0, compaction=1, sort_materials=0, first_bounce_cache=0, use_graphs=1,
-                 stream=None, external_accum=None, trace_depth=None, antialias=0, lens_radius=0.0, focal_distance=0.0):
+                 stream=None, external_accum=None, trace_depth=None, antialias=0, lens_radius=0.0, focal_distance=0.0,
+                 launch_per_bounce=0, deposit_mode=DEPOSIT_ORDERED, time_stages=0, lazy_image=0):
         L = lib()
         self.scene = scene
         self.trace_depth = scene.traceDepth if trace_depth is None else int(trace_depth)
@@ -207,6 +228,7 @@ class Renderer:
         opt.stream = stream
         opt.externalAccum = external_accum
         opt.antialias, opt.lensRadius, opt.focalDistance = int(antialias), float(lens_radius), float(focal_distance)
+        opt.launchPerBounce, opt.depositMode, opt.timeStages, opt.lazyImage = int(launch_per_bounce), int(deposit_mode), int(time_stages), int(lazy_image)
         self._h = C.c_void_p()
         _check(L.ptb_create(C.byref(self._h), C.byref(desc), C.byref(opt)))
 
@@ -278,11 +300,35 @@ class Renderer:
     def stats(self):
         s = PtbStats()
         _check(lib().ptb_stats(self._h, C.byref(s)))
-        return {"iterations": s.iterations, "segments": s.segments, "kernel_launches": s.kernelLaunches,
-                "alive_per_depth": [int(s.alivePerDepth[d]) for d in range(s.traceDepth)],
-                "trace_depth": s.traceDepth, "num_geoms": s.numGeoms, "bvh_nodes": s.bvhNodes,
-                "batch_iters": s.batchIters, "path_state_bytes": s.pathStateBytes,
-                "scene_upload_bytes": s.sceneUploadBytes}
+        return _stats_dict(s)
+
+    # ---- several GPUs, one process per GPU: NCCL inside the library (include/ptb200.h, ptb_comm_*) ----
+    def comm_init_rank(self, unique_id, rank, nranks):
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        _check(lib().ptb_comm_init_rank(self._h, buf, int(rank), int(nranks)))
+
+    def comm_reduce(self, root=0):
+        """ncclReduce(sum) of this rank's accumulation buffer into the root's frame buffer (asynchronous, collective)"""
+        _check(lib().ptb_comm_reduce(self._h, int(root)))
+
+    def frame_device_ptr(self):
+        p = C.c_void_p()
+        _check(lib().ptb_frame_device_ptr(self._h, C.byref(p)))
+        return p.value
+
+    def frame_download(self, out=None):
+        if out is None:
+            out = np.zeros((self.scene.pixels, 3), np.float32)
+        _check(lib().ptb_frame_download(self._h, out.ctypes.data))
+        return out
+
+    def frame_download_to(self, host_ptr):
+        _check(lib().ptb_frame_download(self._h, host_ptr))
+
+    def frame_resolve_rgb8(self, samples):
+        out = np.zeros((self.scene.height, self.scene.width, 3), np.uint8)
+        _check(lib().ptb_frame_resolve_rgb8(self._h, samples, out.ctypes.data))
+        return out
 
     def accum_device_ptr(self):
         p = C.c_void_p()
@@ -358,6 +404,83 @@ class Renderer:
         out = np.zeros(n, np.float32)
         _check(lib().ptb_stage_rng(self._h, it, index, depth, n, out.ctypes.data))
         return out
+
+
+def comm_unique_id():
+    """ncclGetUniqueId through the library: rank 0 calls it, the launcher's plumbing (torch.distributed, MPI, a file) broadcasts it."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    _check(lib().ptb_comm_unique_id(buf))
+    return bytes(buf)
+
+
+def _stats_dict(s):
+    return {"iterations": s.iterations, "segments": s.segments, "kernel_launches": s.kernelLaunches,
+            "alive_per_depth": [int(s.alivePerDepth[d]) for d in range(s.traceDepth)],
+            "trace_depth": s.traceDepth, "num_geoms": s.numGeoms, "bvh_nodes": s.bvhNodes,
+            "batch_iters": s.batchIters, "path_state_bytes": s.pathStateBytes,
+            "scene_upload_bytes": s.sceneUploadBytes,
+            "stage_us": {n: float(s.stageUs[i]) for i, n in enumerate(STAGE_NAMES)},
+            "stage_launches": {n: int(s.stageLaunches[i]) for i, n in enumerate(STAGE_NAMES)}}
+
+
+class MultiRenderer:
+    """One process, several devices (PtbMulti): n contexts + ncclCommInitAll inside the library; device g renders iterations
+    g+1, g+1+G, ... and `frame` is ONE grouped ncclReduce of the accumulation buffers to device 0."""
+
+    def __init__(self, scene, devices, **kw):
+        L = lib()
+        self.scene = scene
+        tmp = Renderer.__new__(Renderer)
+        tmp.trace_depth = scene.traceDepth if kw.get("trace_depth") is None else int(kw["trace_depth"])
+        desc = Renderer._desc(tmp, scene)
+        self._keep = tmp._keep
+        opt = PtbOptions()
+        L.ptb_default_options(C.byref(opt))
+        for k_py, k_c in (("bsdf", "bsdfMode"), ("pipeline", "pipeline"), ("accel", "accel"), ("batch_iters", "batchIters"),
+                          ("first_bounce_cache", "firstBounceCache"), ("deposit_mode", "depositMode"), ("antialias", "antialias")):
+            if k_py in kw:
+                setattr(opt, k_c, int(kw[k_py]))
+        devs = np.ascontiguousarray(devices, np.int32)
+        self.devices = [int(d) for d in devs]
+        self._h = C.c_void_p()
+        _check(L.ptb_multi_create(C.byref(self._h), C.byref(desc), C.byref(opt), devs.ctypes.data, len(devs)))
+
+    def close(self):
+        if self._h:
+            lib().ptb_multi_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _check(lib().ptb_multi_reset(self._h))
+
+    def render(self, iter_begin, count):
+        _check(lib().ptb_multi_render(self._h, iter_begin, count))
+
+    def frame(self, samples, want_sum=True, want_rgb8=False):
+        """-> (sum image or None, rgb8 or None, milliseconds of the NCCL reduce on the root's stream)"""
+        img = np.zeros((self.scene.pixels, 3), np.float32) if want_sum else None
+        rgb = np.zeros((self.scene.height, self.scene.width, 3), np.uint8) if want_rgb8 else None
+        ms = C.c_float(0.0)
+        _check(lib().ptb_multi_frame(self._h, int(samples), img.ctypes.data if want_sum else None,
+                                     rgb.ctypes.data if want_rgb8 else None, C.byref(ms)))
+        return img, rgb, float(ms.value)
+
+    def stats(self):
+        s = PtbStats()
+        _check(lib().ptb_multi_stats(self._h, C.byref(s)))
+        return _stats_dict(s)
 
 
 # ---- the reference's three entry points (src/pathtrace.h:6-8), global-state form ----

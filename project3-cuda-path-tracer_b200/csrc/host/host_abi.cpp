@@ -5,19 +5,22 @@
 #include "scene.h"
 #include "image.h"
 #include <cstring>
+#include <string>
+
+extern "C" int ptb_set_last_error(int code, const char *msg);     // ptb200.cu
 
 extern "C" {
 
 // new Scene(filename) (src/scene.cpp:7-33)
 int ptb_scene_load(const char *path, void **sceneOut) {
-    if (!path || !sceneOut) return PTB_ERR_INVALID;
+    if (!path || !sceneOut) return ptb_set_last_error(PTB_ERR_INVALID, "ptb_scene_load: null argument");
     Scene *s = new Scene(std::string(path), false);
-    if (!s->ok) { delete s; *sceneOut = nullptr; return PTB_ERR_IO; }
+    if (!s->ok) { delete s; *sceneOut = nullptr; return ptb_set_last_error(PTB_ERR_IO, (std::string("ptb_scene_load: cannot read ") + path).c_str()); }
     *sceneOut = s;
     return PTB_OK;
 }
 int ptb_scene_counts(void *scene, int32_t *numGeoms, int32_t *numMaterials) {
-    if (!scene) return PTB_ERR_INVALID;
+    if (!scene) return ptb_set_last_error(PTB_ERR_INVALID, "null scene handle");
     Scene *s = static_cast<Scene *>(scene);
     if (numGeoms) *numGeoms = (int32_t)s->geoms.size();
     if (numMaterials) *numMaterials = (int32_t)s->materials.size();
@@ -25,7 +28,7 @@ int ptb_scene_counts(void *scene, int32_t *numGeoms, int32_t *numMaterials) {
 }
 int ptb_scene_get(void *scene, PtbGeom *geoms, PtbMaterial *materials, PtbCamera *camera,
                   int32_t *iterations, int32_t *traceDepth, char *imageName, int nameCap) {
-    if (!scene) return PTB_ERR_INVALID;
+    if (!scene) return ptb_set_last_error(PTB_ERR_INVALID, "null scene handle");
     Scene *s = static_cast<Scene *>(scene);
     if (geoms && !s->geoms.empty()) memcpy(geoms, s->geoms.data(), s->geoms.size() * sizeof(Geom));
     if (materials && !s->materials.empty()) memcpy(materials, s->materials.data(), s->materials.size() * sizeof(Material));
@@ -36,12 +39,12 @@ int ptb_scene_get(void *scene, PtbGeom *geoms, PtbMaterial *materials, PtbCamera
     return PTB_OK;
 }
 int ptb_scene_mesh_counts(void *scene, int32_t *numTriangles) {
-    if (!scene) return PTB_ERR_INVALID;
+    if (!scene) return ptb_set_last_error(PTB_ERR_INVALID, "null scene handle");
     if (numTriangles) *numTriangles = (int32_t)static_cast<Scene *>(scene)->triangles.size();
     return PTB_OK;
 }
 int ptb_scene_get_meshes(void *scene, PtbTriangle *triangles, int32_t *meshRanges) {
-    if (!scene) return PTB_ERR_INVALID;
+    if (!scene) return ptb_set_last_error(PTB_ERR_INVALID, "null scene handle");
     Scene *s = static_cast<Scene *>(scene);
     static_assert(sizeof(Triangle) == sizeof(PtbTriangle), "triangle layout");
     if (triangles && !s->triangles.empty()) memcpy(triangles, s->triangles.data(), s->triangles.size() * sizeof(Triangle));
@@ -79,7 +82,7 @@ void ptb_camera_fixup(PtbCamera *pc) {
 // saveImage (src/main.cpp:78-99): pixel (x, y) of the accumulated sum goes to (W-1-x, y) divided by
 // the sample count, then image::savePNG.  `baseFilename` gets ".png" appended like the reference.
 static int saveImpl(const char *baseFilename, int w, int h, const float *sum, float samples, int flipX, bool hdr) {
-    if (!baseFilename || !sum || w <= 0 || h <= 0 || !(samples > 0)) return PTB_ERR_INVALID;
+    if (!baseFilename || !sum || w <= 0 || h <= 0 || !(samples > 0)) return ptb_set_last_error(PTB_ERR_INVALID, "ptb_save_*: bad argument");
     image img(w, h);
     for (int x = 0; x < w; x++)
         for (int y = 0; y < h; y++) {
@@ -88,7 +91,7 @@ static int saveImpl(const char *baseFilename, int w, int h, const float *sum, fl
             img.setPixel(flipX ? w - 1 - x : x, y, pix / samples);
         }
     const bool ok = hdr ? img.saveHDR(baseFilename, true) : img.savePNG(baseFilename, true);
-    return ok ? PTB_OK : PTB_ERR_IO;
+    return ok ? PTB_OK : ptb_set_last_error(PTB_ERR_IO, (std::string("cannot write ") + baseFilename).c_str());
 }
 int ptb_save_png(const char *baseFilename, int w, int h, const float *sum, float samples, int flipX) {
     return saveImpl(baseFilename, w, h, sum, samples, flipX, false);

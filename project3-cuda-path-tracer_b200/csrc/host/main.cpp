@@ -4,12 +4,17 @@
 //
 //   ptb200_headless SCENEFILE.txt [--iters N] [--depth D] [--bsdf full|golden-diffuse] [--batch B]
 //                   [--per-iteration] [--out BASENAME] [--hdr] [--staged] [--sort] [--no-compaction]
-//                   [--device K] [--quiet]
+//                   [--device K] [--gpus G] [--res W H] [--atomic-deposit] [--time-stages] [--quiet]
+//
+// --gpus G: samples-per-pixel split over devices 0 .. G-1 inside the library (ptb_multi_*: one context per device,
+// ncclCommInitAll, interleaved iterations, ONE ncclReduce of the 3*W*H float accumulation buffers to device 0 per frame).
+// --res W H overrides the scene file's RES line (BASELINE.json configs[3] is cornell.txt at 3840 x 2160).
 //
 // Default: renders state.iterations iterations (ITERATIONS of the scene file) through the batched
 // loop and writes <FILE>.<UTC start time>.<N>samp.png exactly like saveImage().  --per-iteration uses
 // the reference's pathtrace(pbo, frame, iteration) call, one call and one image download per iteration.
 #include <chrono>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -59,7 +64,7 @@ int main(int argc, char **argv) {
     startTimeString = currentTimeString();
     if (argc < 2) { printf("Usage: %s SCENEFILE.txt [options]\n", argv[0]); return 1; }
     const char *sceneFile = argv[1];
-    int iters = -1, depth = -1, batch = 0, device = -1;
+    int iters = -1, depth = -1, batch = 0, device = -1, gpus = 0, resW = 0, resH = 0;
     bool perIteration = false, hdr = false, quiet = false;
     std::string outBase;
     PtbOptions opt;
@@ -71,6 +76,10 @@ int main(int argc, char **argv) {
         else if (a == "--depth") depth = atoi(next());
         else if (a == "--batch") batch = atoi(next());
         else if (a == "--device") device = atoi(next());
+        else if (a == "--gpus") gpus = atoi(next());
+        else if (a == "--res") { resW = atoi(next()); resH = atoi(next()); }
+        else if (a == "--atomic-deposit") opt.depositMode = PTB_DEPOSIT_ATOMIC;
+        else if (a == "--time-stages") opt.timeStages = 1;
         else if (a == "--out") outBase = next();
         else if (a == "--bsdf") opt.bsdfMode = strcmp(next(), "golden-diffuse") == 0 ? PTB_BSDF_GOLDEN_DIFFUSE : PTB_BSDF_FULL;
         else if (a == "--per-iteration") perIteration = true;
@@ -92,6 +101,15 @@ int main(int argc, char **argv) {
     iteration = 0;
     renderState = &scene->state;
     Camera &cam = renderState->camera;
+    if (resW > 0 && resH > 0) {
+        // what loadCamera derives from RES (src/scene.cpp:133-140): fovx from the aspect ratio, pixelLength, the host image
+        cam.resolution.x = resW; cam.resolution.y = resH;
+        const float yscaled = tan(cam.fov.y * (PI / 180));
+        const float xscaled = (yscaled * resW) / resH;
+        cam.fov.x = (atan(xscaled) * 180) / PI;
+        cam.pixelLength = glm::vec2(2 * xscaled / (float)resW, 2 * yscaled / (float)resH);
+        renderState->image.assign((size_t)resW * resH, glm::vec3());
+    }
     width = cam.resolution.x;
     height = cam.resolution.y;
     if (iters >= 0) renderState->iterations = (unsigned)iters;
@@ -99,6 +117,30 @@ int main(int argc, char **argv) {
 
     // src/main.cpp:53-67 + :102-120 -- the camera is rebuilt from (zoom, phi, theta) before frame 1
     ptb_camera_fixup(reinterpret_cast<PtbCamera *>(&cam));
+
+    if (gpus > 0) {
+        // several devices: the library's own multi-GPU path (no pathtrace() shim: that is the reference's single-device call)
+        PtbSceneDesc desc;
+        pathtraceSceneDesc(scene, &desc);
+        PtbMulti *multi = NULL;
+        if (ptb_multi_create(&multi, &desc, &opt, NULL, gpus) != PTB_OK) { fprintf(stderr, "ptb_multi_create: %s\n", ptb_last_error()); return 1; }
+        auto m0 = std::chrono::steady_clock::now();
+        float reduceMs = 0.f;
+        iteration = (int)renderState->iterations;
+        if (ptb_multi_render(multi, 1, iteration) != PTB_OK ||
+            ptb_multi_frame(multi, iteration, reinterpret_cast<float *>(renderState->image.data()), NULL, &reduceMs) != PTB_OK) {
+            fprintf(stderr, "multi-GPU render: %s\n", ptb_last_error());
+            return 1;
+        }
+        const double msecs = std::chrono::duration<double>(std::chrono::steady_clock::now() - m0).count();
+        PtbStats mst;
+        ptb_multi_stats(multi, &mst);
+        if (!quiet) printf("%d GPUs: %d iterations in %.3f s: %.1f iterations/s, %.4e path segments/s, NCCL reduce of the %.1f MB frame %.3f ms\n",
+                           gpus, iteration, msecs, iteration / msecs, mst.segments / msecs, width * height * 12 / 1e6, reduceMs);
+        if (iteration > 0) saveImage(outBase, hdr, quiet);
+        ptb_multi_destroy(multi);
+        return 0;
+    }
 
     pathtraceSetOptions(&opt);
     pathtraceFree();                                           // src/main.cpp:126-127 (free precedes the first init)
@@ -119,6 +161,10 @@ int main(int argc, char **argv) {
 
     PtbStats st;
     ptb_stats(pathtraceContext(), &st);
+    if (!quiet && opt.timeStages) {
+        static const char *names[] = {"raygen", "intersect", "sort", "shade", "compact", "gather", "fused bounce 0", "fused bounces 1..", "control"};
+        for (int k = 0; k < 9; ++k) if (st.stageLaunches[k]) printf("stage %-18s %8lld launches %12.1f us\n", names[k], (long long)st.stageLaunches[k], st.stageUs[k]);
+    }
     if (!quiet) {
         printf("%d iterations in %.3f s: %.1f iterations/s, %.4e path segments/s\n", iteration, secs, iteration / secs, st.segments / secs);
         printf("paths entering each bounce (per iteration):");

@@ -24,12 +24,8 @@ void pathtraceSetOptions(const PtbOptions *opts) {
     if (opts) { g_opts = *opts; g_haveOpts = true; } else g_haveOpts = false;
 }
 
-void pathtraceInit(Scene *scene) {
-    static_assert(sizeof(Geom) == sizeof(PtbGeom) && sizeof(Material) == sizeof(PtbMaterial) && sizeof(Camera) == sizeof(PtbCamera),
-                  "boundary structs must stay byte-identical to src/sceneStructs.h");
-    if (g_ctx) { ptb_destroy(g_ctx); g_ctx = NULL; }          // re-init on camera change resets the accumulation (src/main.cpp:125-128)
-    hst_scene = scene;
-    PtbSceneDesc d;
+void pathtraceSceneDesc(Scene *scene, PtbSceneDesc *desc) {
+    PtbSceneDesc &d = *desc;
     memset(&d, 0, sizeof d);
     d.geoms = reinterpret_cast<const PtbGeom *>(scene->geoms.data());
     d.numGeoms = (int)scene->geoms.size();
@@ -42,6 +38,15 @@ void pathtraceInit(Scene *scene) {
     d.triangles = reinterpret_cast<const PtbTriangle *>(scene->triangles.data());
     d.meshRanges = scene->meshRanges.data();
 #endif
+}
+
+void pathtraceInit(Scene *scene) {
+    static_assert(sizeof(Geom) == sizeof(PtbGeom) && sizeof(Material) == sizeof(PtbMaterial) && sizeof(Camera) == sizeof(PtbCamera),
+                  "boundary structs must stay byte-identical to src/sceneStructs.h");
+    if (g_ctx) { ptb_destroy(g_ctx); g_ctx = NULL; }          // re-init on camera change resets the accumulation (src/main.cpp:125-128)
+    hst_scene = scene;
+    PtbSceneDesc d;
+    pathtraceSceneDesc(scene, &d);
     PtbOptions o;
     if (g_haveOpts) o = g_opts; else ptb_default_options(&o);
     check(ptb_create(&g_ctx, &d, &o), "pathtraceInit");

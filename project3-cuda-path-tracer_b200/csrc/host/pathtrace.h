@@ -13,6 +13,9 @@ void pathtrace(uchar4 *pbo, int frame, int iteration);
 // loop without the per-iteration device->host copy, and access to the underlying context.
 struct PtbOptions;
 struct PtbContext;
+struct PtbSceneDesc;
+// what pathtraceInit hands to the library: the POD view of `scene` (geoms, materials, camera, depth, meshes); borrows scene's arrays
+void pathtraceSceneDesc(Scene *scene, PtbSceneDesc *desc);
 void pathtraceSetOptions(const PtbOptions *opts);
 void pathtraceBatch(int iterBegin, int count);        // then pathtraceDownload() fills scene->state.image
 void pathtraceDownload();

@@ -6,6 +6,9 @@
 #include "ptb_kernels.cuh"
 #include "ptb_bvh.h"
 
+#include <dlfcn.h>
+#include <nccl.h>                   // types and prototypes only: libnccl.so.2 is dlopen'ed on first multi-GPU use
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -15,7 +18,7 @@
 #include <vector>
 
 #ifndef PTB_SMEM_NODES
-#define PTB_SMEM_NODES 511          // leading BVH nodes (BFS order = top levels) staged in shared memory by the BVH kernels
+#define PTB_SMEM_NODES 255          // leading BVH nodes (BFS order = top levels) staged in shared memory by trace_kernel
 #endif
 using namespace ptb;
 
@@ -41,6 +44,19 @@ int fail(int code, const char *fmt, ...) {
                         cudaGetErrorString(e_));                                                   \
     } while (0)
 
+// Every entry point makes the context's device current for its own duration and restores the caller's (a multi-GPU host
+// such as torch keeps its own current device; src/preview.cpp:106-111 of the reference pins device 0 once instead).
+struct DeviceScope {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceScope(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; err = cudaSetDevice(dev); }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(dev)                                                                             \
+    DeviceScope deviceScope_(dev);                                                                 \
+    if (deviceScope_.err != cudaSuccess)                                                           \
+        return fail(PTB_ERR_CUDA, "cudaSetDevice(%d): %s", (int)(dev), cudaGetErrorString(deviceScope_.err))
+
 template <typename T> struct DevBuf {
     T *p = nullptr;
     size_t n = 0;
@@ -51,9 +67,49 @@ template <typename T> struct DevBuf {
         return cudaMalloc(&p, count * sizeof(T));
     }
     void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }                  // an early error return of a ptb_stage_* call frees what it had allocated
 };
 
 } // namespace
+
+// ---- NCCL, loaded on first use ----------------------------------------------------------------------------------------
+struct NcclApi {
+    void *handle = nullptr;
+    decltype(&ncclGetUniqueId) getUniqueId = nullptr;
+    decltype(&ncclCommInitRank) commInitRank = nullptr;
+    decltype(&ncclCommInitAll) commInitAll = nullptr;
+    decltype(&ncclCommDestroy) commDestroy = nullptr;
+    decltype(&ncclReduce) reduce = nullptr;
+    decltype(&ncclGroupStart) groupStart = nullptr;
+    decltype(&ncclGroupEnd) groupEnd = nullptr;
+    decltype(&ncclGetErrorString) getErrorString = nullptr;
+};
+static NcclApi *ncclApi(std::string &err) {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        // a copy a host framework (torch) already mapped wins: same soname
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (api.handle) break;
+        }
+        if (api.handle) {
+#define PTB_NCCL_SYM(field, sym) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, #sym))
+            PTB_NCCL_SYM(getUniqueId, ncclGetUniqueId); PTB_NCCL_SYM(commInitRank, ncclCommInitRank); PTB_NCCL_SYM(commInitAll, ncclCommInitAll);
+            PTB_NCCL_SYM(commDestroy, ncclCommDestroy); PTB_NCCL_SYM(reduce, ncclReduce); PTB_NCCL_SYM(groupStart, ncclGroupStart);
+            PTB_NCCL_SYM(groupEnd, ncclGroupEnd); PTB_NCCL_SYM(getErrorString, ncclGetErrorString);
+#undef PTB_NCCL_SYM
+            if (!api.getUniqueId || !api.commInitRank || !api.commInitAll || !api.commDestroy || !api.reduce || !api.groupStart ||
+                !api.groupEnd || !api.getErrorString) { dlclose(api.handle); api.handle = nullptr; }
+        }
+    }
+    if (!api.handle) { err = "libnccl.so.2 could not be loaded (multi-GPU rendering needs NCCL)"; return nullptr; }
+    return &api;
+}
 
 struct PtbContext {
     int device = 0;
@@ -102,18 +158,41 @@ struct PtbContext {
     DevBuf<uint8_t> rgb8;
 
     Params base{};
-    int gridFused = 0, gridStaged = 0;
+    int gridFused = 0, gridStaged = 0, gridTrace = 0;
     size_t smemBrute = 0, smemBvh = 0;
+    int bvhDepth = 0;                    // depth of the BVH last uploaded
+    DevBuf<int> stackSpill;              // trace_kernel: traversal-stack entries beyond the shared-memory part
+    int spillCap = 0;
+    DevBuf<float> partial;               // ordered deposit: batch partial images
+    uint32_t partialStride = 0;
+    // several GPUs: communicator of this context (owned unless it belongs to a PtbMulti), the reduced frame on the root
+    ncclComm_t comm = nullptr;
+    bool ownComm = false;
+    int commRank = 0, commRanks = 1;
+    DevBuf<float> frame;
+    bool frameValid = false;             // the last ptb_comm_reduce landed here (root of a > 1-rank communicator)
 
     cudaGraphExec_t graphExec = nullptr;
+    int graphKernels = 0;                // kernels per replay of the captured batch
+    bool capturing = false;
+    // PtbOptions.timeStages: event pairs of the launches since the last fold, and the per-stage sums
+    std::vector<cudaEvent_t> events;
+    size_t evUsed = 0;
+    std::vector<int> evStage;
+    double stageUs[PTB_NUM_STAGES] = {};
+    int64_t stageLaunches[PTB_NUM_STAGES] = {};
     int64_t launches = 0;
     int64_t hostIterations = 0;
 
     ~PtbContext() {
         if (graphExec) cudaGraphExecDestroy(graphExec);
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+        if (comm && ownComm) { std::string err; if (NcclApi *n = ncclApi(err)) n->commDestroy(comm); }
+        frame.release();
         geoms.release(); geomsScene.release(); bvh.release(); mats.release(); sceneMatDev.release();
         image.release();
         for (int i = 0; i < 2; ++i) { A[i].release(); B[i].release(); C[i].release(); }
+        stackSpill.release(); partial.release();
         hitTn.release(); hitMeta.release(); sortKeys.release(); sortOrder.release(); sortHist.release(); segCounts.release(); fbTn.release(); fbMeta.release();
         ctrl.release(); rgb8.release(); hdr.release();
         if (pinned) cudaFreeHost(pinned);
@@ -262,7 +341,7 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     // the render path uses it only when useBvh is set
     HostBvh hb;
     int maxLeaf = 1;                     // one primitive per leaf: its padded bound IS the leaf box (measured: 4 -> 7.28, 2 -> 6.62, 1 -> 6.29 ms per iteration of the 100k-object scene)
-    if (const char *e = getenv("PTB_BVH_LEAF")) maxLeaf = std::max(1, atoi(e));                       // tuning knob (experiments)
+    if (const char *e = tuningEnv("PTB_BVH_LEAF")) maxLeaf = std::max(1, atoi(e));                       // tuning knob (experiments)
     {
         // Sphere boxes also cover the hits the reference's sphere test reports for rays passing OUTSIDE the sphere, for every ray that
         // starts inside the scene (ptb_bvh.cpp geomBounds / defaultFarPadScene; PTB_BVH_FAR_PAD=0 opts out).
@@ -300,6 +379,7 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     }
     c->numNodes = (int)hb.nodes.size();
     c->smemNodes = std::min(c->numNodes, PTB_SMEM_NODES);
+    c->bvhDepth = hb.maxDepth;
     for (int i = 0; i < M; ++i) {
         const PtbMaterial &m = scene->materials[i];
         mats[3 * i + 0] = make_float4(m.color[0], m.color[1], m.color[2], m.emittance);
@@ -330,6 +410,47 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
 }
 
 // ---- launch sequences -------------------------------------------------------------------------
+// Every kernel of a batch goes out through LAUNCH: it counts the launch and, with PtbOptions.timeStages, brackets it with a pair
+// of CUDA events whose elapsed time is summed per stage (PtbStats.stageUs) the next time the stream is synchronised.
+struct StageScope {
+    PtbContext *c; bool on;
+    StageScope(PtbContext *ctx, int stage) : c(ctx), on(ctx->opt.timeStages && !ctx->capturing) {
+        if (!on) return;
+        if (c->evUsed + 2 > c->events.size()) {
+            cudaEvent_t a = nullptr, b = nullptr;
+            if (cudaEventCreate(&a) != cudaSuccess || cudaEventCreate(&b) != cudaSuccess) { on = false; return; }
+            c->events.push_back(a); c->events.push_back(b);
+        }
+        c->evStage.push_back(stage);
+        cudaEventRecord(c->events[c->evUsed], c->stream);
+    }
+    ~StageScope() {
+        if (!on) return;
+        cudaEventRecord(c->events[c->evUsed + 1], c->stream);
+        c->evUsed += 2;
+    }
+};
+#define LAUNCH(stage, kernel, grid, block, smem, ...)                                              \
+    do {                                                                                           \
+        StageScope stageScope_(c, stage);                                                          \
+        kernel<<<grid, block, smem, c->stream>>>(__VA_ARGS__);                                     \
+        c->launches++;                                                                             \
+    } while (0)
+
+// folds the recorded event pairs into the per-stage sums (the stream must be idle)
+void foldStageTimers(PtbContext *c) {
+    for (size_t i = 0; i + 1 < c->evUsed; i += 2) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, c->events[i], c->events[i + 1]) == cudaSuccess) {
+            const int stg = c->evStage[i / 2];
+            c->stageUs[stg] += (double)ms * 1e3;
+            c->stageLaunches[stg]++;
+        }
+    }
+    c->evUsed = 0;
+    c->evStage.clear();
+}
+
 // fused: traceDepth bounce kernels + the advance kernel.  Buffers ping-pong per bounce.
 template <bool EXT, bool MESH>
 void launchFusedBounces(PtbContext *c) {
@@ -338,34 +459,35 @@ void launchFusedBounces(PtbContext *c) {
         // bounce d reads buffer (d-1)&1... bounce 0 reads nothing and writes buffer 0
         Params p = makeParams(c, d == 0 ? 1 : ((d - 1) & 1));
         if (c->useBvh) {
-            // closest hit first (persistent threads, dynamic ray fetch), then shade / scatter / compact
+            // closest hit first (persistent threads, R rays multiplexed per lane), then shade / scatter / compact
             const bool cached = d == 0 && p.fbTn != nullptr;
             if (!cached) {
-                if (d == 0) trace_bvh_kernel<true, EXT, MESH><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
-                else        trace_bvh_kernel<false, false, MESH><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
-                c->launches++;
+                if (d == 0) LAUNCH(PTB_STAGE_INTERSECT, (trace_kernel<SRC_CAMERA, EXT, MESH>), c->gridTrace, kTraceBlock, smem, p, d, TraceIO{});
+                else        LAUNCH(PTB_STAGE_INTERSECT, (trace_kernel<SRC_SEGMENTS, false, MESH>), c->gridTrace, kTraceBlock, smem, p, d, TraceIO{});
             }
-            if (d == 0) bounce_kernel<true, true, EXT><<<c->gridFused, kBlock, 0, c->stream>>>(p, d);
-            else        bounce_kernel<false, true, EXT><<<c->gridFused, kBlock, 0, c->stream>>>(p, d);
+            if (d == 0) LAUNCH(PTB_STAGE_SHADE, (bounce_kernel<true, true, EXT>), c->gridFused, kBlock, 0, p, d);
+            else        LAUNCH(PTB_STAGE_SHADE, (bounce_kernel<false, true, EXT>), c->gridFused, kBlock, 0, p, d);
         } else {
-            if (d == 0) bounce_kernel<true, false, EXT><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+            if (d == 0) LAUNCH(PTB_STAGE_FUSED_BOUNCE0, (bounce_kernel<true, false, EXT>), c->gridFused, kBlock, smem, p, d);
             else if (c->loopBounces) {
                 // bounces 1 .. traceDepth-1 in one launch: every CTA walks its own segment through them
-                bounce_loop_kernel<EXT><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
-                c->launches++;
+                LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT>), c->gridFused, kBlock, smem, p, d);
                 break;
             }
-            else        bounce_kernel<false, false, EXT><<<c->gridFused, kBlock, smem, c->stream>>>(p, d);
+            else        LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_kernel<false, false, EXT>), c->gridFused, kBlock, smem, p, d);
         }
-        c->launches++;
     }
+}
+// end of a batch: the ordered deposit's partial images into image[] (slot = iteration order), then the control block
+void launchBatchTail(PtbContext *c) {
+    if (c->base.partial) LAUNCH(PTB_STAGE_GATHER, deposit_reduce_kernel, c->gridStaged, kBlock, 0, c->base);
+    LAUNCH(PTB_STAGE_CONTROL, advance_kernel, 1, 32, 0, c->ctrl.p, c->traceDepth, c->numPixels);
 }
 int launchFusedBatch(PtbContext *c) {
     const bool mesh = c->numTriangles > 0;
     if (c->ext) { if (mesh) launchFusedBounces<true, true>(c); else launchFusedBounces<true, false>(c); }
     else        { if (mesh) launchFusedBounces<false, true>(c); else launchFusedBounces<false, false>(c); }
-    advance_kernel<<<1, 32, 0, c->stream>>>(c->ctrl.p, c->traceDepth, c->numPixels);
-    c->launches++;
+    launchBatchTail(c);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PTB_ERR_CUDA, "fused batch launch: %s", cudaGetErrorString(e));
     return PTB_OK;
@@ -377,42 +499,37 @@ int launchStagedBatch(PtbContext *c) {
     const int grid = c->gridStaged;
     int cur = 0;
     Params p = makeParams(c, cur);
-    raygen_kernel<<<grid, kBlock, 0, c->stream>>>(p);
-    c->launches++;
+    LAUNCH(PTB_STAGE_RAYGEN, raygen_kernel, grid, kBlock, 0, p);
     const int compaction = c->opt.compaction;
     for (int d = 0; d < c->traceDepth; ++d) {
         p = makeParams(c, cur);
-        if (c->useBvh) intersect_kernel<true><<<grid, kBlock, smem, c->stream>>>(p, d);
-        else           intersect_kernel<false><<<grid, kBlock, smem, c->stream>>>(p, d);
-        c->launches++;
+        if (c->useBvh) {
+            // raw hit records through the BVH, then the deferred normals in place
+            LAUNCH(PTB_STAGE_INTERSECT, (trace_kernel<SRC_PATHS, false, true>), c->gridTrace, kTraceBlock, smem, p, d, TraceIO{});
+            LAUNCH(PTB_STAGE_INTERSECT, resolve_hits_kernel, grid, kBlock, 0, p, &c->ctrl.p->counts[d], 0u, p.hits.tn, p.hits.meta);
+        } else LAUNCH(PTB_STAGE_INTERSECT, intersect_kernel, grid, kBlock, smem, p, d);
         const int *order = nullptr;
         if (c->opt.sortMaterials) {
             const int numKeys = c->numMats + 1;
-            cudaMemsetAsync(c->sortHist.p, 0, sizeof(uint32_t) * numKeys, c->stream);
-            sort_keys_kernel<<<grid, kBlock, 0, c->stream>>>(p, d, c->sortKeys.p);
-            sort_hist_dev_kernel<<<grid, kBlock, sizeof(uint32_t) * numKeys, c->stream>>>(c->sortKeys.p, c->ctrl.p, d, numKeys, c->sortHist.p);
-            sort_scan_kernel<<<1, 32, 0, c->stream>>>(c->sortHist.p, numKeys);
-            sort_scatter_dev_kernel<<<grid, kBlock, 0, c->stream>>>(c->sortKeys.p, c->ctrl.p, d, c->sortHist.p, c->sortOrder.p);
-            c->launches += 4;
+            LAUNCH(PTB_STAGE_SORT, sort_keys_kernel, grid, kBlock, 0, p, d, c->sortKeys.p, c->sortHist.p, numKeys);
+            LAUNCH(PTB_STAGE_SORT, sort_hist_dev_kernel, grid, kBlock, sizeof(uint32_t) * numKeys, c->sortKeys.p, c->ctrl.p, d, numKeys, c->sortHist.p);
+            LAUNCH(PTB_STAGE_SORT, sort_scan_kernel, 1, 32, 0, c->sortHist.p, numKeys);
+            LAUNCH(PTB_STAGE_SORT, sort_scatter_dev_kernel, grid, kBlock, 0, c->sortKeys.p, c->ctrl.p, d, c->sortHist.p, c->sortOrder.p);
             order = c->sortOrder.p;
         }
-        shade_kernel<<<grid, kBlock, 0, c->stream>>>(p, d, order, compaction ? 1 : 0);
-        c->launches++;
+        LAUNCH(PTB_STAGE_SHADE, shade_kernel, grid, kBlock, 0, p, d, order, compaction ? 1 : 0);
         if (compaction) {
-            compact_kernel<<<grid, kBlock, 0, c->stream>>>(p, d);
+            LAUNCH(PTB_STAGE_COMPACT, compact_kernel, grid, kBlock, 0, p, d);
             cur ^= 1;
         } else {
-            carry_count_kernel<<<1, 32, 0, c->stream>>>(c->ctrl.p, d);
+            LAUNCH(PTB_STAGE_COMPACT, carry_count_kernel, 1, 32, 0, c->ctrl.p, d);
         }
-        c->launches++;
     }
     if (!compaction) {
         p = makeParams(c, cur);
-        gather_kernel<<<grid, kBlock, 0, c->stream>>>(p, c->numPixels * (uint32_t)c->batch);
-        c->launches++;
+        LAUNCH(PTB_STAGE_GATHER, gather_kernel, grid, kBlock, 0, p);
     }
-    advance_kernel<<<1, 32, 0, c->stream>>>(c->ctrl.p, c->traceDepth, c->numPixels);
-    c->launches++;
+    launchBatchTail(c);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PTB_ERR_CUDA, "staged batch launch: %s", cudaGetErrorString(e));
     return PTB_OK;
@@ -422,22 +539,15 @@ int launchBatch(PtbContext *c) {
     return c->opt.pipeline == PTB_PIPELINE_STAGED ? launchStagedBatch(c) : launchFusedBatch(c);
 }
 
-int kernelsPerBatch(const PtbContext *c) {
-    if (c->opt.pipeline == PTB_PIPELINE_STAGED) {
-        int per = 1 /*intersect*/ + 1 /*shade*/ + 1 /*compact or carry*/ + (c->opt.sortMaterials ? 4 : 0);
-        return 1 + per * c->traceDepth + (c->opt.compaction ? 0 : 1) + 1;
-    }
-    if (c->useBvh) return 2 * c->traceDepth + 1 - (c->opt.firstBounceCache ? 1 : 0);   // trace + bounce per depth
-    if (c->loopBounces) return (c->traceDepth > 1 ? 2 : 1) + 1;                         // bounce 0, bounces 1.., advance
-    return c->traceDepth + 1;
-}
-
 int buildGraph(PtbContext *c) {
     if (c->graphExec) return PTB_OK;
     cudaGraph_t graph = nullptr;
     CU(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
     const int64_t before = c->launches;
+    c->capturing = true;
     int rc = launchBatch(c);
+    c->capturing = false;
+    c->graphKernels = (int)(c->launches - before);    // kernels one replay of the graph launches
     c->launches = before;                         // capture does not execute anything
     cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
     if (rc != PTB_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -452,12 +562,30 @@ int buildGraph(PtbContext *c) {
 int ensureFirstBounceCache(PtbContext *c) {
     if (!c->opt.firstBounceCache || c->opt.pipeline != PTB_PIPELINE_FUSED || c->fbValid) return PTB_OK;
     Params p = c->base;
-    if (c->useBvh) fb_cache_kernel<true><<<c->gridStaged, kBlock, c->smemBvh, c->stream>>>(p, c->fbTn.p, c->fbMeta.p);
-    else           fb_cache_kernel<false><<<c->gridStaged, kBlock, c->smemBrute, c->stream>>>(p, c->fbTn.p, c->fbMeta.p);
+    if (c->useBvh) {
+        // p.hits is free between batches: raw hit records of the pixels' camera rays there, then normals into the cache
+        trace_kernel<SRC_PIXELS, false, true><<<c->gridTrace, kTraceBlock, c->smemBvh, c->stream>>>(p, 0, TraceIO{});
+        resolve_hits_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(p, nullptr, c->numPixels, c->fbTn.p, c->fbMeta.p);
+        c->launches++;
+    } else fb_cache_kernel<<<c->gridStaged, kBlock, c->smemBrute, c->stream>>>(p, c->fbTn.p, c->fbMeta.p);
     c->launches++;
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(PTB_ERR_CUDA, "first-bounce cache fill: %s", cudaGetErrorString(e));
     c->fbValid = true;
+    return PTB_OK;
+}
+
+// trace_kernel keeps kStackSmem traversal-stack entries per ray slot in shared memory; a deeper tree (the stack never holds
+// more entries than the tree has levels) gets the rest in global memory
+int ensureStackSpill(PtbContext *c) {
+    const int need = std::max(0, c->bvhDepth + 2 - kStackSmem);
+    if (need > c->spillCap) {
+        CU(cudaStreamSynchronize(c->stream));
+        CU(c->stackSpill.alloc((size_t)c->gridTrace * kTraceBlock * kTraceRays * need));
+        c->spillCap = need;
+        if (c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }    // new launch parameters: re-capture
+    }
+    c->base.stackSpill = c->stackSpill.p; c->base.spillCap = c->spillCap;
     return PTB_OK;
 }
 
@@ -466,22 +594,22 @@ int runBatches(PtbContext *c, int iterBegin, int count, int iterStride) {
     int done = 0;
     while (done < count) {
         const int b = std::min(c->batch, count - done);
-        set_control_kernel<<<1, 32, 0, c->stream>>>(c->ctrl.p, iterBegin + done * iterStride, iterStride, b);
-        c->launches++;
+        LAUNCH(PTB_STAGE_CONTROL, set_control_kernel, 1, 32, 0, c->ctrl.p, iterBegin + done * iterStride, iterStride, b);
         // full batches replay back to back: advance_kernel moves iterBase on the device
         int reps = (b == c->batch) ? (count - done) / c->batch : 1;
         for (int r = 0; r < reps; ++r) {
-            if (c->opt.useGraphs) {
+            if (c->opt.useGraphs && !c->opt.timeStages) {
                 int rc = buildGraph(c);
                 if (rc != PTB_OK) return rc;
                 CU(cudaGraphLaunch(c->graphExec, c->stream));
-                c->launches += kernelsPerBatch(c);
+                c->launches += c->graphKernels;
             } else {
                 int rc = launchBatch(c);
                 if (rc != PTB_OK) return rc;
             }
         }
         done += reps * b;
+        if (c->opt.timeStages && c->evUsed > 8192) { CU(cudaStreamSynchronize(c->stream)); foldStageTimers(c); }   // bound the event pool
     }
     c->hostIterations += count;
     return PTB_OK;
@@ -493,6 +621,8 @@ int runBatches(PtbContext *c, int iterBegin, int count, int iterStride) {
 extern "C" {
 
 const char *ptb_last_error(void) { return g_lastError.c_str(); }
+// for the host-only translation units of the library (ptb_bvh.cpp, host/host_abi.cpp): same thread-local message
+int ptb_set_last_error(int code, const char *msg) { g_lastError = msg ? msg : ""; return code; }
 int ptb_abi_version(void) { return PTB_ABI_VERSION; }
 
 void ptb_default_options(PtbOptions *o) {
@@ -528,7 +658,7 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     int dev = opt.device;
     if (dev < 0) CU(cudaGetDevice(&dev));
     if (dev >= ndev) return fail(PTB_ERR_INVALID, "device %d of %d", dev, ndev);
-    CU(cudaSetDevice(dev));
+    ON_DEVICE(dev);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, dev));
 
@@ -584,31 +714,43 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
 
     // ---- launch geometry ----
     c->smemBrute = bruteBytes;
-    c->smemBvh = (size_t)PTB_SMEM_NODES * sizeof(BvhNode);     // fixed: the node count may change in ptb_update_scene
+    c->smemBvh = traceSmemBytes(PTB_SMEM_NODES);                // fixed: the node count may change in ptb_update_scene
     if (bruteBytes <= 200 * 1024) {                  // brute force is only launchable when the geoms fit in shared memory
         int rc = PTB_OK;
         rc |= setSmem(bounce_kernel<true, false, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, false>, c->smemBrute);
         rc |= setSmem(bounce_kernel<true, false, true>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, true>, c->smemBrute);
         rc |= setSmem(bounce_loop_kernel<false>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true>, c->smemBrute);
-        rc |= setSmem(intersect_kernel<false>, c->smemBrute); rc |= setSmem(stage_intersect_kernel<false>, c->smemBrute);
-        rc |= setSmem(fb_cache_kernel<false>, c->smemBrute);
+        rc |= setSmem(intersect_kernel, c->smemBrute); rc |= setSmem(stage_intersect_kernel, c->smemBrute);
+        rc |= setSmem(fb_cache_kernel, c->smemBrute);
         if (rc != PTB_OK) return bail(rc);
     }
-    int occ = 0;
-    const size_t smem = c->useBvh ? c->smemBvh : c->smemBrute;
-    if (c->useBvh) CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_bvh_kernel<false, false, false>, kBlock, smem));
-    else           CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, false, false>, kBlock, smem));
+    {
+        int rc = PTB_OK;
+        rc |= setSmem(trace_kernel<SRC_CAMERA, false, false>, c->smemBvh); rc |= setSmem(trace_kernel<SRC_CAMERA, true, false>, c->smemBvh);
+        rc |= setSmem(trace_kernel<SRC_CAMERA, false, true>, c->smemBvh); rc |= setSmem(trace_kernel<SRC_CAMERA, true, true>, c->smemBvh);
+        rc |= setSmem(trace_kernel<SRC_SEGMENTS, false, false>, c->smemBvh); rc |= setSmem(trace_kernel<SRC_SEGMENTS, false, true>, c->smemBvh);
+        rc |= setSmem(trace_kernel<SRC_PATHS, false, true>, c->smemBvh); rc |= setSmem(trace_kernel<SRC_PIXELS, false, true>, c->smemBvh);
+        rc |= setSmem(trace_kernel<SRC_RAYS, false, true>, c->smemBvh);
+        if (rc != PTB_OK) return bail(rc);
+    }
+    int occ = 0, occTrace = 0;
+    CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occTrace, trace_kernel<SRC_SEGMENTS, false, true>, kTraceBlock, c->smemBvh));
+    // persistent grid of the BVH traversal: one wave of resident CTAs, each serving several CTA-owned path segments back to back
+    c->gridTrace = c->numSMs * std::max(1, occTrace);
+    if (c->useBvh) CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, true, false>, kBlock, 0));
+    else           CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, false, false>, kBlock, c->smemBrute));
     // brute-force scenes: bounces 1.. in one launch (bounce_loop_kernel), every CTA walking its own segment through them
-    c->loopBounces = !c->useBvh;
-    if (const char *e = getenv("PTB_LOOP_BOUNCES")) c->loopBounces = c->loopBounces && atoi(e) != 0;   // tuning knob (experiments)
+    c->loopBounces = !c->useBvh && !opt.launchPerBounce;
+    if (const char *e = tuningEnv("PTB_LOOP_BOUNCES")) c->loopBounces = c->loopBounces && atoi(e) != 0;   // tuning knob (experiments)
     // Several CTAs per resident slot: the CTA-owned segments cannot be rebalanced inside a launch, so a few waves of
     // smaller CTAs keep the tail short.  Measured per cornell iteration, one launch per bounce: x1 142 us, x2 138, x4 134.5,
     // x8 135.4, x16 142 (round 1, first build); with the one-launch bounce loop the per-CTA set-up is paid once per
     // wavefront and x8 wins: x2 119.0, x4 114.8, x8 112.9, x16 112.7 (profiles/r01n_loop_ab.txt)
     const size_t wavefrontTiles = ((size_t)c->numPixels * c->batch + kBlock - 1) / kBlock;
     int gridMult = (c->loopBounces && wavefrontTiles >= (size_t)c->numSMs * std::max(1, occ) * 8 * 4) ? 8 : 4;   // >= 4 tiles per CTA
-    if (const char *e = getenv("PTB_GRID_MULT")) gridMult = std::max(1, atoi(e));           // tuning knob (experiments)
+    if (const char *e = tuningEnv("PTB_GRID_MULT")) gridMult = std::max(1, atoi(e));           // tuning knob (experiments)
     c->gridFused = c->numSMs * std::max(1, occ) * gridMult;
+    c->gridFused = std::min(c->gridFused, c->gridTrace * kMaxVirtualSegs);      // trace_kernel serves at most kMaxVirtualSegs segments per CTA
     c->gridStaged = c->numSMs * 8;
 
     // ---- state (src/pathtrace.cu:84-87, 95-96) ----
@@ -631,6 +773,14 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     if (opt.firstBounceCache && opt.pipeline == PTB_PIPELINE_FUSED) { CUB(c->fbTn.alloc(c->numPixels)); CUB(c->fbMeta.alloc(c->numPixels)); }
     CUB(c->ctrl.alloc(1));
     CUB(cudaMemset(c->ctrl.p, 0, sizeof(Control)));
+    // ordered deposit (default): one partial image per slot of the wavefront, all-zero between wavefronts
+    if (c->batch > 1 && opt.depositMode == PTB_DEPOSIT_ORDERED) {
+        if (reinterpret_cast<uintptr_t>(c->imagePtr) & 15u) return bail(fail(PTB_ERR_INVALID, "ptb_create: externalAccum must be 16-byte aligned"));
+        c->partialStride = (c->numPixels * 3u + 3u) & ~3u;
+        CUB(c->partial.alloc((size_t)c->batch * c->partialStride));
+        CUB(cudaMemset(c->partial.p, 0, (size_t)c->batch * c->partialStride * sizeof(float)));
+    }
+    { int rc = ensureStackSpill(c); if (rc != PTB_OK) return bail(rc); }
 
     Params &p = c->base;
     memset(&p, 0, sizeof p);
@@ -646,9 +796,12 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     p.bsdfMode = opt.bsdfMode;
     p.pixBits = c->pixBits;
     p.numPixels = c->numPixels;
-    p.atomicGather = c->batch > 1 ? 1 : 0;
+    p.atomicGather = (c->batch > 1 && opt.depositMode != PTB_DEPOSIT_ORDERED) ? 1 : 0;
     p.segCounts = c->segCounts.p;
     p.segCap = c->segCap;
+    p.vgrid = (uint32_t)c->gridFused;
+    p.stackSpill = c->stackSpill.p; p.spillCap = c->spillCap;
+    p.partial = c->partial.p; p.partialStride = c->partialStride;
     p.fbTn = c->fbTn.p; p.fbMeta = c->fbMeta.p;          // NULL when the cache is off
     CUB(cudaDeviceSynchronize());
 #undef CUB
@@ -666,17 +819,19 @@ int ptb_update_scene(PtbContext *c, const PtbSceneDesc *scene) {
     if (scene->numGeoms != c->numGeoms || scene->numMaterials != c->numMats || scene->camera.resolution[0] != c->W ||
         scene->camera.resolution[1] != c->H || scene->traceDepth != c->traceDepth)
         return fail(PTB_ERR_INVALID, "ptb_update_scene: geometry/material counts, resolution and depth must match ptb_create");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     CU(cudaStreamSynchronize(c->stream));           // the pinned staging buffer is about to be rewritten
     rc = uploadScene(c, scene);
     if (rc != PTB_OK) return rc;
     c->fbValid = false;                              // new geometry / camera: the cached bounce-0 hits are stale
+    rc = ensureStackSpill(c);                        // the rebuilt tree may be deeper
+    if (rc != PTB_OK) return rc;
     return ptb_reset(c);
 }
 
 int ptb_destroy(PtbContext *c) {
     if (!c) return PTB_OK;                          // pathtraceFree before any pathtraceInit (src/main.cpp:126)
-    cudaSetDevice(c->device);
+    DeviceScope deviceScope_(c->device);
     cudaStreamSynchronize(c->stream);
     delete c;
     return PTB_OK;
@@ -687,13 +842,14 @@ int ptb_render(PtbContext *c, int iterBegin, int count, int iterStride) {
     if (count < 0 || iterStride < 1 || iterBegin < 0) return fail(PTB_ERR_INVALID, "ptb_render: bad range");
     // makeSeededRandomEngine packs iter into 22 bits and depth into 9 (src/pathtrace.cu:43)
     if ((int64_t)iterBegin + (int64_t)(count - 1) * iterStride >= (1 << 22)) return fail(PTB_ERR_INVALID, "ptb_render: iteration beyond 2^22 aliases the RNG seed");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     return runBatches(c, iterBegin, count, iterStride);
 }
 
 int ptb_write_pbo(PtbContext *c, PtbUchar4 *pbo, int samples) {
     if (!c || !pbo) return fail(PTB_ERR_INVALID, "ptb_write_pbo: null argument");
-    CU(cudaSetDevice(c->device));
+    if (samples <= 0) return fail(PTB_ERR_INVALID, "ptb_write_pbo: samples %d (the divisor of sendImageToPBO must be positive)", samples);
+    ON_DEVICE(c->device);
     pbo_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(reinterpret_cast<uchar4 *>(pbo), c->imagePtr, c->numPixels, samples);
     c->launches++;
     CU(cudaGetLastError());
@@ -702,7 +858,7 @@ int ptb_write_pbo(PtbContext *c, PtbUchar4 *pbo, int samples) {
 
 int ptb_download(PtbContext *c, float *hostImage) {
     if (!c || !hostImage) return fail(PTB_ERR_INVALID, "ptb_download: null argument");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     CU(cudaMemcpyAsync(hostImage, c->imagePtr, (size_t)c->numPixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return PTB_OK;
@@ -711,7 +867,7 @@ int ptb_download(PtbContext *c, float *hostImage) {
 int ptb_pathtrace(PtbContext *c, PtbUchar4 *pbo, int frame, int iter, float *hostImage) {
     (void)frame;                                     // unused by the reference as well (src/main.cpp:136)
     if (!c) return fail(PTB_ERR_INVALID, "ptb_pathtrace: not initialised");
-    if (iter < 0) return fail(PTB_ERR_INVALID, "ptb_pathtrace: iter %d", iter);
+    if (iter < 1) return fail(PTB_ERR_INVALID, "ptb_pathtrace: iteration %d (the reference's iterations are 1-based, src/main.cpp:132)", iter);
     int rc = ptb_render(c, iter, 1, 1);
     if (rc != PTB_OK) return rc;
     if (pbo) { rc = ptb_write_pbo(c, pbo, iter); if (rc != PTB_OK) return rc; }
@@ -721,27 +877,35 @@ int ptb_pathtrace(PtbContext *c, PtbUchar4 *pbo, int frame, int iter, float *hos
 
 int ptb_reset(PtbContext *c) {
     if (!c) return fail(PTB_ERR_INVALID, "ptb_reset: not initialised");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     CU(cudaMemsetAsync(c->imagePtr, 0, (size_t)c->numPixels * 3 * sizeof(float), c->stream));
     CU(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Control), c->stream));
     c->hostIterations = 0;
+    c->frameValid = false;
+    if (c->opt.timeStages) {
+        CU(cudaStreamSynchronize(c->stream));
+        foldStageTimers(c);
+        for (int k = 0; k < PTB_NUM_STAGES; ++k) { c->stageUs[k] = 0.0; c->stageLaunches[k] = 0; }
+    }
     return PTB_OK;
 }
 
 int ptb_sync(PtbContext *c) {
     if (!c) return fail(PTB_ERR_INVALID, "ptb_sync: not initialised");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     CU(cudaStreamSynchronize(c->stream));
     return PTB_OK;
 }
 
 int ptb_stats(PtbContext *c, PtbStats *out) {
     if (!c || !out) return fail(PTB_ERR_INVALID, "ptb_stats: null argument");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     Control h;
     CU(cudaMemcpyAsync(&h, c->ctrl.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
+    foldStageTimers(c);
     memset(out, 0, sizeof *out);
+    for (int k = 0; k < PTB_NUM_STAGES; ++k) { out->stageUs[k] = c->stageUs[k]; out->stageLaunches[k] = c->stageLaunches[k]; }
     out->iterations = (int64_t)h.iterations;
     out->segments = (int64_t)h.segments;
     out->kernelLaunches = c->launches;
@@ -763,7 +927,7 @@ int ptb_accum_device_ptr(PtbContext *c, float **devPtr) {
 
 int ptb_resolve_rgb8(PtbContext *c, int samples, uint8_t *hostRgb8) {
     if (!c || !hostRgb8 || samples <= 0) return fail(PTB_ERR_INVALID, "ptb_resolve_rgb8: bad argument");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     if (!c->rgb8.p) CU(c->rgb8.alloc((size_t)c->numPixels * 3));
     resolve_rgb8_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(c->rgb8.p, c->imagePtr, c->W, c->H, (float)samples);
     c->launches++;
@@ -773,12 +937,231 @@ int ptb_resolve_rgb8(PtbContext *c, int samples, uint8_t *hostRgb8) {
     return PTB_OK;
 }
 
+// ---- several GPUs (include/ptb200.h) ---------------------------------------------------------------
+#define NC(call)                                                                                   \
+    do {                                                                                           \
+        ncclResult_t r_ = (call);                                                                  \
+        if (r_ != ncclSuccess) return fail(PTB_ERR_CUDA, "NCCL error (%s:%d): %s: %s", "ptb200.cu", __LINE__, #call, nccl->getErrorString(r_)); \
+    } while (0)
+
+int ptb_comm_unique_id(uint8_t id[PTB_COMM_ID_BYTES]) {
+    if (!id) return fail(PTB_ERR_INVALID, "ptb_comm_unique_id: null argument");
+    std::string err;
+    NcclApi *nccl = ncclApi(err);
+    if (!nccl) return fail(PTB_ERR_UNSUPPORTED, "%s", err.c_str());
+    static_assert(sizeof(ncclUniqueId) == PTB_COMM_ID_BYTES, "ncclUniqueId size");
+    ncclUniqueId u;
+    NC(nccl->getUniqueId(&u));
+    memcpy(id, &u, sizeof u);
+    return PTB_OK;
+}
+
+static int ensureFrame(PtbContext *c) {
+    if (!c->frame.p) CU(c->frame.alloc((size_t)c->numPixels * 3));
+    return PTB_OK;
+}
+
+int ptb_comm_init_rank(PtbContext *c, const uint8_t id[PTB_COMM_ID_BYTES], int rank, int nranks) {
+    if (!c || !id || nranks < 1 || rank < 0 || rank >= nranks) return fail(PTB_ERR_INVALID, "ptb_comm_init_rank: bad argument");
+    if (c->comm) return fail(PTB_ERR_INVALID, "ptb_comm_init_rank: the context already has a communicator");
+    std::string err;
+    NcclApi *nccl = ncclApi(err);
+    if (!nccl) return fail(PTB_ERR_UNSUPPORTED, "%s", err.c_str());
+    ON_DEVICE(c->device);
+    ncclUniqueId u;
+    memcpy(&u, id, sizeof u);
+    NC(nccl->commInitRank(&c->comm, nranks, u, rank));
+    c->ownComm = true; c->commRank = rank; c->commRanks = nranks;
+    return PTB_OK;
+}
+
+int ptb_comm_reduce(PtbContext *c, int root) {
+    if (!c || !c->comm) return fail(PTB_ERR_INVALID, "ptb_comm_reduce: no communicator (ptb_comm_init_rank / ptb_multi_create)");
+    if (root < 0 || root >= c->commRanks) return fail(PTB_ERR_INVALID, "ptb_comm_reduce: root %d of %d", root, c->commRanks);
+    std::string err;
+    NcclApi *nccl = ncclApi(err);
+    if (!nccl) return fail(PTB_ERR_UNSUPPORTED, "%s", err.c_str());
+    ON_DEVICE(c->device);
+    if (c->commRank == root) { int rc = ensureFrame(c); if (rc != PTB_OK) return rc; }
+    // one collective per frame: count = 3 * W * H floats; recvbuff only matters on the root
+    NC(nccl->reduce(c->imagePtr, c->commRank == root ? c->frame.p : nullptr, (size_t)c->numPixels * 3, ncclFloat32, ncclSum, root, c->comm, c->stream));
+    c->frameValid = c->commRank == root;
+    return PTB_OK;
+}
+
+static float *framePtr(PtbContext *c) { return (c->frameValid && c->frame.p) ? c->frame.p : c->imagePtr; }
+
+int ptb_frame_device_ptr(PtbContext *c, float **devPtr) {
+    if (!c || !devPtr) return fail(PTB_ERR_INVALID, "ptb_frame_device_ptr: null argument");
+    *devPtr = framePtr(c);
+    return PTB_OK;
+}
+int ptb_frame_download(PtbContext *c, float *hostImage) {
+    if (!c || !hostImage) return fail(PTB_ERR_INVALID, "ptb_frame_download: null argument");
+    ON_DEVICE(c->device);
+    CU(cudaMemcpyAsync(hostImage, framePtr(c), (size_t)c->numPixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+static int resolveFrom(PtbContext *c, const float *src, int samples, uint8_t *hostRgb8) {
+    if (!c->rgb8.p) CU(c->rgb8.alloc((size_t)c->numPixels * 3));
+    resolve_rgb8_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(c->rgb8.p, src, c->W, c->H, (float)samples);
+    c->launches++;
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(hostRgb8, c->rgb8.p, (size_t)c->numPixels * 3, cudaMemcpyDeviceToHost, c->stream));
+    CU(cudaStreamSynchronize(c->stream));
+    return PTB_OK;
+}
+int ptb_frame_resolve_rgb8(PtbContext *c, int samples, uint8_t *hostRgb8) {
+    if (!c || !hostRgb8 || samples <= 0) return fail(PTB_ERR_INVALID, "ptb_frame_resolve_rgb8: bad argument");
+    ON_DEVICE(c->device);
+    return resolveFrom(c, framePtr(c), samples, hostRgb8);
+}
+
+} // extern "C"
+
+struct PtbMulti {
+    std::vector<PtbContext *> ctx;
+    std::vector<ncclComm_t> comms;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;       // on the root's device: reduce timing
+};
+
+extern "C" {
+
+int ptb_multi_destroy(PtbMulti *m) {
+    if (!m) return PTB_OK;
+    std::string err;
+    NcclApi *nccl = ncclApi(err);
+    for (size_t g = 0; g < m->ctx.size(); ++g) {
+        if (m->ctx[g]) { cudaSetDevice(m->ctx[g]->device); cudaStreamSynchronize(m->ctx[g]->stream); }
+    }
+    if (nccl) for (ncclComm_t cm : m->comms) if (cm) nccl->commDestroy(cm);
+    if (!m->ctx.empty() && m->ctx[0]) {
+        DeviceScope ds(m->ctx[0]->device);
+        if (m->ev0) cudaEventDestroy(m->ev0);
+        if (m->ev1) cudaEventDestroy(m->ev1);
+    }
+    for (PtbContext *c : m->ctx) if (c) { c->comm = nullptr; ptb_destroy(c); }
+    delete m;
+    return PTB_OK;
+}
+
+int ptb_multi_create(PtbMulti **out, const PtbSceneDesc *scene, const PtbOptions *optIn, const int32_t *devices, int32_t n) {
+    if (!out || !scene || n < 1) return fail(PTB_ERR_INVALID, "ptb_multi_create: bad argument");
+    *out = nullptr;
+    int ndev = 0;
+    CU(cudaGetDeviceCount(&ndev));
+    std::vector<int> devs(n);
+    for (int g = 0; g < n; ++g) {
+        devs[g] = devices ? devices[g] : g;
+        if (devs[g] < 0 || devs[g] >= ndev) return fail(PTB_ERR_INVALID, "ptb_multi_create: device %d of %d", devs[g], ndev);
+        for (int k = 0; k < g; ++k) if (devs[k] == devs[g]) return fail(PTB_ERR_INVALID, "ptb_multi_create: device %d listed twice", devs[g]);
+    }
+    std::string err;
+    NcclApi *nccl = n > 1 ? ncclApi(err) : nullptr;
+    if (n > 1 && !nccl) return fail(PTB_ERR_UNSUPPORTED, "%s", err.c_str());
+    PtbMulti *m = new PtbMulti();
+    m->ctx.assign(n, nullptr);
+    PtbOptions opt;
+    if (optIn) opt = *optIn; else ptb_default_options(&opt);
+    opt.stream = nullptr; opt.externalAccum = nullptr;
+    for (int g = 0; g < n; ++g) {
+        opt.device = devs[g];
+        int rc = ptb_create(&m->ctx[g], scene, &opt);
+        if (rc != PTB_OK) { const std::string keep = g_lastError; ptb_multi_destroy(m); g_lastError = keep; return rc; }
+    }
+    if (n > 1) {
+        m->comms.assign(n, nullptr);
+        ncclResult_t r = nccl->commInitAll(m->comms.data(), n, devs.data());
+        if (r != ncclSuccess) { ptb_multi_destroy(m); return fail(PTB_ERR_CUDA, "ncclCommInitAll: %s", nccl->getErrorString(r)); }
+        for (int g = 0; g < n; ++g) { m->ctx[g]->comm = m->comms[g]; m->ctx[g]->ownComm = false; m->ctx[g]->commRank = g; m->ctx[g]->commRanks = n; }
+    }
+    {
+        DeviceScope ds(m->ctx[0]->device);
+        if (cudaEventCreate(&m->ev0) != cudaSuccess || cudaEventCreate(&m->ev1) != cudaSuccess) { ptb_multi_destroy(m); return fail(PTB_ERR_CUDA, "cudaEventCreate"); }
+    }
+    *out = m;
+    return PTB_OK;
+}
+
+int ptb_multi_reset(PtbMulti *m) {
+    if (!m) return fail(PTB_ERR_INVALID, "ptb_multi_reset: null argument");
+    for (PtbContext *c : m->ctx) { int rc = ptb_reset(c); if (rc != PTB_OK) return rc; c->frameValid = false; }
+    return PTB_OK;
+}
+
+int ptb_multi_render(PtbMulti *m, int iterBegin, int count) {
+    if (!m || count < 0) return fail(PTB_ERR_INVALID, "ptb_multi_render: bad argument");
+    const int G = (int)m->ctx.size();
+    // device g renders iterBegin + g, + G, ...: every prefix of the sample sequence stays balanced.  Asynchronous launches:
+    // the devices run concurrently under one host thread (the whole batch loop is CUDA-graph replays).
+    for (int g = 0; g < G; ++g) {
+        const int mine = count > g ? (count - g + G - 1) / G : 0;
+        if (!mine) continue;
+        int rc = ptb_render(m->ctx[g], iterBegin + g, mine, G);
+        if (rc != PTB_OK) return rc;
+    }
+    return PTB_OK;
+}
+
+int ptb_multi_frame(PtbMulti *m, int samples, float *hostImage, uint8_t *hostRgb8, float *reduceMs) {
+    if (!m || (hostRgb8 && samples <= 0)) return fail(PTB_ERR_INVALID, "ptb_multi_frame: bad argument");
+    const int G = (int)m->ctx.size();
+    PtbContext *root = m->ctx[0];
+    if (reduceMs) *reduceMs = 0.f;
+    if (G > 1) {
+        std::string err;
+        NcclApi *nccl = ncclApi(err);
+        if (!nccl) return fail(PTB_ERR_UNSUPPORTED, "%s", err.c_str());
+        { ON_DEVICE(root->device); int rc = ensureFrame(root); if (rc != PTB_OK) return rc; CU(cudaEventRecord(m->ev0, root->stream)); }
+        // ONE grouped collective per frame: ncclReduce(sum, float32, 3*W*H) from every device's private accumulation to the root's frame
+        NC(nccl->groupStart());
+        for (int g = 0; g < G; ++g) {
+            PtbContext *c = m->ctx[g];
+            ncclResult_t r = nccl->reduce(c->imagePtr, g == 0 ? root->frame.p : nullptr, (size_t)c->numPixels * 3, ncclFloat32, ncclSum, 0, c->comm, c->stream);
+            if (r != ncclSuccess) { nccl->groupEnd(); return fail(PTB_ERR_CUDA, "ncclReduce (device %d): %s", c->device, nccl->getErrorString(r)); }
+        }
+        NC(nccl->groupEnd());
+        root->frameValid = true;
+        { ON_DEVICE(root->device); CU(cudaEventRecord(m->ev1, root->stream)); }
+    }
+    // the senders finish their part of the collective on their own streams
+    for (int g = 1; g < G; ++g) { int rc = ptb_sync(m->ctx[g]); if (rc != PTB_OK) return rc; }
+    if (hostRgb8) { ON_DEVICE(root->device); int rc = resolveFrom(root, framePtr(root), samples, hostRgb8); if (rc != PTB_OK) return rc; }
+    if (hostImage) { int rc = ptb_frame_download(root, hostImage); if (rc != PTB_OK) return rc; }
+    { int rc = ptb_sync(root); if (rc != PTB_OK) return rc; }
+    if (G > 1 && reduceMs) { ON_DEVICE(root->device); CU(cudaEventElapsedTime(reduceMs, m->ev0, m->ev1)); }
+    return PTB_OK;
+}
+
+int ptb_multi_stats(PtbMulti *m, PtbStats *sum) {
+    if (!m || !sum) return fail(PTB_ERR_INVALID, "ptb_multi_stats: null argument");
+    memset(sum, 0, sizeof *sum);
+    for (size_t g = 0; g < m->ctx.size(); ++g) {
+        PtbStats s;
+        int rc = ptb_stats(m->ctx[g], &s);
+        if (rc != PTB_OK) return rc;
+        sum->iterations += s.iterations; sum->segments += s.segments; sum->kernelLaunches += s.kernelLaunches;
+        for (int d = 0; d < 64; ++d) sum->alivePerDepth[d] += s.alivePerDepth[d];
+        for (int k = 0; k < PTB_NUM_STAGES; ++k) { sum->stageUs[k] += s.stageUs[k]; sum->stageLaunches[k] += s.stageLaunches[k]; }
+        sum->traceDepth = s.traceDepth; sum->numGeoms = s.numGeoms; sum->bvhNodes = s.bvhNodes; sum->batchIters = s.batchIters;
+        sum->pathStateBytes += s.pathStateBytes; sum->sceneUploadBytes += s.sceneUploadBytes;
+    }
+    return PTB_OK;
+}
+
+int ptb_multi_context(PtbMulti *m, int index, PtbContext **ctx) {
+    if (!m || !ctx || index < 0 || index >= (int)m->ctx.size()) return fail(PTB_ERR_INVALID, "ptb_multi_context: bad argument");
+    *ctx = m->ctx[index];
+    return PTB_OK;
+}
+
 // ---- stage-level entry points ---------------------------------------------------------------------
 int ptb_stage_raygen(PtbContext *c, float *origins, float *dirs) { return ptb_stage_raygen_iter(c, 1, origins, dirs); }
 
 int ptb_stage_raygen_iter(PtbContext *c, int iter, float *origins, float *dirs) {
     if (!c || !origins || !dirs) return fail(PTB_ERR_INVALID, "ptb_stage_raygen: null argument");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     const size_t n = (size_t)c->numPixels * 3;
     DevBuf<float> o, d;
     CU(o.alloc(n)); CU(d.alloc(n));
@@ -795,18 +1178,26 @@ int ptb_stage_raygen_iter(PtbContext *c, int iter, float *origins, float *dirs) 
 int ptb_stage_intersect(PtbContext *c, int accel, const float *origins, const float *dirs, int n,
                         int32_t *hit, float *t, float *normal, int32_t *outside) {
     if (!c || !origins || !dirs || !hit || !t || !normal || !outside || n < 0) return fail(PTB_ERR_INVALID, "ptb_stage_intersect: bad argument");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     bool bvh = accel == PTB_ACCEL_BVH || (accel == PTB_ACCEL_AUTO && c->useBvh);
     if (!bvh && c->numPrims != c->numGeoms) return fail(PTB_ERR_UNSUPPORTED, "ptb_stage_intersect: scenes with meshes have no brute-force table");
     if (!bvh && c->smemBrute > 200 * 1024) return fail(PTB_ERR_UNSUPPORTED, "brute force needs %zu B of shared memory", c->smemBrute);
     DevBuf<float> o, d, dt, dn; DevBuf<int> dh, dout;
+    DevBuf<float4> rawTn; DevBuf<int> rawMeta;
     CU(o.alloc((size_t)n * 3)); CU(d.alloc((size_t)n * 3)); CU(dt.alloc(n)); CU(dn.alloc((size_t)n * 3)); CU(dh.alloc(n)); CU(dout.alloc(n));
     if (n) {
         CU(cudaMemcpyAsync(o.p, origins, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
         CU(cudaMemcpyAsync(d.p, dirs, (size_t)n * 12, cudaMemcpyHostToDevice, c->stream));
         Params p = c->base;
-        if (bvh) { p.geoms = c->geoms.p; stage_intersect_kernel<true><<<c->gridStaged, kBlock, c->smemBvh, c->stream>>>(p, o.p, d.p, n, dh.p, dt.p, dn.p, dout.p); }
-        else { p.geoms = c->geomsScene.p; stage_intersect_kernel<false><<<c->gridStaged, kBlock, c->smemBrute, c->stream>>>(p, o.p, d.p, n, dh.p, dt.p, dn.p, dout.p); }
+        if (bvh) {
+            // raw hit records through trace_kernel (the traversal every BVH render runs), then normals / scene indices
+            CU(rawTn.alloc(n)); CU(rawMeta.alloc(n));
+            p.geoms = c->geoms.p; p.hits.tn = rawTn.p; p.hits.meta = rawMeta.p;
+            trace_kernel<SRC_RAYS, false, true><<<c->gridTrace, kTraceBlock, c->smemBvh, c->stream>>>(p, 0, TraceIO{o.p, d.p, n});
+            stage_hits_out_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(p, n, dh.p, dt.p, dn.p, dout.p);
+            c->launches++;
+        }
+        else { p.geoms = c->geomsScene.p; stage_intersect_kernel<<<c->gridStaged, kBlock, c->smemBrute, c->stream>>>(p, o.p, d.p, n, dh.p, dt.p, dn.p, dout.p); }
         c->launches++;
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(hit, dh.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
@@ -823,7 +1214,7 @@ int ptb_stage_shade(PtbContext *c, int n, const int32_t *hit, const float *t, co
                     const int32_t *outside, const int32_t *iter, const int32_t *pixelIndex,
                     const int32_t *depth, float *origins, float *dirs, float *colors, int32_t *remaining) {
     if (!c || n < 0) return fail(PTB_ERR_INVALID, "ptb_stage_shade: bad argument");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     DevBuf<int> dh, dout, dit, dpx, ddp, drem; DevBuf<float> dt, dn, o, d, col;
     CU(dh.alloc(n)); CU(dout.alloc(n)); CU(dit.alloc(n)); CU(dpx.alloc(n)); CU(ddp.alloc(n)); CU(drem.alloc(n));
     CU(dt.alloc(n)); CU(dn.alloc((size_t)n * 3)); CU(o.alloc((size_t)n * 3)); CU(d.alloc((size_t)n * 3)); CU(col.alloc((size_t)n * 3));
@@ -849,7 +1240,7 @@ int ptb_stage_shade(PtbContext *c, int n, const int32_t *hit, const float *t, co
 
 int ptb_stage_compact(PtbContext *c, int n, const int32_t *ids, const int32_t *flags, int32_t *outIds, int32_t *outCount) {
     if (!c || n < 0 || !outCount) return fail(PTB_ERR_INVALID, "ptb_stage_compact: bad argument");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     DevBuf<int> di, df, dout; DevBuf<uint32_t> cnt;
     CU(di.alloc(n)); CU(df.alloc(n)); CU(dout.alloc(n)); CU(cnt.alloc(1));
     CU(cudaMemsetAsync(cnt.p, 0, 4, c->stream));
@@ -872,7 +1263,7 @@ int ptb_stage_compact(PtbContext *c, int n, const int32_t *ids, const int32_t *f
 int ptb_stage_sort_keys(PtbContext *c, int n, const int32_t *keys, int numKeys, int32_t *outOrder) {
     if (!c || n < 0 || numKeys <= 0 || numKeys > 8192) return fail(PTB_ERR_INVALID, "ptb_stage_sort_keys: bad argument");
     for (int i = 0; i < n; ++i) if (keys[i] < 0 || keys[i] >= numKeys) return fail(PTB_ERR_INVALID, "ptb_stage_sort_keys: key %d out of range", keys[i]);
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     DevBuf<int> dk, dord; DevBuf<uint32_t> hist;
     CU(dk.alloc(n)); CU(dord.alloc(n)); CU(hist.alloc(numKeys));
     CU(cudaMemsetAsync(hist.p, 0, sizeof(uint32_t) * numKeys, c->stream));
@@ -892,7 +1283,7 @@ int ptb_stage_sort_keys(PtbContext *c, int n, const int32_t *keys, int numKeys, 
 
 int ptb_stage_arith(PtbContext *c, int n, const float *a, const float *b, float *quot, float *root, float *normY) {
     if (!c || n < 0 || !a || !b || !quot || !root || !normY) return fail(PTB_ERR_INVALID, "ptb_stage_arith: bad argument");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     DevBuf<float> da, db, dq, dr, dn;
     CU(da.alloc(n)); CU(db.alloc(n)); CU(dq.alloc(n)); CU(dr.alloc(n)); CU(dn.alloc(n));
     if (n) {
@@ -912,7 +1303,7 @@ int ptb_stage_arith(PtbContext *c, int n, const float *a, const float *b, float 
 
 int ptb_stage_sincos(PtbContext *c, int n, const float *angles, float *sinOut, float *cosOut) {
     if (!c || n < 0 || !angles || !sinOut || !cosOut) return fail(PTB_ERR_INVALID, "ptb_stage_sincos: bad argument");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     DevBuf<float> da, ds, dc;
     CU(da.alloc(n)); CU(ds.alloc(n)); CU(dc.alloc(n));
     if (n) {
@@ -930,7 +1321,7 @@ int ptb_stage_sincos(PtbContext *c, int n, const float *angles, float *sinOut, f
 
 int ptb_stage_rng(PtbContext *c, int iter, int index, int depth, int n, float *out) {
     if (!c || n < 0 || !out) return fail(PTB_ERR_INVALID, "ptb_stage_rng: bad argument");
-    CU(cudaSetDevice(c->device));
+    ON_DEVICE(c->device);
     DevBuf<float> d;
     CU(d.alloc(n));
     if (n) {

@@ -40,8 +40,8 @@ void geomBounds(const PtbGeom &g, float lo[3], float hi[3], double reach) {
         if (!std::isfinite(farPad)) farPad = 4.0 * reach;
     }
     // knobs of A/B and validation runs (tools/gpu_bvh_pathdiff.py); read per call, the tests flip them between builds
-    const bool tight = [] { const char *e = getenv("PTB_BVH_TIGHT_SPHERES"); return e ? atoi(e) != 0 : PTB_BVH_TIGHT_SPHERES != 0; }();
-    const double extra = [] { const char *x = getenv("PTB_BVH_EXTRA_PAD"); return x ? atof(x) : 0.0; }();
+    const bool tight = [] { const char *e = tuningEnv("PTB_BVH_TIGHT_SPHERES"); return e ? atoi(e) != 0 : PTB_BVH_TIGHT_SPHERES != 0; }();
+    const double extra = [] { const char *x = tuningEnv("PTB_BVH_EXTRA_PAD"); return x ? atof(x) : 0.0; }();
     for (int r = 0; r < 3; ++r) {
         const double c = m[12 + r];
         const double rowAbs = std::fabs((double)m[0 + r]) + std::fabs((double)m[4 + r]) + std::fabs((double)m[8 + r]);
@@ -170,9 +170,11 @@ struct Builder {
         const int me = (int)nodes.size();
         nodes.push_back(nd);
         maxDepth = std::max(maxDepth, depth);
-        if (count <= maxLeaf || depth > 56) {
-            if (count <= 8 || depth > 56) return me;                    // forced leaf (bounded by the 64-entry stack)
-        }
+        if (count <= maxLeaf) return me;                                // leaves hold at most maxLeaf (<= 8) primitives: the 4-bit count of the leaf encoding
+        // A degenerate chain (SAH peeling one primitive per level off a pathological centroid distribution) is finished with
+        // median splits: this subtree then adds at most log2(count) <= 27 levels, so the tree is never deeper than ~70 levels
+        // and the traversal stack (sized from maxDepth, ptb200.cu) stays small.
+        const bool medianOnly = depth > 40;
         // binned SAH: the cheapest of the bin boundaries of all three centroid axes (falling back to a median split on
         // the widest axis).  Searching the widest axis only: 4 451 instead of 3 999 us per iteration of the 100 k-object scene.
         int axis = 0;
@@ -180,9 +182,9 @@ struct Builder {
         for (int a = 1; a < 3; ++a) if (cb.hi[a] - cb.lo[a] > ext) { ext = cb.hi[a] - cb.lo[a]; axis = a; }
         int mid = first + count / 2;
         constexpr int NB = PTB_BVH_BINS;
-        const bool allAxes = [] { const char *e = getenv("PTB_BVH_ALL_AXES"); return e ? atoi(e) != 0 : PTB_BVH_ALL_AXES != 0; }();   // knob for A/B runs
+        const bool allAxes = [] { const char *e = tuningEnv("PTB_BVH_ALL_AXES"); return e ? atoi(e) != 0 : PTB_BVH_ALL_AXES != 0; }();   // knob for A/B runs
         float bestCost = FLT_MAX; int bestB = -1, bestAxis = -1; float bestK = 0.f;
-        for (int ax = 0; ax < 3; ++ax) {
+        for (int ax = 0; ax < 3 && !medianOnly; ++ax) {
             const float e = cb.hi[ax] - cb.lo[ax];
             if (!(e > 0.f)) continue;
             if (!allAxes && ax != axis) continue;
@@ -206,7 +208,6 @@ struct Builder {
             }
         }
         if (bestB >= 0) {
-            if (count <= maxLeaf && bestCost >= nd.box.area() * count) return me;   // a leaf is cheaper
             const int ax = bestAxis; const float k = bestK;
             auto it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](const Prim &p) {
                 int b = (int)((p.cen[ax] - cb.lo[ax]) * k);
@@ -216,7 +217,6 @@ struct Builder {
             mid = (int)(it - prims.begin());
         }
         if (mid <= first || mid >= first + count) {
-            if (count <= maxLeaf) return me;
             mid = first + count / 2;
             std::nth_element(prims.begin() + first, prims.begin() + mid, prims.begin() + first + count,
                              [&](const Prim &a, const Prim &b) { return a.cen[axis] < b.cen[axis]; });
@@ -237,7 +237,7 @@ struct Builder {
 // of that scene).
 FarPadScene defaultFarPadScene(const PtbGeom *geoms, int n, const float *cameraPosition) {
     FarPadScene s;
-    if (const char *e = getenv("PTB_BVH_FAR_PAD")) if (atoi(e) == 0) return s;
+    if (const char *e = tuningEnv("PTB_BVH_FAR_PAD")) if (atoi(e) == 0) return s;
     for (int a = 0; a < 3; ++a) { s.lo[a] = DBL_MAX; s.hi[a] = -DBL_MAX; }
     if (cameraPosition) for (int a = 0; a < 3; ++a) s.lo[a] = s.hi[a] = cameraPosition[a];
     for (int i = 0; i < n; ++i) {
@@ -343,8 +343,8 @@ void buildBvhBoxes(const float *lo, const float *hi, int n, int maxLeaf, HostBvh
 // (same bounds, same builder, same PTB_BVH_* knobs), returned as HostBvhNode records.  No CUDA call.
 extern "C" int ptb_bvh_build_host(const PtbGeom *geoms, int32_t numGeoms, int32_t maxLeaf, double farPadDiameter, float *nodes, int32_t nodeCap,
                                   int32_t *order, int32_t *numNodes, int32_t *maxDepth) {
-    if (numGeoms < 0 || (numGeoms > 0 && !geoms) || !numNodes) return PTB_ERR_INVALID;
-    for (int i = 0; i < numGeoms; ++i) if (geoms[i].type != 0 && geoms[i].type != 1) return PTB_ERR_INVALID;
+    if (numGeoms < 0 || (numGeoms > 0 && !geoms) || !numNodes) return ptb_set_last_error(PTB_ERR_INVALID, "ptb_bvh_build_host: bad argument");
+    for (int i = 0; i < numGeoms; ++i) if (geoms[i].type != 0 && geoms[i].type != 1) return ptb_set_last_error(PTB_ERR_INVALID, "ptb_bvh_build_host: only SPHERE / CUBE geoms");
     ptb::HostBvh hb;
     if (farPadDiameter < 0.0) {
         const ptb::FarPadScene scene = ptb::defaultFarPadScene(geoms, numGeoms, nullptr);
@@ -353,7 +353,7 @@ extern "C" int ptb_bvh_build_host(const PtbGeom *geoms, int32_t numGeoms, int32_
     *numNodes = (int32_t)hb.nodes.size();
     if (maxDepth) *maxDepth = hb.maxDepth;
     if (nodes) {
-        if (nodeCap < (int32_t)hb.nodes.size()) return PTB_ERR_INVALID;
+        if (nodeCap < (int32_t)hb.nodes.size()) return ptb_set_last_error(PTB_ERR_INVALID, "ptb_bvh_build_host: nodeCap smaller than the node count");
         std::copy(hb.nodes.begin(), hb.nodes.end(), reinterpret_cast<ptb::HostBvhNode *>(nodes));
     }
     if (order) std::copy(hb.order.begin(), hb.order.end(), order);
@@ -363,7 +363,7 @@ extern "C" int ptb_bvh_build_host(const PtbGeom *geoms, int32_t numGeoms, int32_
 // Host-only: the pruning bounds of one SPHERE / CUBE geom as ptb_create packs them for the kernels (ptb200.cu packGeom: the padded
 // world box of geomBounds with the given reach, and for spheres the bounding sphere and discriminant slack of sphereBounds).
 extern "C" int ptb_geom_bounds_host(const PtbGeom *geom, double reach, float lo[3], float hi[3], float centre[3], float *radius2, float *errK) {
-    if (!geom || !lo || !hi || (geom->type != 0 && geom->type != 1)) return PTB_ERR_INVALID;
+    if (!geom || !lo || !hi || (geom->type != 0 && geom->type != 1)) return ptb_set_last_error(PTB_ERR_INVALID, "ptb_geom_bounds_host: bad argument (SPHERE / CUBE geoms only)");
     ptb::geomBounds(*geom, lo, hi, reach > 0.0 ? reach : 0.0);
     if (geom->type == 0 && centre && radius2) ptb::sphereBounds(*geom, centre, radius2, errK);
     return PTB_OK;

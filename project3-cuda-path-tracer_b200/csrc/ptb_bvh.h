@@ -3,10 +3,23 @@
 // a hierarchical structure is an assignment ask, INSTRUCTION.md:123-140).
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <vector>
 #include "ptb200.h"
 
+// sets the thread-local message ptb_last_error() returns (defined in ptb200.cu); returns `code`
+extern "C" int ptb_set_last_error(int code, const char *msg);
+
 namespace ptb {
+
+// Environment knobs of A/B and validation runs (PTB_BVH_*, PTB_LOOP_BOUNCES, PTB_GRID_MULT ...) exist in TUNING builds only
+// (make tuning -> libptb200_tuning.so, -DPTB_TUNING).  Several of them change which hits are found (PTB_BVH_TIGHT_SPHERES=1 and
+// PTB_BVH_FAR_PAD=0 lose reference hits): the release library never reads the environment.
+#ifdef PTB_TUNING
+inline const char *tuningEnv(const char *name) { return getenv(name); }
+#else
+inline const char *tuningEnv(const char *) { return nullptr; }
+#endif
 
 struct HostBvhNode {             // mirrors ptb::BvhNode (64 B)
     float llo[3]; int32_t lref; float lhi[3]; int32_t lcount;

@@ -91,6 +91,11 @@ struct Params {
     const int     *fbMeta;       // ... and geom slot | outside << 30, -1 = miss
     uint32_t      *segCounts;    // fused pipeline: 2 x grid per-CTA survivor counts (ping-pong by depth parity)
     uint32_t       segCap;       // fused pipeline: path slots per CTA segment
+    uint32_t       vgrid;        // fused pipeline: number of CTA-owned segments (= grid of the bounce kernels); trace_kernel serves them with its own grid
+    int           *stackSpill;   // trace_kernel: traversal-stack entries beyond the shared-memory part (NULL when the tree is shallow enough)
+    int            spillCap;     // ... per ray slot
+    float         *partial;      // ordered deposit (PTB_DEPOSIT_ORDERED, batch > 1): batch partial images of partialStride floats; NULL = deposit into image
+    uint32_t       partialStride;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -387,113 +392,6 @@ PTB_DEV GeomRec loadGeom(const GeomRec *gp) {
     return g;
 }
 
-// Stage C of the BVH searches: the reference-exact test of primitive `cand` (leaf-order table) and the
-// closest-hit rule.  type 2 = mesh triangle (its vertices are the record's nrm rows).
-// MESH = false compiles the triangle path out (scenes without meshes run the round-1 code).
-template <bool MESH>
-PTB_DEV void exactCandidate(const GeomRec *geoms, int cand, int candType, f3 o, f3 qo, f3 qu, Candidate &best, int &bestOrig) {
-    const float4 *gp = reinterpret_cast<const float4 *>(geoms + cand);
-    Affine fwd, vtx;
-    fwd.r0 = __ldg(gp + 3); fwd.r1 = __ldg(gp + 4); fwd.r2 = __ldg(gp + 5);
-    vtx.r0 = vtx.r1 = vtx.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
-    const int2 ord = __ldg(reinterpret_cast<const int2 *>(gp + 9) + 1);          // tag.z = scene order, tag.w = object index
-    bool sameMesh = false;
-    if (MESH && candType == 2) {
-        vtx.r0 = __ldg(gp + 6); vtx.r1 = __ldg(gp + 7); vtx.r2 = __ldg(gp + 8);
-        if (best.slot >= 0) sameMesh = __ldg(reinterpret_cast<const int *>(geoms + best.slot) + 39) == ord.y;   // word 39 = tag.w
-    }
-    int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
-    const float t = exactTestCore<MESH>(candType, fwd, vtx, o, qo, qu, outside, a, b, c);
-    if (takesOver(sameMesh, t, a, ord.x, best.t, best.a, bestOrig)) {            // src/pathtrace.cu:192 + index tie rule
-        best.t = t; best.slot = cand; best.outside = outside; best.a = a; best.b = b; best.c = c; bestOrig = ord.x;
-    }
-}
-
-// Closest hit through the flat BVH.  Warp-collective (all 32 lanes call it; `valid` = the lane carries a
-// ray).  Three kinds of work alternate, and the expensive one is entered by the lanes TOGETHER:
-//   A. traversal steps: fetch a 64-byte node (shared memory for the top levels), slab-test both child
-//      boxes, descend into the nearer child and push the other (interior node index, or an encoded
-//      leaf) on the per-lane stack;
-//   B. per-primitive pruning of the pending leaf: the padded world-space bound of the primitive
-//      (48 bytes: tag, b0, b1), then -- only when that lower bound can still beat the best distance
-//      -- the exact object-space ray (48 more bytes) and the sure-miss filter;
-//   C. the reference-exact test of a primitive that survived B.
-// A lane runs A/B in a cheap loop until it HAS a candidate for C (or is finished); `__any_sync` then
-// brings the lanes together and every lane with a candidate runs the one copy of the exact test.  With
-// the exact test inlined in the traversal loop (one lane at a leaf, 31 waiting) only 4 of 32 lanes
-// were active on the 100 k-object scene.
-// Pruning uses padded boxes and slackened distance bounds only; the winner is the same
-// (t, scene index)-lexicographic minimum that the reference's index-ordered loop finds
-// (src/pathtrace.cu:176-199).
-PTB_DEV void closestHitBvh(const Params &p, const BvhNode *snodes, const int smemNodes, f3 o, f3 d, bool valid, Candidate &best) {
-    best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
-    int bestOrig = 0x7fffffff;
-    const float dd = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
-    const float rinv = rsqrtApprox(dd);
-    const float rdLen = dd * rinv;                                // |d|
-    const f3 dn = mk3(d.x * rinv, d.y * rinv, d.z * rinv);
-    const f3 invD = mk3(rcpApprox(d.x), rcpApprox(d.y), rcpApprox(d.z));
-    const float dl = rdLen * 0.9999f;
-    const float slack = 2e-5f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f);
-    int stack[64];
-    int sp = 0;
-    int node = valid ? 0 : -1;                                    // -1: take the next entry from the stack
-    bool done = !valid;
-    int primRef = 0, primCnt = 0;                                 // pending leaf: geoms[primRef .. primRef + primCnt)
-    int cand = -1;                                                // primitive waiting for the exact test
-    f3 qo = mk3(0.f, 0.f, 0.f), qu = qo;
-    int candType = 0;
-    // One warp-uniform loop; the votes at its head make the lanes reconverge EVERY step (a per-lane
-    // `while` with early exits lets divergent groups drift apart for the whole traversal).
-    for (;;) {
-        const unsigned waiting = __ballot_sync(0xffffffffu, cand >= 0);
-        const unsigned working = __ballot_sync(0xffffffffu, cand < 0 && !done);
-        if (!(waiting | working)) break;
-        if (waiting && (!working || __popc(waiting) >= 8)) {
-            if (cand >= 0) {
-                // ---- C: the reference-exact test
-                exactCandidate<true>(p.geoms, cand, candType, o, qo, qu, best, bestOrig);
-                cand = -1;
-            }
-            continue;
-        }
-        if (cand >= 0 || done) continue;
-        if (primCnt > 0) {
-            // ---- B: prune one primitive of the pending leaf
-            const int slot = primRef;
-            ++primRef; --primCnt;
-            const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + slot);
-            const int4 tag = __ldg(reinterpret_cast<const int4 *>(gp + 9));
-            const float4 b0 = __ldg(gp + 10), b1 = __ldg(gp + 11);
-            const bool isCube = tag.x == 1;
-            const float e = boundEntryRaw(tag.x != 0, b0, b1, o, invD, dn, rdLen);       // cubes and triangles: padded world box
-            if (e >= 0.0f && fmaf(e, 0.99998f, -slack) <= best.t) {
-                Affine inv;
-                inv.r0 = __ldg(gp); inv.r1 = __ldg(gp + 1); inv.r2 = __ldg(gp + 2);
-                qo = mulMVPoint(inv, o);
-                qu = mulMV(inv, d, 0.0f);
-                if (tag.x == 2 || !sureMissT(isCube, qo, qu)) { cand = slot; candType = tag.x; }
-            }
-            continue;
-        }
-        // ---- A: one traversal step
-        if (node < 0) {
-            if (sp == 0) { done = true; continue; }
-            const int e = stack[--sp];
-            if (e < 0) { const int enc = ~e; primRef = enc & 0x7ffffff; primCnt = enc >> 27; continue; }
-            node = e;
-        }
-        int next, far; bool haveNext, haveFar;
-        bvhNodeStep(snodes, smemNodes, p.bvh, node, o, invD, dl, best.t, next, haveNext, far, haveFar);
-        if (haveFar && sp < 64) stack[sp++] = far;
-        node = -1;
-        if (haveNext) {
-            if (next < 0) { const int enc = ~next; primRef = enc & 0x7ffffff; primCnt = enc >> 27; }
-            else node = next;
-        }
-    }
-}
-
 struct Mat { f3 color; float emittance; f3 spec; float refl; float refr; float ior; float specex; };
 PTB_DEV Mat loadMat(const float4 *mats, int id) {
     float4 a = __ldg(&mats[3 * id]), b = __ldg(&mats[3 * id + 1]), c = __ldg(&mats[3 * id + 2]);
@@ -601,8 +499,18 @@ PTB_DEV bool shadeStep(const Params &p, int depth, int iter, uint32_t pix, bool 
 }
 
 // image[pixelIndex] += color (src/pathtrace.cu:276).  A zero colour is skipped: x + 0 == x.
-PTB_DEV void deposit(const Params &p, uint32_t pix, f3 c) {
+// One iteration per wavefront (batch 1): one writer per pixel, a plain read-modify-write.  Several iterations per wavefront:
+//   * ordered (default): slot s (= iteration iterBase + s * iterStride) STORES into its own partial image -- every (slot, pixel)
+//     pair terminates exactly once per wavefront -- and deposit_reduce_kernel adds the partial images to image[] in slot order,
+//     which is bit for bit the sum the reference's loop builds one iteration at a time, reproducible for any batch size;
+//   * atomic: float atomicAdd into image[] (the order of the additions inside a wavefront is not defined).
+PTB_DEV void deposit(const Params &p, uint32_t pix, uint32_t slot, f3 c) {
     if (c.x == 0.0f && c.y == 0.0f && c.z == 0.0f) return;
+    if (p.partial) {
+        float *px = p.partial + (size_t)slot * p.partialStride + 3 * (size_t)pix;
+        px[0] = c.x; px[1] = c.y; px[2] = c.z;
+        return;
+    }
     float *px = p.image + 3 * (size_t)pix;
     if (p.atomicGather) {
         atomicAdd(px + 0, c.x); atomicAdd(px + 1, c.y); atomicAdd(px + 2, c.z);
@@ -683,198 +591,9 @@ PTB_DEV uint32_t compactSlot(bool keep, uint32_t *counter, int *warpTotals, uint
     return dst;
 }
 
-// ------------------------------------------------------------------------------------------------
-// BVH scenes, fused pipeline: closest hit as its own PERSISTENT-THREADS kernel with dynamic ray fetch.
-//
-// The traversal length of a ray through the 100 k-object scene varies by an order of magnitude, and a
-// warp that owns 32 fixed rays runs until its longest one is finished: measured on the fused bounce
-// kernel, 545 traversal steps per warp against 170 per ray, 8.9 of 32 lanes active.  Here a lane that
-// finishes its ray writes the raw hit record and goes idle; as soon as kRefillLanes lanes of the warp are
-// idle (or all of them) the warp takes that many tickets from the CTA's queue with ONE shared-memory atomic
-// and the idle lanes start new rays, so the warp stays populated until the CTA's rays run out.
-// The rays of a CTA are the paths of its own segment (bounce_kernel's CTA-owned path segments), so the
-// hit record of path slot i lands at hits[i] and the bounce kernel that follows (USE_BVH: shade, scatter,
-// compact) reads it back with the path: 20 B written + 20 B read per segment, against ~10^4 thread
-// instructions of traversal.
-// Raw hit record: hits.tn[i] = (t, a, b, c) -- (a, b, c) is what the deferred normal needs (Candidate) --
-// and hits.meta[i] = geom slot | outside << 30, or -1 for a miss.
-// The traversal itself is closestHitBvh's A / B / C state machine.
-// ------------------------------------------------------------------------------------------------
-#ifndef PTB_REFILL_LANES
-#define PTB_REFILL_LANES 8
-#endif
-constexpr int kRefillLanes = PTB_REFILL_LANES;
-// Stage thresholds of the state machine below, tuned on the synthetic 100 k-object scene (profiles/r02_bvh_state_machine_ab.txt:
-// 5 994 -> 4 442 us per iteration):
-#ifndef PTB_BVH_STEPS
-#define PTB_BVH_STEPS 8
-#endif
-constexpr int kStepsPerPass = PTB_BVH_STEPS;                       // traversal steps (stage A) per pass
-#ifndef PTB_PRUNE_LANES
-#define PTB_PRUNE_LANES 8
-#endif
-constexpr int kPruneLanes = PTB_PRUNE_LANES;                       // lanes with a pending leaf that gather before stage B runs
-#ifndef PTB_EXACT_LANES
-#define PTB_EXACT_LANES 1
-#endif
-constexpr int kExactLanes = PTB_EXACT_LANES;                       // lanes with a candidate that gather before stage C runs
-
-#ifndef PTB_BVH_MINBLOCKS
-#define PTB_BVH_MINBLOCKS PTB_MINBLOCKS
-#endif
-template <bool FIRST, bool EXT, bool MESH>
-__global__ void __launch_bounds__(kBlock, PTB_BVH_MINBLOCKS) trace_bvh_kernel(const __grid_constant__ Params p, const int depth) {
-    extern __shared__ float4 smem4[];
-    __shared__ uint32_t sNextTicket;
-    if (threadIdx.x == 0) sNextTicket = 0u;
-    const int smemNodes = p.hdr->smemNodes;
-    stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);      // ends with __syncthreads
-    const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
-    CameraParams cam;
-    if (FIRST) cam = p.hdr->cam;
-    int iterBase = 0, iterStride = 0;
-    if (FIRST && EXT) { iterBase = p.ctrl->iterBase; iterStride = p.ctrl->iterStride; }
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t laneBelow = (1u << lane) - 1u;
-    const uint32_t segBase = blockIdx.x * p.segCap;
-    uint32_t total, nTickets;
-    if (FIRST) {
-        total = p.numPixels * (uint32_t)p.ctrl->batch;
-        const uint32_t tiles = (total + kBlock - 1) / kBlock;
-        nTickets = (tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u) * kBlock;
-    } else {
-        total = p.segCounts[((depth + 1) & 1) * gridDim.x + blockIdx.x];
-        nTickets = total;
-    }
-
-    // per-lane ray and traversal state
-    f3 o = mk3(0.f, 0.f, 0.f), d = o, invD = o, dn = o;
-    float rdLen = 0.f, dl = 0.f, slack = 0.f;
-    Candidate best;
-    best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
-    int bestOrig = 0x7fffffff;
-    int stack[64];
-    int sp = 0, node = -1;
-    int primRef = 0, primCnt = 0;                                 // pending leaf: geoms[primRef .. primRef + primCnt)
-    int cand = -1;                                                // primitive waiting for the exact test
-    f3 qo = o, qu = o;
-    int candType = 0;
-    bool done = true;                                             // the lane holds no ray
-    bool drained = false;                                         // warp-uniform: the CTA's queue is empty
-    uint32_t idx = 0;                                             // hit-record index of the lane's ray
-
-    for (;;) {
-        // ---- refill: idle lanes take tickets
-        const unsigned idle = __ballot_sync(0xffffffffu, done);
-        if (!drained && (idle == 0xffffffffu || __popc(idle) >= kRefillLanes)) {
-            const uint32_t want = (uint32_t)__popc(idle);
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&sNextTicket, want);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            drained = base + want >= nTickets;
-            if (done) {
-                const uint32_t k = base + (uint32_t)__popc(idle & laneBelow);
-                bool have = k < nTickets;
-                if (have) {
-                    if (FIRST) {
-                        const uint32_t tile = blockIdx.x + (k / kBlock) * gridDim.x;
-                        idx = tile * kBlock + (k % kBlock);
-                        have = idx < total;
-                        if (have) {
-                            const uint32_t slot = idx / p.numPixels;
-                            cameraRayIter<EXT>(cam, idx - slot * p.numPixels, iterBase + (int)slot * iterStride, o, d);
-                        }
-                    } else {
-                        idx = segBase + k;
-                        const float4 a = p.in.A[idx], b = p.in.B[idx];
-                        o = mk3(a.x, a.y, a.z); d = mk3(a.w, b.x, b.y);
-                    }
-                }
-                if (have) {
-                    const float dd = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
-                    const float rinv = rsqrtApprox(dd);
-                    rdLen = dd * rinv;                            // |d|
-                    dn = mk3(d.x * rinv, d.y * rinv, d.z * rinv);
-                    invD = mk3(rcpApprox(d.x), rcpApprox(d.y), rcpApprox(d.z));
-                    dl = rdLen * 0.9999f;
-                    slack = 2e-5f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f);
-                    best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
-                    bestOrig = 0x7fffffff;
-                    sp = 0; node = 0; primCnt = 0; cand = -1;
-                    done = false;
-                }
-            }
-        }
-        if (__ballot_sync(0xffffffffu, !done) == 0u) {
-            if (drained) break;
-            continue;                                             // every lane idle: the next pass refills
-        }
-        // One pass = kStepsPerPass x A, then B (when kPruneLanes lanes hold a pending leaf, or nobody can step), then C
-        // (when kExactLanes lanes hold a candidate, or nobody else can work), each a plain `if` the lanes reconverge
-        // after: a lane whose leaf survives B can take part in this pass's exact test.
-        // ---- A: traversal steps (lanes with nothing pending); kStepsPerPass of them per pass, because a pass costs
-        // ~40 instructions of votes and branches whatever its lanes do and most passes are traversal only
-#pragma unroll 1
-        for (int rep = 0; rep < kStepsPerPass; ++rep)
-        if (!done && cand < 0 && primCnt == 0) {
-            if (node < 0) {
-                if (sp == 0) {
-                    // the ray is finished: raw hit record out, lane idle
-                    p.hits.tn[idx] = make_float4(best.slot >= 0 ? best.t : -1.0f, best.a, best.b, best.c);
-                    p.hits.meta[idx] = best.slot >= 0 ? (best.slot | (best.outside << 30)) : -1;
-                    done = true;
-                } else {
-                    const int e = stack[--sp];
-                    if (e < 0) { const int enc = ~e; primRef = enc & 0x7ffffff; primCnt = enc >> 27; }
-                    else node = e;
-                }
-            }
-            if (node >= 0) {
-                int next, far; bool haveNext, haveFar;
-                bvhNodeStep(snodes, smemNodes, p.bvh, node, o, invD, dl, best.t, next, haveNext, far, haveFar);
-                if (haveFar && sp < 64) stack[sp++] = far;
-                node = -1;
-                if (haveNext) {
-                    if (next < 0) { const int enc = ~next; primRef = enc & 0x7ffffff; primCnt = enc >> 27; }
-                    else node = next;
-                }
-            }
-        }
-        // ---- B: prune one primitive of the pending leaf, entered by kPruneLanes lanes together (or when no lane has
-        // traversal work left): with every lane pruning on its own this stage ran with 2 of 32 lanes active
-        const bool pending = !done && cand < 0 && primCnt > 0;
-        const unsigned pend = __ballot_sync(0xffffffffu, pending);
-        const unsigned canStep = __ballot_sync(0xffffffffu, !done && cand < 0 && primCnt == 0);
-        if (pend && ((int)__popc(pend) >= kPruneLanes || !canStep) && pending) {
-            const int slot = primRef;
-            ++primRef; --primCnt;
-            const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + slot);
-            const int4 tag = __ldg(reinterpret_cast<const int4 *>(gp + 9));
-            const float4 b0 = __ldg(gp + 10), b1 = __ldg(gp + 11);
-            const bool isCube = tag.x == 1;
-            const float e = boundEntryRaw(tag.x != 0, b0, b1, o, invD, dn, rdLen);       // cubes and triangles: padded world box
-            if (e >= 0.0f && fmaf(e, 0.99998f, -slack) <= best.t) {
-                Affine inv;
-                inv.r0 = __ldg(gp); inv.r1 = __ldg(gp + 1); inv.r2 = __ldg(gp + 2);
-                qo = mulMVPoint(inv, o);
-                qu = mulMV(inv, d, 0.0f);
-                bool miss = boxSureMiss(qo, qu);
-                if (!isCube) miss = sphereSureMiss(qo, qu);
-                if (MESH && tag.x == 2) miss = false;                                     // triangles go straight to the exact test
-                if (!miss) { cand = slot; candType = tag.x; }
-            }
-        }
-        // ---- C: the reference-exact test, entered by the waiting lanes together
-        const unsigned waiting = __ballot_sync(0xffffffffu, cand >= 0);
-        const unsigned working = __ballot_sync(0xffffffffu, cand < 0 && !done);
-        if (waiting && (!working || __popc(waiting) >= kExactLanes)) {
-            if (cand >= 0) {
-                exactCandidate<MESH>(p.geoms, cand, candType, o, qo, qu, best, bestOrig);
-                cand = -1;
-            }
-        }
-    }
-}
+} // namespace ptb
+#include "ptb_trace.cuh"
+namespace ptb {
 
 // ------------------------------------------------------------------------------------------------
 // THE FAST PATH: one launch per bounce.  FIRST = bounce 0 (camera rays generated in registers, no
@@ -934,7 +653,7 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
         const bool cached = FIRST && p.fbTn != nullptr;            // warp-uniform
         if (!USE_BVH && !cached) closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
         if (USE_BVH && !cached && valid) {
-            // BVH scenes: trace_bvh_kernel ran before this launch and left the raw hit record of every path
+            // BVH scenes: trace_kernel ran before this launch and left the raw hit record of every path
             const uint32_t h = FIRST ? hitIndex : segBase + chunk * 32u + lane;
             const int meta = p.hits.meta[h];
             best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
@@ -980,7 +699,7 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
             }
             const int iter = iterBase + (int)slot * iterStride;
             alive = shadeStep<EXT>(p, depth, iter, pix, isHit, matId, best.t, n, best.outside, o, d, c, remainingBefore);
-            if (!alive) deposit(p, pix, c);                               // gather at termination
+            if (!alive) deposit(p, pix, slot, c);                         // gather at termination
         }
         // CTA-local stream compaction: ballot + popc prefix, one shared-memory atomic per warp
         const unsigned ballot = __ballot_sync(0xffffffffu, alive);
@@ -1000,7 +719,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
 
     if (threadIdx.x == 0) sOutCount = 0u;
     const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
-    // USE_BVH: the closest hits were found by trace_bvh_kernel (raw hit records in p.hits); nothing to stage
+    // USE_BVH: the closest hits were found by trace_kernel (raw hit records in p.hits); nothing to stage
     if (USE_BVH) __syncthreads();
     else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);      // ends with __syncthreads
     const GeomRec *sgeoms = heldSharedBase<GeomRec>(smem4);
@@ -1068,15 +787,12 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_loop_kernel(cons
 
 // First-bounce cache fill (INSTRUCTION.md:87-89): the bounce-0 hit record of every pixel, computed once
 // per scene/camera upload with the same closest-hit code the bounce kernels run.
-template <bool USE_BVH>
+// Brute-force scenes; BVH scenes fill the cache with trace_kernel<SRC_PIXELS> + resolve_hits_kernel.
 __global__ void __launch_bounds__(kBlock) fb_cache_kernel(const __grid_constant__ Params p, float4 *tnOut, int *metaOut) {
     extern __shared__ float4 smem4[];
-    const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
-    const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
-    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
-    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
+    const int numCubes = p.hdr->numCubes;
+    stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
-    const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
     const CameraParams cam = p.hdr->cam;
     for (uint32_t base = blockIdx.x * kBlock; base < p.numPixels; base += gridDim.x * kBlock) {   // warp-uniform trip count
         const uint32_t pix = base + threadIdx.x;
@@ -1084,12 +800,10 @@ __global__ void __launch_bounds__(kBlock) fb_cache_kernel(const __grid_constant_
         f3 o = mk3(0.f, 0.f, 0.f), d = o;
         if (valid) cameraRay(cam, pix, o, d);
         Candidate best;
-        if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, valid, best);
-        else         closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
+        closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
         if (!valid) continue;
         if (best.slot < 0) { tnOut[pix] = make_float4(-1.0f, 0.f, 0.f, 0.f); metaOut[pix] = -1; continue; }
-        const GeomRec &g = USE_BVH ? p.geoms[best.slot] : sgeoms[best.slot];
-        const f3 n = candidateNormal(g, best);
+        const f3 n = candidateNormal(sgeoms[best.slot], best);
         tnOut[pix] = make_float4(best.t, n.x, n.y, n.z);
         metaOut[pix] = best.slot | (best.outside << 30);
     }
@@ -1130,15 +844,12 @@ __global__ void __launch_bounds__(kBlock) raygen_kernel(const __grid_constant__ 
 }
 
 // computeIntersections (src/pathtrace.cu:149-213): writes one hit record per live path
-template <bool USE_BVH>
+// Brute-force scenes; BVH scenes run trace_kernel<SRC_PATHS> + resolve_hits_kernel instead.
 __global__ void __launch_bounds__(kBlock) intersect_kernel(const __grid_constant__ Params p, const int depth) {
     extern __shared__ float4 smem4[];
-    const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
-    const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
-    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
-    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
+    const int numCubes = p.hdr->numCubes;
+    stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
-    const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
     const uint32_t nIn = p.ctrl->counts[depth];
     for (uint32_t base = blockIdx.x * kBlock; base < nIn; base += gridDim.x * kBlock) {   // warp-uniform trip count
         const uint32_t i = base + threadIdx.x;
@@ -1146,16 +857,14 @@ __global__ void __launch_bounds__(kBlock) intersect_kernel(const __grid_constant
         if (i < nIn) loadPath(p.in, i, o, d, c, id);
         const bool valid = !(id & kDeadBit);                             // no-compaction mode: dead path stays in place
         Candidate best;
-        if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, valid, best);
-        else         closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
+        closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
         if (i >= nIn) continue;
         if (!valid) { p.hits.meta[i] = -1; continue; }
         if (best.slot < 0) {
             p.hits.tn[i] = make_float4(-1.0f, 0.f, 0.f, 0.f);             // src/pathtrace.cu:203
             p.hits.meta[i] = -1;
         } else {
-            const GeomRec &g = USE_BVH ? p.geoms[best.slot] : sgeoms[best.slot];
-            const f3 n = candidateNormal(g, best);
+            const f3 n = candidateNormal(sgeoms[best.slot], best);
             p.hits.tn[i] = make_float4(best.t, n.x, n.y, n.z);
             p.hits.meta[i] = best.slot | (best.outside << 30);
         }
@@ -1188,7 +897,7 @@ __global__ void __launch_bounds__(kBlock) shade_kernel(const __grid_constant__ P
         const bool alive = shadeStep<true>(p, depth, iterBase + (int)slot * iterStride, pix, isHit, matId, t, n, outside,
                                      o, d, c, p.traceDepth - depth);
         if (!alive) {
-            if (depositAtTermination) deposit(p, pix, c);
+            if (depositAtTermination) deposit(p, pix, slot, c);
             id |= kDeadBit;
         }
         storePath(p.in, i, o, d, c, id);
@@ -1217,13 +926,50 @@ __global__ void carry_count_kernel(Control *ctrl, int depth) {
 
 // finalGather (src/pathtrace.cu:269-278): image[pixelIndex] += color for every path slot.
 // Paths that never ended on a light carry colour 0 by then.
-__global__ void __launch_bounds__(kBlock) gather_kernel(const __grid_constant__ Params p, const uint32_t nPaths) {
+// The slot count is read on the device (a partial last batch traces fewer slots than the context's batch size, and the
+// launch is replayed from a captured graph: a host constant would gather stale slots of the previous full batch).
+__global__ void __launch_bounds__(kBlock) gather_kernel(const __grid_constant__ Params p) {
     const uint32_t pixMask = (1u << p.pixBits) - 1u;
+    const uint32_t nPaths = p.numPixels * (uint32_t)p.ctrl->batch;
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < nPaths; i += gridDim.x * kBlock) {
         f3 o, d, c; uint32_t id;
         loadPath(p.in, i, o, d, c, id);
         if (!(id & kDeadBit)) c = mk3(0.f, 0.f, 0.f);      // still alive after the last bounce: exhausted
-        deposit(p, id & pixMask, c);
+        deposit(p, id & pixMask, (id & ~kDeadBit) >> p.pixBits, c);
+    }
+}
+
+// Ordered deposit, end of a wavefront: image[i] = (...((image[i] + part[0][i]) + part[1][i]) + ...) over the slots of this
+// batch, i.e. the iterations in ascending order, each a round-to-nearest float add like finalGather's `+=` (src/pathtrace.cu:276).
+// Entries that were written are cleared on the way, so the partial images are all-zero again for the next wavefront.
+// Pure streaming: reads batch x 12 B per pixel (HBM roofline; ~1 % of a cornell wavefront).
+__global__ void __launch_bounds__(kBlock) deposit_reduce_kernel(const __grid_constant__ Params p) {
+    const uint32_t batch = (uint32_t)p.ctrl->batch;
+    const uint32_t n = p.numPixels * 3u, n4 = n / 4u;
+    float4 *img4 = reinterpret_cast<float4 *>(p.image);
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n4; i += gridDim.x * kBlock) {
+        float4 acc = img4[i];
+        bool touched = false;
+        for (uint32_t s = 0; s < batch; ++s) {
+            float4 *q = reinterpret_cast<float4 *>(p.partial + (size_t)s * p.partialStride) + i;
+            const float4 v = *q;
+            if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) {
+                acc.x = add(acc.x, v.x); acc.y = add(acc.y, v.y); acc.z = add(acc.z, v.z); acc.w = add(acc.w, v.w);
+                *q = make_float4(0.f, 0.f, 0.f, 0.f);
+                touched = true;
+            }
+        }
+        if (touched) img4[i] = acc;
+    }
+    // the last n % 4 floats
+    for (uint32_t i = n4 * 4u + blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        float acc = p.image[i];
+        for (uint32_t s = 0; s < batch; ++s) {
+            float *q = p.partial + (size_t)s * p.partialStride + i;
+            const float v = *q;
+            if (v != 0.0f) { acc = add(acc, v); *q = 0.0f; }
+        }
+        p.image[i] = acc;
     }
 }
 
@@ -1236,10 +982,20 @@ __global__ void __launch_bounds__(kBlock) sort_hist_kernel(const int *keys, uint
     __syncthreads();
     for (int k = threadIdx.x; k < numKeys; k += blockDim.x) if (sh[k]) atomicAdd(&hist[k], sh[k]);
 }
-__global__ void sort_scan_kernel(uint32_t *hist, int numKeys) {     // exclusive scan, numKeys is small
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        uint32_t run = 0;
-        for (int k = 0; k < numKeys; ++k) { uint32_t v = hist[k]; hist[k] = run; run += v; }
+__global__ void sort_scan_kernel(uint32_t *hist, int numKeys) {     // exclusive scan by one warp, 32 keys per shuffle scan
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    const int lane = threadIdx.x;
+    uint32_t run = 0;
+    for (int base = 0; base < numKeys; base += 32) {
+        const uint32_t v = base + lane < numKeys ? hist[base + lane] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int sft = 1; sft < 32; sft <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, sft);
+            if (lane >= sft) incl += y;
+        }
+        if (base + lane < numKeys) hist[base + lane] = run + incl - v;
+        run += __shfl_sync(0xffffffffu, incl, 31);
     }
 }
 __global__ void __launch_bounds__(kBlock) sort_scatter_kernel(const int *keys, uint32_t n, uint32_t *cursor, int *order) {
@@ -1262,7 +1018,9 @@ __global__ void __launch_bounds__(kBlock) sort_scatter_kernel(const int *keys, u
     }
 }
 // key of a path for the material sort: its hit material, or numMats for misses / dead slots
-__global__ void __launch_bounds__(kBlock) sort_keys_kernel(const __grid_constant__ Params p, const int depth, int *keys) {
+// (also clears the histogram the next kernel of the sort fills)
+__global__ void __launch_bounds__(kBlock) sort_keys_kernel(const __grid_constant__ Params p, const int depth, int *keys, uint32_t *hist, int numKeys) {
+    if (blockIdx.x == 0) for (int k = threadIdx.x; k < numKeys; k += kBlock) hist[k] = 0u;
     const uint32_t nIn = p.ctrl->counts[depth];
     for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < nIn; i += gridDim.x * kBlock) {
         const int meta = p.hits.meta[i];
@@ -1329,16 +1087,12 @@ __global__ void __launch_bounds__(kBlock) resolve_rgb8_kernel(uint8_t *rgb, cons
 }
 
 // ---- stage-level test kernels (host arrays in / out through ptb_stage_*) ----
-template <bool USE_BVH>
 __global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_constant__ Params p, const float *origins,
         const float *dirs, int n, int *hit, float *t, float *normal, int *outside) {
     extern __shared__ float4 smem4[];
-    const int smemNodes = USE_BVH ? p.hdr->smemNodes : 0;
-    const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
-    if (USE_BVH) stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);
-    else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
+    const int numCubes = p.hdr->numCubes;
+    stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);
     const GeomRec *sgeoms = reinterpret_cast<const GeomRec *>(smem4);
-    const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
     for (int base = blockIdx.x * kBlock; base < n; base += gridDim.x * kBlock) {          // warp-uniform trip count
         const int i = base + threadIdx.x;
         const bool valid = i < n;
@@ -1348,18 +1102,33 @@ __global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_co
             d = mk3(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2]);
         }
         Candidate best;
-        if (USE_BVH) closestHitBvh(p, snodes, smemNodes, o, d, valid, best);
-        else         closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
+        closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
         if (!valid) continue;
         if (best.slot < 0) {
             hit[i] = -1; t[i] = -1.0f; outside[i] = 1;
             normal[3 * (size_t)i] = normal[3 * (size_t)i + 1] = normal[3 * (size_t)i + 2] = 0.f;
         } else {
-            const GeomRec &g = USE_BVH ? p.geoms[best.slot] : sgeoms[best.slot];
+            const GeomRec &g = sgeoms[best.slot];
             const f3 nn = candidateNormal(g, best);
-            hit[i] = USE_BVH ? g.tag.w : g.tag.z; t[i] = best.t; outside[i] = best.outside;       // scene geom (object) index
+            hit[i] = g.tag.z; t[i] = best.t; outside[i] = best.outside;       // scene geom (object) index
             normal[3 * (size_t)i] = nn.x; normal[3 * (size_t)i + 1] = nn.y; normal[3 * (size_t)i + 2] = nn.z;
         }
+    }
+}
+// the same outputs from the raw hit records trace_kernel<SRC_RAYS> left in p.hits (BVH table: tag.w = scene geom index)
+__global__ void __launch_bounds__(kBlock) stage_hits_out_kernel(const __grid_constant__ Params p, int n, int *hit, float *t, float *normal, int *outside) {
+    for (int i = blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        const int meta = p.hits.meta[i];
+        if (meta < 0) {
+            hit[i] = -1; t[i] = -1.0f; outside[i] = 1;
+            normal[3 * (size_t)i] = normal[3 * (size_t)i + 1] = normal[3 * (size_t)i + 2] = 0.f;
+            continue;
+        }
+        const float4 r = p.hits.tn[i];
+        const GeomRec g = loadGeom(p.geoms + (meta & 0x3fffffff));
+        const f3 nn = exactNormal(g, (meta >> 30) & 1, r.y, r.z, r.w);
+        hit[i] = g.tag.w; t[i] = r.x; outside[i] = (meta >> 30) & 1;
+        normal[3 * (size_t)i] = nn.x; normal[3 * (size_t)i + 1] = nn.y; normal[3 * (size_t)i + 2] = nn.z;
     }
 }
 

@@ -29,3 +29,19 @@ def reduce_frame(accum, frame=None, dst=0, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.reduce(frame, dst=dst, op=dist.ReduceOp.SUM, group=group)
     return frame
+
+
+def init_library_comm(renderer, rank, world, pkg):
+    """One process per GPU (torchrun): give `renderer`'s context an NCCL communicator INSIDE libptb200.so (ptb_comm_init_rank).
+    Rank 0 asks the library for the ncclUniqueId; torch.distributed only carries those 128 bytes to the other ranks."""
+    import torch.distributed as dist
+    box = [pkg.comm_unique_id() if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(box, src=0)
+    renderer.comm_init_rank(box[0], rank, world)
+
+
+def reduce_frame_library(renderer, root=0):
+    """The frame collective through the library: ONE ncclReduce(sum, float32, 3*W*H) of every rank's private accumulation
+    buffer into the root's frame buffer, on the renderer's own stream (include/ptb200.h ptb_comm_reduce)."""
+    renderer.comm_reduce(root)

@@ -74,3 +74,22 @@ def to_oracle_scene(ms):
     return orclib.Scene(ms.geoms.view(orclib.GEOM_DT), ms.materials.view(orclib.MATERIAL_DT), ms.camera.view(orclib.CAMERA_DT),
                         ms.iterations, ms.traceDepth, ms.imageName,
                         ms.triangles if len(ms.triangles) else None, ms.mesh_ranges if len(ms.triangles) else None)
+
+
+_tuning = None
+
+
+def pkg_tuning():
+    """The package bound to libptb200_tuning.so (csrc/Makefile `tuning`, -DPTB_TUNING): the same library with the environment
+    knobs of A/B and validation runs compiled in.  Tests use it ONLY for failing controls (boxes that are known to lose
+    reference hits); the release library never reads the environment."""
+    global _tuning
+    if _tuning is None:
+        import importlib.util
+        base = pkg()
+        spec = importlib.util.spec_from_file_location("ptb200_tuning", os.path.join(os.path.dirname(base.__file__), "__init__.py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        mod.LIB_PATH = os.path.join(os.path.dirname(base.__file__), "libptb200_tuning.so")
+        _tuning = mod
+    return _tuning

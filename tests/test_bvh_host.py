@@ -12,7 +12,7 @@ import pytest
 
 import orclib
 import scenes
-from common import pkg, to_oracle_scene
+from common import pkg, pkg_tuning, to_oracle_scene
 
 F = np.float32
 
@@ -200,8 +200,9 @@ def test_far_sphere_hit_the_reference_reports_outside_the_sphere(port, tmp_path,
     assert depth < 60
     lost, checked = pruned_hits(nodes, order, o, d, hit, t)
     assert not lost and checked > 4096 * 10
-    monkeypatch.setenv("PTB_BVH_TIGHT_SPHERES", "1")
-    tight, order2, _ = m.bvh_build_host(s.geoms, 1)
+    monkeypatch.setenv("PTB_BVH_TIGHT_SPHERES", "1")            # read by the TUNING build only
+    assert m.bvh_build_host(s.geoms, 1)[0].tobytes() == nodes.tobytes()     # the release library ignores the environment
+    tight, order2, _ = pkg_tuning().bvh_build_host(s.geoms, 1)
     lost, _ = pruned_hits(tight, order2, o, d, hit, t)
     assert lost and np.all(hit[lost] == 31153)
 
@@ -358,8 +359,9 @@ def test_far_grazing_hits_need_the_rigorous_sphere_boxes(port, monkeypatch):
     span = anchors["translation"][1].astype(np.float64) - anchors["translation"][0] + 4.0
     loU, hiU = leaf_boxes(*m.bvh_build_host(gm, 1, 1.05 * float(np.linalg.norm(span)))[:2])
     assert np.all(lo >= loU) and np.all(hi <= hiU) and np.any(lo > loU)
-    monkeypatch.setenv("PTB_BVH_FAR_PAD", "0")
-    assert m.bvh_build_host(gm, 1)[0].tobytes() == nodes0.tobytes()
+    monkeypatch.setenv("PTB_BVH_FAR_PAD", "0")                  # the knob exists in the TUNING build only
+    assert pkg_tuning().bvh_build_host(gm, 1)[0].tobytes() == nodes0.tobytes()
+    assert m.bvh_build_host(gm, 1)[0].tobytes() == nodes.tobytes()
 
 
 def test_sphere_pruning_bound_carries_the_anisotropy_slack(port, monkeypatch):

@@ -262,29 +262,111 @@ def test_bounce_loop_launch_matches_one_launch_per_bounce(m, scene_dir, monkeypa
         s = m.Scene.load(scene_dir + "/%s.txt" % name)
         out = {}
         for loop in ("0", "1"):
-            monkeypatch.setenv("PTB_LOOP_BOUNCES", loop)          # read by ptb_create (tuning knob)
-            with m.Renderer(s, device=0, bsdf=1, batch_iters=1) as r:
+            with m.Renderer(s, device=0, bsdf=1, batch_iters=1, launch_per_bounce=int(loop == "0")) as r:
                 r.render(1, 3)
                 out[loop] = (r.download(), r.stats())
-        monkeypatch.delenv("PTB_LOOP_BOUNCES")
         assert same_bits(out["0"][0], out["1"][0]), name
         assert out["0"][1]["alive_per_depth"] == out["1"][1]["alive_per_depth"], name
         assert out["1"][1]["kernel_launches"] < out["0"][1]["kernel_launches"], name
 
 
 def test_batched_wavefront_matches_sequential(m, scene_dir):
-    """B iterations per wavefront deposit with float atomics: same sums up to addition order."""
+    """B iterations per wavefront.  Ordered deposit (the default): every slot stores into its own partial image and the partial
+    images are added in iteration order, so the accumulated SUM is bit for bit what one iteration per wavefront builds
+    (src/pathtrace.cu:269-278 adds one iteration at a time) -- for any batch size, partial last batches included, run to run.
+    Atomic deposit (opt-in): same sums up to the order of the float additions."""
     s = m.Scene.load(scene_dir + "/cornell.txt")
     with m.Renderer(s, device=0, bsdf=1, batch_iters=1) as r:
         r.render(1, 12)
         a = r.download()
         sa = r.stats()
-    with m.Renderer(s, device=0, bsdf=1, batch_iters=8) as r:
-        r.render(1, 12)          # one full batch + a partial one
-        b = r.download()
-        sb = r.stats()
-    assert sa["alive_per_depth"] == sb["alive_per_depth"] and sa["iterations"] == sb["iterations"] == 12
-    assert np.allclose(a, b, rtol=2e-6, atol=0)
+    for batch in (8, 5):
+        with m.Renderer(s, device=0, bsdf=1, batch_iters=batch) as r:
+            r.render(1, 12)          # full batches + a partial one
+            b = r.download()
+            sb = r.stats()
+            r.reset()
+            r.render(1, 12)
+            b2 = r.download()
+        assert sa["alive_per_depth"] == sb["alive_per_depth"] and sa["iterations"] == sb["iterations"] == 12
+        assert same_bits(a, b) and same_bits(b, b2), batch
+    with m.Renderer(s, device=0, bsdf=1, batch_iters=8, deposit_mode=m.DEPOSIT_ATOMIC) as r:
+        r.render(1, 12)
+        c = r.download()
+    assert np.allclose(a, c, rtol=2e-6, atol=0)
+
+
+def test_staged_pipeline_partial_batches(m, scene_dir):
+    """Staged pipeline with several iterations per wavefront and a count that is not a multiple of it: the gather of the
+    no-compaction layout reads its slot count on the device (a host constant baked into the captured graph gathered the stale
+    slots of the previous full batch a second time).  All variants equal the fused one-iteration-per-wavefront image bit for bit."""
+    s = m.Scene.load(scene_dir + "/cornell.txt")
+    with m.Renderer(s, device=0, bsdf=1, batch_iters=1) as r:
+        r.render(1, 6)
+        want = r.download()
+        wst = r.stats()
+    for kw in (dict(pipeline=1, compaction=0, batch_iters=4), dict(pipeline=1, compaction=1, batch_iters=4),
+               dict(pipeline=1, compaction=0, batch_iters=4, use_graphs=0), dict(pipeline=1, compaction=1, sort_materials=1, batch_iters=3)):
+        with m.Renderer(s, device=0, bsdf=1, **kw) as r:
+            r.render(1, 6)           # one full batch, then a partial one
+            img = r.download()
+            st = r.stats()
+            r.reset()
+            r.render(1, 2)           # the partial batch FIRST: slots beyond it were never written
+            r.render(3, 4)
+            img2 = r.download()
+        assert st["iterations"] == 6
+        if kw["compaction"]:
+            assert st["alive_per_depth"] == wst["alive_per_depth"]
+        assert same_bits(img, want), kw
+        assert same_bits(img2, want), kw
+
+
+def test_bench_configuration_against_the_oracle(m, port, scene_dir):
+    """The configuration bench.py times -- cornell 800x800 depth 8, full BSDF, 128 iterations per wavefront, 256 iterations
+    per step, with and without the first-bounce cache -- against the oracle's render of the same 256 iterations: per-depth
+    path counts exact, per-pixel radiance within 1e-4 relative on every lit pixel (north_star), in fact bit-identical
+    (ordered deposit), and identical bits when rendered twice."""
+    s = m.Scene.load(scene_dir + "/cornell.txt")
+    os_ = port.load_scene(scene_dir + "/cornell.txt")
+    want, walive, wseg = port.render(os_, orclib.MODE_FULL, 1, 256)
+    for fbc in (0, 1):
+        with m.Renderer(s, device=0, bsdf=m.BSDF_FULL, batch_iters=128, first_bounce_cache=fbc) as r:
+            r.render(1, 256)
+            img = r.download()
+            st = r.stats()
+            r.reset()
+            r.render(1, 256)
+            again = r.download()
+        assert st["batch_iters"] == 128 and st["iterations"] == 256
+        assert st["alive_per_depth"] == list(walive) and st["segments"] == wseg
+        rel, lit = rel_err_lit(img, want)
+        assert lit.sum() > 400000 and float(rel.max()) <= RADIANCE_RTOL, (fbc, float(rel.max()))
+        assert same_bits(img, want), "fbc=%d: %d pixels differ from the oracle" % (fbc, int((bits(img) != bits(want)).any(1).sum()))
+        assert same_bits(img, again)
+
+
+def test_stage_timers(m, scene_dir):
+    """PtbOptions.timeStages: per-stage device time by CUDA events (INSTRUCTION.md:339-355 asks for this analysis); the image is
+    the one the untimed run produces, every stage that ran has a launch count and a positive time."""
+    s = m.Scene.load(scene_dir + "/cornell.txt")
+    with m.Renderer(s, device=0, bsdf=1, batch_iters=2) as r:
+        r.render(1, 4)
+        want = r.download()
+        assert sum(r.stats()["stage_launches"].values()) == 0
+    for kw, stages in ((dict(batch_iters=2), ("fused_bounce0", "fused_bounces", "gather", "control")),
+                       (dict(batch_iters=2, launch_per_bounce=1), ("fused_bounce0", "fused_bounces")),
+                       (dict(pipeline=1, compaction=1, sort_materials=1, batch_iters=2), ("raygen", "intersect", "sort", "shade", "compact")),
+                       (dict(pipeline=1, compaction=0, batch_iters=2), ("raygen", "intersect", "shade", "compact", "gather")),
+                       (dict(batch_iters=2, accel=m.ACCEL_BVH), ("intersect", "shade"))):
+        with m.Renderer(s, device=0, bsdf=1, time_stages=1, **kw) as r:
+            r.render(1, 4)
+            img = r.download()
+            st = r.stats()
+        assert same_bits(img, want), kw
+        for name in stages:
+            assert st["stage_launches"][name] > 0 and st["stage_us"][name] > 0.0, (kw, name, st["stage_us"])
+        assert sum(st["stage_launches"].values()) == st["kernel_launches"], (kw, st)
 
 
 @pytest.mark.parametrize("scene,accel", [("cornell", 0), ("glass", 0), ("glass", 2)])
@@ -308,9 +390,9 @@ def test_first_bounce_cache_is_result_neutral(m, scene_dir, scene, accel):
     assert same_bits(out[0][0], out[1][0]) and out[0][1] == out[1][1]
     assert same_bits(out[0][2], out[1][2]) and out[0][3] == out[1][3]
     assert not same_bits(out[0][0] * (2.0 / 3.0), out[0][2])           # the moved camera really renders another image
-    # one cache-fill launch; on BVH scenes the cached wavefronts also skip their bounce-0 trace_bvh_kernel
-    # (3 single-iteration wavefronts had run when the launch count was read)
-    assert out[1][4] == out[0][4] + 1 - (3 if accel == 2 else 0)
+    # one cache-fill launch (BVH scenes: trace_kernel<SRC_PIXELS> + resolve_hits_kernel); on BVH scenes the cached wavefronts
+    # also skip their bounce-0 trace_kernel (3 single-iteration wavefronts had run when the launch count was read)
+    assert out[1][4] == out[0][4] + (2 - 3 if accel == 2 else 1)
 
 
 def test_every_bounce_hits_bit_exact_on_gpu_rays(m, port, scene_dir):

@@ -158,3 +158,83 @@ def test_converges_to_the_reference_image(m, scene_dir):
     assert rel_rmse_blocks <= 1e-2
     assert np.all(np.abs(mean_ratio - 1) < 5e-3)
     assert rel_rmse_pixels < 0.12          # 0.0155 / 0.1804 = 0.086 is the seed-to-seed floor
+
+
+def _scene_from_geoms(m, g, res=(64, 64)):
+    """A product-side Scene around caller-built geoms (one diffuse material, a camera that is never used by the stage calls)."""
+    mats = np.zeros(2, m.MATERIAL_DT)
+    mats["color"] = 0.8
+    cam = np.zeros(1, m.CAMERA_DT)
+    cam["resolution"] = res
+    cam["position"] = (0, 0, 300); cam["view"] = (0, 0, -1); cam["up"] = (0, 1, 0); cam["right"] = (1, 0, 0)
+    cam["pixelLength"] = (0.01, 0.01)
+    return m.Scene(g.view(m.GEOM_DT), mats, cam, 1, 4, "band")
+
+
+def test_far_grazing_band_on_the_gpu(m, port, monkeypatch):
+    """GPU twin of tests/test_bvh_host.py::test_far_grazing_hits_need_the_rigorous_sphere_boxes: 1.2 M rays aimed at the silhouettes
+    of thin ellipsoids from 160-230 world units away, where the reference's sphere test (src/intersections.h:102-144) reports hits
+    for rays that pass OUTSIDE the sphere.  trace_kernel over the shipped (far-padded) boxes == the brute-force kernel == the
+    oracle, bit for bit; the round-1 boxes (PTB_BVH_FAR_PAD=0, tuning build only) lose some of those hits -- the failing control."""
+    from test_bvh_host import random_spheres, grazing_band
+    from common import pkg_tuning
+    rs = np.random.RandomState(1)
+    g = random_spheres(port, rs, 300, 0.3, 1.2)
+    o, d, owner = grazing_band(port, g, rs, 8, 512, (160.0, 230.0), 1.2)
+    anchors = random_spheres(port, rs, 2, 1.0, 1.0, kind=1)
+    for k, t in enumerate(([-290.0, -240.0, -340.0], [290.0, 340.0, 240.0])):
+        anchors["translation"][k] = t
+        anchors["transform"][k], anchors["inverseTransform"][k], anchors["invTranspose"][k] = \
+            port.build_transform(np.float32(t), anchors["rotation"][k], anchors["scale"][k])
+    g = np.concatenate([g, anchors])
+    want = port.closest_hit(g, o, d)
+    assert (want[0] == owner).sum() > 300000
+    s = _scene_from_geoms(m, g)
+    with m.Renderer(s, device=0, bsdf=1, batch_iters=1, accel=m.ACCEL_BVH) as r:
+        bvh = r.stage_intersect(o, d, m.ACCEL_BVH)
+        brute = r.stage_intersect(o, d, m.ACCEL_BRUTE)
+    for got in (bvh, brute):
+        assert np.array_equal(got[0], want[0]) and same_bits(got[1], want[1]) and same_bits(got[2], want[2]) and np.array_equal(got[3], want[3])
+    mt = pkg_tuning()
+    monkeypatch.setenv("PTB_BVH_FAR_PAD", "0")
+    with mt.Renderer(_scene_from_geoms(mt, g), device=0, bsdf=1, batch_iters=1, accel=mt.ACCEL_BVH) as r:
+        ctl = r.stage_intersect(o, d, mt.ACCEL_BVH)
+    lost = np.flatnonzero(ctl[0] != want[0])
+    assert len(lost) > 0 and np.all(want[0][lost] == owner[lost])          # hits of the grazed sphere, dropped by its round-1 box
+
+
+def test_real_paths_agree_between_the_pad_policies(m, port, synthetic, monkeypatch):
+    """tools/gpu_bvh_pathdiff.py as a regression: one iteration of the REAL paths of the 100 k-object scene (all 16 bounces, the
+    render's own RNG) walked through the shipped BVH and through the round-1 boxes (tuning build, PTB_BVH_FAR_PAD=0); every ray on
+    which the two disagree goes to the oracle's brute-force loop, and the shipped BVH must never be the one that is wrong."""
+    from common import pkg_tuning, bits
+    mt = pkg_tuning()
+    s = m.Scene.load(synthetic)
+    os_ = port.load_scene(synthetic)
+    monkeypatch.setenv("PTB_BVH_FAR_PAD", "0")
+    r_ctl = mt.Renderer(mt.Scene.load(synthetic), device=0, bsdf=1, batch_iters=1)
+    r_new = m.Renderer(s, device=0, bsdf=1, batch_iters=1)
+    try:
+        o, dd = r_new.stage_raygen(1)
+        P = len(o)
+        pix = np.arange(P, dtype=np.int32); col = np.ones((P, 3), np.float32); rem = np.full(P, s.traceDepth, np.int32)
+        rays = wrong = 0
+        for depth in range(s.traceDepth):
+            a = r_ctl.stage_intersect(o, dd, mt.ACCEL_BVH)
+            b = r_new.stage_intersect(o, dd, m.ACCEL_BVH)
+            same = (a[0] == b[0]) & (bits(a[1]) == bits(b[1])) & (bits(a[2]) == bits(b[2])).all(1) & (a[3] == b[3])
+            diff = np.flatnonzero(~same)
+            rays += len(o)
+            hit, t, nrm, outside = b
+            if len(diff):
+                want = port.closest_hit(os_.geoms, o[diff], dd[diff])
+                wrong += int(((b[0][diff] != want[0]) | (bits(b[1][diff]) != bits(want[1]))).sum())
+            itv = np.full(len(pix), 1, np.int32); dep = np.full(len(pix), depth, np.int32)
+            go, gd, gc, grem = r_new.stage_shade(hit, t, nrm, outside, itv, pix, dep, o, dd, col, rem)
+            keep = grem > 0
+            o, dd, col, rem, pix = go[keep], gd[keep], gc[keep], grem[keep], pix[keep]
+            if not len(o):
+                break
+        assert rays > 6000000 and wrong == 0
+    finally:
+        r_ctl.close(); r_new.close()

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), "libptb200.so does not export %s" % name
     L.ptb_abi_version.restype = C.c_int
-    assert L.ptb_abi_version() == 3      # PTB_ABI_VERSION: 2 added antialias / lens options, 3 added triangle meshes to PtbSceneDesc
+    assert L.ptb_abi_version() == 4      # PTB_ABI_VERSION: 2 added antialias / lens options, 3 triangle meshes in PtbSceneDesc, 4 deposit mode / stage timers / lazy image
 
 
 def test_struct_sizes_match_reference_layout():

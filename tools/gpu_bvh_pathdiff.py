@@ -11,6 +11,7 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import __graft_entry__ as g
 import orclib, scenes
 m = g.load_package(); orc = orclib.load("port")
+m.LIB_PATH = os.path.join(os.path.dirname(m.__file__), "libptb200_tuning.so")      # the PTB_BVH_* knobs exist in the tuning build only
 d = tempfile.mkdtemp(); path = os.path.join(d, "synthetic.txt")
 open(path, "w").write(scenes.synthetic_text(100000))
 scene = m.Scene.load(path); osc = orc.load_scene(path)

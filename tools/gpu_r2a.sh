@@ -7,7 +7,7 @@ TAG=${1:-r2a}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${TAG}_smi.txt 2>&1
 ( time python -m pytest tests -m gpu -x -q ) > gpurun_out/${TAG}_pytest_gpu.log 2>&1
 tail -3 gpurun_out/${TAG}_pytest_gpu.log
-( PTB_B=16 python tools/gpu_time_synth.py; PTB_BVH_FAR_PAD=0 PTB_B=16 python tools/gpu_time_synth.py ) > gpurun_out/${TAG}_synth_pad.txt 2>&1
+( PTB_B=16 python tools/gpu_time_synth.py; PTB_SO=project3-cuda-path-tracer_b200/libptb200_tuning.so PTB_BVH_FAR_PAD=0 PTB_B=16 python tools/gpu_time_synth.py ) > gpurun_out/${TAG}_synth_pad.txt 2>&1
 cat gpurun_out/${TAG}_synth_pad.txt
 PTB_B=4 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_synth_launches.csv \
     python tools/gpu_time_synth.py > gpurun_out/${TAG}_synth_under_ncu.log 2>&1
