@@ -80,6 +80,7 @@ int main(int argc, char **argv) {
         else if (a == "--res") { resW = atoi(next()); resH = atoi(next()); }
         else if (a == "--atomic-deposit") opt.depositMode = PTB_DEPOSIT_ATOMIC;
         else if (a == "--time-stages") opt.timeStages = 1;
+        else if (a == "--lazy-image") opt.lazyImage = 1;              // with --per-iteration: the image copy of iteration i overlaps iteration i + 1
         else if (a == "--out") outBase = next();
         else if (a == "--bsdf") opt.bsdfMode = strcmp(next(), "golden-diffuse") == 0 ? PTB_BSDF_GOLDEN_DIFFUSE : PTB_BSDF_FULL;
         else if (a == "--per-iteration") perIteration = true;
@@ -152,6 +153,7 @@ int main(int argc, char **argv) {
             iteration++;
             pathtrace(NULL, 0, iteration);
         }
+        pathtraceSync();
     } else {
         pathtraceBatch(1, (int)renderState->iterations);
         iteration = (int)renderState->iterations;

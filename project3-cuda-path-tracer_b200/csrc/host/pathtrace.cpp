@@ -66,4 +66,5 @@ void pathtrace(uchar4 *pbo, int frame, int iteration) {
 
 void pathtraceBatch(int iterBegin, int count) { check(ptb_render(g_ctx, iterBegin, count, 1), "pathtraceBatch"); }
 void pathtraceDownload() { check(ptb_download(g_ctx, reinterpret_cast<float *>(hst_scene->state.image.data())), "pathtraceDownload"); }
+void pathtraceSync() { check(ptb_sync(g_ctx), "pathtraceSync"); }
 PtbContext *pathtraceContext() { return g_ctx; }

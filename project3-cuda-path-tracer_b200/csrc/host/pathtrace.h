@@ -19,4 +19,5 @@ void pathtraceSceneDesc(Scene *scene, PtbSceneDesc *desc);
 void pathtraceSetOptions(const PtbOptions *opts);
 void pathtraceBatch(int iterBegin, int count);        // then pathtraceDownload() fills scene->state.image
 void pathtraceDownload();
+void pathtraceSync();                                 // PtbOptions.lazyImage: scene->state.image is valid after this
 PtbContext *pathtraceContext();

@@ -14,12 +14,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <vector>
 
-#ifndef PTB_SMEM_NODES
-#define PTB_SMEM_NODES 255          // leading BVH nodes (BFS order = top levels) staged in shared memory by trace_kernel
-#endif
 using namespace ptb;
 
 namespace {
@@ -131,7 +129,7 @@ struct PtbContext {
     DevBuf<GeomRec> geomsScene;          // brute-force table (cubes first, then spheres), also used by ptb_stage_intersect(BRUTE)
     int numCubes = 0;
     DevBuf<BvhNode> bvh;
-    int numNodes = 0, smemNodes = 0;
+    int numNodes = 0;
     DevBuf<float4> mats;
     DevBuf<int> sceneMatDev;
     DevBuf<SceneHeader> hdr;
@@ -171,6 +169,16 @@ struct PtbContext {
     int commRank = 0, commRanks = 1;
     DevBuf<float> frame;
     bool frameValid = false;             // the last ptb_comm_reduce landed here (root of a > 1-rank communicator)
+    // ptb_pathtrace: the caller's host image (scene->state.image) is page-locked once so that its per-iteration copy is a DMA at
+    // PCIe rate; PtbOptions.lazyImage additionally snapshots the image (device to device) and copies it out on a second stream
+    // while the next iteration renders
+    float *pinnedHost = nullptr;
+    size_t pinnedHostBytes = 0;
+    bool pinHostFailed = false;
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t evImage[2] = {nullptr, nullptr}, evCopy[2] = {nullptr, nullptr};
+    DevBuf<float> snap[2];
+    int snapIdx = 0;
 
     cudaGraphExec_t graphExec = nullptr;
     int graphKernels = 0;                // kernels per replay of the captured batch
@@ -189,6 +197,9 @@ struct PtbContext {
         for (cudaEvent_t e : events) cudaEventDestroy(e);
         if (comm && ownComm) { std::string err; if (NcclApi *n = ncclApi(err)) n->commDestroy(comm); }
         frame.release();
+        if (copyStream) { cudaStreamSynchronize(copyStream); cudaStreamDestroy(copyStream); }
+        for (int k = 0; k < 2; ++k) { if (evImage[k]) cudaEventDestroy(evImage[k]); if (evCopy[k]) cudaEventDestroy(evCopy[k]); snap[k].release(); }
+        if (pinnedHost) cudaHostUnregister(pinnedHost);
         geoms.release(); geomsScene.release(); bvh.release(); mats.release(); sceneMatDev.release();
         image.release();
         for (int i = 0; i < 2; ++i) { A[i].release(); B[i].release(); C[i].release(); }
@@ -369,7 +380,13 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
         nodes[i].x = make_float4(h.llo[0], h.rlo[0], h.lhi[0], h.rhi[0]);
         nodes[i].y = make_float4(h.llo[1], h.rlo[1], h.lhi[1], h.rhi[1]);
         nodes[i].z = make_float4(h.llo[2], h.rlo[2], h.lhi[2], h.rhi[2]);
-        nodes[i].m = make_int4(h.lref, h.rref, h.lcount, h.rcount);
+        // child links as the traversal pushes them: interior -> node index, leaf -> ~(first slot | count << 27); an absent child
+        // (scenes of 0 or 1 primitives) gets NaN planes: every comparison of the slab test is false for it
+        auto code = [](int32_t ref, int32_t count) { return count > 0 ? ~(ref | (count << 27)) : ref; };
+        nodes[i].m = make_int4(code(h.lref, h.lcount), code(h.rref, h.rcount), 0, 0);
+        const float qnan = std::numeric_limits<float>::quiet_NaN();
+        if (h.lref < 0) { nodes[i].x.x = nodes[i].x.z = nodes[i].y.x = nodes[i].y.z = nodes[i].z.x = nodes[i].z.z = qnan; nodes[i].m.x = -1; }
+        if (h.rref < 0) { nodes[i].x.y = nodes[i].x.w = nodes[i].y.y = nodes[i].y.w = nodes[i].z.y = nodes[i].z.w = qnan; nodes[i].m.y = -1; }
     }
     for (int sIdx = 0; sIdx < P; ++sIdx) {
         const int k = hb.order[sIdx];
@@ -378,7 +395,6 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
                                                : packGeom(g, prims[k].first, k);
     }
     c->numNodes = (int)hb.nodes.size();
-    c->smemNodes = std::min(c->numNodes, PTB_SMEM_NODES);
     c->bvhDepth = hb.maxDepth;
     for (int i = 0; i < M; ++i) {
         const PtbMaterial &m = scene->materials[i];
@@ -397,7 +413,7 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
         for (int i = 0; i < M; ++i) ext = ext || (scene->materials[i].hasReflective > 0.0f && scene->materials[i].specularExponent > 0.0f);
     if (ext != c->ext && c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }   // other kernels: re-capture
     c->ext = ext;
-    hdr->numNodes = c->numNodes; hdr->smemNodes = c->smemNodes;
+    hdr->numNodes = c->numNodes;
 
     if (bytesBrute) CU(cudaMemcpyAsync(c->geomsScene.p, bruteOrder, bytesBrute, cudaMemcpyHostToDevice, c->stream));
     CU(cudaMemcpyAsync(c->geoms.p, leafOrder, bytesGeoms, cudaMemcpyHostToDevice, c->stream));
@@ -581,7 +597,7 @@ int ensureStackSpill(PtbContext *c) {
     const int need = std::max(0, c->bvhDepth + 2 - kStackSmem);
     if (need > c->spillCap) {
         CU(cudaStreamSynchronize(c->stream));
-        CU(c->stackSpill.alloc((size_t)c->gridTrace * kTraceBlock * kTraceRays * need));
+        CU(c->stackSpill.alloc((size_t)c->gridTrace * kTraceBlock * kTraceRays * need * 2));      // 8-byte entries (child, entry distance)
         c->spillCap = need;
         if (c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }    // new launch parameters: re-capture
     }
@@ -714,7 +730,7 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
 
     // ---- launch geometry ----
     c->smemBrute = bruteBytes;
-    c->smemBvh = traceSmemBytes(PTB_SMEM_NODES);                // fixed: the node count may change in ptb_update_scene
+    c->smemBvh = traceSmemBytes();
     if (bruteBytes <= 200 * 1024) {                  // brute force is only launchable when the geoms fit in shared memory
         int rc = PTB_OK;
         rc |= setSmem(bounce_kernel<true, false, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, false>, c->smemBrute);
@@ -864,6 +880,16 @@ int ptb_download(PtbContext *c, float *hostImage) {
     return PTB_OK;
 }
 
+// page-locks the caller's image buffer the first time it is seen (the reference copies into the pageable std::vector of
+// scene->state.image every iteration, src/pathtrace.cu:389-390: a staged copy at a fraction of the PCIe rate)
+static void pinHostImage(PtbContext *c, float *hostImage, size_t bytes) {
+    if (c->pinnedHost == hostImage && c->pinnedHostBytes == bytes) return;
+    if (c->pinnedHost) { cudaStreamSynchronize(c->stream); if (c->copyStream) cudaStreamSynchronize(c->copyStream); cudaHostUnregister(c->pinnedHost); c->pinnedHost = nullptr; }
+    if (c->pinHostFailed) return;
+    if (cudaHostRegister(hostImage, bytes, cudaHostRegisterDefault) == cudaSuccess) { c->pinnedHost = hostImage; c->pinnedHostBytes = bytes; }
+    else { cudaGetLastError(); c->pinHostFailed = true; }       // already pinned by the caller, or not registrable: plain copies still work
+}
+
 int ptb_pathtrace(PtbContext *c, PtbUchar4 *pbo, int frame, int iter, float *hostImage) {
     (void)frame;                                     // unused by the reference as well (src/main.cpp:136)
     if (!c) return fail(PTB_ERR_INVALID, "ptb_pathtrace: not initialised");
@@ -871,7 +897,34 @@ int ptb_pathtrace(PtbContext *c, PtbUchar4 *pbo, int frame, int iter, float *hos
     int rc = ptb_render(c, iter, 1, 1);
     if (rc != PTB_OK) return rc;
     if (pbo) { rc = ptb_write_pbo(c, pbo, iter); if (rc != PTB_OK) return rc; }
-    if (hostImage) return ptb_download(c, hostImage);
+    if (!hostImage) return PTB_OK;
+    ON_DEVICE(c->device);
+    const size_t bytes = (size_t)c->numPixels * 3 * sizeof(float);
+    pinHostImage(c, hostImage, bytes);
+    if (!c->opt.lazyImage) {
+        // the reference's semantic: the accumulated SUM is in the host image when the call returns
+        CU(cudaMemcpyAsync(hostImage, c->imagePtr, bytes, cudaMemcpyDeviceToHost, c->stream));
+        CU(cudaStreamSynchronize(c->stream));
+        return PTB_OK;
+    }
+    // lazy image: snapshot on the render stream (7.68 MB device to device), copy out on the copy stream while the next
+    // iteration renders; two snapshots alternate, each reused only after its previous copy has left
+    if (!c->copyStream) {
+        CU(cudaStreamCreateWithFlags(&c->copyStream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) {
+            CU(cudaEventCreateWithFlags(&c->evImage[k], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->evCopy[k], cudaEventDisableTiming));
+            CU(c->snap[k].alloc((size_t)c->numPixels * 3));
+        }
+    }
+    const int k = c->snapIdx;
+    c->snapIdx ^= 1;
+    CU(cudaStreamWaitEvent(c->stream, c->evCopy[k], 0));           // (a never-recorded event counts as complete)
+    CU(cudaMemcpyAsync(c->snap[k].p, c->imagePtr, bytes, cudaMemcpyDeviceToDevice, c->stream));
+    CU(cudaEventRecord(c->evImage[k], c->stream));
+    CU(cudaStreamWaitEvent(c->copyStream, c->evImage[k], 0));
+    CU(cudaMemcpyAsync(hostImage, c->snap[k].p, bytes, cudaMemcpyDeviceToHost, c->copyStream));
+    CU(cudaEventRecord(c->evCopy[k], c->copyStream));
     return PTB_OK;
 }
 
@@ -894,6 +947,7 @@ int ptb_sync(PtbContext *c) {
     if (!c) return fail(PTB_ERR_INVALID, "ptb_sync: not initialised");
     ON_DEVICE(c->device);
     CU(cudaStreamSynchronize(c->stream));
+    if (c->copyStream) CU(cudaStreamSynchronize(c->copyStream));   // lazy images of ptb_pathtrace have landed
     return PTB_OK;
 }
 

@@ -32,8 +32,8 @@ constexpr uint32_t kDeadBit = 0x80000000u;
 
 struct BvhNode {                 // 64 B = four 128-bit loads: a binary node holding BOTH child boxes, the planes of the
     float4 x, y, z;              // two children paired per axis: x = (left.lo.x, right.lo.x, left.hi.x, right.hi.x), ...
-    int4   m;                    // left ref, right ref, left count, right count.  count > 0: leaf, ref = first geom slot;
-};                               //              count == 0: interior, ref = node index; ref < 0: empty
+    int4   m;                    // x, y: the left / right child as the traversal uses it -- interior: node index (>= 0); leaf:
+};                               // ~(first geom slot | count << 27); an absent child has NaN planes (no ray enters it).  z, w unused
 
 struct PathPlanes { float4 *A; float4 *B; float2 *C; };
 
@@ -67,7 +67,7 @@ struct CameraParams {
 struct SceneHeader {             // device-resident, rewritten by ptb_update_scene without touching launch parameters
     CameraParams cam;
     int          numNodes;
-    int          smemNodes;      // leading BVH nodes (BFS order = top levels) staged in shared memory
+    int          pad0;
     int          numCubes;       // brute-force table: the cubes come first (this many), then the spheres
 };
 
@@ -352,34 +352,6 @@ PTB_DEV void slabNearPair(float4 X, float4 Y, float4 Z, f3 o, f3 inv, float &tl,
     const float fr = fminf(fminf(fmaxf(rx0, rx1), fmaxf(ry0, ry1)), fmaxf(rz0, rz1));
     hl = tl <= fl * 1.00001f + 1e-5f;
     hr = tr <= fr * 1.00001f + 1e-5f;
-}
-
-// One traversal step at `node`: slab-test both child boxes against the best distance so far; returns the children to
-// visit as stack entries (interior -> node index (>= 0), leaf -> ~(ref | count << 27) (< 0)): `next` (haveNext) is
-// the nearer one, `far` (haveFar) the other.
-PTB_DEV void bvhNodeStep(const BvhNode *snodes, int smemNodes, const BvhNode *gnodes, int node, f3 o, f3 invD, float dl, float bestT,
-                         int &next, bool &haveNext, int &far, bool &haveFar) {
-    float4 X, Y, Z; int4 m;
-    if (node < smemNodes) { X = snodes[node].x; Y = snodes[node].y; Z = snodes[node].z; m = snodes[node].m; }
-    else {
-        const float4 *np = reinterpret_cast<const float4 *>(gnodes + node);
-        X = __ldg(np); Y = __ldg(np + 1); Z = __ldg(np + 2); m = __ldg(reinterpret_cast<const int4 *>(np + 3));
-    }
-    float tl, tr; bool hl, hr;
-    slabNearPair(X, Y, Z, o, invD, tl, tr, hl, hr);
-    // tNear * |d| (slackened) is a lower bound of the world distance of anything inside the box
-    const bool vl = m.x >= 0 && hl && tl * dl - 1e-4f <= bestT;
-    const bool vr = m.y >= 0 && hr && tr * dl - 1e-4f <= bestT;
-    const int cl = m.z > 0 ? ~(m.x | (m.z << 27)) : m.x;
-    const int cr = m.w > 0 ? ~(m.y | (m.w << 27)) : m.y;
-    haveNext = true; haveFar = false; next = 0; far = 0;
-    if (vl && vr) {
-        const bool leftFirst = tl <= tr;
-        next = leftFirst ? cl : cr;
-        far = leftFirst ? cr : cl; haveFar = true;
-    } else if (vl) next = cl;
-    else if (vr) next = cr;
-    else haveNext = false;
 }
 
 PTB_DEV GeomRec loadGeom(const GeomRec *gp) {

@@ -3,27 +3,31 @@
 // hierarchical structure is an assignment ask (INSTRUCTION.md:123-140).
 //
 // ONE kernel serves every caller (fused pipeline: camera rays / the CTA-owned path segments; staged pipeline; first-bounce
-// cache; the ptb_stage_intersect test entry): `trace_kernel<SRC, ...>`, a persistent-threads kernel in which every lane
-// MULTIPLEXES R rays.
+// cache; the ptb_stage_intersect test entry): `trace_kernel<SRC, ...>`, persistent threads with dynamic ray fetch and
+// SPECULATIVE traversal.
 //
-// Why.  A ray through the 100 k-object scene needs ~20 traversal steps, ~1 leaf primitive to prune and ~0.3 reference-exact
-// tests, and it finishes after a number of steps that varies by an order of magnitude.  Round 1 kept one ray per lane and
-// gathered the lanes of a warp before each of the three kinds of work; ncu on that kernel (profiles/r02l / r2a_trace*):
-// 74 % of the warp instructions were traversal steps executed with 11.6 of 32 lanes, because a lane whose ray sat at a leaf
-// (or had finished) idled until enough others joined it.  Here a lane that cannot step its ray steps its OTHER ray:
-//   * every lane owns R ray SLOTS in shared memory (origin, direction, hit-record index, best distance, pending leaf,
-//     candidate, traversal stack); the traversal state of ONE of them (the active slot) is cached in registers;
-//   * a slot is IDLE (wants a ray), STEP (can take a traversal step), LEAF (a leaf primitive waits for the pruning stage)
-//     or CAND (a primitive that survived pruning waits for the reference-exact test);
-//   * the warp runs, in a loop: ray fetch when kFetchLanes lanes have an idle slot, the exact test when kExactLanes lanes hold
-//     a candidate, pruning when kPruneLanes lanes hold a leaf -- each also whenever nothing else can run -- and then kSteps
-//     traversal steps in which a lane whose active slot is blocked switches to its other slot (~25 instructions).
-// The per-lane traversal stack lives in SHARED memory (kStackSmem entries per slot, [entry][slot][thread]: conflict-free);
-// deeper entries -- only trees deeper than kStackSmem levels can produce them -- go to a global spill area sized from the
-// depth of the tree (no local-memory array: ptxas reported a 304-byte stack frame for the round-1 `int stack[64]`).
+// Why.  A bounce ray through the 100 k-object scene takes ~35 traversal steps, reaches ~1 leaf primitive that has to be pruned in
+// object space and gets ~0.3 reference-exact tests; it finishes after a number of steps that varies by an order of magnitude.
+// The three kinds of work have to be entered by many lanes of a warp together or the warp runs them with one or two lanes.
+// Round 1 gathered the lanes before each kind: a lane whose ray stood at a leaf (or had finished) idled until enough others
+// joined it, and ncu showed the traversal steps -- 3/4 of the instructions -- running with 12-14 of 32 lanes.  Giving every
+// lane a second ray parked in shared memory raised that to 22 lanes but paid for it in switching and bookkeeping
+// (profiles/r2_trace_design.txt).  What ships keeps ONE ray per lane, all of its traversal state in registers, and lets it run ahead:
+//   * a leaf the traversal reaches goes into a two-entry leaf queue of the lane and the traversal CONTINUES with the next node
+//     (speculative: the hit that leaf may hold cannot cull yet); the lane only stops when both entries are taken;
+//   * the pruning stage (object-space ray + sure-miss filter of one queued primitive per lane) runs when kPruneLanes lanes
+//     have something queued, the reference-exact test when kExactLanes lanes hold a survivor, the ray fetch when kFetchLanes
+//     lanes are done -- each also whenever nothing else can run;
+//   * the closest hit is order-independent ((t, scene index)-lexicographic minimum, src/pathtrace.cu:192), so testing
+//     primitives later than the front-to-back order would changes nothing but the amount of culling.
+// Stack entries carry the entry distance of their box: an entry that can no longer beat the best hit is dropped when it is
+// popped, without fetching its node.  The stack lives in SHARED memory (kStackSmem 8-byte entries per lane, [entry][thread]:
+// conflict-free); deeper entries -- only trees deeper than kStackSmem levels can produce them -- go to a global spill area
+// sized from the depth of the tree (no local-memory array: ptxas reported a 304-byte frame for round 1's `int stack[64]`).
+// Nodes are read through L1 (the kernel's small shared-memory footprint leaves it ~170 KB): child links are pre-encoded on
+// the host (interior >= 0; leaf = ~(first primitive | count << 27); an absent child has a NaN box that no ray enters).
 // The accepted hit goes straight to the global hit record (hits.tn / hits.meta of the ray's index): it is written ~0.3 times
-// per ray, so it does not need to live in the slot; ties in t (src/pathtrace.cu:192: lowest scene index wins) and the
-// same-mesh ordering rule read it back.
+// per ray; ties in t and the same-mesh ordering rule read it back.  A ray is recorded as a miss when it is fetched.
 //
 // Nothing here computes an output value except exactTestCore (ptb_math.cuh): traversal and pruning use padded boxes,
 // approximate reciprocals and slackened bounds, and only decide WHICH primitives get the exact test.
@@ -35,30 +39,31 @@ namespace ptb {
 #define PTB_TRACE_BLOCK 256
 #endif
 #ifndef PTB_TRACE_MINBLOCKS
-#define PTB_TRACE_MINBLOCKS 3
-#endif
-#ifndef PTB_TRACE_RAYS
-#define PTB_TRACE_RAYS 2               // R: ray slots per lane
+#define PTB_TRACE_MINBLOCKS 4
 #endif
 #ifndef PTB_TRACE_STACK
-#define PTB_TRACE_STACK 12             // traversal-stack entries per slot kept in shared memory
+#define PTB_TRACE_STACK 16             // traversal-stack entries per lane kept in shared memory
 #endif
 #ifndef PTB_TRACE_STEPS
 #define PTB_TRACE_STEPS 4              // traversal steps between two looks at the other stages
+#endif
+#ifndef PTB_TRACE_QUEUE
+#define PTB_TRACE_QUEUE 0              // leaf-queue entries per lane: 0 = the traversal stops at every leaf until it is pruned; 1, 2 = run ahead (speculative)
 #endif
 #ifndef PTB_TRACE_FETCH_LANES
 #define PTB_TRACE_FETCH_LANES 8
 #endif
 #ifndef PTB_TRACE_PRUNE_LANES
-#define PTB_TRACE_PRUNE_LANES 12
+#define PTB_TRACE_PRUNE_LANES 8
 #endif
 #ifndef PTB_TRACE_EXACT_LANES
-#define PTB_TRACE_EXACT_LANES 6
+#define PTB_TRACE_EXACT_LANES 3
 #endif
 constexpr int kTraceBlock = PTB_TRACE_BLOCK;
-constexpr int kTraceRays = PTB_TRACE_RAYS;
+constexpr int kTraceRays = 1;          // ray slots per lane (spill-area sizing on the host)
 constexpr int kStackSmem = PTB_TRACE_STACK;
 constexpr int kTraceSteps = PTB_TRACE_STEPS;
+constexpr int kLeafQueue = PTB_TRACE_QUEUE;
 constexpr int kFetchLanes = PTB_TRACE_FETCH_LANES;
 constexpr int kPruneLanes = PTB_TRACE_PRUNE_LANES;
 constexpr int kExactLanes = PTB_TRACE_EXACT_LANES;
@@ -78,25 +83,36 @@ struct TraceIO {        // SRC_RAYS only
     int          n;
 };
 
-// slot words in shared memory (all 32-bit): [word][slot][thread]
-enum { W_OX, W_OY, W_OZ, W_DX, W_DY, W_DZ, W_IX, W_IY, W_IZ, W_DL, W_IDX, W_BEST, W_NODE, W_SP, W_CAND, kSlotWords };
-// what a slot needs next.  The state is IMPLICIT in (cand, node, sp): cand >= 0 -> S_CAND; node < -1 (an encoded leaf) -> S_LEAF;
-// node >= 0, or node == -1 (nothing current) with a non-empty stack -> S_STEP; node == -1 and an empty stack -> S_IDLE (the ray
-// is finished: a miss was recorded when it was fetched, a hit when it was accepted).
-enum { S_IDLE = 0, S_STEP = 1, S_LEAF = 2, S_CAND = 3 };
-constexpr int kNoNode = -1;
+constexpr int kNoNode = -1;            // "nothing": no current node / empty queue entry / no candidate
+// per-lane words in shared memory besides the stack: the ray direction (pruning and the exact test need it, traversal does not)
+// and the index of the ray's hit record
+enum { W_DX, W_DY, W_DZ, W_IDX, kLaneWords };
 
-constexpr size_t traceSmemBytes(int smemNodes) {
-    return (size_t)smemNodes * sizeof(BvhNode) + (size_t)(kSlotWords + kStackSmem) * kTraceRays * kTraceBlock * sizeof(uint32_t);
+constexpr size_t traceSmemBytes() { return (size_t)(kLaneWords + 2 * kStackSmem) * kTraceBlock * sizeof(uint32_t); }
+
+// One traversal step: slab-test both child boxes of `node` (planes paired per axis, ptb_kernels.cuh slabNearPair), keep the
+// children whose entry parameter can still beat the best hit (bestTs: best distance in units of the ray parameter, slackened).
+// near / far: encoded children in front-to-back order, kNoNode when absent; tNear / tFar their entry parameters.
+PTB_DEV void nodeStep(const BvhNode *nodes, int node, f3 o, f3 invD, float bestTs, int &near, float &tNear, int &far, float &tFar) {
+    const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
+    const float4 X = __ldg(np), Y = __ldg(np + 1), Z = __ldg(np + 2);
+    const int2 m = __ldg(reinterpret_cast<const int2 *>(np + 3));
+    float tl, tr; bool hl, hr;
+    slabNearPair(X, Y, Z, o, invD, tl, tr, hl, hr);
+    const bool vl = hl && tl <= bestTs;
+    const bool vr = hr && tr <= bestTs;
+    const bool leftFirst = tl <= tr;
+    const int cl = vl ? m.x : kNoNode, cr = vr ? m.y : kNoNode;
+    const bool swap = vr && !(vl && leftFirst);                  // the right child goes first: it is the only one, or the nearer one
+    near = swap ? cr : cl; tNear = swap ? tr : tl;
+    far = (vl && vr) ? (swap ? cl : cr) : kNoNode; tFar = swap ? tl : tr;
 }
 
 template <int SRC, bool EXT, bool MESH>
 __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel(const __grid_constant__ Params p, const int depth, const TraceIO io) {
-    constexpr int R = kTraceRays;
     extern __shared__ float4 smem4[];
     __shared__ uint32_t sNextTicket, sTotal;
     __shared__ uint32_t sPrefix[kMaxVirtualSegs + 1];
-    const int smemNodes = p.hdr->smemNodes;
     if (threadIdx.x == 0) sNextTicket = 0u;
 
     // ---- this CTA's rays.  Segment / camera sources: the virtual CTAs (segments) v = blockIdx.x, + gridDim.x, ... of the fused
@@ -128,14 +144,13 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
         flatLo = min(n, blockIdx.x * chunk);
         if (threadIdx.x == 0) sTotal = min(chunk, n - flatLo);
     }
-    stageShared(smem4, reinterpret_cast<const float4 *>(p.bvh), smemNodes * 4);      // ends with __syncthreads
-    const BvhNode *snodes = reinterpret_cast<const BvhNode *>(smem4);
-    uint32_t *sw = reinterpret_cast<uint32_t *>(smem4 + (size_t)smemNodes * 4);
-    uint32_t *stk = sw + kSlotWords * R * kTraceBlock;
+    __syncthreads();
+    uint32_t *sw = reinterpret_cast<uint32_t *>(smem4);
+    uint2 *stk = reinterpret_cast<uint2 *>(sw + kLaneWords * kTraceBlock);
     const uint32_t nTickets = sTotal;
-#define SW(w, r) sw[((w) * R + (r)) * kTraceBlock + threadIdx.x]
-#define SWF(w, r) __uint_as_float(SW(w, r))
-#define STK(k, r) stk[((k) * R + (r)) * kTraceBlock + threadIdx.x]
+#define SW(w) sw[(w) * kTraceBlock + threadIdx.x]
+#define SWF(w) __uint_as_float(SW(w))
+#define STK(k) stk[(k) * kTraceBlock + threadIdx.x]
 
     CameraParams cam;
     if (SRC == SRC_CAMERA || SRC == SRC_PIXELS) cam = p.hdr->cam;
@@ -143,59 +158,44 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
     if (SRC == SRC_CAMERA && EXT) { iterBase = p.ctrl->iterBase; iterStride = p.ctrl->iterStride; }
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t laneBelow = (1u << lane) - 1u;
-    int *spill = p.stackSpill ? p.stackSpill + ((size_t)blockIdx.x * kTraceBlock + threadIdx.x) * R * p.spillCap : nullptr;
+    int2 *spill = p.stackSpill ? reinterpret_cast<int2 *>(p.stackSpill) + ((size_t)blockIdx.x * kTraceBlock + threadIdx.x) * p.spillCap : nullptr;
+    const BvhNode *nodes = p.bvh;
 
-    // ---- per-lane state: the ACTIVE slot's traversal state in registers; the category of every parked slot in `parked`
-    // (2 bits per slot; a parked slot does not change until the lane switches back to it: every stage works on the active slot)
+    // ---- per-lane state, all in registers
     f3 o = mk3(0.f, 0.f, 0.f), invD = o;
-    float dl = 0.f, bestT = FLT_MAX;
-    int node = kNoNode, sp = 0, cand = -1;
-    int act = 0;
-    uint32_t parked = 0u;                                            // all S_IDLE
+    float rdl = 1.f;                                                 // 1 / (|d| * 0.9999)
+    float bestT = FLT_MAX, bestTs = FLT_MAX;                         // best distance; the same in units of the ray parameter, slackened
+    int node = kNoNode, sp = 0;                                      // current interior node, or a leaf that found the queue full
+    int q0 = kNoNode, q1 = kNoNode;                                  // leaf queue (encoded leaves), q0 first
+    int cand = kNoNode;                                              // primitive that survived pruning
     bool drained = false;                                            // warp-uniform: the CTA's queue is empty
-    auto activeCat = [&]() -> uint32_t {
-        return cand >= 0 ? (uint32_t)S_CAND : (node < kNoNode ? (uint32_t)S_LEAF : ((node >= 0 || sp > 0) ? (uint32_t)S_STEP : (uint32_t)S_IDLE));
+    auto enqueue = [&](int leaf) {                                   // leaf: encoded, < kNoNode
+        if (kLeafQueue >= 1 && q0 == kNoNode) q0 = leaf;
+        else if (kLeafQueue >= 2 && q1 == kNoNode) q1 = leaf;
+        else node = leaf;                                            // no room: the lane waits for the pruning stage
     };
-    auto has = [&](uint32_t s) -> bool {                             // some slot of this lane is in category s
-        bool f = activeCat() == s;
-        if (R > 1) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) f = f || (r != act && ((parked >> (2 * r)) & 3u) == s);
-        }
-        return f;
-    };
-    // makes a slot of category s the active one (the caller checked has(s)); ~25 instructions when it has to switch
-    auto activate = [&](uint32_t s) {
-        if (R == 1 || activeCat() == s) return;
-        int r = 0;
-#pragma unroll
-        for (int k = R - 1; k >= 0; --k) if (k != act && ((parked >> (2 * k)) & 3u) == s) r = k;
-        // park the active slot ...
-        parked = (parked & ~(3u << (2 * act))) | (activeCat() << (2 * act));
-        SW(W_NODE, act) = (uint32_t)node; SW(W_SP, act) = (uint32_t)sp; SW(W_CAND, act) = (uint32_t)cand; SW(W_BEST, act) = __float_as_uint(bestT);
-        // ... and load slot r
-        o = mk3(SWF(W_OX, r), SWF(W_OY, r), SWF(W_OZ, r));
-        invD = mk3(SWF(W_IX, r), SWF(W_IY, r), SWF(W_IZ, r));
-        dl = SWF(W_DL, r); bestT = SWF(W_BEST, r);
-        node = (int)SW(W_NODE, r); sp = (int)SW(W_SP, r); cand = (int)SW(W_CAND, r);
-        act = r;
-    };
+    // room in the leaf queue (a leaf held in `node` moves in as soon as there is)
+    auto queueHasRoom = [&]() -> bool { return kLeafQueue >= 2 ? q1 == kNoNode : (kLeafQueue == 1 ? q0 == kNoNode : false); };
 
     for (;;) {
-        const unsigned mStep = __ballot_sync(0xffffffffu, has(S_STEP));
-        unsigned mLeaf = __ballot_sync(0xffffffffu, has(S_LEAF));
-        const unsigned mCand = __ballot_sync(0xffffffffu, has(S_CAND));
-        const unsigned mIdle = drained ? 0u : __ballot_sync(0xffffffffu, has(S_IDLE));
+        const bool canStep = node >= 0 || (node == kNoNode && sp > 0) || (node < kNoNode && queueHasRoom());
+        const bool hasLeaf = (kLeafQueue == 0 ? node < kNoNode : q0 != kNoNode) && cand == kNoNode;
+        const bool hasCand = cand != kNoNode;
+        const bool finished = node == kNoNode && sp == 0 && q0 == kNoNode && cand == kNoNode;
+        const unsigned mStep = __ballot_sync(0xffffffffu, canStep);
+        unsigned mLeaf = __ballot_sync(0xffffffffu, hasLeaf);
+        unsigned mCand = __ballot_sync(0xffffffffu, hasCand);
+        const unsigned mIdle = drained ? 0u : __ballot_sync(0xffffffffu, finished);
         if (!(mStep | mLeaf | mCand | mIdle)) break;
 
-        // ---- fetch: one new ray for every lane with an idle slot
+        // ---- fetch: a new ray for every finished lane
         if (mIdle && ((int)__popc(mIdle) >= kFetchLanes || !(mStep | mLeaf | mCand))) {
             const uint32_t want = (uint32_t)__popc(mIdle);
             uint32_t base = 0;
             if (lane == 0) base = atomicAdd(&sNextTicket, want);
             base = __shfl_sync(0xffffffffu, base, 0);
             drained = base + want >= nTickets;
-            if (has(S_IDLE)) {
+            if (finished) {
                 const uint32_t k = base + (uint32_t)__popc(mIdle & laneBelow);
                 bool have = k < nTickets;
                 uint32_t idx = 0;
@@ -237,38 +237,48 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
                 }
                 if (have) {
                     p.hits.meta[idx] = -1;                            // a miss until a hit is accepted
-                    // the ray's direction enters the traversal only through 1 / d and |d| (slackened)
+                    SW(W_DX) = __float_as_uint(rd.x); SW(W_DY) = __float_as_uint(rd.y); SW(W_DZ) = __float_as_uint(rd.z);
+                    SW(W_IDX) = idx;
+                    // the direction enters the traversal only through 1 / d and |d| (slackened: ray parameter * |d| * 0.9999 is a
+                    // lower bound of the world distance)
                     const float dd = fmaf(rd.x, rd.x, fmaf(rd.y, rd.y, rd.z * rd.z));
-                    const float rdl = dd * rsqrtApprox(dd) * 0.9999f;
-                    const f3 rinv = mk3(rcpApprox(rd.x), rcpApprox(rd.y), rcpApprox(rd.z));
-                    int r = act;                                      // the active slot when it is the idle one, else the lowest idle parked slot
-                    if (R > 1 && activeCat() != S_IDLE) {
-#pragma unroll
-                        for (int q = R - 1; q >= 0; --q) if (q != act && ((parked >> (2 * q)) & 3u) == S_IDLE) r = q;
-                    }
-                    SW(W_DX, r) = __float_as_uint(rd.x); SW(W_DY, r) = __float_as_uint(rd.y); SW(W_DZ, r) = __float_as_uint(rd.z);
-                    SW(W_IDX, r) = idx;
-                    if (R > 1) {
-                        SW(W_OX, r) = __float_as_uint(ro.x); SW(W_OY, r) = __float_as_uint(ro.y); SW(W_OZ, r) = __float_as_uint(ro.z);
-                        SW(W_IX, r) = __float_as_uint(rinv.x); SW(W_IY, r) = __float_as_uint(rinv.y); SW(W_IZ, r) = __float_as_uint(rinv.z);
-                        SW(W_DL, r) = __float_as_uint(rdl);
-                    }
-                    if (R == 1 || r == act) {
-                        o = ro; invD = rinv; dl = rdl; bestT = FLT_MAX; node = 0; sp = 0; cand = -1;
-                    } else {
-                        SW(W_BEST, r) = __float_as_uint(FLT_MAX); SW(W_NODE, r) = 0u; SW(W_SP, r) = 0u; SW(W_CAND, r) = 0xffffffffu;
-                        parked = (parked & ~(3u << (2 * r))) | ((uint32_t)S_STEP << (2 * r));
-                    }
+                    rdl = rsqrtApprox(dd) * 1.0002f;
+                    o = ro; invD = mk3(rcpApprox(rd.x), rcpApprox(rd.y), rcpApprox(rd.z));
+                    bestT = FLT_MAX; bestTs = FLT_MAX;
+                    node = 0; sp = 0;
                 }
             }
         }
 
-        // ---- the reference-exact test of one candidate per lane
+        // ---- pruning: the first queued primitive of every lane that has one -- object-space ray + sure-miss filter
+        if (mLeaf && ((int)__popc(mLeaf) >= kPruneLanes || !mStep)) {
+            if (hasLeaf) {
+                int &head = kLeafQueue == 0 ? node : q0;              // no queue: the leaf the traversal stopped at
+                const uint32_t code = (uint32_t)~head;                // first primitive | count << 27
+                const int slot = (int)(code & 0x7ffffffu);
+                const uint32_t cnt = code >> 27;
+                if (cnt > 1u) head = ~(int)((uint32_t)(slot + 1) | ((cnt - 1u) << 27));
+                else if (kLeafQueue == 0) node = kNoNode;
+                else { q0 = q1; q1 = kNoNode; }
+                const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + slot);
+                const int type = __ldg(reinterpret_cast<const int *>(gp + 9));
+                Affine inv;
+                inv.r0 = __ldg(gp); inv.r1 = __ldg(gp + 1); inv.r2 = __ldg(gp + 2);
+                const f3 rd = mk3(SWF(W_DX), SWF(W_DY), SWF(W_DZ));
+                const f3 qo = mulMVPoint(inv, o), qu = mulMV(inv, rd, 0.0f);
+                bool miss = boxSureMiss(qo, qu);
+                if (type == 0) miss = sphereSureMiss(qo, qu);
+                if (MESH && type == 2) miss = false;                  // triangles go straight to the exact test
+                if (!miss) cand = slot;
+            }
+            mCand = __ballot_sync(0xffffffffu, cand != kNoNode);
+        }
+
+        // ---- the reference-exact test of every lane's candidate
         if (mCand && ((int)__popc(mCand) >= kExactLanes || !mStep)) {
-            if (has(S_CAND)) {
-                activate(S_CAND);
-                const uint32_t idx = SW(W_IDX, act);
-                const f3 rd = mk3(SWF(W_DX, act), SWF(W_DY, act), SWF(W_DZ, act));
+            if (cand != kNoNode) {
+                const uint32_t idx = SW(W_IDX);
+                const f3 rd = mk3(SWF(W_DX), SWF(W_DY), SWF(W_DZ));
                 const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + cand);
                 Affine inv, fwd, vtx;
                 inv.r0 = __ldg(gp); inv.r1 = __ldg(gp + 1); inv.r2 = __ldg(gp + 2);
@@ -294,53 +304,40 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
                     p.hits.tn[idx] = make_float4(t, a, b, c);
                     p.hits.meta[idx] = cand | (outside << 30);
                     bestT = t;
+                    bestTs = (t + 1e-4f) * rdl;                       // box entry parameter beyond which nothing can win any more
                 }
-                cand = -1;                                            // back to S_LEAF (more primitives in the leaf), S_STEP or S_IDLE
-            }
-            mLeaf = __ballot_sync(0xffffffffu, has(S_LEAF));
-        }
-
-        // ---- pruning: one primitive of a pending leaf per lane -- object-space ray + sure-miss filter
-        if (mLeaf && ((int)__popc(mLeaf) >= kPruneLanes || !__ballot_sync(0xffffffffu, has(S_STEP)))) {
-            if (has(S_LEAF)) {
-                activate(S_LEAF);
-                const uint32_t code = (uint32_t)~node;                // ref | count << 27
-                const int slot = (int)(code & 0x7ffffffu);
-                const uint32_t cnt = code >> 27;
-                node = cnt > 1u ? ~(int)((uint32_t)(slot + 1) | ((cnt - 1u) << 27)) : kNoNode;
-                const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + slot);
-                const int type = __ldg(reinterpret_cast<const int *>(gp + 9));
-                Affine inv;
-                inv.r0 = __ldg(gp); inv.r1 = __ldg(gp + 1); inv.r2 = __ldg(gp + 2);
-                const f3 rd = mk3(SWF(W_DX, act), SWF(W_DY, act), SWF(W_DZ, act));
-                const f3 qo = mulMVPoint(inv, o), qu = mulMV(inv, rd, 0.0f);
-                bool miss = boxSureMiss(qo, qu);
-                if (type == 0) miss = sphereSureMiss(qo, qu);
-                if (MESH && type == 2) miss = false;                  // triangles go straight to the exact test
-                if (!miss) cand = slot;
+                cand = kNoNode;
             }
         }
 
-        // ---- traversal steps: lanes whose active slot cannot step switch to one that can, once per pass
-        if (R > 1 && has(S_STEP)) activate(S_STEP);
+        // ---- traversal steps
 #pragma unroll 1
         for (int rep = 0; rep < kTraceSteps; ++rep) {
-            // nothing current: take the top of the stack (a node, or a leaf that then waits for the pruning stage)
-            if (cand < 0 && node == kNoNode && sp > 0) {
+            // a leaf that found the queue full gets in as soon as there is room
+            if (kLeafQueue > 0 && node < kNoNode && queueHasRoom()) { const int leaf = node; node = kNoNode; enqueue(leaf); }
+            // nothing current: the top of the stack, unless its box can no longer beat the best hit
+            if (node == kNoNode && sp > 0) {
                 --sp;
-                node = sp < kStackSmem ? (int)STK(sp, act) : spill[(size_t)act * p.spillCap + (sp - kStackSmem)];
+                const uint2 e = sp < kStackSmem ? STK(sp) : *reinterpret_cast<const uint2 *>(&spill[sp - kStackSmem]);
+                if (__uint_as_float(e.y) <= bestTs) {
+                    if ((int)e.x < kNoNode) enqueue((int)e.x);
+                    else node = (int)e.x;
+                }
             }
-            const bool stepping = cand < 0 && node >= 0;
-            if (!__any_sync(0xffffffffu, stepping)) break;
+            const bool stepping = node >= 0;
+            if (!__any_sync(0xffffffffu, stepping || (node == kNoNode && sp > 0))) break;
             if (stepping) {
-                int next, far; bool haveNext, haveFar;
-                bvhNodeStep(snodes, smemNodes, p.bvh, node, o, invD, dl, bestT, next, haveNext, far, haveFar);
-                if (haveFar) {
-                    if (sp < kStackSmem) STK(sp, act) = (uint32_t)far;
-                    else spill[(size_t)act * p.spillCap + (sp - kStackSmem)] = far;
+                int near, far; float tNear, tFar;
+                nodeStep(nodes, node, o, invD, bestTs, near, tNear, far, tFar);
+                if (far != kNoNode) {
+                    const uint2 e = make_uint2((uint32_t)far, __float_as_uint(tFar));
+                    if (sp < kStackSmem) STK(sp) = e;
+                    else *reinterpret_cast<uint2 *>(&spill[sp - kStackSmem]) = e;
                     ++sp;
                 }
-                node = haveNext ? next : kNoNode;                     // an interior node, an encoded leaf (< -1), or nothing
+                node = kNoNode;
+                if (near < kNoNode) enqueue(near);                    // a leaf: queue it and go on with the stack
+                else node = near;                                     // an interior node, or nothing
             }
         }
     }

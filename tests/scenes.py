@@ -56,6 +56,13 @@ def cornell_text(**kw):
     return emit(_CORNELL_MATERIALS, _CORNELL_OBJECTS, name="cornell", **kw)
 
 
+def closed_cornell_text(**kw):
+    """cornell.txt with a front wall behind the camera: no path leaves the box, so every path runs until it meets the light or
+    the depth limit (the "open vs closed scene" comparison of the stream-compaction analysis, INSTRUCTION.md:78-89, 339-355)."""
+    objs = list(_CORNELL_OBJECTS) + [("Front wall", "cube", 1, "0 5 11", "0 90 0", ".01 10 10")]
+    return emit(_CORNELL_MATERIALS, objs, name="cornell_closed", **kw)
+
+
 def sphere_text(**kw):
     return emit(_SPHERE_MATERIALS, _SPHERE_OBJECTS, name="sphere", **kw)
 

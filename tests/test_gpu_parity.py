@@ -456,6 +456,36 @@ def test_reference_entry_points(m, scene_dir):
         m.pathtrace(None, 0, 1)                     # after free
 
 
+def test_lazy_image_of_the_per_iteration_call(m, scene_dir):
+    """pathtrace(pbo, frame, iter) with a host image: strict (the reference's semantic, src/pathtrace.cu:389-390: the SUM is in
+    the host array on return) and PtbOptions.lazyImage (the copy of iteration i overlaps iteration i + 1; valid after ptb_sync).
+    Both leave the same bits; the caller's pageable array is page-locked by the library on first use."""
+    s = m.Scene.load(scene_dir + "/cornell.txt")
+    want = []
+    with m.Renderer(s, device=0, bsdf=1, batch_iters=1) as r:
+        for it in range(1, 7):
+            r.render(it, 1)
+            want.append(r.download())
+    for lazy in (0, 1):
+        host = np.full((s.pixels, 3), -1.0, np.float32)
+        with m.Renderer(s, device=0, bsdf=1, batch_iters=1, lazy_image=lazy) as r:
+            for it in range(1, 7):
+                r.pathtrace(None, 0, it, host)
+                if not lazy:
+                    assert same_bits(host, want[it - 1]), it
+                elif it == 3:
+                    r.sync()
+                    assert same_bits(host, want[2])
+            r.sync()
+            assert same_bits(host, want[5]), lazy
+            other = np.zeros_like(host)                         # a different host array: re-registered
+            r.pathtrace(None, 0, 7, other)
+            r.sync()
+            assert other.any() and not same_bits(other, host)
+            with pytest.raises(m.PtbError):
+                r.pathtrace(None, 0, 0, host)                    # iterations are 1-based (src/main.cpp:132)
+
+
 def test_resolve_rgb8_follows_save_image(m, scene_dir, tmp_path):
     from PIL import Image
     s = m.Scene.load(scene_dir + "/cornell.txt")

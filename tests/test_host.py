@@ -193,3 +193,26 @@ def test_headless_driver_usage_and_errors(tmp_path):
     assert r.returncode == 1 and "Usage" in r.stdout                    # src/main.cpp:36-39
     r = subprocess.run([exe, str(tmp_path / "nope.txt"), "--quiet"], capture_output=True, text=True)
     assert r.returncode == 1 and "Error reading from file" in r.stderr  # src/scene.cpp:12-15
+
+
+def test_reference_gl_shell_links_over_the_library(tmp_path):
+    """the reference's own display shell -- src/main.cpp, preview.cpp, glslUtility.cpp, image.cpp, scene.cpp,
+    utilities.cpp, stb.cpp, UNMODIFIED and compiled where they lie (oracle/Makefile `glshell`) -- links against the product's
+    pathtraceInit / pathtraceFree / pathtrace, with oracle/gl_stub.cpp standing in for the GL stack this image does not have.
+    Here (no GPU): the binary exists, takes its three renderer symbols from the shim over libptb200.so, prints the app's usage
+    line, and dies with checkCUDAError's message at pathtraceInit.  tests/test_gpu_dropin.py runs it for real."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_gl_shell")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_gl_shell is built where /root/reference is mounted")
+    syms = subprocess.run(["nm", "-D", "--undefined-only", exe], capture_output=True, text=True).stdout
+    for need in ("ptb_create", "ptb_destroy", "ptb_pathtrace"):
+        assert need in syms, need
+    assert "libptb200.so" in subprocess.run(["ldd", exe], capture_output=True, text=True).stdout
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "Usage" in r.stdout + r.stderr              # src/main.cpp:36-39
+    scene = tmp_path / "cornell.txt"
+    scene.write_text(scenes.cornell_text(res=(32, 32), iterations=2))
+    run = subprocess.run([exe, str(scene)], capture_output=True, text=True, cwd=str(tmp_path))
+    if not has_gpu():
+        assert run.returncode == 1 and "CUDA error" in run.stderr

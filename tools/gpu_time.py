@@ -11,7 +11,7 @@ for name in (sys.argv[1:] or ["cornell.txt"]):
     scene = m.Scene.load(files[name])
     B = int(os.environ.get("PTB_B", "16"))
     with m.Renderer(scene, device=0, bsdf=1, batch_iters=B, first_bounce_cache=int(os.environ.get("PTB_FBC", "0"))) as r:
-        n = 8 * B
+        n = max(8 * B, 256)
         r.render(1, n); r.sync()
         best = 1e9
         for _ in range(3):
