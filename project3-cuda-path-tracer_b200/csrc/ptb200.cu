@@ -152,6 +152,7 @@ struct PtbContext {
     DevBuf<uint32_t> sortHist, segCounts;
     uint32_t segCap = 0;
     bool loopBounces = false;      // fused pipeline, brute force: one launch for bounces 1 .. traceDepth-1
+    bool sharedFirstHit = false;   // fused pipeline: the camera ray is iteration-independent, bounce 0 shares one hit per pixel across the slots
     DevBuf<Control> ctrl;
     DevBuf<uint8_t> rgb8;
 
@@ -474,6 +475,14 @@ void launchFusedBounces(PtbContext *c) {
     for (int d = 0; d < c->traceDepth; ++d) {
         // bounce d reads buffer (d-1)&1... bounce 0 reads nothing and writes buffer 0
         Params p = makeParams(c, d == 0 ? 1 : ((d - 1) & 1));
+        if (d == 0 && c->sharedFirstHit) {
+            // the camera ray does not depend on the iteration: one closest hit per pixel serves every slot of the wavefront
+            if (c->useBvh) {
+                if (p.fbTn == nullptr) LAUNCH(PTB_STAGE_INTERSECT, (trace_kernel<SRC_PIXELS, false, MESH>), c->gridTrace, kTraceBlock, smem, p, 0, TraceIO{});
+                LAUNCH(PTB_STAGE_SHADE, (bounce0_shared_kernel<true, EXT>), c->gridFused, kBlock, 0, p);
+            } else LAUNCH(PTB_STAGE_FUSED_BOUNCE0, (bounce0_shared_kernel<false, EXT>), c->gridFused, kBlock, smem, p);
+            continue;
+        }
         if (c->useBvh) {
             // closest hit first (persistent threads, R rays multiplexed per lane), then shade / scatter / compact
             const bool cached = d == 0 && p.fbTn != nullptr;
@@ -530,7 +539,7 @@ int launchStagedBatch(PtbContext *c) {
             LAUNCH(PTB_STAGE_SORT, sort_keys_kernel, grid, kBlock, 0, p, d, c->sortKeys.p, c->sortHist.p, numKeys);
             LAUNCH(PTB_STAGE_SORT, sort_hist_dev_kernel, grid, kBlock, sizeof(uint32_t) * numKeys, c->sortKeys.p, c->ctrl.p, d, numKeys, c->sortHist.p);
             LAUNCH(PTB_STAGE_SORT, sort_scan_kernel, 1, 32, 0, c->sortHist.p, numKeys);
-            LAUNCH(PTB_STAGE_SORT, sort_scatter_dev_kernel, grid, kBlock, 0, c->sortKeys.p, c->ctrl.p, d, c->sortHist.p, c->sortOrder.p);
+            LAUNCH(PTB_STAGE_SORT, sort_scatter_dev_kernel, grid, kBlock, 0, c->sortKeys.p, c->ctrl.p, d, c->sortHist.p, c->sortOrder.p, 0u, numKeys);
             order = c->sortOrder.p;
         }
         LAUNCH(PTB_STAGE_SHADE, shade_kernel, grid, kBlock, 0, p, d, order, compaction ? 1 : 0);
@@ -736,6 +745,7 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
         rc |= setSmem(bounce_kernel<true, false, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, false>, c->smemBrute);
         rc |= setSmem(bounce_kernel<true, false, true>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, true>, c->smemBrute);
         rc |= setSmem(bounce_loop_kernel<false>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true>, c->smemBrute);
+        rc |= setSmem(bounce0_shared_kernel<false, false>, c->smemBrute); rc |= setSmem(bounce0_shared_kernel<false, true>, c->smemBrute);
         rc |= setSmem(intersect_kernel, c->smemBrute); rc |= setSmem(stage_intersect_kernel, c->smemBrute);
         rc |= setSmem(fb_cache_kernel, c->smemBrute);
         if (rc != PTB_OK) return bail(rc);
@@ -746,6 +756,7 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
         rc |= setSmem(trace_kernel<SRC_CAMERA, false, true>, c->smemBvh); rc |= setSmem(trace_kernel<SRC_CAMERA, true, true>, c->smemBvh);
         rc |= setSmem(trace_kernel<SRC_SEGMENTS, false, false>, c->smemBvh); rc |= setSmem(trace_kernel<SRC_SEGMENTS, false, true>, c->smemBvh);
         rc |= setSmem(trace_kernel<SRC_PATHS, false, true>, c->smemBvh); rc |= setSmem(trace_kernel<SRC_PIXELS, false, true>, c->smemBvh);
+        rc |= setSmem(trace_kernel<SRC_PIXELS, false, false>, c->smemBvh);
         rc |= setSmem(trace_kernel<SRC_RAYS, false, true>, c->smemBvh);
         if (rc != PTB_OK) return bail(rc);
     }
@@ -763,7 +774,12 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     // x8 135.4, x16 142 (round 1, first build); with the one-launch bounce loop the per-CTA set-up is paid once per
     // wavefront and x8 wins: x2 119.0, x4 114.8, x8 112.9, x16 112.7 (profiles/r01n_loop_ab.txt)
     const size_t wavefrontTiles = ((size_t)c->numPixels * c->batch + kBlock - 1) / kBlock;
-    int gridMult = (c->loopBounces && wavefrontTiles >= (size_t)c->numSMs * std::max(1, occ) * 8 * 4) ? 8 : 4;   // >= 4 tiles per CTA
+    // (one iteration per wavefront -- the per-iteration pathtrace() call: 2 500 tiles at 800 x 800 -- x1 147.6 us, x2 158.2, x4 / x8 176.4,
+    // profiles/r2i_b1_grid.txt: the multiplier is the largest that still leaves every CTA four tiles)
+    int gridMult = 1;
+    if (c->useBvh) gridMult = 4;
+    else for (int mlt : {8, 4, 2}) if (wavefrontTiles >= (size_t)c->numSMs * std::max(1, occ) * mlt * 4) { gridMult = mlt; break; }
+    if (!c->loopBounces && !c->useBvh) gridMult = std::min(gridMult, 4);
     if (const char *e = tuningEnv("PTB_GRID_MULT")) gridMult = std::max(1, atoi(e));           // tuning knob (experiments)
     c->gridFused = c->numSMs * std::max(1, occ) * gridMult;
     c->gridFused = std::min(c->gridFused, c->gridTrace * kMaxVirtualSegs);      // trace_kernel serves at most kMaxVirtualSegs segments per CTA
@@ -773,8 +789,11 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     if (opt.externalAccum) c->imagePtr = opt.externalAccum;
     else { CUB(c->image.alloc((size_t)c->numPixels * 3)); c->imagePtr = c->image.p; CUB(cudaMemset(c->imagePtr, 0, (size_t)c->numPixels * 3 * sizeof(float))); }
     const size_t maxPaths = (size_t)c->numPixels * c->batch;
-    // fused pipeline: every CTA owns a segment of ceil(tiles / grid) 256-path tiles of the path buffers
-    const size_t tiles = (maxPaths + kBlock - 1) / kBlock;
+    c->sharedFirstHit = opt.pipeline == PTB_PIPELINE_FUSED && !opt.antialias && !(opt.lensRadius > 0.0f);
+    // fused pipeline: every CTA owns a segment of ceil(tiles / grid) 256-path tiles of the path buffers (bounce0_shared_kernel's
+    // tiles are 32 pixels x min(batch, 8) slots: at most 256 paths each, possibly more of them)
+    const size_t sharedTiles = (((size_t)c->numPixels + 31) / 32) * (((size_t)c->batch + std::min<size_t>(c->batch, kSlotBlock) - 1) / std::min<size_t>(c->batch, kSlotBlock));
+    const size_t tiles = std::max((maxPaths + kBlock - 1) / kBlock, sharedTiles);
     c->segCap = (uint32_t)(((tiles + c->gridFused - 1) / c->gridFused) * kBlock);
     const size_t pathSlots = std::max(maxPaths, (size_t)c->segCap * c->gridFused);
     for (int i = 0; i < 2; ++i) {
@@ -1129,6 +1148,21 @@ int ptb_multi_create(PtbMulti **out, const PtbSceneDesc *scene, const PtbOptions
         ncclResult_t r = nccl->commInitAll(m->comms.data(), n, devs.data());
         if (r != ncclSuccess) { ptb_multi_destroy(m); return fail(PTB_ERR_CUDA, "ncclCommInitAll: %s", nccl->getErrorString(r)); }
         for (int g = 0; g < n; ++g) { m->ctx[g]->comm = m->comms[g]; m->ctx[g]->ownComm = false; m->ctx[g]->commRank = g; m->ctx[g]->commRanks = n; }
+        // one collective now (over the still all-zero accumulation buffers): NCCL sets its channels up on first use, which would
+        // otherwise be charged to the first frame (35 ms on 2 B200s against ~0.1 ms for the reduce itself)
+        int rc = PTB_OK;
+        { DeviceScope ds(m->ctx[0]->device); rc = ensureFrame(m->ctx[0]); }
+        if (rc == PTB_OK) {
+            nccl->groupStart();
+            for (int g = 0; g < n; ++g) {
+                PtbContext *c = m->ctx[g];
+                nccl->reduce(c->imagePtr, g == 0 ? c->frame.p : nullptr, (size_t)c->numPixels * 3, ncclFloat32, ncclSum, 0, c->comm, c->stream);
+            }
+            ncclResult_t r2 = nccl->groupEnd();
+            if (r2 != ncclSuccess) rc = fail(PTB_ERR_CUDA, "ncclReduce (set-up): %s", nccl->getErrorString(r2));
+            for (int g = 0; g < n && rc == PTB_OK; ++g) rc = ptb_sync(m->ctx[g]);
+        }
+        if (rc != PTB_OK) { const std::string keep = g_lastError; ptb_multi_destroy(m); g_lastError = keep; return rc; }
     }
     {
         DeviceScope ds(m->ctx[0]->device);
@@ -1325,7 +1359,7 @@ int ptb_stage_sort_keys(PtbContext *c, int n, const int32_t *keys, int numKeys, 
         CU(cudaMemcpyAsync(dk.p, keys, (size_t)n * 4, cudaMemcpyHostToDevice, c->stream));
         sort_hist_kernel<<<c->gridStaged, kBlock, sizeof(uint32_t) * numKeys, c->stream>>>(dk.p, (uint32_t)n, numKeys, hist.p);
         sort_scan_kernel<<<1, 32, 0, c->stream>>>(hist.p, numKeys);
-        sort_scatter_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(dk.p, (uint32_t)n, hist.p, dord.p);
+        sort_scatter_dev_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(dk.p, nullptr, 0, hist.p, dord.p, (uint32_t)n, numKeys);
         c->launches += 3;
         CU(cudaGetLastError());
         CU(cudaMemcpyAsync(outOrder, dord.p, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));

@@ -108,6 +108,21 @@ PTB_DEV void nodeStep(const BvhNode *nodes, int node, f3 o, f3 invD, float bestT
     far = (vl && vr) ? (swap ? cl : cr) : kNoNode; tFar = swap ? tl : tr;
 }
 
+// Primitive records are read once per pruning / exact test; sending them past L1 (ld.global.nc.L1::no_allocate) so that the BVH
+// nodes keep it measured 1 % SLOWER on the 100 k-object scene (profiles/r2i_variants.txt: 3 311 against 3 274 us): off.
+#ifndef PTB_TRACE_GEOM_NC
+#define PTB_TRACE_GEOM_NC 0
+#endif
+PTB_DEV float4 ldGeom4(const float4 *q) {
+#if PTB_TRACE_GEOM_NC
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(q));
+    return v;
+#else
+    return __ldg(q);
+#endif
+}
+
 template <int SRC, bool EXT, bool MESH>
 __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel(const __grid_constant__ Params p, const int depth, const TraceIO io) {
     extern __shared__ float4 smem4[];
@@ -263,7 +278,7 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
                 const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + slot);
                 const int type = __ldg(reinterpret_cast<const int *>(gp + 9));
                 Affine inv;
-                inv.r0 = __ldg(gp); inv.r1 = __ldg(gp + 1); inv.r2 = __ldg(gp + 2);
+                inv.r0 = ldGeom4(gp); inv.r1 = ldGeom4(gp + 1); inv.r2 = ldGeom4(gp + 2);
                 const f3 rd = mk3(SWF(W_DX), SWF(W_DY), SWF(W_DZ));
                 const f3 qo = mulMVPoint(inv, o), qu = mulMV(inv, rd, 0.0f);
                 bool miss = boxSureMiss(qo, qu);
@@ -281,8 +296,8 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
                 const f3 rd = mk3(SWF(W_DX), SWF(W_DY), SWF(W_DZ));
                 const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + cand);
                 Affine inv, fwd, vtx;
-                inv.r0 = __ldg(gp); inv.r1 = __ldg(gp + 1); inv.r2 = __ldg(gp + 2);
-                fwd.r0 = __ldg(gp + 3); fwd.r1 = __ldg(gp + 4); fwd.r2 = __ldg(gp + 5);
+                inv.r0 = ldGeom4(gp); inv.r1 = ldGeom4(gp + 1); inv.r2 = ldGeom4(gp + 2);
+                fwd.r0 = ldGeom4(gp + 3); fwd.r1 = ldGeom4(gp + 4); fwd.r2 = ldGeom4(gp + 5);
                 const int4 tag = __ldg(reinterpret_cast<const int4 *>(gp + 9));    // x type, z scene order, w object index
                 vtx.r0 = vtx.r1 = vtx.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (MESH && tag.x == 2) { vtx.r0 = __ldg(gp + 6); vtx.r1 = __ldg(gp + 7); vtx.r2 = __ldg(gp + 8); }
