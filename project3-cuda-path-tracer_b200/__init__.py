@@ -16,7 +16,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libptb200.so")
+# PTB200_LIB: load another build of the same library (tuning variants of tools/build_variant.sh under the GPU test suite)
+LIB_PATH = os.environ.get("PTB200_LIB") or os.path.join(_HERE, "libptb200.so")
 
 GEOM_DT = np.dtype([("type", "<i4"), ("materialid", "<i4"), ("translation", "<f4", 3),
                     ("rotation", "<f4", 3), ("scale", "<f4", 3), ("transform", "<f4", 16),

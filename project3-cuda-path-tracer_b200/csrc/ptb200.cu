@@ -20,6 +20,21 @@
 
 using namespace ptb;
 
+// which BVH traversal the library launches: the per-lane trace_kernel, or trace_pool_kernel (64 ray slots per warp in shared
+// memory, any lane runs any slot) -- csrc/ptb_trace.cuh
+#ifndef PTB_TRACE_POOL
+#define PTB_TRACE_POOL 0
+#endif
+#if PTB_TRACE_POOL
+#define TRACE_KERNEL trace_pool_kernel
+constexpr int kTraceStackSmem = kPoolStack, kTraceSlotsPerThread = 2;
+constexpr size_t traceKernelSmem() { return poolSmemBytes(); }
+#else
+#define TRACE_KERNEL trace_kernel
+constexpr int kTraceStackSmem = kStackSmem, kTraceSlotsPerThread = 1;
+constexpr size_t traceKernelSmem() { return traceSmemBytes(); }
+#endif
+
 namespace {
 
 thread_local std::string g_lastError;
@@ -478,7 +493,7 @@ void launchFusedBounces(PtbContext *c) {
         if (d == 0 && c->sharedFirstHit) {
             // the camera ray does not depend on the iteration: one closest hit per pixel serves every slot of the wavefront
             if (c->useBvh) {
-                if (p.fbTn == nullptr) LAUNCH(PTB_STAGE_INTERSECT, (trace_kernel<SRC_PIXELS, false, MESH>), c->gridTrace, kTraceBlock, smem, p, 0, TraceIO{});
+                if (p.fbTn == nullptr) LAUNCH(PTB_STAGE_INTERSECT, (TRACE_KERNEL<SRC_PIXELS, false, MESH>), c->gridTrace, kTraceBlock, smem, p, 0, TraceIO{});
                 LAUNCH(PTB_STAGE_SHADE, (bounce0_shared_kernel<true, EXT>), c->gridFused, kBlock, 0, p);
             } else LAUNCH(PTB_STAGE_FUSED_BOUNCE0, (bounce0_shared_kernel<false, EXT>), c->gridFused, kBlock, smem, p);
             continue;
@@ -487,8 +502,8 @@ void launchFusedBounces(PtbContext *c) {
             // closest hit first (persistent threads, R rays multiplexed per lane), then shade / scatter / compact
             const bool cached = d == 0 && p.fbTn != nullptr;
             if (!cached) {
-                if (d == 0) LAUNCH(PTB_STAGE_INTERSECT, (trace_kernel<SRC_CAMERA, EXT, MESH>), c->gridTrace, kTraceBlock, smem, p, d, TraceIO{});
-                else        LAUNCH(PTB_STAGE_INTERSECT, (trace_kernel<SRC_SEGMENTS, false, MESH>), c->gridTrace, kTraceBlock, smem, p, d, TraceIO{});
+                if (d == 0) LAUNCH(PTB_STAGE_INTERSECT, (TRACE_KERNEL<SRC_CAMERA, EXT, MESH>), c->gridTrace, kTraceBlock, smem, p, d, TraceIO{});
+                else        LAUNCH(PTB_STAGE_INTERSECT, (TRACE_KERNEL<SRC_SEGMENTS, false, MESH>), c->gridTrace, kTraceBlock, smem, p, d, TraceIO{});
             }
             if (d == 0) LAUNCH(PTB_STAGE_SHADE, (bounce_kernel<true, true, EXT>), c->gridFused, kBlock, 0, p, d);
             else        LAUNCH(PTB_STAGE_SHADE, (bounce_kernel<false, true, EXT>), c->gridFused, kBlock, 0, p, d);
@@ -530,7 +545,7 @@ int launchStagedBatch(PtbContext *c) {
         p = makeParams(c, cur);
         if (c->useBvh) {
             // raw hit records through the BVH, then the deferred normals in place
-            LAUNCH(PTB_STAGE_INTERSECT, (trace_kernel<SRC_PATHS, false, true>), c->gridTrace, kTraceBlock, smem, p, d, TraceIO{});
+            LAUNCH(PTB_STAGE_INTERSECT, (TRACE_KERNEL<SRC_PATHS, false, true>), c->gridTrace, kTraceBlock, smem, p, d, TraceIO{});
             LAUNCH(PTB_STAGE_INTERSECT, resolve_hits_kernel, grid, kBlock, 0, p, &c->ctrl.p->counts[d], 0u, p.hits.tn, p.hits.meta);
         } else LAUNCH(PTB_STAGE_INTERSECT, intersect_kernel, grid, kBlock, smem, p, d);
         const int *order = nullptr;
@@ -589,7 +604,7 @@ int ensureFirstBounceCache(PtbContext *c) {
     Params p = c->base;
     if (c->useBvh) {
         // p.hits is free between batches: raw hit records of the pixels' camera rays there, then normals into the cache
-        trace_kernel<SRC_PIXELS, false, true><<<c->gridTrace, kTraceBlock, c->smemBvh, c->stream>>>(p, 0, TraceIO{});
+        TRACE_KERNEL<SRC_PIXELS, false, true><<<c->gridTrace, kTraceBlock, c->smemBvh, c->stream>>>(p, 0, TraceIO{});
         resolve_hits_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(p, nullptr, c->numPixels, c->fbTn.p, c->fbMeta.p);
         c->launches++;
     } else fb_cache_kernel<<<c->gridStaged, kBlock, c->smemBrute, c->stream>>>(p, c->fbTn.p, c->fbMeta.p);
@@ -603,10 +618,10 @@ int ensureFirstBounceCache(PtbContext *c) {
 // trace_kernel keeps kStackSmem traversal-stack entries per ray slot in shared memory; a deeper tree (the stack never holds
 // more entries than the tree has levels) gets the rest in global memory
 int ensureStackSpill(PtbContext *c) {
-    const int need = std::max(0, c->bvhDepth + 2 - kStackSmem);
+    const int need = std::max(0, c->bvhDepth + 2 - kTraceStackSmem);
     if (need > c->spillCap) {
         CU(cudaStreamSynchronize(c->stream));
-        CU(c->stackSpill.alloc((size_t)c->gridTrace * kTraceBlock * kTraceRays * need * 2));      // 8-byte entries (child, entry distance)
+        CU(c->stackSpill.alloc((size_t)c->gridTrace * kTraceBlock * kTraceSlotsPerThread * need * 2));      // 8-byte entries (child, entry distance)
         c->spillCap = need;
         if (c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }    // new launch parameters: re-capture
     }
@@ -739,7 +754,7 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
 
     // ---- launch geometry ----
     c->smemBrute = bruteBytes;
-    c->smemBvh = traceSmemBytes();
+    c->smemBvh = traceKernelSmem();
     if (bruteBytes <= 200 * 1024) {                  // brute force is only launchable when the geoms fit in shared memory
         int rc = PTB_OK;
         rc |= setSmem(bounce_kernel<true, false, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, false>, c->smemBrute);
@@ -752,16 +767,16 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     }
     {
         int rc = PTB_OK;
-        rc |= setSmem(trace_kernel<SRC_CAMERA, false, false>, c->smemBvh); rc |= setSmem(trace_kernel<SRC_CAMERA, true, false>, c->smemBvh);
-        rc |= setSmem(trace_kernel<SRC_CAMERA, false, true>, c->smemBvh); rc |= setSmem(trace_kernel<SRC_CAMERA, true, true>, c->smemBvh);
-        rc |= setSmem(trace_kernel<SRC_SEGMENTS, false, false>, c->smemBvh); rc |= setSmem(trace_kernel<SRC_SEGMENTS, false, true>, c->smemBvh);
-        rc |= setSmem(trace_kernel<SRC_PATHS, false, true>, c->smemBvh); rc |= setSmem(trace_kernel<SRC_PIXELS, false, true>, c->smemBvh);
-        rc |= setSmem(trace_kernel<SRC_PIXELS, false, false>, c->smemBvh);
-        rc |= setSmem(trace_kernel<SRC_RAYS, false, true>, c->smemBvh);
+        rc |= setSmem(TRACE_KERNEL<SRC_CAMERA, false, false>, c->smemBvh); rc |= setSmem(TRACE_KERNEL<SRC_CAMERA, true, false>, c->smemBvh);
+        rc |= setSmem(TRACE_KERNEL<SRC_CAMERA, false, true>, c->smemBvh); rc |= setSmem(TRACE_KERNEL<SRC_CAMERA, true, true>, c->smemBvh);
+        rc |= setSmem(TRACE_KERNEL<SRC_SEGMENTS, false, false>, c->smemBvh); rc |= setSmem(TRACE_KERNEL<SRC_SEGMENTS, false, true>, c->smemBvh);
+        rc |= setSmem(TRACE_KERNEL<SRC_PATHS, false, true>, c->smemBvh); rc |= setSmem(TRACE_KERNEL<SRC_PIXELS, false, true>, c->smemBvh);
+        rc |= setSmem(TRACE_KERNEL<SRC_PIXELS, false, false>, c->smemBvh);
+        rc |= setSmem(TRACE_KERNEL<SRC_RAYS, false, true>, c->smemBvh);
         if (rc != PTB_OK) return bail(rc);
     }
     int occ = 0, occTrace = 0;
-    CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occTrace, trace_kernel<SRC_SEGMENTS, false, true>, kTraceBlock, c->smemBvh));
+    CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occTrace, TRACE_KERNEL<SRC_SEGMENTS, false, true>, kTraceBlock, c->smemBvh));
     // persistent grid of the BVH traversal: one wave of resident CTAs, each serving several CTA-owned path segments back to back
     c->gridTrace = c->numSMs * std::max(1, occTrace);
     if (c->useBvh) CUB(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bounce_kernel<false, true, false>, kBlock, 0));
@@ -1281,7 +1296,7 @@ int ptb_stage_intersect(PtbContext *c, int accel, const float *origins, const fl
             // raw hit records through trace_kernel (the traversal every BVH render runs), then normals / scene indices
             CU(rawTn.alloc(n)); CU(rawMeta.alloc(n));
             p.geoms = c->geoms.p; p.hits.tn = rawTn.p; p.hits.meta = rawMeta.p;
-            trace_kernel<SRC_RAYS, false, true><<<c->gridTrace, kTraceBlock, c->smemBvh, c->stream>>>(p, 0, TraceIO{o.p, d.p, n});
+            TRACE_KERNEL<SRC_RAYS, false, true><<<c->gridTrace, kTraceBlock, c->smemBvh, c->stream>>>(p, 0, TraceIO{o.p, d.p, n});
             stage_hits_out_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(p, n, dh.p, dt.p, dn.p, dout.p);
             c->launches++;
         }

@@ -361,6 +361,282 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
 #undef STK
 }
 
+// ------------------------------------------------------------------------------------------------
+// trace_pool_kernel: the same search with a POOL of 64 ray slots per warp in shared memory (PTB_TRACE_POOL).
+//
+// In trace_kernel a lane keeps its ray until it is finished, so whenever the ray waits (for the pruning stage, the exact test, a
+// new ray) the lane idles: the traversal step runs with ~19 of 32 lanes.  Here the 64 rays of a warp live in shared memory
+// (origin, direction, hit-record index, best distance, current node / pending leaf, stack pointer, candidate, stack) and no lane
+// owns any of them: every pass the warp looks at all 64 slots (two per lane, ballots), picks ONE kind of work -- kPoolSteps
+// traversal steps while at least kPoolStepMin slots can step, else whichever of fetch / prune / exact has the most slots waiting
+// -- and hands the first 32 slots of that kind to its lanes.  A waiting ray costs nothing but its slot, and prune / exact passes
+// fill up on their own while the warp keeps stepping.  Per pass: ~90 instructions of classification, list building and state
+// load / store against ~100 per traversal step.
+// ------------------------------------------------------------------------------------------------
+#ifndef PTB_POOL_STEPS
+#define PTB_POOL_STEPS 8
+#endif
+#ifndef PTB_POOL_STEP_MIN
+#define PTB_POOL_STEP_MIN 24
+#endif
+#ifndef PTB_POOL_STACK
+#define PTB_POOL_STACK 10
+#endif
+#ifndef PTB_POOL_MINBLOCKS
+#define PTB_POOL_MINBLOCKS 3
+#endif
+constexpr int kPoolSteps = PTB_POOL_STEPS;
+constexpr int kPoolStepMin = PTB_POOL_STEP_MIN;
+constexpr int kPoolStack = PTB_POOL_STACK;
+constexpr int kPoolSlots = 2 * kTraceBlock;                       // per CTA: 64 per warp
+enum { P_OX, P_OY, P_OZ, P_DX, P_DY, P_DZ, P_IDX, P_BEST, P_NODE, P_SP, P_CAND, kPoolWords };
+enum { T_NONE = 0, T_STEP = 1, T_LEAF = 2, T_CAND = 3, T_IDLE = 4 };
+constexpr size_t poolSmemBytes() { return (size_t)(kPoolWords + 2 * kPoolStack) * kPoolSlots * sizeof(uint32_t) + (size_t)kPoolSlots; }
+
+template <int SRC, bool EXT, bool MESH>
+__global__ void __launch_bounds__(kTraceBlock, PTB_POOL_MINBLOCKS) trace_pool_kernel(const __grid_constant__ Params p, const int depth, const TraceIO io) {
+    extern __shared__ float4 smem4[];
+    __shared__ uint32_t sNextTicket, sTotal;
+    __shared__ uint32_t sPrefix[kMaxVirtualSegs + 1];
+    if (threadIdx.x == 0) sNextTicket = 0u;
+    const uint32_t vgrid = p.vgrid;
+    uint32_t flatLo = 0;
+    if (SRC == SRC_CAMERA || SRC == SRC_SEGMENTS) {
+        const uint32_t nv = vgrid > blockIdx.x ? (vgrid - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
+        uint32_t cnt = 0;
+        if (threadIdx.x < nv) {
+            const uint32_t v = blockIdx.x + threadIdx.x * gridDim.x;
+            if (SRC == SRC_CAMERA) {
+                const uint32_t total = p.numPixels * (uint32_t)p.ctrl->batch;
+                const uint32_t tiles = (total + kBlock - 1) / kBlock;
+                cnt = (tiles > v ? (tiles - v + vgrid - 1) / vgrid : 0u) * kBlock;
+            } else cnt = p.segCounts[((depth + 1) & 1) * vgrid + v];
+        }
+        if (threadIdx.x < kMaxVirtualSegs) sPrefix[threadIdx.x + 1] = threadIdx.x < nv ? cnt : 0u;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t run = 0;
+            sPrefix[0] = 0u;
+            for (uint32_t j = 1; j <= kMaxVirtualSegs; ++j) { run += sPrefix[j]; sPrefix[j] = run; }
+            sTotal = run;
+        }
+    } else {
+        const uint32_t n = SRC == SRC_PATHS ? p.ctrl->counts[depth] : (SRC == SRC_PIXELS ? p.numPixels : (uint32_t)io.n);
+        const uint32_t chunk = (((n + gridDim.x - 1) / gridDim.x) + 31u) & ~31u;
+        flatLo = min(n, blockIdx.x * chunk);
+        if (threadIdx.x == 0) sTotal = min(chunk, n - flatLo);
+    }
+    __syncthreads();
+    const uint32_t nTickets = sTotal;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t laneBelow = (1u << lane) - 1u;
+    uint32_t *sw = reinterpret_cast<uint32_t *>(smem4);
+    uint2 *stk = reinterpret_cast<uint2 *>(sw + kPoolWords * kPoolSlots);
+    uint8_t *lst = reinterpret_cast<uint8_t *>(stk + kPoolStack * kPoolSlots) + warp * 64;
+#define PW(w, s) sw[(w) * kPoolSlots + warp * 64 + (s)]
+#define PWF(w, s) __uint_as_float(PW(w, s))
+#define PSTK(k, s) stk[(k) * kPoolSlots + warp * 64 + (s)]
+    CameraParams cam;
+    if (SRC == SRC_CAMERA || SRC == SRC_PIXELS) cam = p.hdr->cam;
+    int iterBase = 0, iterStride = 0;
+    if (SRC == SRC_CAMERA && EXT) { iterBase = p.ctrl->iterBase; iterStride = p.ctrl->iterStride; }
+    int2 *spillBase = p.stackSpill ? reinterpret_cast<int2 *>(p.stackSpill) + ((size_t)blockIdx.x * kPoolSlots + warp * 64) * p.spillCap : nullptr;
+    const BvhNode *nodes = p.bvh;
+
+    // all 64 slots of the warp start idle
+    for (int j = 0; j < 2; ++j) { PW(P_NODE, lane + 32 * j) = (uint32_t)kNoNode; PW(P_SP, lane + 32 * j) = 0u; PW(P_CAND, lane + 32 * j) = (uint32_t)kNoNode; }
+    __syncwarp();
+    bool drained = false;
+
+    for (;;) {
+        // ---- what does every slot need?  (two slots per lane)
+        uint32_t cat[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int nd = (int)PW(P_NODE, lane + 32 * j), spj = (int)PW(P_SP, lane + 32 * j), cd = (int)PW(P_CAND, lane + 32 * j);
+            cat[j] = cd != kNoNode ? T_CAND : (nd < kNoNode ? T_LEAF : ((nd >= 0 || spj > 0) ? T_STEP : T_IDLE));
+        }
+        const unsigned bS0 = __ballot_sync(0xffffffffu, cat[0] == T_STEP), bS1 = __ballot_sync(0xffffffffu, cat[1] == T_STEP);
+        const unsigned bL0 = __ballot_sync(0xffffffffu, cat[0] == T_LEAF), bL1 = __ballot_sync(0xffffffffu, cat[1] == T_LEAF);
+        const unsigned bC0 = __ballot_sync(0xffffffffu, cat[0] == T_CAND), bC1 = __ballot_sync(0xffffffffu, cat[1] == T_CAND);
+        const unsigned bI0 = __ballot_sync(0xffffffffu, cat[0] == T_IDLE), bI1 = __ballot_sync(0xffffffffu, cat[1] == T_IDLE);
+        const int nStep = __popc(bS0) + __popc(bS1), nLeaf = __popc(bL0) + __popc(bL1), nCand = __popc(bC0) + __popc(bC1);
+        const int nIdle = drained ? 0 : __popc(bI0) + __popc(bI1);
+        // ---- one kind of work for this pass
+        uint32_t type = T_NONE;
+        unsigned m0 = 0u, m1 = 0u;
+        if (nStep >= kPoolStepMin) type = T_STEP;
+        else {
+            int best = 0;
+            if (nIdle > best) { best = nIdle; type = T_IDLE; }
+            if (nLeaf > best) { best = nLeaf; type = T_LEAF; }
+            if (2 * nCand > best) { best = 2 * nCand; type = T_CAND; }      // a survivor's test is what lets its ray cull: served earlier
+            if (type == T_NONE && nStep > 0) type = T_STEP;
+        }
+        if (type == T_NONE) break;
+        if (type == T_STEP) { m0 = bS0; m1 = bS1; } else if (type == T_LEAF) { m0 = bL0; m1 = bL1; }
+        else if (type == T_CAND) { m0 = bC0; m1 = bC1; } else { m0 = bI0; m1 = bI1; }
+        // ---- the first 32 slots of that kind, one per lane
+        const int n0 = __popc(m0);
+        if (cat[0] == type) { const int r = __popc(m0 & laneBelow); if (r < 32) lst[r] = (uint8_t)lane; }
+        if (cat[1] == type) { const int r = n0 + __popc(m1 & laneBelow); if (r < 32) lst[r] = (uint8_t)(lane + 32); }
+        __syncwarp();
+        const int nItems = min(32, n0 + __popc(m1));
+        const bool have = (int)lane < nItems;
+        const int s = have ? (int)lst[lane] : 0;
+        __syncwarp();
+
+        if (type == T_STEP) {
+            // the lanes step in lockstep (votes at every step): with per-lane `break` / `continue` the warp never reconverged inside
+            // the pass and the node step ran with 11 of 32 lanes (profiles/r2l)
+            f3 o = mk3(0.f, 0.f, 0.f), invD = o;
+            float bestTs = 0.f;
+            int node = kNoNode, sp = 0;
+            int2 *spill = nullptr;
+            if (have) {
+                o = mk3(PWF(P_OX, s), PWF(P_OY, s), PWF(P_OZ, s));
+                const f3 rd = mk3(PWF(P_DX, s), PWF(P_DY, s), PWF(P_DZ, s));
+                const float dd = fmaf(rd.x, rd.x, fmaf(rd.y, rd.y, rd.z * rd.z));
+                const float rdl = rsqrtApprox(dd) * 1.0002f;
+                invD = mk3(rcpApprox(rd.x), rcpApprox(rd.y), rcpApprox(rd.z));
+                const float bestT = PWF(P_BEST, s);
+                bestTs = bestT == FLT_MAX ? FLT_MAX : (bestT + 1e-4f) * rdl;
+                node = (int)PW(P_NODE, s); sp = (int)PW(P_SP, s);
+                spill = spillBase ? spillBase + (size_t)s * p.spillCap : nullptr;
+            }
+#pragma unroll 1
+            for (int rep = 0; rep < kPoolSteps; ++rep) {
+                if (node == kNoNode && sp > 0) {
+                    --sp;
+                    const uint2 e = sp < kPoolStack ? PSTK(sp, s) : *reinterpret_cast<const uint2 *>(&spill[sp - kPoolStack]);
+                    if (__uint_as_float(e.y) <= bestTs) node = (int)e.x;
+                }
+                const bool stepping = node >= 0;
+                if (!__any_sync(0xffffffffu, stepping || (node == kNoNode && sp > 0))) break;
+                if (stepping) {
+                    int near, far; float tNear, tFar;
+                    nodeStep(nodes, node, o, invD, bestTs, near, tNear, far, tFar);
+                    if (far != kNoNode) {
+                        const uint2 e = make_uint2((uint32_t)far, __float_as_uint(tFar));
+                        if (sp < kPoolStack) PSTK(sp, s) = e;
+                        else *reinterpret_cast<uint2 *>(&spill[sp - kPoolStack]) = e;
+                        ++sp;
+                    }
+                    node = near;                                      // an interior node, a leaf (< -1: the pruning stage is next), or nothing
+                }
+            }
+            if (have) { PW(P_NODE, s) = (uint32_t)node; PW(P_SP, s) = (uint32_t)sp; }
+        } else if (type == T_LEAF) {
+            if (have) {
+                const int leaf = (int)PW(P_NODE, s);
+                const uint32_t code = (uint32_t)~leaf;                // first primitive | count << 27
+                const int slot = (int)(code & 0x7ffffffu);
+                const uint32_t cnt = code >> 27;
+                PW(P_NODE, s) = cnt > 1u ? (uint32_t)~(int)((uint32_t)(slot + 1) | ((cnt - 1u) << 27)) : (uint32_t)kNoNode;
+                const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + slot);
+                const int gtype = __ldg(reinterpret_cast<const int *>(gp + 9));
+                Affine inv;
+                inv.r0 = ldGeom4(gp); inv.r1 = ldGeom4(gp + 1); inv.r2 = ldGeom4(gp + 2);
+                const f3 o = mk3(PWF(P_OX, s), PWF(P_OY, s), PWF(P_OZ, s));
+                const f3 rd = mk3(PWF(P_DX, s), PWF(P_DY, s), PWF(P_DZ, s));
+                const f3 qo = mulMVPoint(inv, o), qu = mulMV(inv, rd, 0.0f);
+                bool miss = boxSureMiss(qo, qu);
+                if (gtype == 0) miss = sphereSureMiss(qo, qu);
+                if (MESH && gtype == 2) miss = false;
+                if (!miss) PW(P_CAND, s) = (uint32_t)slot;
+            }
+        } else if (type == T_CAND) {
+            if (have) {
+                const int cand = (int)PW(P_CAND, s);
+                const uint32_t idx = PW(P_IDX, s);
+                const f3 o = mk3(PWF(P_OX, s), PWF(P_OY, s), PWF(P_OZ, s));
+                const f3 rd = mk3(PWF(P_DX, s), PWF(P_DY, s), PWF(P_DZ, s));
+                const float bestT = PWF(P_BEST, s);
+                const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + cand);
+                Affine inv, fwd, vtx;
+                inv.r0 = ldGeom4(gp); inv.r1 = ldGeom4(gp + 1); inv.r2 = ldGeom4(gp + 2);
+                fwd.r0 = ldGeom4(gp + 3); fwd.r1 = ldGeom4(gp + 4); fwd.r2 = ldGeom4(gp + 5);
+                const int4 tag = __ldg(reinterpret_cast<const int4 *>(gp + 9));
+                vtx.r0 = vtx.r1 = vtx.r2 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (MESH && tag.x == 2) { vtx.r0 = __ldg(gp + 6); vtx.r1 = __ldg(gp + 7); vtx.r2 = __ldg(gp + 8); }
+                const f3 qo = mulMVPoint(inv, o), qu = mulMV(inv, rd, 0.0f);
+                int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
+                const float t = exactTestCore<MESH>(tag.x, fwd, vtx, o, qo, qu, outside, a, b, c);
+                bool take = t > 0.0f && bestT > t;
+                if (t > 0.0f && bestT < FLT_MAX && (bestT == t || (MESH && tag.x == 2))) {
+                    const int bm = p.hits.meta[idx];
+                    const int bslot = bm & 0x3fffffff;
+                    const int2 bord = __ldg(reinterpret_cast<const int2 *>(reinterpret_cast<const float4 *>(p.geoms + bslot) + 9) + 1);
+                    const bool sameMesh = MESH && tag.x == 2 && __ldg(reinterpret_cast<const int *>(p.geoms + bslot) + 36) == 2 && bord.y == tag.w;
+                    const float bestA = sameMesh ? p.hits.tn[idx].y : 0.0f;
+                    take = takesOver(sameMesh, t, a, tag.z, bestT, bestA, bord.x);
+                }
+                if (take) {
+                    p.hits.tn[idx] = make_float4(t, a, b, c);
+                    p.hits.meta[idx] = cand | (outside << 30);
+                    PW(P_BEST, s) = __float_as_uint(t);
+                }
+                PW(P_CAND, s) = (uint32_t)kNoNode;
+            }
+        } else {
+            // ---- fetch: new rays into idle slots
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&sNextTicket, (uint32_t)nItems);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            drained = base + (uint32_t)nItems >= nTickets;
+            const uint32_t k = base + lane;
+            bool got = have && k < nTickets;
+            uint32_t idx = 0;
+            f3 ro = mk3(0.f, 0.f, 0.f), rd = ro;
+            if (got) {
+                if (SRC == SRC_CAMERA || SRC == SRC_SEGMENTS) {
+                    uint32_t j = 0;
+#pragma unroll 1
+                    for (uint32_t step = kMaxVirtualSegs / 2; step > 0; step >>= 1) if (sPrefix[j + step] <= k) j += step;
+                    const uint32_t off = k - sPrefix[j];
+                    const uint32_t v = blockIdx.x + j * gridDim.x;
+                    if (SRC == SRC_CAMERA) {
+                        idx = (v + (off / kBlock) * vgrid) * kBlock + (off % kBlock);
+                        got = idx < p.numPixels * (uint32_t)p.ctrl->batch;
+                        if (got) {
+                            const uint32_t slot = idx / p.numPixels;
+                            cameraRayIter<EXT>(cam, idx - slot * p.numPixels, iterBase + (int)slot * iterStride, ro, rd);
+                        }
+                    } else {
+                        idx = v * p.segCap + off;
+                        const float4 a = p.in.A[idx];
+                        const float2 b = *reinterpret_cast<const float2 *>(&p.in.B[idx]);
+                        ro = mk3(a.x, a.y, a.z); rd = mk3(a.w, b.x, b.y);
+                    }
+                } else {
+                    idx = flatLo + k;
+                    if (SRC == SRC_PATHS) {
+                        const float4 a = p.in.A[idx];
+                        const float2 b = *reinterpret_cast<const float2 *>(&p.in.B[idx]);
+                        ro = mk3(a.x, a.y, a.z); rd = mk3(a.w, b.x, b.y);
+                        if (__float_as_uint(p.in.C[idx].y) & kDeadBit) { p.hits.meta[idx] = -1; got = false; }
+                    } else if (SRC == SRC_PIXELS) cameraRay(cam, idx, ro, rd);
+                    else {
+                        ro = mk3(io.origins[3 * (size_t)idx], io.origins[3 * (size_t)idx + 1], io.origins[3 * (size_t)idx + 2]);
+                        rd = mk3(io.dirs[3 * (size_t)idx], io.dirs[3 * (size_t)idx + 1], io.dirs[3 * (size_t)idx + 2]);
+                    }
+                }
+            }
+            if (got) {
+                p.hits.meta[idx] = -1;                                // a miss until a hit is accepted
+                PW(P_OX, s) = __float_as_uint(ro.x); PW(P_OY, s) = __float_as_uint(ro.y); PW(P_OZ, s) = __float_as_uint(ro.z);
+                PW(P_DX, s) = __float_as_uint(rd.x); PW(P_DY, s) = __float_as_uint(rd.y); PW(P_DZ, s) = __float_as_uint(rd.z);
+                PW(P_IDX, s) = idx; PW(P_BEST, s) = __float_as_uint(FLT_MAX);
+                PW(P_NODE, s) = 0u; PW(P_SP, s) = 0u;
+            }
+        }
+        __syncwarp();
+    }
+#undef PW
+#undef PWF
+#undef PSTK
+}
+
 // Raw hit records (t, a, b, c | geom slot, outside) -> what the staged pipeline, the first-bounce cache and the stage entry
 // consume: (t, normal) + meta, the normal built by the same deferred exactNormal the fused bounce kernel uses.
 __global__ void __launch_bounds__(kBlock) resolve_hits_kernel(const __grid_constant__ Params p, const uint32_t *countPtr, uint32_t countImm,
