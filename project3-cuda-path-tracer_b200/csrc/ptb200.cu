@@ -615,10 +615,15 @@ int ensureFirstBounceCache(PtbContext *c) {
     return PTB_OK;
 }
 
-// trace_kernel keeps kStackSmem traversal-stack entries per ray slot in shared memory; a deeper tree (the stack never holds
-// more entries than the tree has levels) gets the rest in global memory
+// trace_kernel keeps kStackSmem traversal-stack entries per lane in shared memory (the stack never holds more entries than the
+// tree has levels); a deeper tree gets a global spill area its lanes move blocks of kSpillBlock old entries to and from
+// (trace_pool_kernel: the entries beyond kPoolStack live there one by one)
 int ensureStackSpill(PtbContext *c) {
+#if PTB_TRACE_POOL
     const int need = std::max(0, c->bvhDepth + 2 - kTraceStackSmem);
+#else
+    const int need = c->bvhDepth + 2 <= kTraceStackSmem ? 0 : (c->bvhDepth + 2 + kSpillBlock - 1) / kSpillBlock * kSpillBlock;
+#endif
     if (need > c->spillCap) {
         CU(cudaStreamSynchronize(c->stream));
         CU(c->stackSpill.alloc((size_t)c->gridTrace * kTraceBlock * kTraceSlotsPerThread * need * 2));      // 8-byte entries (child, entry distance)

@@ -50,6 +50,9 @@ namespace ptb {
 #ifndef PTB_TRACE_QUEUE
 #define PTB_TRACE_QUEUE 0              // leaf-queue entries per lane: 0 = the traversal stops at every leaf until it is pruned; 1, 2 = run ahead (speculative)
 #endif
+#ifndef PTB_TRACE_POP_ATTEMPTS
+#define PTB_TRACE_POP_ATTEMPTS 1       // stack entries a lane may pop per step while they turn out culled
+#endif
 #ifndef PTB_TRACE_FETCH_LANES
 #define PTB_TRACE_FETCH_LANES 8
 #endif
@@ -64,6 +67,7 @@ constexpr int kTraceRays = 1;          // ray slots per lane (spill-area sizing 
 constexpr int kStackSmem = PTB_TRACE_STACK;
 constexpr int kTraceSteps = PTB_TRACE_STEPS;
 constexpr int kLeafQueue = PTB_TRACE_QUEUE;
+constexpr int kPopAttempts = PTB_TRACE_POP_ATTEMPTS;
 constexpr int kFetchLanes = PTB_TRACE_FETCH_LANES;
 constexpr int kPruneLanes = PTB_TRACE_PRUNE_LANES;
 constexpr int kExactLanes = PTB_TRACE_EXACT_LANES;
@@ -84,19 +88,39 @@ struct TraceIO {        // SRC_RAYS only
 };
 
 constexpr int kNoNode = -1;            // "nothing": no current node / empty queue entry / no candidate
-// per-lane words in shared memory besides the stack: the ray direction (pruning and the exact test need it, traversal does not)
-// and the index of the ray's hit record
-enum { W_DX, W_DY, W_DZ, W_IDX, kLaneWords };
+// per-lane words in shared memory besides the stack, all of them only touched by the fetch / pruning / exact stages: the ray
+// direction, the index of the ray's hit record, the best distance so far, 1 / |d| (slackened), the lane's entries in the spill area
+enum { W_DX, W_DY, W_DZ, W_IDX, W_BEST, W_RDL, W_SPILLED, kLaneWords };
 
-constexpr size_t traceSmemBytes() { return (size_t)(kLaneWords + 2 * kStackSmem) * kTraceBlock * sizeof(uint32_t); }
+constexpr size_t traceSmemBytes() { return (size_t)(kLaneWords + 2 * (kStackSmem + 2)) * kTraceBlock * sizeof(uint32_t); }     // + dummy and sentinel entries
 
 // One traversal step: slab-test both child boxes of `node` (planes paired per axis, ptb_kernels.cuh slabNearPair), keep the
 // children whose entry parameter can still beat the best hit (bestTs: best distance in units of the ray parameter, slackened).
 // near / far: encoded children in front-to-back order, kNoNode when absent; tNear / tFar their entry parameters.
+// A node is fetched with TWO 256-bit loads (sm_100: ld.global.nc.v8): divergent lanes cost the L1 data pipe one pass per lane and
+// load instruction, and with three 128-bit loads + one 64-bit load per node that pipe ran at 82 % of its peak while the issue slots
+// were 56 % busy (profiles/r2n_trace_ncu.csv).
+#ifndef PTB_TRACE_LD256
+#define PTB_TRACE_LD256 1
+#endif
+PTB_DEV void ldNode(const BvhNode *n, float4 &X, float4 &Y, float4 &Z, int2 &m) {
+#if PTB_TRACE_LD256
+    float4 M;
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(X.x), "=f"(X.y), "=f"(X.z), "=f"(X.w), "=f"(Y.x), "=f"(Y.y), "=f"(Y.z), "=f"(Y.w) : "l"(n));
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(Z.x), "=f"(Z.y), "=f"(Z.z), "=f"(Z.w), "=f"(M.x), "=f"(M.y), "=f"(M.z), "=f"(M.w) : "l"(reinterpret_cast<const float4 *>(n) + 2));
+    m = make_int2(__float_as_int(M.x), __float_as_int(M.y));
+#else
+    const float4 *np = reinterpret_cast<const float4 *>(n);
+    X = __ldg(np); Y = __ldg(np + 1); Z = __ldg(np + 2);
+    m = __ldg(reinterpret_cast<const int2 *>(np + 3));
+#endif
+}
+
 PTB_DEV void nodeStep(const BvhNode *nodes, int node, f3 o, f3 invD, float bestTs, int &near, float &tNear, int &far, float &tFar) {
-    const float4 *np = reinterpret_cast<const float4 *>(nodes + node);
-    const float4 X = __ldg(np), Y = __ldg(np + 1), Z = __ldg(np + 2);
-    const int2 m = __ldg(reinterpret_cast<const int2 *>(np + 3));
+    float4 X, Y, Z; int2 m;
+    ldNode(nodes + node, X, Y, Z, m);
     float tl, tr; bool hl, hr;
     slabNearPair(X, Y, Z, o, invD, tl, tr, hl, hr);
     const bool vl = hl && tl <= bestTs;
@@ -121,6 +145,31 @@ PTB_DEV float4 ldGeom4(const float4 *q) {
 #else
     return __ldg(q);
 #endif
+}
+
+// The traversal stack of a lane: 8-byte entries (child, entry parameter of its box) in shared memory, [entry][thread]
+// (conflict-free), addressed through a 32-bit shared-memory POINTER to the top entry that the lane keeps instead of a count.
+// Entry 0 is a dummy and entry 1 a SENTINEL (child kEmpty, entry parameter -inf: never culled); popping the sentinel makes the
+// lane's node kEmpty = "stack empty", so neither pop nor push tests a count or builds an address: a pop is one load, one
+// subtract and two selects, a push one store and one add (as counted branches they were 45 of the ~110 warp instructions of a
+// traversal step, run by 4-6 lanes: profiles/r2n_step_loop.txt).
+// Entries 2 .. kStackSmem + 1 hold the real stack.  Only a tree deeper than that can overflow it; then the OLDEST kSpillBlock
+// entries move to a global spill area (sized from the tree's depth, ptb200.cu::ensureStackSpill) and come back when the sentinel is
+// reached -- checked once per pass of kTraceSteps steps, outside the step loop.
+constexpr int kEmpty = (int)0x80000000;                             // as a leaf code: 15 primitives from slot 0x7ffffff -- the builder never makes it
+constexpr int kSpillBlock = kStackSmem / 2;
+constexpr uint32_t kStackStride = (uint32_t)kTraceBlock * 8u;       // bytes between consecutive entries of one lane
+static_assert(kStackSmem - kTraceSteps >= kSpillBlock && kSpillBlock >= 1, "a spill must find kSpillBlock live entries");
+PTB_DEV uint2 ldsEntry(uint32_t addr) {
+    uint2 e;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(e.x), "=r"(e.y) : "r"(addr));
+    return e;
+}
+PTB_DEV void stsEntry(uint32_t addr, uint2 e) {
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" :: "r"(addr), "r"(e.x), "r"(e.y) : "memory");
+}
+PTB_DEV uint2 *spillArea(const Params &p) {
+    return reinterpret_cast<uint2 *>(p.stackSpill) + ((size_t)blockIdx.x * kTraceBlock + threadIdx.x) * p.spillCap;
 }
 
 template <int SRC, bool EXT, bool MESH>
@@ -165,7 +214,8 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
     const uint32_t nTickets = sTotal;
 #define SW(w) sw[(w) * kTraceBlock + threadIdx.x]
 #define SWF(w) __uint_as_float(SW(w))
-#define STK(k) stk[(k) * kTraceBlock + threadIdx.x]
+    // shared-memory address of entry k of this lane's stack (only outside the step loop)
+#define STK_ADDR(k) ((uint32_t)__cvta_generic_to_shared(stk + threadIdx.x) + (uint32_t)(k) * kStackStride)
 
     CameraParams cam;
     if (SRC == SRC_CAMERA || SRC == SRC_PIXELS) cam = p.hdr->cam;
@@ -173,30 +223,50 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
     if (SRC == SRC_CAMERA && EXT) { iterBase = p.ctrl->iterBase; iterStride = p.ctrl->iterStride; }
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t laneBelow = (1u << lane) - 1u;
-    int2 *spill = p.stackSpill ? reinterpret_cast<int2 *>(p.stackSpill) + ((size_t)blockIdx.x * kTraceBlock + threadIdx.x) * p.spillCap : nullptr;
     const BvhNode *nodes = p.bvh;
+    const bool canSpill = p.stackSpill != nullptr;                   // uniform: the tree is deeper than the shared-memory stack
+    {
+        const uint2 sentinel = make_uint2((uint32_t)kEmpty, 0xff800000u);     // -inf: the sentinel is never culled
+        stsEntry(STK_ADDR(0), sentinel); stsEntry(STK_ADDR(1), sentinel);
+        SW(W_SPILLED) = 0u;
+    }
 
     // ---- per-lane state, all in registers
     f3 o = mk3(0.f, 0.f, 0.f), invD = o;
-    float rdl = 1.f;                                                 // 1 / (|d| * 0.9999)
-    float bestT = FLT_MAX, bestTs = FLT_MAX;                         // best distance; the same in units of the ray parameter, slackened
-    int node = kNoNode, sp = 0;                                      // current interior node, or a leaf that found the queue full
-    int q0 = kNoNode, q1 = kNoNode;                                  // leaf queue (encoded leaves), q0 first
+    float bestTs = FLT_MAX;                                          // best distance in units of the ray parameter, slackened: the culling bound
+    int node = kEmpty;                                               // interior node (>= 0) | kNoNode: pop next | leaf code (< kNoNode): waits for
+                                                                     // the pruning stage | kEmpty: the stack ran empty, the ray is finished
+    uint32_t top = STK_ADDR(1);                                      // shared-memory address of the top stack entry
     int cand = kNoNode;                                              // primitive that survived pruning
     bool drained = false;                                            // warp-uniform: the CTA's queue is empty
-    auto enqueue = [&](int leaf) {                                   // leaf: encoded, < kNoNode
-        if (kLeafQueue >= 1 && q0 == kNoNode) q0 = leaf;
-        else if (kLeafQueue >= 2 && q1 == kNoNode) q1 = leaf;
-        else node = leaf;                                            // no room: the lane waits for the pruning stage
-    };
-    // room in the leaf queue (a leaf held in `node` moves in as soon as there is)
-    auto queueHasRoom = [&]() -> bool { return kLeafQueue >= 2 ? q1 == kNoNode : (kLeafQueue == 1 ? q0 == kNoNode : false); };
+    uint32_t segCur = 0;                                             // warp-uniform: virtual segment of the last fetch's first ticket
 
     for (;;) {
-        const bool canStep = node >= 0 || (node == kNoNode && sp > 0) || (node < kNoNode && queueHasRoom());
-        const bool hasLeaf = (kLeafQueue == 0 ? node < kNoNode : q0 != kNoNode) && cand == kNoNode;
+        // ---- the stack against its shared-memory window, once per pass (a pass pushes at most kTraceSteps entries per lane)
+        if (canSpill) {
+            const int used = (int)(top - STK_ADDR(1)) / (int)kStackStride;        // -1 once the sentinel has been popped
+            if (used > kStackSmem - kTraceSteps) {
+                // the oldest kSpillBlock entries go to the spill area, the rest move down
+                uint2 *area = spillArea(p);
+                const uint32_t spilled = SW(W_SPILLED);
+                for (int k = 0; k < kSpillBlock; ++k) area[spilled + k] = ldsEntry(STK_ADDR(2 + k));
+                for (int k = 2; k + kSpillBlock <= used + 1; ++k) stsEntry(STK_ADDR(k), ldsEntry(STK_ADDR(k + kSpillBlock)));
+                SW(W_SPILLED) = spilled + kSpillBlock;
+                top -= kSpillBlock * kStackStride;
+            } else if (node == kEmpty && SW(W_SPILLED) > 0u) {
+                // the sentinel was reached with entries still parked in the spill area: the newest block comes back
+                const uint2 *area = spillArea(p);
+                const uint32_t spilled = SW(W_SPILLED) - kSpillBlock;
+                for (int k = 0; k < kSpillBlock; ++k) stsEntry(STK_ADDR(2 + k), area[spilled + k]);
+                SW(W_SPILLED) = spilled;
+                top = STK_ADDR(1 + kSpillBlock);
+                node = kNoNode;
+            }
+        }
+        const bool canStep = node >= kNoNode;
+        const bool hasLeaf = node < kNoNode && node != kEmpty && cand == kNoNode;
         const bool hasCand = cand != kNoNode;
-        const bool finished = node == kNoNode && sp == 0 && q0 == kNoNode && cand == kNoNode;
+        const bool finished = node == kEmpty && cand == kNoNode;
         const unsigned mStep = __ballot_sync(0xffffffffu, canStep);
         unsigned mLeaf = __ballot_sync(0xffffffffu, hasLeaf);
         unsigned mCand = __ballot_sync(0xffffffffu, hasCand);
@@ -210,6 +280,10 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
             if (lane == 0) base = atomicAdd(&sNextTicket, want);
             base = __shfl_sync(0xffffffffu, base, 0);
             drained = base + want >= nTickets;
+            if (SRC == SRC_CAMERA || SRC == SRC_SEGMENTS) {
+                // tickets only grow: the segment of the warp's first new ticket is found from the one of the previous fetch
+                while (segCur + 1 < kMaxVirtualSegs && sPrefix[segCur + 1] <= base) ++segCur;
+            }
             if (finished) {
                 const uint32_t k = base + (uint32_t)__popc(mIdle & laneBelow);
                 bool have = k < nTickets;
@@ -218,9 +292,8 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
                 if (have) {
                     if (SRC == SRC_CAMERA || SRC == SRC_SEGMENTS) {
                         // ticket -> (virtual segment j, offset): the segments of this CTA back to back
-                        uint32_t j = 0;
-#pragma unroll 1
-                        for (uint32_t step = kMaxVirtualSegs / 2; step > 0; step >>= 1) if (sPrefix[j + step] <= k) j += step;
+                        uint32_t j = segCur;
+                        while (sPrefix[j + 1] <= k) ++j;              // k < nTickets = sPrefix[kMaxVirtualSegs]
                         const uint32_t off = k - sPrefix[j];
                         const uint32_t v = blockIdx.x + j * gridDim.x;
                         if (SRC == SRC_CAMERA) {
@@ -257,24 +330,21 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
                     // the direction enters the traversal only through 1 / d and |d| (slackened: ray parameter * |d| * 0.9999 is a
                     // lower bound of the world distance)
                     const float dd = fmaf(rd.x, rd.x, fmaf(rd.y, rd.y, rd.z * rd.z));
-                    rdl = rsqrtApprox(dd) * 1.0002f;
+                    SW(W_RDL) = __float_as_uint(rsqrtApprox(dd) * 1.0002f);                 // 1 / (|d| * 0.9999)
                     o = ro; invD = mk3(rcpApprox(rd.x), rcpApprox(rd.y), rcpApprox(rd.z));
-                    bestT = FLT_MAX; bestTs = FLT_MAX;
-                    node = 0; sp = 0;
+                    SW(W_BEST) = __float_as_uint(FLT_MAX); bestTs = FLT_MAX;
+                    node = 0; top = STK_ADDR(1);
                 }
             }
         }
 
-        // ---- pruning: the first queued primitive of every lane that has one -- object-space ray + sure-miss filter
+        // ---- pruning: the next primitive of the leaf every waiting lane stands at -- object-space ray + sure-miss filter
         if (mLeaf && ((int)__popc(mLeaf) >= kPruneLanes || !mStep)) {
             if (hasLeaf) {
-                int &head = kLeafQueue == 0 ? node : q0;              // no queue: the leaf the traversal stopped at
-                const uint32_t code = (uint32_t)~head;                // first primitive | count << 27
+                const uint32_t code = (uint32_t)~node;                // first primitive | count << 27
                 const int slot = (int)(code & 0x7ffffffu);
                 const uint32_t cnt = code >> 27;
-                if (cnt > 1u) head = ~(int)((uint32_t)(slot + 1) | ((cnt - 1u) << 27));
-                else if (kLeafQueue == 0) node = kNoNode;
-                else { q0 = q1; q1 = kNoNode; }
+                node = cnt > 1u ? ~(int)((uint32_t)(slot + 1) | ((cnt - 1u) << 27)) : kNoNode;
                 const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + slot);
                 const int type = __ldg(reinterpret_cast<const int *>(gp + 9));
                 Affine inv;
@@ -293,6 +363,7 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
         if (mCand && ((int)__popc(mCand) >= kExactLanes || !mStep)) {
             if (cand != kNoNode) {
                 const uint32_t idx = SW(W_IDX);
+                const float bestT = SWF(W_BEST);
                 const f3 rd = mk3(SWF(W_DX), SWF(W_DY), SWF(W_DZ));
                 const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + cand);
                 Affine inv, fwd, vtx;
@@ -318,47 +389,39 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
                 if (take) {
                     p.hits.tn[idx] = make_float4(t, a, b, c);
                     p.hits.meta[idx] = cand | (outside << 30);
-                    bestT = t;
-                    bestTs = (t + 1e-4f) * rdl;                       // box entry parameter beyond which nothing can win any more
+                    SW(W_BEST) = __float_as_uint(t);
+                    bestTs = (t + 1e-4f) * SWF(W_RDL);                // box entry parameter beyond which nothing can win any more
                 }
                 cand = kNoNode;
             }
         }
 
-        // ---- traversal steps
+        // ---- traversal steps: every lane that can pops (when it has no node) and steps, in lockstep
 #pragma unroll 1
         for (int rep = 0; rep < kTraceSteps; ++rep) {
-            // a leaf that found the queue full gets in as soon as there is room
-            if (kLeafQueue > 0 && node < kNoNode && queueHasRoom()) { const int leaf = node; node = kNoNode; enqueue(leaf); }
-            // nothing current: the top of the stack, unless its box can no longer beat the best hit
-            if (node == kNoNode && sp > 0) {
-                --sp;
-                const uint2 e = sp < kStackSmem ? STK(sp) : *reinterpret_cast<const uint2 *>(&spill[sp - kStackSmem]);
-                if (__uint_as_float(e.y) <= bestTs) {
-                    if ((int)e.x < kNoNode) enqueue((int)e.x);
-                    else node = (int)e.x;
-                }
+            // nothing current: the top of the stack, unless its box can no longer beat the best hit (the sentinel: kEmpty)
+#pragma unroll
+            for (int attempt = 0; attempt < kPopAttempts; ++attempt) {
+                const bool doPop = node == kNoNode;
+                const uint2 e = ldsEntry(top);
+                top -= doPop ? kStackStride : 0u;
+                node = (doPop && __uint_as_float(e.y) <= bestTs) ? (int)e.x : node;
             }
-            const bool stepping = node >= 0;
-            if (!__any_sync(0xffffffffu, stepping || (node == kNoNode && sp > 0))) break;
-            if (stepping) {
+            if (!__any_sync(0xffffffffu, node >= kNoNode)) break;
+            if (node >= 0) {
                 int near, far; float tNear, tFar;
                 nodeStep(nodes, node, o, invD, bestTs, near, tNear, far, tFar);
                 if (far != kNoNode) {
-                    const uint2 e = make_uint2((uint32_t)far, __float_as_uint(tFar));
-                    if (sp < kStackSmem) STK(sp) = e;
-                    else *reinterpret_cast<uint2 *>(&spill[sp - kStackSmem]) = e;
-                    ++sp;
+                    top += kStackStride;
+                    stsEntry(top, make_uint2((uint32_t)far, __float_as_uint(tFar)));
                 }
-                node = kNoNode;
-                if (near < kNoNode) enqueue(near);                    // a leaf: queue it and go on with the stack
-                else node = near;                                     // an interior node, or nothing
+                node = near;                                          // an interior node, a leaf (the pruning stage is next), or nothing
             }
         }
     }
 #undef SW
 #undef SWF
-#undef STK
+#undef STK_ADDR
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -1,0 +1,13 @@
+#!/bin/bash
+# pass o: 256-bit node loads, stage thresholds -- variants, BVH tests, ncu of the bounce-1 launch
+set -u
+mkdir -p gpurun_out
+TAG=${1:-r2o}
+for so in project3-cuda-path-tracer_b200/libptb200.so variants/*.so; do
+  PTB_SO=$so PTB_B=16 timeout 120 python tools/gpu_time_synth.py 2>&1 | grep -E "TIMING|Error|error" | tail -2
+done | tee gpurun_out/${TAG}_variants.txt
+( time timeout 900 python -m pytest tests/test_gpu_scale.py tests/test_gpu_meshes.py -m gpu -q -x ) > gpurun_out/${TAG}_pytest_bvh.log 2>&1
+tail -4 gpurun_out/${TAG}_pytest_bvh.log
+PTB_B=4 ncu --set full --clock-control none --import-source on -k regex:trace_kernel -s 16 -c 3 -f -o gpurun_out/${TAG}_trace \
+      python tools/gpu_time_synth.py > gpurun_out/${TAG}_trace_ncu.log 2>&1
+tail -2 gpurun_out/${TAG}_trace_ncu.log
