@@ -45,10 +45,13 @@ namespace ptb {
 #define PTB_TRACE_STACK 16             // traversal-stack entries per lane kept in shared memory
 #endif
 #ifndef PTB_TRACE_STEPS
-#define PTB_TRACE_STEPS 4              // traversal steps between two looks at the other stages
+#define PTB_TRACE_STEPS 5              // traversal steps between two looks at the other stages
 #endif
 #ifndef PTB_TRACE_QUEUE
 #define PTB_TRACE_QUEUE 0              // leaf-queue entries per lane: 0 = the traversal stops at every leaf until it is pruned; 1, 2 = run ahead (speculative)
+#endif
+#ifndef PTB_TRACE_POP_PTX
+#define PTB_TRACE_POP_PTX 1
 #endif
 #ifndef PTB_TRACE_POP_ATTEMPTS
 #define PTB_TRACE_POP_ATTEMPTS 1       // stack entries a lane may pop per step while they turn out culled
@@ -402,10 +405,22 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
             // nothing current: the top of the stack, unless its box can no longer beat the best hit (the sentinel: kEmpty)
 #pragma unroll
             for (int attempt = 0; attempt < kPopAttempts; ++attempt) {
+#if PTB_TRACE_POP_PTX
+                // straight-line by construction (the compiler otherwise branches around the load): 5 instructions
+                asm volatile("{\n\t.reg .pred p, q;\n\t.reg .b32 ex, ey;\n\t.reg .f32 fy;\n\t"
+                             "setp.eq.s32 p, %0, -1;\n\t"
+                             "ld.shared.v2.u32 {ex, ey}, [%1];\n\t"
+                             "@p sub.u32 %1, %1, %3;\n\t"
+                             "mov.b32 fy, ey;\n\t"
+                             "setp.le.and.f32 q, fy, %2, p;\n\t"
+                             "@q mov.b32 %0, ex;\n\t}"
+                             : "+r"(node), "+r"(top) : "f"(bestTs), "n"(kStackStride));
+#else
                 const bool doPop = node == kNoNode;
                 const uint2 e = ldsEntry(top);
                 top -= doPop ? kStackStride : 0u;
                 node = (doPop && __uint_as_float(e.y) <= bestTs) ? (int)e.x : node;
+#endif
             }
             if (!__any_sync(0xffffffffu, node >= kNoNode)) break;
             if (node >= 0) {

@@ -1,5 +1,5 @@
 #!/bin/bash
-# pass o: 256-bit node loads, stage thresholds -- variants, BVH tests, ncu of the bounce-1 launch
+# pass o, p: 256-bit node loads, stage thresholds, straight-line pop, stack depth -- variants, BVH tests, ncu of the bounce-1 launch
 set -u
 mkdir -p gpurun_out
 TAG=${1:-r2o}
