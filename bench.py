@@ -227,7 +227,7 @@ def extra_configs(m, torch, stream, local, tmp, hbm_peak, sm_max):
     specs = [
         ("configs[1] sphere.txt 800x800 depth 8", scenes.sphere_text(), dict(batch_iters=128), 1024),
         ("configs[3] cornell.txt 3840x2160 depth 8 (one GPU, 64 of the 5000 spp)", scenes.cornell_text(res=(3840, 2160)), dict(), 64),
-        ("configs[4] synthetic 100k SPHERE/CUBE 1920x1080 depth 16 (flat BVH)", scenes.synthetic_text(100000), dict(), 32),
+        ("configs[4] synthetic 100k SPHERE/CUBE 1920x1080 depth 16 (flat BVH)", scenes.synthetic_text(100000), dict(), 64),
     ]
     for name, text, kw, n in specs:
         path = os.path.join(tmp, "extra.txt")

@@ -725,9 +725,15 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     while ((1ull << bits) < c->numPixels) ++bits;
     c->pixBits = bits;
     const int maxSlots = 1 << std::min(31 - bits, 12);
-    // default wavefront: about 40 M paths (1.6 GB per path buffer), a power of two between 1 and 64 iterations
+    // default wavefront: a power of two between 1 and 64 iterations of about 140 M paths (~112 B per path with both path buffers, the
+    // BVH hit records and the partial images: 16 GB) when the device has the room, about 40 M otherwise.  Bigger wavefronts amortise
+    // the tails of the per-bounce launches: 100 k-object scene at 1920x1080, 8 / 16 / 32 / 64 iterations per wavefront:
+    // 2 454 / 2 265 / 2 171 / 2 111 us per iteration (profiles/r2q_wavefront_size.txt)
+    size_t freeBytes = 0, totalBytes = 0;
+    if (cudaMemGetInfo(&freeBytes, &totalBytes) != cudaSuccess) { cudaGetLastError(); freeBytes = 0; }
+    const uint64_t pathBudget = freeBytes >= (64ull << 30) ? 140000000ull : 40000000ull;
     int autoBatch = 1;
-    while (autoBatch < 64 && (uint64_t)(autoBatch * 2) * c->numPixels <= 40000000ull) autoBatch <<= 1;
+    while (autoBatch < 64 && (uint64_t)(autoBatch * 2) * c->numPixels <= pathBudget) autoBatch <<= 1;
     int batch = opt.batchIters > 0 ? opt.batchIters : autoBatch;
     if (opt.pipeline == PTB_PIPELINE_STAGED && opt.batchIters <= 0) batch = 1;
     // keep the wavefront within 2^31 paths and a sane memory budget (2 x 40 B per path)

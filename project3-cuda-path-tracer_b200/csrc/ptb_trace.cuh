@@ -106,12 +106,15 @@ constexpr size_t traceSmemBytes() { return (size_t)(kLaneWords + 2 * (kStackSmem
 #ifndef PTB_TRACE_LD256
 #define PTB_TRACE_LD256 1
 #endif
+#ifndef PTB_TRACE_NODE_POLICY
+#define PTB_TRACE_NODE_POLICY ""            // L1 eviction-priority qualifier of the node loads (tuning: ".L1::evict_last")
+#endif
 PTB_DEV void ldNode(const BvhNode *n, float4 &X, float4 &Y, float4 &Z, int2 &m) {
 #if PTB_TRACE_LD256
     float4 M;
-    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+    asm volatile("ld.global.nc" PTB_TRACE_NODE_POLICY ".v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=f"(X.x), "=f"(X.y), "=f"(X.z), "=f"(X.w), "=f"(Y.x), "=f"(Y.y), "=f"(Y.z), "=f"(Y.w) : "l"(n));
-    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+    asm volatile("ld.global.nc" PTB_TRACE_NODE_POLICY ".v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
                  : "=f"(Z.x), "=f"(Z.y), "=f"(Z.z), "=f"(Z.w), "=f"(M.x), "=f"(M.y), "=f"(M.z), "=f"(M.w) : "l"(reinterpret_cast<const float4 *>(n) + 2));
     m = make_int2(__float_as_int(M.x), __float_as_int(M.y));
 #else
@@ -348,9 +351,9 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
                 const int slot = (int)(code & 0x7ffffffu);
                 const uint32_t cnt = code >> 27;
                 node = cnt > 1u ? ~(int)((uint32_t)(slot + 1) | ((cnt - 1u) << 27)) : kNoNode;
+                Affine inv;
                 const float4 *gp = reinterpret_cast<const float4 *>(p.geoms + slot);
                 const int type = __ldg(reinterpret_cast<const int *>(gp + 9));
-                Affine inv;
                 inv.r0 = ldGeom4(gp); inv.r1 = ldGeom4(gp + 1); inv.r2 = ldGeom4(gp + 2);
                 const f3 rd = mk3(SWF(W_DX), SWF(W_DY), SWF(W_DZ));
                 const f3 qo = mulMVPoint(inv, o), qu = mulMV(inv, rd, 0.0f);

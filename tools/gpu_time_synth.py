@@ -10,7 +10,8 @@ d = tempfile.mkdtemp(); path = os.path.join(d, "synthetic.txt")
 open(path, "w").write(scenes.synthetic_text(100000))
 scene = m.Scene.load(path)
 B = int(os.environ.get("PTB_B", "16"))
-with m.Renderer(scene, device=0, bsdf=1, batch_iters=B) as r:
+with m.Renderer(scene, device=0, bsdf=1, batch_iters=B) as r:            # PTB_B=0: the library's default wavefront
+    B = r.stats()["batch_iters"]
     n = 2 * B
     r.render(1, n); r.sync()
     best = 1e9
