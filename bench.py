@@ -533,7 +533,7 @@ def main():
                                    "note": "PtbOptions.firstBounceCache = 1: bounce-0 hit records reused across iterations (bit-identical images)"},
             "strong_scaling": strong,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "ptb::bounce_kernel (bounce 0) + ptb::bounce_loop_kernel (bounces 1..)",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src, "kernel": "ptb::bounce0_shared_kernel (bounce 0) + ptb::bounce_loop_kernel (bounces 1..)",
                          "algorithmic_bytes": "88 B/segment + 24 B/pixel/iteration (SURVEY.md 8(d))",
                          "bounce_launches_in_timed_region_per_gpu": bounce_launches,
                          "avg_launch_us": ms * 1e3 / max(1.0, bounce_launches),
