@@ -1,5 +1,5 @@
 #!/bin/bash
-# pass u: 32-byte quantised BVH nodes (QNode, one 256-bit load per step) against the 64-byte float nodes; whole GPU suite on the new default; ncu
+# pass u, v: node format A/B; exact-test passes of one primitive type; whole GPU suite; ncu
 set -u
 mkdir -p gpurun_out
 TAG=${1:-r2u}
