@@ -354,13 +354,17 @@ PTB_DEV void slabNearPair(float4 X, float4 Y, float4 Z, f3 o, f3 inv, float &tl,
     hr = tr <= fr * 1.00001f + 1e-5f;
 }
 
+// The part of a BVH leaf record the shading side needs (exactNormal, the material id): the tag, then the ONE matrix the normal of its type
+// uses -- 64 of the record's 192 bytes (all ten rows were fetched before: 160 B per shaded path from L2, profiles/r2w_bvh_shade.txt)
 PTB_DEV GeomRec loadGeom(const GeomRec *gp) {
     GeomRec g;
     const float4 *src = reinterpret_cast<const float4 *>(gp);
-    float4 *dst = reinterpret_cast<float4 *>(&g);
-#pragma unroll
-    for (int q = 0; q < 10; ++q) dst[q] = __ldg(src + q);      // the pruning bound (b0, b1) is not needed for the normal
-    g.b0 = g.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 tagBits = __ldg(src + 9);
+    g.tag = make_int4(__float_as_int(tagBits.x), __float_as_int(tagBits.y), __float_as_int(tagBits.z), __float_as_int(tagBits.w));
+    const float4 *rows = src + (g.tag.x == 1 ? 3 : 6);           // a cube's normal goes through `fwd` (src/intersections.h:86), the others' through `nrm`
+    const float4 r0 = __ldg(rows), r1 = __ldg(rows + 1), r2 = __ldg(rows + 2);
+    g.fwd.r0 = g.nrm.r0 = r0; g.fwd.r1 = g.nrm.r1 = r1; g.fwd.r2 = g.nrm.r2 = r2;
+    g.inv.r0 = g.inv.r1 = g.inv.r2 = g.b0 = g.b1 = make_float4(0.f, 0.f, 0.f, 0.f);
     return g;
 }
 
