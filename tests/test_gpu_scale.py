@@ -203,6 +203,22 @@ def test_far_grazing_band_on_the_gpu(m, port, monkeypatch):
     assert len(lost) > 0 and np.all(want[0][lost] == owner[lost])          # hits of the grazed sphere, dropped by its round-1 box
 
 
+def test_stack_spill_path_renders_the_same_image(m, synthetic):
+    """trace_kernel keeps 16 traversal-stack entries per lane in shared memory and moves blocks of old entries to a global spill area
+    when a deeper tree needs more (csrc/ptb_trace.cuh).  The tuning build keeps only 8, so on the 100 k-object scene its lanes spill
+    and refill all the time: it must render the same image and the same per-depth path counts, bit for bit, as the release build."""
+    from common import pkg_tuning
+    mt = pkg_tuning()
+    out = []
+    for mod in (m, mt):
+        with mod.Renderer(mod.Scene.load(synthetic), device=0, bsdf=1, batch_iters=2) as r:
+            r.render(1, 2)
+            out.append((r.download(), r.stats()))
+    (img, st), (img_t, st_t) = out
+    assert st["alive_per_depth"] == st_t["alive_per_depth"] and st["segments"] == st_t["segments"] and st["segments"] > 10000000
+    assert same_bits(img, img_t) and float(img.sum()) > 0.0
+
+
 def test_real_paths_agree_between_the_pad_policies(m, port, synthetic, monkeypatch):
     """tools/gpu_bvh_pathdiff.py as a regression: one iteration of the REAL paths of the 100 k-object scene (all 16 bounces, the
     render's own RNG) walked through the shipped BVH and through the round-1 boxes (tuning build, PTB_BVH_FAR_PAD=0); every ray on
