@@ -106,7 +106,8 @@ typedef struct PtbOptions {
     int32_t bsdfMode;               /* PtbBsdfMode */
     int32_t pipeline;               /* PtbPipeline */
     int32_t accel;                  /* PtbAccel */
-    int32_t batchIters;             /* iterations traced per wavefront (fused pipeline); 0 = default */
+    int32_t batchIters;             /* iterations traced per wavefront (fused pipeline); 0 = default: the largest power of two <= 64 that keeps the
+                                       wavefront near 140 M paths (~16 GB of state) when the device has >= 64 GB free, near 40 M otherwise */
     int32_t compaction;             /* staged pipeline: 1 = ballot/popc stream compaction, 0 = none (skeleton layout) */
     int32_t sortMaterials;          /* staged pipeline: 1 = sort paths by material id before shading */
     int32_t firstBounceCache;       /* fused pipeline: 1 = cache the bounce-0 hit record of every pixel across iterations
