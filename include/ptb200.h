@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 4
+#define PTB_ABI_VERSION 5
 
 /* ---- POD mirrors of src/sceneStructs.h (byte-identical; matrices column-major like glm) ---- */
 typedef struct PtbGeom {            /* struct Geom, src/sceneStructs.h:20-29, 236 bytes */
@@ -127,6 +127,10 @@ typedef struct PtbOptions {
     int32_t lazyImage;              /* ptb_pathtrace only: 1 = the host image copy of iteration i is queued on a copy stream and
                                        overlaps iteration i+1; the host image is valid after ptb_sync (or the next call's return
                                        for the previous iteration).  0 = the reference's semantic: valid on return (src/pathtrace.cu:389-390) */
+    int32_t regroupMaterials;       /* fused pipeline, BVH scenes (default 0): 1 = the material sort of the fused path (INSTRUCTION.md:78-86): every warp
+                                       regroups 128 paths of its CTA's segment by material class (Lambertian / mirror / dielectric) before
+                                       shading, so that each arm of the shader runs with full warps; 0 = shade in path order.  Identical images
+                                       and per-depth counts either way; scenes with more than 256 materials are shaded in path order */
 } PtbOptions;
 /* antialias / lensRadius make the camera rays depend on the iteration, so they cannot be combined with
  * firstBounceCache (INSTRUCTION.md:113: "keep in mind how this influences the first-bounce cache"):

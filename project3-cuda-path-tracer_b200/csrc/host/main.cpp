@@ -3,7 +3,7 @@
 // preview (src/preview.cpp, glslUtility.cpp) is display only and out of scope.
 //
 //   ptb200_headless SCENEFILE.txt [--iters N] [--depth D] [--bsdf full|golden-diffuse] [--batch B]
-//                   [--per-iteration] [--out BASENAME] [--hdr] [--staged] [--sort] [--no-compaction]
+//                   [--per-iteration] [--out BASENAME] [--hdr] [--staged] [--sort] [--regroup] [--no-compaction]
 //                   [--device K] [--gpus G] [--res W H] [--atomic-deposit] [--time-stages] [--quiet]
 //
 // --gpus G: samples-per-pixel split over devices 0 .. G-1 inside the library (ptb_multi_*: one context per device,
@@ -87,6 +87,7 @@ int main(int argc, char **argv) {
         else if (a == "--hdr") hdr = true;
         else if (a == "--staged") opt.pipeline = PTB_PIPELINE_STAGED;
         else if (a == "--sort") opt.sortMaterials = 1;
+        else if (a == "--regroup") opt.regroupMaterials = 1;           // fused pipeline, BVH scenes: regroup the paths by material class before shading
         else if (a == "--no-compaction") opt.compaction = 0;
         else if (a == "--quiet") quiet = true;
         else if (a == "--cache-first-bounce") opt.firstBounceCache = 1;

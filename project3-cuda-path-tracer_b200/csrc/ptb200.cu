@@ -35,6 +35,12 @@ constexpr int kTraceStackSmem = kStackSmem, kTraceSlotsPerThread = 1;
 constexpr size_t traceKernelSmem() { return traceSmemBytes(); }
 #endif
 
+// the fused pipeline's material sort (bounce_regroup_kernel) halves the instructions of the BVH shading kernel but that kernel waits on DRAM,
+// not on issue slots: 2 284 against 2 255 us per iteration of the 100 k-object scene (profiles/r3b_regroup.txt) -- a toggle, off by default
+#ifndef PTB_REGROUP_DEFAULT
+#define PTB_REGROUP_DEFAULT 0
+#endif
+
 namespace {
 
 thread_local std::string g_lastError;
@@ -506,6 +512,7 @@ void launchFusedBounces(PtbContext *c) {
                 else        LAUNCH(PTB_STAGE_INTERSECT, (TRACE_KERNEL<SRC_SEGMENTS, false, MESH>), c->gridTrace, kTraceBlock, smem, p, d, TraceIO{});
             }
             if (d == 0) LAUNCH(PTB_STAGE_SHADE, (bounce_kernel<true, true, EXT>), c->gridFused, kBlock, 0, p, d);
+            else if (c->opt.regroupMaterials && c->numMats <= kMaxClassTable) LAUNCH(PTB_STAGE_SHADE, (bounce_regroup_kernel<EXT>), c->gridFused, kBlock, 0, p, d);
             else        LAUNCH(PTB_STAGE_SHADE, (bounce_kernel<false, true, EXT>), c->gridFused, kBlock, 0, p, d);
         } else {
             if (d == 0) LAUNCH(PTB_STAGE_FUSED_BOUNCE0, (bounce_kernel<true, false, EXT>), c->gridFused, kBlock, smem, p, d);
@@ -682,6 +689,7 @@ void ptb_default_options(PtbOptions *o) {
     o->sortMaterials = 0;
     o->firstBounceCache = 0;
     o->useGraphs = 1;
+    o->regroupMaterials = PTB_REGROUP_DEFAULT;
 }
 
 int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *optIn) {

@@ -726,6 +726,128 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// bounce_regroup_kernel: bounces >= 1 of BVH scenes with the MATERIAL SORT of the fused pipeline (INSTRUCTION.md:78-86;
+// PtbOptions.regroupMaterials).  shadeStep has one arm per material class -- Lambertian, mirror, dielectric -- and on a scene whose
+// materials are mixed (configs[4]: 4 diffuse, 1 mirror, 1 glass) bounce_kernel ran the three arms of every 32-path chunk with 12, 3
+// and 7 lanes (profiles/r2w_shade ncu).  Here a warp takes 128 consecutive paths of its CTA's segment, reads their hit records,
+// classifies them through a shared-memory table of the materials' classes and writes one index list per class (ballot + popc, the
+// lists live in shared memory: 3 x 128 bytes per warp); then it shades class by class, 32 listed paths at a time, so every arm runs
+// with full warps except for one partial batch per class.  Misses, and at the last bounce every non-emissive hit, deposit nothing and
+// are dropped at classification.  Per path it is bounce_kernel's arithmetic: same images, same per-depth counts, only the order of the
+// survivors inside a segment differs (nothing depends on it: RNG and deposit are keyed by pixel and iteration).
+// ------------------------------------------------------------------------------------------------
+constexpr int kRegroupChunks = 4;                                  // 32-path chunks a warp classifies together
+constexpr int kMaxClassTable = 256;                                // materials whose class fits the shared-memory table (host: else bounce_kernel)
+enum { CLASS_NONE = 0, CLASS_GLASS = 1, CLASS_MIRROR = 2, CLASS_DIFFUSE = 3 };   // DIFFUSE also takes the emitters (their arm is three multiplies)
+template <bool EXT>
+__global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_regroup_kernel(const __grid_constant__ Params p, const int depth) {
+    constexpr uint32_t kGroup = 32u * kRegroupChunks;
+    __shared__ uint32_t sOutCount, sNextGroup;
+    __shared__ uint8_t sClass[kMaxClassTable];
+    __shared__ uint8_t sList[kBlock / 32][3][kGroup];
+    __shared__ int sMeta[kBlock / 32][kGroup];                       // hit record word of every path of the group ...
+    __shared__ uint16_t sInfo[kBlock / 32][kGroup];                  // ... and primitive type << 14 | material id: the shading pass starts all its loads at once
+    if (threadIdx.x == 0) { sOutCount = 0u; sNextGroup = 0u; }
+    const int remainingBefore = p.traceDepth - depth;
+    for (int id = threadIdx.x; id < p.numMats && id < kMaxClassTable; id += kBlock) {
+        const float emittance = __ldg(&p.mats[3 * id]).w, refl = __ldg(&p.mats[3 * id + 1]).w, refr = __ldg(&p.mats[3 * id + 2]).x;
+        int cls = CLASS_DIFFUSE;                                        // shadeStep's order: emitter, budget, dielectric, mirror, Lambertian
+        if (!(emittance > 0.0f)) {
+            if (remainingBefore <= 1) cls = CLASS_NONE;
+            else if (p.bsdfMode == 1 && refr > 0.0f) cls = CLASS_GLASS;
+            else if (p.bsdfMode == 1 && refl > 0.0f) cls = CLASS_MIRROR;
+        }
+        sClass[id] = (uint8_t)cls;
+    }
+    __syncthreads();
+    Control *ctrl = p.ctrl;
+    const int iterBase = ctrl->iterBase, iterStride = ctrl->iterStride;
+    const uint32_t total = p.segCounts[((depth + 1) & 1) * gridDim.x + blockIdx.x];
+    const uint32_t pixMask = (1u << p.pixBits) - 1u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const uint32_t laneBelow = (1u << lane) - 1u;
+    const uint32_t segBase = blockIdx.x * p.segCap;
+    for (;;) {
+        // groups go to the warps by ticket: with four chunks per group a static split leaves the warps of a CTA unevenly loaded
+        uint32_t group = 0;
+        if (lane == 0) group = atomicAdd(&sNextGroup, 1u);
+        group = __shfl_sync(0xffffffffu, group, 0);
+        const uint32_t base = group * kGroup;
+        if (base >= total) break;
+        // ---- classify the group's paths
+        uint32_t n[3] = {0u, 0u, 0u};
+#pragma unroll
+        for (int ch = 0; ch < kRegroupChunks; ++ch) {
+            const uint32_t k = base + ch * 32u + lane;
+            int cls = CLASS_NONE;
+            if (k < total) {
+                const int meta = p.hits.meta[segBase + k];
+                if (meta >= 0) {
+                    const int2 tag = __ldg(reinterpret_cast<const int2 *>(&p.geoms[meta & 0x3fffffff].tag));    // type, material id
+                    cls = sClass[tag.y];
+                    sMeta[warp][ch * 32 + lane] = meta;
+                    sInfo[warp][ch * 32 + lane] = (uint16_t)((tag.x << 14) | tag.y);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                const unsigned m = __ballot_sync(0xffffffffu, cls == c + 1);
+                if (cls == c + 1) sList[warp][c][n[c] + __popc(m & laneBelow)] = (uint8_t)(ch * 32 + lane);
+                n[c] += __popc(m);
+            }
+        }
+        __syncwarp();
+        // ---- shade class by class
+#pragma unroll 1
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll 1
+            for (uint32_t b = 0; b < n[c]; b += 32u) {
+                const bool valid = b + lane < n[c];
+                bool alive = false;
+                f3 o = mk3(0.f, 0.f, 0.f), d = o, col = o;
+                uint32_t id = 0;
+                if (valid) {
+                    const uint32_t off = sList[warp][c][b + lane];
+                    const uint32_t k = segBase + base + off;
+                    const int meta = sMeta[warp][off];
+                    const uint32_t info = sInfo[warp][off];
+                    // every load of the path starts here: ray, hit record, throughput, the matrix of the normal (shadeStep: the material)
+                    loadPathRay(p.in, k, o, d);
+                    const float4 r = p.hits.tn[k];
+                    loadPathTail(p.in, k, col, id);
+                    GeomRec g;
+                    g.tag = make_int4((int)(info >> 14), (int)(info & 0x3fffu), 0, 0);
+                    const float4 *rows = reinterpret_cast<const float4 *>(p.geoms + (meta & 0x3fffffff)) + (g.tag.x == 1 ? 3 : 6);
+                    const float4 r0 = __ldg(rows), r1 = __ldg(rows + 1), r2 = __ldg(rows + 2);
+                    g.fwd.r0 = g.nrm.r0 = r0; g.fwd.r1 = g.nrm.r1 = r1; g.fwd.r2 = g.nrm.r2 = r2;
+                    Candidate best;
+                    best.t = r.x; best.a = r.y; best.b = r.z; best.c = r.w;
+                    best.slot = meta & 0x3fffffff; best.outside = (meta >> 30) & 1;
+                    const uint32_t pix = id & pixMask, slot = (id & ~kDeadBit) >> p.pixBits;
+                    const f3 nrm = candidateNormal(g, best);
+                    alive = shadeStep<EXT>(p, depth, iterBase + (int)slot * iterStride, pix, true, g.tag.y, best.t, nrm, best.outside, o, d, col, remainingBefore);
+                    if (!alive) deposit(p, pix, slot, col);
+                }
+                const unsigned ballot = __ballot_sync(0xffffffffu, alive);
+                if (ballot) {
+                    uint32_t off = 0;
+                    if (lane == 0) off = atomicAdd(&sOutCount, (uint32_t)__popc(ballot));
+                    off = __shfl_sync(0xffffffffu, off, 0);
+                    if (alive) storePath(p.out, segBase + off + (uint32_t)__popc(ballot & laneBelow), o, d, col, id);
+                }
+            }
+        }
+        __syncwarp();                                                    // the lists are rewritten by the next group
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const uint32_t cnt = sOutCount;
+        p.segCounts[(depth & 1) * gridDim.x + blockIdx.x] = cnt;
+        if (cnt) atomicAdd(&ctrl->counts[depth + 1], cnt);
+    }
+}
+
 // Bounce 0 when the camera ray does not depend on the iteration (no antialiasing, no thin lens: generateRayFromCamera,
 // src/pathtrace.cu:122-143, ignores `iter`).  The closest hit of a pixel is then the same for every slot of the wavefront, so a
 // warp takes one tile of 32 pixels x up to kSlotBlock slots, finds (brute force) or reads (BVH: trace_kernel<SRC_PIXELS> ran once

@@ -203,6 +203,20 @@ def test_far_grazing_band_on_the_gpu(m, port, monkeypatch):
     assert len(lost) > 0 and np.all(want[0][lost] == owner[lost])          # hits of the grazed sphere, dropped by its round-1 box
 
 
+def test_material_regrouping_in_the_fused_path_is_bit_neutral(m, synthetic):
+    """PtbOptions.regroupMaterials: the fused pipeline's material sort on BVH scenes (bounce_regroup_kernel: every warp regroups 128 paths
+    of its CTA's segment by material class before shading).  Only the order of the survivors inside a segment changes: the image and the
+    per-depth path counts of the 100 k-object scene (diffuse, mirror and glass materials mixed) are those of the path-order kernel, bit for bit."""
+    out = []
+    for rg in (0, 1):
+        with m.Renderer(m.Scene.load(synthetic), device=0, bsdf=1, batch_iters=3, regroup_materials=rg) as r:
+            r.render(1, 5)                                               # a full wavefront and a partial one
+            out.append((r.download(), r.stats()))
+    (img, st), (img_r, st_r) = out
+    assert st["alive_per_depth"] == st_r["alive_per_depth"] and st["segments"] == st_r["segments"] and st["segments"] > 30000000
+    assert same_bits(img, img_r) and float(img.sum()) > 0.0
+
+
 def test_stack_spill_path_renders_the_same_image(m, synthetic):
     """trace_kernel keeps 16 traversal-stack entries per lane in shared memory and moves blocks of old entries to a global spill area
     when a deeper tree needs more (csrc/ptb_trace.cuh).  The tuning build keeps only 8, so on the 100 k-object scene its lanes spill
