@@ -179,6 +179,7 @@ struct PtbContext {
 
     Params base{};
     int gridFused = 0, gridStaged = 0, gridTrace = 0;
+    uint32_t slotBlock = 8;              // bounce0_shared_kernel: slots per tile
     size_t smemBrute = 0, smemBvh = 0;
     int bvhDepth = 0;                    // depth of the BVH last uploaded
     DevBuf<int> stackSpill;              // trace_kernel: traversal-stack entries beyond the shared-memory part
@@ -824,11 +825,15 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     else { CUB(c->image.alloc((size_t)c->numPixels * 3)); c->imagePtr = c->image.p; CUB(cudaMemset(c->imagePtr, 0, (size_t)c->numPixels * 3 * sizeof(float))); }
     const size_t maxPaths = (size_t)c->numPixels * c->batch;
     c->sharedFirstHit = opt.pipeline == PTB_PIPELINE_FUSED && !opt.antialias && !(opt.lensRadius > 0.0f);
-    // fused pipeline: every CTA owns a segment of ceil(tiles / grid) 256-path tiles of the path buffers (bounce0_shared_kernel's
-    // tiles are 32 pixels x min(batch, 8) slots: at most 256 paths each, possibly more of them)
-    const size_t sharedTiles = (((size_t)c->numPixels + 31) / 32) * (((size_t)c->batch + std::min<size_t>(c->batch, kSlotBlock) - 1) / std::min<size_t>(c->batch, kSlotBlock));
-    const size_t tiles = std::max((maxPaths + kBlock - 1) / kBlock, sharedTiles);
-    c->segCap = (uint32_t)(((tiles + c->gridFused - 1) / c->gridFused) * kBlock);
+    // fused pipeline: every CTA owns a segment of the path buffers that holds the survivors of the tiles it gets at bounce 0:
+    // ceil(tiles / grid) tiles of 256 camera paths (bounce_kernel<FIRST>), or of 32 pixels x min(batch, slotBlock) slots (bounce0_shared_kernel)
+    c->slotBlock = c->useBvh ? kSlotBlockBvh : kSlotBlockBrute;
+    const size_t slotBlock = std::min<size_t>(c->batch, c->slotBlock);
+    const size_t sharedTiles = (((size_t)c->numPixels + 31) / 32) * (((size_t)c->batch + slotBlock - 1) / slotBlock);
+    const size_t pathTiles = (maxPaths + kBlock - 1) / kBlock;
+    const size_t capShared = ((sharedTiles + c->gridFused - 1) / c->gridFused) * 32 * slotBlock;
+    const size_t capTiles = ((pathTiles + c->gridFused - 1) / c->gridFused) * kBlock;
+    c->segCap = (uint32_t)std::max(capShared, capTiles);
     const size_t pathSlots = std::max(maxPaths, (size_t)c->segCap * c->gridFused);
     for (int i = 0; i < 2; ++i) {
         CUB(c->A[i].alloc(pathSlots)); CUB(c->B[i].alloc(pathSlots)); CUB(c->C[i].alloc(pathSlots));
@@ -867,7 +872,7 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     p.numPixels = c->numPixels;
     p.atomicGather = (c->batch > 1 && opt.depositMode != PTB_DEPOSIT_ORDERED) ? 1 : 0;
     p.segCounts = c->segCounts.p;
-    p.segCap = c->segCap;
+    p.segCap = c->segCap; p.slotBlock = c->slotBlock;
     p.vgrid = (uint32_t)c->gridFused;
     p.stackSpill = c->stackSpill.p; p.spillCap = c->spillCap;
     p.partial = c->partial.p; p.partialStride = c->partialStride;

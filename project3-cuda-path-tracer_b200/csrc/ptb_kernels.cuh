@@ -91,6 +91,7 @@ struct Params {
     const int     *fbMeta;       // ... and geom slot | outside << 30, -1 = miss
     uint32_t      *segCounts;    // fused pipeline: 2 x grid per-CTA survivor counts (ping-pong by depth parity)
     uint32_t       segCap;       // fused pipeline: path slots per CTA segment
+    uint32_t       slotBlock;    // bounce0_shared_kernel: slots of the wavefront that share one hit per pixel tile (kSlotBlockBrute / kSlotBlockBvh)
     uint32_t       vgrid;        // fused pipeline: number of CTA-owned segments (= grid of the bounce kernels); trace_kernel serves them with its own grid
     int           *stackSpill;   // trace_kernel: traversal-stack entries beyond the shared-memory part (NULL when the tree is shallow enough)
     int            spillCap;     // ... per ray slot
@@ -850,12 +851,14 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_regroup_kernel(c
 
 // Bounce 0 when the camera ray does not depend on the iteration (no antialiasing, no thin lens: generateRayFromCamera,
 // src/pathtrace.cu:122-143, ignores `iter`).  The closest hit of a pixel is then the same for every slot of the wavefront, so a
-// warp takes one tile of 32 pixels x up to kSlotBlock slots, finds (brute force) or reads (BVH: trace_kernel<SRC_PIXELS> ran once
+// warp takes one tile of 32 pixels x up to Params::slotBlock slots, finds (brute force) or reads (BVH: trace_kernel<SRC_PIXELS> ran once
 // per wavefront; first-bounce cache: once per scene) the hit ONCE, builds normal and material once, and runs only the
 // per-iteration part -- RNG, scatter, deposit, compaction -- per slot.  Per path it is bounce_kernel<FIRST>'s arithmetic, so the
-// results are identical; 7/8 of bounce 0's intersection work is gone (cornell: 110 -> ~98 us per iteration).
+// results are identical; 31/32 of bounce 0's intersection work is gone (7/8 with the 8 slots per tile of the first version) (cornell: 110 -> ~98 us per iteration).
 // Tiles go to the CTAs round-robin like bounce_kernel<FIRST>'s, every CTA packs its survivors into its own segment.
-constexpr uint32_t kSlotBlock = 8;                                 // 32 pixels x 8 slots = one 256-path tile
+// slots of the wavefront one tile carries: 32 on brute-force scenes (cornell, us per iteration at 4 / 8 / 16 / 32: 98.5 / 96.7 / 96.3 / 96.1,
+// profiles/r3c_slot_block.txt), 8 on BVH scenes, where the hit is only read and bigger tiles measured 1-2 % slower (100 k objects: 2 141 against 2 102)
+constexpr uint32_t kSlotBlockBrute = 32, kSlotBlockBvh = 8;
 #ifndef PTB_SHARED0_MINBLOCKS
 #define PTB_SHARED0_MINBLOCKS 3                                    // 80 registers: the hit (ray, t, normal, material) stays live across the slot loop
 #endif
@@ -872,7 +875,7 @@ __global__ void __launch_bounds__(kBlock, PTB_SHARED0_MINBLOCKS) bounce0_shared_
     const CameraParams cam = p.hdr->cam;
     const int iterBase = ctrl->iterBase, iterStride = ctrl->iterStride;
     const uint32_t batch = (uint32_t)ctrl->batch;
-    const uint32_t S = min(batch, kSlotBlock);
+    const uint32_t S = min(batch, p.slotBlock);
     const uint32_t groups = (p.numPixels + 31u) / 32u;
     const uint32_t tiles = groups * ((batch + S - 1u) / S);
     const uint32_t myTiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
