@@ -919,20 +919,24 @@ __global__ void __launch_bounds__(kBlock, PTB_SHARED0_MINBLOCKS) bounce0_shared_
             isHit = valid && best.slot >= 0;
             if (isHit) { t = best.t; n = candidateNormal(sgeoms[best.slot], best); matId = sgeoms[best.slot].tag.y; outside = best.outside; }
         }
-        // ---- the per-iteration part
+        // ---- the per-iteration part.  Whether a path survives bounce 0 does not depend on the iteration either (shadeStep: a hit on a
+        // non-emissive material with bounces left always scatters), so the warp reserves the output slots of the WHOLE tile with one
+        // shared-memory atomic and every slot of the wavefront packs its survivors at (slot - slot0) * n + rank -- no ballot, atomic and
+        // shuffle per slot
+        const bool survives = valid && isHit && p.traceDepth > 1 && !(__ldg(&p.mats[3 * matId]).w > 0.0f);
+        const unsigned ballot = __ballot_sync(0xffffffffu, survives);
+        const uint32_t nSurv = (uint32_t)__popc(ballot), rank = (uint32_t)__popc(ballot & ((1u << lane) - 1u));
+        uint32_t off = 0;
+        if (ballot) {
+            if (lane == 0) off = atomicAdd(&sOutCount, nSurv * (slot1 - slot0));
+            off = __shfl_sync(0xffffffffu, off, 0);
+        }
         for (uint32_t slot = slot0; slot < slot1; ++slot) {          // warp-uniform trip count
             f3 ro = o, rd = d, c = mk3(1.0f, 1.0f, 1.0f);           // src/pathtrace.cu:132
-            bool alive = false;
             if (valid) {
-                alive = shadeStep<EXT>(p, 0, iterBase + (int)slot * iterStride, pix, isHit, matId, t, n, outside, ro, rd, c, p.traceDepth);
+                const bool alive = shadeStep<EXT>(p, 0, iterBase + (int)slot * iterStride, pix, isHit, matId, t, n, outside, ro, rd, c, p.traceDepth);
                 if (!alive) deposit(p, pix, slot, c);
-            }
-            const unsigned ballot = __ballot_sync(0xffffffffu, alive);
-            if (ballot) {
-                uint32_t off = 0;
-                if (lane == 0) off = atomicAdd(&sOutCount, (uint32_t)__popc(ballot));
-                off = __shfl_sync(0xffffffffu, off, 0);
-                if (alive) storePath(p.out, segBase + off + (uint32_t)__popc(ballot & ((1u << lane) - 1u)), ro, rd, c, pix | (slot << p.pixBits));
+                else if (survives) storePath(p.out, segBase + off + (slot - slot0) * nSurv + rank, ro, rd, c, pix | (slot << p.pixBits));
             }
         }
     }
