@@ -409,8 +409,10 @@ def main():
     if world == 1:
         dropin = {}
         hp = host_frame.data_ptr()
-        for mode, lazy in (("strict", 0), ("lazy_image", 1)):
-            with m.Renderer(scene, device=local, bsdf=m.BSDF_FULL, batch_iters=1, lazy_image=lazy) as rd:
+        # *_lookahead = PtbOptions.lookahead: the call for iteration i traces the wavefront i .. i + 63 at the batched rate and every call adds
+        # only its own iteration to the image (bit-identical: tests/test_gpu_parity.py::test_pathtrace_lookahead_is_bit_identical)
+        for mode, lazy, la_batch in (("strict", 0, 0), ("lazy_image", 1, 0), ("strict_lookahead", 0, 64), ("lazy_image_lookahead", 1, 64)):
+            with m.Renderer(scene, device=local, bsdf=m.BSDF_FULL, batch_iters=la_batch or 1, lazy_image=lazy, lookahead=1 if la_batch else 0) as rd:
                 for it in range(1, 9):
                     m._check(m.lib().ptb_pathtrace(rd._h, None, 0, it, hp))
                 rd.sync()
@@ -423,6 +425,8 @@ def main():
                 sdi = rd.stats()
             dropin[mode] = {"iters_per_s": n_it / dt, "us_per_call": dt / n_it * 1e6,
                             "segments_per_s": sdi["segments"] / sdi["iterations"] * n_it / dt, "d2h_bytes_per_iter": P * 12}
+            if la_batch:
+                dropin[mode]["iterations_per_window"] = la_batch
         # the PCIe floor of the strict semantic: 7.68 MB device->host per call at the measured pinned D2H rate
         src = torch.empty(P * 3, dtype=torch.float32, device=dev)
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -563,7 +567,11 @@ def main():
                         "pathtrace_call_strict": {"segments_per_s": dropin["strict"]["segments_per_s"] / sk["segments_per_s"],
                                                   "iters_per_s": dropin["strict"]["iters_per_s"] / sk["iters_per_s"]},
                         "pathtrace_call_lazy_image": {"segments_per_s": dropin["lazy_image"]["segments_per_s"] / sk["segments_per_s"],
-                                                      "iters_per_s": dropin["lazy_image"]["iters_per_s"] / sk["iters_per_s"]}},
+                                                      "iters_per_s": dropin["lazy_image"]["iters_per_s"] / sk["iters_per_s"]},
+                        "pathtrace_call_strict_lookahead": {"segments_per_s": dropin["strict_lookahead"]["segments_per_s"] / sk["segments_per_s"],
+                                                            "iters_per_s": dropin["strict_lookahead"]["iters_per_s"] / sk["iters_per_s"]},
+                        "pathtrace_call_lazy_image_lookahead": {"segments_per_s": dropin["lazy_image_lookahead"]["segments_per_s"] / sk["segments_per_s"],
+                                                                "iters_per_s": dropin["lazy_image_lookahead"]["iters_per_s"] / sk["iters_per_s"]}},
                     "target": "BASELINE.json north_star: >= 10x the skeleton's own CUDA loop on cornell 800x800 depth 8"}
         if not args.no_cpu_baseline and world == 1:
             try:

@@ -131,6 +131,15 @@ typedef struct PtbOptions {
                                        regroups 128 paths of its CTA's segment by material class (Lambertian / mirror / dielectric) before
                                        shading, so that each arm of the shader runs with full warps; 0 = shade in path order.  Identical images
                                        and per-depth counts either way; scenes with more than 256 materials are shaded in path order */
+    int32_t lookahead;              /* ptb_pathtrace only (default 1; needs the fused pipeline, the ordered deposit, batchIters > 1 and a library-owned
+                                       accumulation buffer): the call for iteration i has the whole wavefront i .. i + batchIters - 1 traced at the
+                                       batched rate on a second stream, and the image after EACH of those iterations built in iteration order; the
+                                       next wavefront is traced while this one is handed out, so a call costs its image copy (the strict semantic of
+                                       src/pathtrace.cu:389-390 runs at the PCIe rate of the copy).  The reference's loop asks for consecutive
+                                       iterations (src/main.cpp:132-136) and an iteration depends only on its number, so every call leaves the bits
+                                       of one iteration per call; any other call order, and every other entry point that renders or touches the
+                                       accumulation, ends the look-ahead and drops what was traced ahead.  PtbStats counts traced iterations.
+                                       0 = every call traces its own iteration */
 } PtbOptions;
 /* antialias / lensRadius make the camera rays depend on the iteration, so they cannot be combined with
  * firstBounceCache (INSTRUCTION.md:113: "keep in mind how this influences the first-bounce cache"):

@@ -214,9 +214,20 @@ struct PtbContext {
     int64_t stageLaunches[PTB_NUM_STAGES] = {};
     int64_t launches = 0;
     int64_t hostIterations = 0;
+    // ptb_pathtrace look-ahead (PtbOptions.lookahead): iterations laBase .. laBase + batch - 1 have been traced on aheadStream and set laSet of
+    // the prefix images holds the image after each of them; laServed of them have been handed out; the window after it is traced into the
+    // other set meanwhile (laNext).  laImage = the image after the last iteration handed out (NULL: the canonical image[] is current)
+    bool laValid = false, laNext = false; int laBase = 0, laServed = 0, laSet = 0;
+    const float *laImage = nullptr;
+    cudaStream_t aheadStream = nullptr;
+    cudaEvent_t evWave[2] = {nullptr, nullptr}, evUser = nullptr;
+    DevBuf<float> prefix[2];             // batch images each
 
     ~PtbContext() {
         if (graphExec) cudaGraphExecDestroy(graphExec);
+        if (aheadStream) { cudaStreamSynchronize(aheadStream); cudaStreamDestroy(aheadStream); }
+        for (int k = 0; k < 2; ++k) { if (evWave[k]) cudaEventDestroy(evWave[k]); prefix[k].release(); }
+        if (evUser) cudaEventDestroy(evUser);
         for (cudaEvent_t e : events) cudaEventDestroy(e);
         if (comm && ownComm) { std::string err; if (NcclApi *n = ncclApi(err)) n->commDestroy(comm); }
         frame.release();
@@ -235,6 +246,10 @@ struct PtbContext {
 };
 
 namespace {
+
+void dropGraphs(PtbContext *c) {
+    if (c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }
+}
 
 GeomRec packGeom(const PtbGeom &g, int sceneIndex, int order = -1) {
     GeomRec r;
@@ -434,7 +449,7 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     bool ext = c->opt.antialias || c->opt.lensRadius > 0.0f;
     if (c->opt.bsdfMode == PTB_BSDF_FULL)
         for (int i = 0; i < M; ++i) ext = ext || (scene->materials[i].hasReflective > 0.0f && scene->materials[i].specularExponent > 0.0f);
-    if (ext != c->ext && c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }   // other kernels: re-capture
+    if (ext != c->ext) dropGraphs(c);                                                                     // other kernels: re-capture
     c->ext = ext;
     hdr->numNodes = c->numNodes;
 
@@ -636,18 +651,29 @@ int ensureStackSpill(PtbContext *c) {
         CU(cudaStreamSynchronize(c->stream));
         CU(c->stackSpill.alloc((size_t)c->gridTrace * kTraceBlock * kTraceSlotsPerThread * need * 2));      // 8-byte entries (child, entry distance)
         c->spillCap = need;
-        if (c->graphExec) { cudaGraphExecDestroy(c->graphExec); c->graphExec = nullptr; }    // new launch parameters: re-capture
+        dropGraphs(c);                                                                        // new launch parameters: re-capture
     }
     c->base.stackSpill = c->stackSpill.p; c->base.spillCap = c->spillCap;
     return PTB_OK;
 }
 
-int runBatches(PtbContext *c, int iterBegin, int count, int iterStride) {
+// End of the look-ahead: whatever was traced ahead and not handed out is dropped, and the image after the last iteration handed out becomes
+// the canonical image[] again -- before anything else renders, resets or reads image[]
+int flushLookahead(PtbContext *c) {
+    if (!c->laValid) return PTB_OK;
+    c->laValid = false; c->laNext = false;
+    CU(cudaStreamSynchronize(c->aheadStream));                     // a window may still be tracing (its partial images are all-zero again when it ends)
+    if (c->laImage) CU(cudaMemcpyAsync(c->imagePtr, c->laImage, (size_t)c->numPixels * 3 * sizeof(float), cudaMemcpyDeviceToDevice, c->stream));
+    c->laImage = nullptr;
+    return PTB_OK;
+}
+
+int runBatches(PtbContext *c, int iterBegin, int count, int iterStride, int deferReduce = 0) {
     { int rc = ensureFirstBounceCache(c); if (rc != PTB_OK) return rc; }
     int done = 0;
     while (done < count) {
         const int b = std::min(c->batch, count - done);
-        LAUNCH(PTB_STAGE_CONTROL, set_control_kernel, 1, 32, 0, c->ctrl.p, iterBegin + done * iterStride, iterStride, b);
+        LAUNCH(PTB_STAGE_CONTROL, set_control_kernel, 1, 32, 0, c->ctrl.p, iterBegin + done * iterStride, iterStride, b, deferReduce);
         // full batches replay back to back: advance_kernel moves iterBase on the device
         int reps = (b == c->batch) ? (count - done) / c->batch : 1;
         for (int r = 0; r < reps; ++r) {
@@ -664,7 +690,38 @@ int runBatches(PtbContext *c, int iterBegin, int count, int iterStride) {
         done += reps * b;
         if (c->opt.timeStages && c->evUsed > 8192) { CU(cudaStreamSynchronize(c->stream)); foldStageTimers(c); }   // bound the event pool
     }
-    c->hostIterations += count;
+    if (!deferReduce) c->hostIterations += count;
+    return PTB_OK;
+}
+
+int ensureLookahead(PtbContext *c) {
+    if (c->aheadStream) return PTB_OK;
+    int least = 0, greatest = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    CU(cudaStreamCreateWithPriority(&c->aheadStream, cudaStreamNonBlocking, least));
+    for (int k = 0; k < 2; ++k) {
+        CU(cudaEventCreateWithFlags(&c->evWave[k], cudaEventDisableTiming));
+        CU(c->prefix[k].alloc((size_t)c->batch * c->partialStride));
+    }
+    CU(cudaEventCreateWithFlags(&c->evUser, cudaEventDisableTiming));
+    return PTB_OK;
+}
+
+// One wavefront of `batch` iterations starting at `iter` on aheadStream, then the image after each of them into set `set` of the prefix
+// images, starting from `base`.  Ordered after everything queued on the caller's stream so far (copies out of that set, resets, uploads).
+int launchWindow(PtbContext *c, int iter, int set, const float *base) {
+    CU(cudaEventRecord(c->evUser, c->stream));
+    CU(cudaStreamWaitEvent(c->aheadStream, c->evUser, 0));
+    std::swap(c->stream, c->aheadStream);
+    int rc = runBatches(c, iter, c->batch, 1, 1);
+    if (rc == PTB_OK) {
+        deposit_prefix_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(c->base, base, c->prefix[set].p, (uint32_t)c->batch);
+        c->launches++;
+        if (cudaGetLastError() != cudaSuccess) rc = fail(PTB_ERR_CUDA, "look-ahead window launch failed");
+    }
+    std::swap(c->stream, c->aheadStream);
+    if (rc != PTB_OK) return rc;
+    CU(cudaEventRecord(c->evWave[set], c->aheadStream));
     return PTB_OK;
 }
 
@@ -691,6 +748,7 @@ void ptb_default_options(PtbOptions *o) {
     o->firstBounceCache = 0;
     o->useGraphs = 1;
     o->regroupMaterials = PTB_REGROUP_DEFAULT;
+    o->lookahead = 1;                    // ptb_pathtrace traces whole wavefronts ahead (bit-identical images; only that entry point is affected)
 }
 
 int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *optIn) {
@@ -758,7 +816,13 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     } while (0)
 
     if (opt.stream) { c->stream = (cudaStream_t)opt.stream; c->ownStream = false; }
-    else { CUB(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->ownStream = true; }
+    else {
+        // the library's own stream gets the highest priority: with PtbOptions.lookahead the per-call passes queued on it must not wait behind
+        // the wavefront that is being traced ahead on the low-priority stream (priorities only matter between streams of this process)
+        int least = 0, greatest = 0;
+        CUB(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        CUB(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, greatest)); c->ownStream = true;
+    }
 
     // ---- scene upload (src/pathtrace.cu:89-93) in the device layout ----
     c->useBvh = hasMeshes || opt.accel == PTB_ACCEL_BVH || (opt.accel == PTB_ACCEL_AUTO && scene->numGeoms > 64);
@@ -894,6 +958,7 @@ int ptb_update_scene(PtbContext *c, const PtbSceneDesc *scene) {
         scene->camera.resolution[1] != c->H || scene->traceDepth != c->traceDepth)
         return fail(PTB_ERR_INVALID, "ptb_update_scene: geometry/material counts, resolution and depth must match ptb_create");
     ON_DEVICE(c->device);
+    { int frc = flushLookahead(c); if (frc != PTB_OK) return frc; }   // the window was traced through the old scene
     CU(cudaStreamSynchronize(c->stream));           // the pinned staging buffer is about to be rewritten
     rc = uploadScene(c, scene);
     if (rc != PTB_OK) return rc;
@@ -906,6 +971,7 @@ int ptb_update_scene(PtbContext *c, const PtbSceneDesc *scene) {
 int ptb_destroy(PtbContext *c) {
     if (!c) return PTB_OK;                          // pathtraceFree before any pathtraceInit (src/main.cpp:126)
     DeviceScope deviceScope_(c->device);
+    if (c->aheadStream) cudaStreamSynchronize(c->aheadStream);
     cudaStreamSynchronize(c->stream);
     delete c;
     return PTB_OK;
@@ -917,6 +983,7 @@ int ptb_render(PtbContext *c, int iterBegin, int count, int iterStride) {
     // makeSeededRandomEngine packs iter into 22 bits and depth into 9 (src/pathtrace.cu:43)
     if ((int64_t)iterBegin + (int64_t)(count - 1) * iterStride >= (1 << 22)) return fail(PTB_ERR_INVALID, "ptb_render: iteration beyond 2^22 aliases the RNG seed");
     ON_DEVICE(c->device);
+    { int rc = flushLookahead(c); if (rc != PTB_OK) return rc; }
     return runBatches(c, iterBegin, count, iterStride);
 }
 
@@ -924,6 +991,7 @@ int ptb_write_pbo(PtbContext *c, PtbUchar4 *pbo, int samples) {
     if (!c || !pbo) return fail(PTB_ERR_INVALID, "ptb_write_pbo: null argument");
     if (samples <= 0) return fail(PTB_ERR_INVALID, "ptb_write_pbo: samples %d (the divisor of sendImageToPBO must be positive)", samples);
     ON_DEVICE(c->device);
+    { int frc = flushLookahead(c); if (frc != PTB_OK) return frc; }
     pbo_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(reinterpret_cast<uchar4 *>(pbo), c->imagePtr, c->numPixels, samples);
     c->launches++;
     CU(cudaGetLastError());
@@ -933,6 +1001,7 @@ int ptb_write_pbo(PtbContext *c, PtbUchar4 *pbo, int samples) {
 int ptb_download(PtbContext *c, float *hostImage) {
     if (!c || !hostImage) return fail(PTB_ERR_INVALID, "ptb_download: null argument");
     ON_DEVICE(c->device);
+    { int frc = flushLookahead(c); if (frc != PTB_OK) return frc; }
     CU(cudaMemcpyAsync(hostImage, c->imagePtr, (size_t)c->numPixels * 3 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
     return PTB_OK;
@@ -952,17 +1021,60 @@ int ptb_pathtrace(PtbContext *c, PtbUchar4 *pbo, int frame, int iter, float *hos
     (void)frame;                                     // unused by the reference as well (src/main.cpp:136)
     if (!c) return fail(PTB_ERR_INVALID, "ptb_pathtrace: not initialised");
     if (iter < 1) return fail(PTB_ERR_INVALID, "ptb_pathtrace: iteration %d (the reference's iterations are 1-based, src/main.cpp:132)", iter);
-    int rc = ptb_render(c, iter, 1, 1);
-    if (rc != PTB_OK) return rc;
-    if (pbo) { rc = ptb_write_pbo(c, pbo, iter); if (rc != PTB_OK) return rc; }
+    int rc;
+    const bool lookahead = c->opt.lookahead && c->batch > 1 && c->base.partial && c->opt.pipeline == PTB_PIPELINE_FUSED && !c->opt.externalAccum;
+    const float *image = c->imagePtr;
+    if (lookahead) {
+        // Look-ahead: the reference's loop asks for iterations 1, 2, 3, ... (src/main.cpp:132-136) and an iteration depends on nothing but its
+        // number (src/pathtrace.cu:41-45), so the call for iteration i has the whole wavefront i .. i + batch - 1 traced at the batched rate
+        // (on a second, low-priority stream) and the image AFTER every one of those iterations built in iteration order (deposit_prefix_kernel:
+        // the additions of one iteration per call, bit for bit); the window after it is traced while this one is handed out.  A call then
+        // costs its image copy: the strict semantic runs at the PCIe rate of the 12 B/pixel copy.  Any other call order, and every other
+        // entry point that renders or touches image[], ends the look-ahead (flushLookahead).
+        ON_DEVICE(c->device);
+        rc = ensureLookahead(c);
+        if (rc != PTB_OK) return rc;
+        if ((int64_t)iter + 2 * (int64_t)c->batch >= (1 << 22)) return fail(PTB_ERR_INVALID, "ptb_pathtrace: iteration beyond 2^22 aliases the RNG seed");
+        if (c->laValid && c->laServed == c->batch && iter == c->laBase + c->batch && c->laNext) {
+            c->laBase += c->batch; c->laSet ^= 1; c->laServed = 0; c->laNext = false;      // the window traced ahead becomes the current one
+        } else if (!(c->laValid && iter == c->laBase + c->laServed && c->laServed < c->batch)) {
+            rc = flushLookahead(c);                                // (also makes image[] current: the base of the new window)
+            if (rc != PTB_OK) return rc;
+            rc = launchWindow(c, iter, 0, c->imagePtr);
+            if (rc != PTB_OK) return rc;
+            c->laValid = true; c->laBase = iter; c->laServed = 0; c->laSet = 0; c->laNext = false;
+        }
+        if (c->laServed == 0) {
+            CU(cudaStreamWaitEvent(c->stream, c->evWave[c->laSet], 0));
+            if (!c->laNext) {
+                // the next window starts from the last image of this one; the copies out of the set it overwrites were queued before this point
+                rc = launchWindow(c, c->laBase + c->batch, c->laSet ^ 1, c->prefix[c->laSet].p + (size_t)(c->batch - 1) * c->partialStride);
+                if (rc != PTB_OK) return rc;
+                c->laNext = true;
+            }
+        }
+        image = c->laImage = c->prefix[c->laSet].p + (size_t)c->laServed * c->partialStride;
+        c->laServed++;
+        c->hostIterations++;
+    } else {
+        rc = ptb_render(c, iter, 1, 1);
+        if (rc != PTB_OK) return rc;
+    }
+    if (pbo) {
+        ON_DEVICE(c->device);
+        pbo_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(reinterpret_cast<uchar4 *>(pbo), image, c->numPixels, iter);
+        c->launches++;
+        CU(cudaGetLastError());
+    }
     if (!hostImage) return PTB_OK;
     ON_DEVICE(c->device);
     const size_t bytes = (size_t)c->numPixels * 3 * sizeof(float);
     pinHostImage(c, hostImage, bytes);
-    if (!c->opt.lazyImage) {
-        // the reference's semantic: the accumulated SUM is in the host image when the call returns
-        CU(cudaMemcpyAsync(hostImage, c->imagePtr, bytes, cudaMemcpyDeviceToHost, c->stream));
-        CU(cudaStreamSynchronize(c->stream));
+    if (!c->opt.lazyImage || lookahead) {
+        // the reference's semantic: the accumulated SUM is in the host image when the call returns.  (Look-ahead + lazy image: the same copy
+        // without the wait -- a prefix image is never written again before its window's set is reused: no snapshot needed)
+        CU(cudaMemcpyAsync(hostImage, image, bytes, cudaMemcpyDeviceToHost, c->stream));
+        if (!c->opt.lazyImage) CU(cudaStreamSynchronize(c->stream));
         return PTB_OK;
     }
     // lazy image: snapshot on the render stream (7.68 MB device to device), copy out on the copy stream while the next
@@ -989,6 +1101,7 @@ int ptb_pathtrace(PtbContext *c, PtbUchar4 *pbo, int frame, int iter, float *hos
 int ptb_reset(PtbContext *c) {
     if (!c) return fail(PTB_ERR_INVALID, "ptb_reset: not initialised");
     ON_DEVICE(c->device);
+    { int frc = flushLookahead(c); if (frc != PTB_OK) return frc; }
     CU(cudaMemsetAsync(c->imagePtr, 0, (size_t)c->numPixels * 3 * sizeof(float), c->stream));
     CU(cudaMemsetAsync(c->ctrl.p, 0, sizeof(Control), c->stream));
     c->hostIterations = 0;
@@ -1012,6 +1125,7 @@ int ptb_sync(PtbContext *c) {
 int ptb_stats(PtbContext *c, PtbStats *out) {
     if (!c || !out) return fail(PTB_ERR_INVALID, "ptb_stats: null argument");
     ON_DEVICE(c->device);
+    if (c->aheadStream) CU(cudaStreamSynchronize(c->aheadStream));       // a look-ahead window may still be tracing: its counts belong to the statistics
     Control h;
     CU(cudaMemcpyAsync(&h, c->ctrl.p, sizeof h, cudaMemcpyDeviceToHost, c->stream));
     CU(cudaStreamSynchronize(c->stream));
@@ -1033,6 +1147,7 @@ int ptb_stats(PtbContext *c, PtbStats *out) {
 
 int ptb_accum_device_ptr(PtbContext *c, float **devPtr) {
     if (!c || !devPtr) return fail(PTB_ERR_INVALID, "ptb_accum_device_ptr: null argument");
+    { ON_DEVICE(c->device); int frc = flushLookahead(c); if (frc != PTB_OK) return frc; }
     *devPtr = c->imagePtr;
     return PTB_OK;
 }
@@ -1040,6 +1155,7 @@ int ptb_accum_device_ptr(PtbContext *c, float **devPtr) {
 int ptb_resolve_rgb8(PtbContext *c, int samples, uint8_t *hostRgb8) {
     if (!c || !hostRgb8 || samples <= 0) return fail(PTB_ERR_INVALID, "ptb_resolve_rgb8: bad argument");
     ON_DEVICE(c->device);
+    { int frc = flushLookahead(c); if (frc != PTB_OK) return frc; }
     if (!c->rgb8.p) CU(c->rgb8.alloc((size_t)c->numPixels * 3));
     resolve_rgb8_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(c->rgb8.p, c->imagePtr, c->W, c->H, (float)samples);
     c->launches++;
@@ -1094,6 +1210,7 @@ int ptb_comm_reduce(PtbContext *c, int root) {
     NcclApi *nccl = ncclApi(err);
     if (!nccl) return fail(PTB_ERR_UNSUPPORTED, "%s", err.c_str());
     ON_DEVICE(c->device);
+    { int frc = flushLookahead(c); if (frc != PTB_OK) return frc; }
     if (c->commRank == root) { int rc = ensureFrame(c); if (rc != PTB_OK) return rc; }
     // one collective per frame: count = 3 * W * H floats; recvbuff only matters on the root
     NC(nccl->reduce(c->imagePtr, c->commRank == root ? c->frame.p : nullptr, (size_t)c->numPixels * 3, ncclFloat32, ncclSum, root, c->comm, c->stream));

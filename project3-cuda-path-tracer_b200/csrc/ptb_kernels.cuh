@@ -46,7 +46,7 @@ struct Control {                 // device-resident loop control: no host round 
     int      iterBase;           // iteration number of slot 0
     int      iterStride;         // iteration distance between slots (G for a G-GPU spp split)
     int      batch;              // slots in this wavefront
-    int      pad;
+    int      deferReduce;        // 1 = the wavefront leaves its deposits in the partial images (ptb_pathtrace look-ahead: deposit_prefix_kernel follows)
     uint32_t counts[68];         // counts[d] = paths entering bounce d of the current batch
     unsigned long long aliveTotals[64];
     unsigned long long segments;
@@ -1019,9 +1019,9 @@ __global__ void advance_kernel(Control *ctrl, int traceDepth, uint32_t numPixels
     ctrl->iterations += (unsigned long long)ctrl->batch;
     ctrl->iterBase += ctrl->batch * ctrl->iterStride;
 }
-__global__ void set_control_kernel(Control *ctrl, int iterBase, int iterStride, int batch) {
+__global__ void set_control_kernel(Control *ctrl, int iterBase, int iterStride, int batch, int deferReduce) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    ctrl->iterBase = iterBase; ctrl->iterStride = iterStride; ctrl->batch = batch;
+    ctrl->iterBase = iterBase; ctrl->iterStride = iterStride; ctrl->batch = batch; ctrl->deferReduce = deferReduce;
     for (int d = 0; d < 68; ++d) ctrl->counts[d] = 0;
 }
 
@@ -1142,6 +1142,7 @@ __global__ void __launch_bounds__(kBlock) gather_kernel(const __grid_constant__ 
 // Entries that were written are cleared on the way, so the partial images are all-zero again for the next wavefront.
 // Pure streaming: reads batch x 12 B per pixel (HBM roofline; ~1 % of a cornell wavefront).
 __global__ void __launch_bounds__(kBlock) deposit_reduce_kernel(const __grid_constant__ Params p) {
+    if (p.ctrl->deferReduce) return;                                   // look-ahead window: deposit_prefix_kernel builds the image after every iteration
     const uint32_t batch = (uint32_t)p.ctrl->batch;
     const uint32_t n = p.numPixels * 3u, n4 = n / 4u;
     float4 *img4 = reinterpret_cast<float4 *>(p.image);
@@ -1168,6 +1169,36 @@ __global__ void __launch_bounds__(kBlock) deposit_reduce_kernel(const __grid_con
             if (v != 0.0f) { acc = add(acc, v); *q = 0.0f; }
         }
         p.image[i] = acc;
+    }
+}
+
+// Look-ahead window (ptb_pathtrace, PtbOptions.lookahead): the image AFTER every iteration of the window, prefix[s] = base + the deposits of
+// slots 0 .. s, added in slot (= iteration) order with the same round-to-nearest adds as finalGather's `+=` (src/pathtrace.cu:269-278): bit
+// for bit the image the reference's loop holds after that iteration.  A call of pathtrace() then only copies its prefix image out.
+// Clears the partial images on the way.  Streams batch x 24 B per pixel once per window (~3 % of the window's tracing time).
+__global__ void __launch_bounds__(kBlock) deposit_prefix_kernel(const __grid_constant__ Params p, const float *base, float *prefix, const uint32_t batch) {
+    const uint32_t n = p.numPixels * 3u, n4 = n / 4u;
+    const float4 *base4 = reinterpret_cast<const float4 *>(base);
+    for (uint32_t i = blockIdx.x * kBlock + threadIdx.x; i < n4; i += gridDim.x * kBlock) {
+        float4 acc = base4[i];
+        for (uint32_t s = 0; s < batch; ++s) {
+            float4 *q = reinterpret_cast<float4 *>(p.partial + (size_t)s * p.partialStride) + i;
+            const float4 v = *q;
+            if (v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f) {
+                acc.x = add(acc.x, v.x); acc.y = add(acc.y, v.y); acc.z = add(acc.z, v.z); acc.w = add(acc.w, v.w);
+                *q = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            reinterpret_cast<float4 *>(prefix + (size_t)s * p.partialStride)[i] = acc;
+        }
+    }
+    for (uint32_t i = n4 * 4u + blockIdx.x * kBlock + threadIdx.x; i < n; i += gridDim.x * kBlock) {
+        float acc = base[i];
+        for (uint32_t s = 0; s < batch; ++s) {
+            float *q = p.partial + (size_t)s * p.partialStride + i;
+            const float v = *q;
+            if (v != 0.0f) { acc = add(acc, v); *q = 0.0f; }
+            prefix[(size_t)s * p.partialStride + i] = acc;
+        }
     }
 }
 

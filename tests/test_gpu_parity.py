@@ -486,6 +486,44 @@ def test_lazy_image_of_the_per_iteration_call(m, scene_dir):
                 r.pathtrace(None, 0, 0, host)                    # iterations are 1-based (src/main.cpp:132)
 
 
+def test_pathtrace_lookahead_is_bit_identical(m, scene_dir):
+    """PtbOptions.lookahead: pathtrace(pbo, frame, i) traces the wavefront i .. i + batchIters - 1 once and every call adds only its own
+    iteration's deposits to the image.  Iterations depend on nothing but their number (src/pathtrace.cu:41-45) and the reference's loop asks
+    for 1, 2, 3, ... (src/main.cpp:132-136), so every call must leave exactly the bits of one iteration per call -- also across windows,
+    after a jump in the iteration number, after ptb_render in between and after a reset."""
+    s = m.Scene.load(scene_dir + "/cornell.txt")
+    calls = list(range(1, 12)) + [40, 41, 42]                     # three windows of four, then a jump (the window 9..12 is dropped after 11)
+    want = []
+    with m.Renderer(s, device=0, bsdf=1, batch_iters=1) as r:
+        host = np.zeros((s.pixels, 3), np.float32)
+        for it in calls:
+            r.pathtrace(None, 0, it, host)
+            want.append(host.copy())
+        r.render(100, 3)
+        want_render = r.download()
+        r.pathtrace(None, 0, 200, host)
+        want_after = host.copy()
+        r.reset()
+        r.pathtrace(None, 0, 1, host)
+        want_reset = host.copy()
+    for lazy in (0, 1):
+        with m.Renderer(s, device=0, bsdf=1, batch_iters=4, lookahead=1, lazy_image=lazy) as r:
+            host = np.zeros((s.pixels, 3), np.float32)
+            for k, it in enumerate(calls):
+                r.pathtrace(None, 0, it, host)
+                if lazy:
+                    r.sync()
+                assert same_bits(host, want[k]), (lazy, it)
+            assert same_bits(r.download(), want[-1])               # the image holds the served iterations only
+            r.render(100, 3)                                       # drops the rest of the window 40..43
+            assert same_bits(r.download(), want_render)
+            r.pathtrace(None, 0, 200, host); r.sync()
+            assert same_bits(host, want_after)
+            r.reset()
+            r.pathtrace(None, 0, 1, host); r.sync()
+            assert same_bits(host, want_reset)
+
+
 def test_resolve_rgb8_follows_save_image(m, scene_dir, tmp_path):
     from PIL import Image
     s = m.Scene.load(scene_dir + "/cornell.txt")
