@@ -3,7 +3,7 @@
 // preview (src/preview.cpp, glslUtility.cpp) is display only and out of scope.
 //
 //   ptb200_headless SCENEFILE.txt [--iters N] [--depth D] [--bsdf full|golden-diffuse] [--batch B]
-//                   [--per-iteration] [--out BASENAME] [--hdr] [--staged] [--sort] [--regroup] [--no-compaction]
+//                   [--per-iteration] [--no-lookahead] [--lazy-image] [--out BASENAME] [--hdr] [--staged] [--sort] [--regroup] [--no-compaction]
 //                   [--device K] [--gpus G] [--res W H] [--atomic-deposit] [--time-stages] [--quiet]
 //
 // --gpus G: samples-per-pixel split over devices 0 .. G-1 inside the library (ptb_multi_*: one context per device,
@@ -87,6 +87,7 @@ int main(int argc, char **argv) {
         else if (a == "--hdr") hdr = true;
         else if (a == "--staged") opt.pipeline = PTB_PIPELINE_STAGED;
         else if (a == "--sort") opt.sortMaterials = 1;
+        else if (a == "--no-lookahead") opt.lookahead = 0;             // with --per-iteration: every pathtrace() call traces its own iteration
         else if (a == "--regroup") opt.regroupMaterials = 1;           // fused pipeline, BVH scenes: regroup the paths by material class before shading
         else if (a == "--no-compaction") opt.compaction = 0;
         else if (a == "--quiet") quiet = true;
@@ -95,7 +96,9 @@ int main(int argc, char **argv) {
         else if (a == "--lens") { opt.lensRadius = (float)atof(next()); opt.focalDistance = (float)atof(next()); }   // --lens RADIUS FOCAL_DISTANCE
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 1; }
     }
-    opt.batchIters = perIteration ? 1 : batch;
+    // --per-iteration: pathtrace() per iteration as the reference's main loop calls it; with the look-ahead (default) the library traces whole
+    // wavefronts behind that call, without it every call traces one iteration
+    opt.batchIters = (perIteration && !opt.lookahead) ? 1 : batch;
     opt.device = device;
 
     scene = new Scene(sceneFile, !quiet);                      // src/main.cpp:44
@@ -169,7 +172,9 @@ int main(int argc, char **argv) {
         for (int k = 0; k < 9; ++k) if (st.stageLaunches[k]) printf("stage %-18s %8lld launches %12.1f us\n", names[k], (long long)st.stageLaunches[k], st.stageUs[k]);
     }
     if (!quiet) {
-        printf("%d iterations in %.3f s: %.1f iterations/s, %.4e path segments/s\n", iteration, secs, iteration / secs, st.segments / secs);
+        // (the statistics count traced iterations: the look-ahead traces up to two wavefronts more than it hands out)
+        printf("%d iterations in %.3f s: %.1f iterations/s, %.4e path segments/s\n", iteration, secs, iteration / secs,
+               (double)st.segments / (double)(st.iterations ? st.iterations : 1) * iteration / secs);
         printf("paths entering each bounce (per iteration):");
         for (int d = 0; d < st.traceDepth; ++d) printf(" %.0f", (double)st.alivePerDepth[d] / (double)(st.iterations ? st.iterations : 1));
         printf("\n");
