@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 5
+#define PTB_ABI_VERSION 6
 
 /* ---- POD mirrors of src/sceneStructs.h (byte-identical; matrices column-major like glm) ---- */
 typedef struct PtbGeom {            /* struct Geom, src/sceneStructs.h:20-29, 236 bytes */
@@ -140,6 +140,10 @@ typedef struct PtbOptions {
                                        of one iteration per call; any other call order, and every other entry point that renders or touches the
                                        accumulation, ends the look-ahead and drops what was traced ahead.  PtbStats counts traced iterations.
                                        0 = every call traces its own iteration */
+    int32_t leaveTest;              /* fused pipeline, brute-force scenes (default 1): every path carries the cube face its ray starts on (2 bytes of
+                                       path state) and the closest-hit search settles that cube with one row of the object-space ray instead of
+                                       walking it as its first candidate (src/intersections.h:48-78: both slab quotients of that axis are negative,
+                                       so the reference's test misses).  A pruning decision only: identical images.  0 = the round-1 search */
 } PtbOptions;
 /* antialias / lensRadius make the camera rays depend on the iteration, so they cannot be combined with
  * firstBounceCache (INSTRUCTION.md:113: "keep in mind how this influences the first-bounce cache"):

@@ -166,6 +166,9 @@ struct PtbContext {
     float *imagePtr = nullptr;           // own or external
     DevBuf<float4> A[2], B[2];
     DevBuf<float2> C[2];
+    DevBuf<uint16_t> L[2];               // leave codes of the paths (PathPlanes::L; brute-force scenes of the fused pipeline, PtbOptions.leaveTest)
+    bool leaveWanted = false;            // ... decided at ptb_create: fused pipeline, brute force, one-launch bounce loop, PtbOptions.leaveTest
+    bool leaveTest = false;              // the LEAVE kernel instantiations run: leaveWanted and the scene's matrices are finite and moderate
     DevBuf<float4> hitTn, fbTn;           // fbTn / fbMeta: first-bounce cache (INSTRUCTION.md:87-89)
     DevBuf<int> fbMeta;
     bool fbValid = false;
@@ -236,7 +239,7 @@ struct PtbContext {
         if (pinnedHost) cudaHostUnregister(pinnedHost);
         geoms.release(); geomsScene.release(); bvh.release(); mats.release(); sceneMatDev.release();
         image.release();
-        for (int i = 0; i < 2; ++i) { A[i].release(); B[i].release(); C[i].release(); }
+        for (int i = 0; i < 2; ++i) { A[i].release(); B[i].release(); C[i].release(); L[i].release(); }
         stackSpill.release(); partial.release();
         hitTn.release(); hitMeta.release(); sortKeys.release(); sortOrder.release(); sortHist.release(); segCounts.release(); fbTn.release(); fbMeta.release();
         ctrl.release(); rgb8.release(); hdr.release();
@@ -313,6 +316,8 @@ Params makeParams(PtbContext *c, int inBuf) {
     Params p = c->base;
     p.in.A = c->A[inBuf].p; p.in.B = c->B[inBuf].p; p.in.C = c->C[inBuf].p;
     p.out.A = c->A[inBuf ^ 1].p; p.out.B = c->B[inBuf ^ 1].p; p.out.C = c->C[inBuf ^ 1].p;
+    // leave codes: only when the LEAVE kernels run (bounce 0 then fills the segments from both ends for bounce_loop_kernel<LEAVE>)
+    p.in.L = c->leaveTest ? c->L[inBuf].p : nullptr; p.out.L = c->leaveTest ? c->L[inBuf ^ 1].p : nullptr;
     return p;
 }
 
@@ -386,6 +391,14 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     }
     c->numCubes = numCubes;
     hdr->numCubes = numCubes;
+    // The leave test of closestHitBrute<LEAVE> argues with finite arithmetic: it runs when the leave codes are kept (ptb_create) and every
+    // inverse transform of the brute-force table is finite and moderate (|m| < 1e9: a ray the kernel accepts as finite -- |o|, |d| < 1e6 --
+    // cannot overflow in the object space of any geom)
+    bool leaveOk = c->leaveWanted && !hasMeshes && G <= kLeaveMaxGeoms;
+    for (int i = 0; i < G && leaveOk; ++i)
+        for (int k = 0; k < 16; ++k) leaveOk = leaveOk && std::fabs(scene->geoms[i].inverseTransform[k]) < 1e9f;      // false for NaN
+    if (leaveOk != c->leaveTest) dropGraphs(c);                                                           // other kernels: re-capture
+    c->leaveTest = leaveOk;
     // the BVH is always built so that ptb_stage_intersect can compare both traversals on any scene;
     // the render path uses it only when useBvh is set
     HostBvh hb;
@@ -531,10 +544,13 @@ void launchFusedBounces(PtbContext *c) {
             else if (c->opt.regroupMaterials && c->numMats <= kMaxClassTable) LAUNCH(PTB_STAGE_SHADE, (bounce_regroup_kernel<EXT>), c->gridFused, kBlock, 0, p, d);
             else        LAUNCH(PTB_STAGE_SHADE, (bounce_kernel<false, true, EXT>), c->gridFused, kBlock, 0, p, d);
         } else {
-            if (d == 0) LAUNCH(PTB_STAGE_FUSED_BOUNCE0, (bounce_kernel<true, false, EXT>), c->gridFused, kBlock, smem, p, d);
-            else if (c->loopBounces) {
+            if (d == 0) {
+                if (c->leaveTest) LAUNCH(PTB_STAGE_FUSED_BOUNCE0, (bounce_kernel<true, false, EXT, true>), c->gridFused, kBlock, smem, p, d);
+                else              LAUNCH(PTB_STAGE_FUSED_BOUNCE0, (bounce_kernel<true, false, EXT>), c->gridFused, kBlock, smem, p, d);
+            } else if (c->loopBounces) {
                 // bounces 1 .. traceDepth-1 in one launch: every CTA walks its own segment through them
-                LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT>), c->gridFused, kBlock, smem, p, d);
+                if (c->leaveTest) LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT, true>), c->gridFused, kBlock, smem, p, d);
+                else              LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT, false>), c->gridFused, kBlock, smem, p, d);
                 break;
             }
             else        LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_kernel<false, false, EXT>), c->gridFused, kBlock, smem, p, d);
@@ -749,6 +765,7 @@ void ptb_default_options(PtbOptions *o) {
     o->useGraphs = 1;
     o->regroupMaterials = PTB_REGROUP_DEFAULT;
     o->lookahead = 1;                    // ptb_pathtrace traces whole wavefronts ahead (bit-identical images; only that entry point is affected)
+    o->leaveTest = 1;                    // brute-force scenes: the cube face a bounce ray starts on is settled with one row of the object-space ray
 }
 
 int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *optIn) {
@@ -828,6 +845,7 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     c->useBvh = hasMeshes || opt.accel == PTB_ACCEL_BVH || (opt.accel == PTB_ACCEL_AUTO && scene->numGeoms > 64);
     const size_t bruteBytes = hasMeshes ? (size_t)201 * 1024 : (size_t)std::max(1, scene->numGeoms) * sizeof(GeomRec);   // meshes: no brute-force table
     if (!c->useBvh && bruteBytes > 200 * 1024) c->useBvh = true;
+    c->leaveWanted = opt.leaveTest && opt.pipeline == PTB_PIPELINE_FUSED && !c->useBvh && !opt.launchPerBounce;
     {
         const size_t Gp = (size_t)std::max(1, scene->numGeoms), Pp = (size_t)std::max(1, c->numPrims);
         CUB(c->geomsScene.alloc(hasMeshes ? 1 : Gp)); CUB(c->geoms.alloc(Pp)); CUB(c->bvh.alloc(Pp)); CUB(c->sceneMatDev.alloc(Gp));
@@ -843,7 +861,9 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
         int rc = PTB_OK;
         rc |= setSmem(bounce_kernel<true, false, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, false>, c->smemBrute);
         rc |= setSmem(bounce_kernel<true, false, true>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, true>, c->smemBrute);
-        rc |= setSmem(bounce_loop_kernel<false>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true>, c->smemBrute);
+        rc |= setSmem(bounce_loop_kernel<false, false>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true, false>, c->smemBrute);
+        rc |= setSmem(bounce_loop_kernel<false, true>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true, true>, c->smemBrute);
+        rc |= setSmem(bounce_kernel<true, false, false, true>, c->smemBrute); rc |= setSmem(bounce_kernel<true, false, true, true>, c->smemBrute);
         rc |= setSmem(bounce0_shared_kernel<false, false>, c->smemBrute); rc |= setSmem(bounce0_shared_kernel<false, true>, c->smemBrute);
         rc |= setSmem(intersect_kernel, c->smemBrute); rc |= setSmem(stage_intersect_kernel, c->smemBrute);
         rc |= setSmem(fb_cache_kernel, c->smemBrute);
@@ -901,9 +921,10 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     const size_t pathSlots = std::max(maxPaths, (size_t)c->segCap * c->gridFused);
     for (int i = 0; i < 2; ++i) {
         CUB(c->A[i].alloc(pathSlots)); CUB(c->B[i].alloc(pathSlots)); CUB(c->C[i].alloc(pathSlots));
+        if (c->leaveWanted) CUB(c->L[i].alloc(pathSlots));
     }
-    CUB(c->segCounts.alloc((size_t)2 * c->gridFused));
-    CUB(cudaMemset(c->segCounts.p, 0, sizeof(uint32_t) * 2 * c->gridFused));
+    CUB(c->segCounts.alloc((size_t)3 * c->gridFused));          // survivors per CTA, ping-pong by depth parity; [2 * grid ..): back of the segments after bounce 0 (LEAVE)
+    CUB(cudaMemset(c->segCounts.p, 0, sizeof(uint32_t) * 3 * c->gridFused));
     if (opt.pipeline == PTB_PIPELINE_STAGED || c->useBvh) {
         CUB(c->hitTn.alloc(pathSlots)); CUB(c->hitMeta.alloc(pathSlots));
         if (opt.sortMaterials) { CUB(c->sortKeys.alloc(maxPaths)); CUB(c->sortOrder.alloc(maxPaths)); CUB(c->sortHist.alloc(scene->numMaterials + 2)); }

@@ -35,12 +35,27 @@ struct BvhNode {                 // 64 B = four 128-bit loads: a binary node hol
     int4   m;                    // x, y: the left / right child as the traversal uses it -- interior: node index (>= 0); leaf:
 };                               // ~(first geom slot | count << 27); an absent child has NaN planes (no ray enters it).  z, w unused
 
-struct PathPlanes { float4 *A; float4 *B; float2 *C; };
+struct PathPlanes { float4 *A; float4 *B; float2 *C; uint16_t *L; };
+// L (brute-force scenes, fused pipeline; NULL = not kept): the LEAVE CODE of a path -- which face of which cube of the brute-force table
+// its ray starts on: geom slot | axis << 11 | (face on the negative side) << 13, kNoLeave when it left a sphere, the inside of a cube or
+// nothing the test below covers.  closestHitBrute<LEAVE> uses it to drop that cube from the search with ONE row of the object-space ray.
+constexpr uint32_t kNoLeave = 0xffffu;
+constexpr int kLeaveMaxGeoms = 2048;                              // geom slots the 11-bit field holds
 
 struct HitPlanes {               // staged pipeline only: ShadeableIntersection (src/sceneStructs.h:72-76) as SoA, 20 B
     float4 *tn;                  // t, n.x, n.y, n.z
     int    *meta;                // -1 = miss, else geom slot | outside << 30
 };
+
+// first-bounce cache record (Params::fbMeta): geom slot (27 bits; the BVH leaf encoding holds 2^27 primitives) | face << 27 | outside << 30,
+// -1 = miss.  face (brute-force scenes): axis | negative side << 2 of the cube face that was hit from outside, 3 = none -- the leave code
+// of every path that starts on this hit (PathPlanes::L)
+constexpr int kFbSlotMask = 0x07ffffff;
+__device__ __forceinline__ int fbFaceBits(uint32_t leaveCode) { return leaveCode == kNoLeave ? 3 << 27 : (int)((leaveCode >> 11) & 7u) << 27; }
+__device__ __forceinline__ uint32_t fbLeaveCode(int meta) {
+    const uint32_t face = ((uint32_t)meta >> 27) & 7u, slot = (uint32_t)meta & (uint32_t)kFbSlotMask;
+    return ((face & 3u) == 3u || slot >= (uint32_t)kLeaveMaxGeoms) ? kNoLeave : (slot | face << 11);
+}
 
 struct Control {                 // device-resident loop control: no host round trip inside a batch
     int      iterBase;           // iteration number of slot 0
@@ -173,6 +188,15 @@ PTB_DEV void testGeom(const GeomRec &g, int slot, f3 o, f3 d, Candidate &best, i
     acceptHit(g, slot, t, outside, a, b, c, best, bestOrig);
 }
 PTB_DEV f3 candidateNormal(const GeomRec &g, const Candidate &c) { return exactNormal(g, c.outside, c.a, c.b, c.c); }
+// Leave code (PathPlanes::L) of a path that scatters off this hit: a cube entered from outside names the face it was hit on -- (a, b, c)
+// is the face normal code of boxIntersectionTest, +-1 on the axis of the entry face (src/intersections.h:66-74) -- everything else none.
+PTB_DEV uint32_t leaveCodeOf(int type, int slot, int outside, float a, float b, float c) {
+    if (type != 1 || !outside || slot >= kLeaveMaxGeoms) return kNoLeave;
+    const int axis = a != 0.0f ? 0 : (b != 0.0f ? 1 : (c != 0.0f ? 2 : 3));
+    if (axis == 3) return kNoLeave;                               // no slab ever qualified (tmin_n stayed zero)
+    const float v = axis == 0 ? a : (axis == 1 ? b : c);
+    return (uint32_t)slot | ((uint32_t)axis << 11) | (v < 0.0f ? 0x2000u : 0u);
+}
 
 // Closest hit, brute force over the shared-memory geoms, in two phases per chunk of 32 geoms:
 //   1. a warp-uniform loop over the geoms evaluates a cheap conservative world-space bound (padded
@@ -223,8 +247,9 @@ PTB_DEV void pushBound(float e, bool reach, int idx, const BruteRay &r, uint32_t
     if (RESCAN) { reach = reach && key >= floorKey; key = reach ? key : kNoCand; }
     insertKey(key, k0, k1, k2);
 }
-template <bool RESCAN>
-PTB_DEV void boundsPhase(const GeomRec *sg, int g0, int c1, int g1, const BruteRay &r, uint32_t floorKey,
+// skipIdx (LEAVE): index in this chunk of the cube the ray provably leaves (closestHitBrute), -1 = none: it gets no key
+template <bool RESCAN, bool LEAVE>
+PTB_DEV void boundsPhase(const GeomRec *sg, int g0, int c1, int g1, const BruteRay &r, uint32_t floorKey, int skipIdx,
                          uint32_t &k0, uint32_t &k1, uint32_t &k2) {
     const float inf = __uint_as_float(kMissKey);
     // cubes [g0, c1): sign-selected (near, far) plane pairs, one 64-bit load and two packed operations per axis
@@ -243,7 +268,7 @@ PTB_DEV void boundsPhase(const GeomRec *sg, int g0, int c1, int g1, const BruteR
         // that errs towards "reachable"
         const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
         const float tf = fminf(fminf(fx, fy), fz);
-        const bool reach = tn <= fmaf(tf, 1.00002f, 1e-6f);
+        const bool reach = tn <= fmaf(tf, 1.00002f, 1e-6f) && !(LEAVE && i == skipIdx);
         pushBound<RESCAN>(reach ? tn * r.rdLen : inf, reach, i, r, floorKey, k0, k1, k2);
     }
     // spheres [max(g0, c1), g1): padded bounding sphere
@@ -265,7 +290,24 @@ __device__ unsigned long long g_walkStats[4 * 8 * 4];
 #endif
 
 // `valid` = this lane carries a ray (callers keep their loops warp-uniform).
-PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o, f3 d, bool valid, Candidate &best) {
+//
+// LEAVE (bounces >= 1 of the fused pipeline, PathPlanes::L): `leaveCode` names the cube face the ray starts on.  A bounce ray starts a
+// hair outside the face it left, so the padded world-space bound of that cube can never reject it: it was the first candidate of every
+// walk, cost an object-space ray plus the sure-miss filter, and was rejected 29.35 M of 29.37 M times on the cornell box
+// (profiles/r01r_walk_stats.txt).  With the code, ONE row of the object-space ray settles it before phase 1: on axis k of the cube,
+//     s * qo_k > 0.5  and  s * qu_k > 0        (s = side of the face; qo_k, qu_k computed exactly as objectRay computes them)
+// means both slab numerators of that axis, -0.5 - qo_k and 0.5 - qo_k, have the sign opposite to the direction component (the sign of
+// qd_k = qu_k / |qu| is that of qu_k): both quotients are negative (or -0 / -inf), tmax ends up <= -0 and the reference's acceptance
+// test `tmax >= tmin && tmax > 0` (src/intersections.h:78) fails -- for every finite ray (`finiteRay`: no NaN can turn a compare
+// around).  Such a cube is left out of the keys.  Everything else -- the test fails, the ray left a sphere or the inside of a cube --
+// stays in the keys and meets the exact test as before.  With the start surface gone the filters of the walk rejected 43 k of 23 M
+// candidates: a walk whose lanes all passed the leave test runs without them (`filters`).
+// `filters` (warp-uniform; always on without LEAVE): the walk runs the object-space sure-miss filters.  The LEAVE pipeline keeps the paths
+// whose start surface the leave test cannot settle (kNoLeave: they left a sphere, the inside of a glass cube, ...) at the BACK of every
+// CTA's segment (two-ended compaction, bounceSegment), so a 32-path chunk is either all "settled" -- its walk is phase 1, then object ray +
+// exact test of the nearest candidate, no filter at all -- or all "unsettled" and walks with both filters as before.
+template <bool LEAVE>
+PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o, f3 d, bool valid, uint32_t leaveCode, const bool filters, Candidate &best) {
     best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
     int orig = 0x7fffffff;
     BruteRay r;
@@ -277,6 +319,17 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
     // slack on every lower bound: rounding of the bound itself plus the deviation of the exact hit
     // point from the ideal ray (a few ulp of the coordinates involved)
     r.slack = 2e-5f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f);
+    int skip = -1;                                                // brute-force slot of the cube the ray provably leaves
+    if (LEAVE && leaveCode != kNoLeave) {
+        // |o| < 1e6 per component and |d| < 1e6 (NaN fails both); the host vouches for the matrices (PtbContext::leaveTest)
+        const bool finiteRay = r.slack < 20.0f && dd < 1e12f;
+        const int lg = (int)(leaveCode & 0x7ffu);
+        const float4 row = reinterpret_cast<const float4 *>(&sg[lg].inv)[(leaveCode >> 11) & 3u];
+        const uint32_t flip = (leaveCode & 0x2000u) << 18;       // the face on the negative side: compare -qo_k, -qu_k
+        const float qok = __uint_as_float(__float_as_uint(mvRowPoint(row, o)) ^ flip);
+        const float quk = __uint_as_float(__float_as_uint(mvRow(row, d, 0.0f)) ^ flip);
+        if (finiteRay && qok > 0.5f && quk > 0.0f) skip = lg;
+    }
     for (int g0 = 0; g0 < numGeoms; g0 += 32) {
         const int g1 = min(numGeoms, g0 + 32);
         const int c1 = min(max(numCubes, g0), g1);                // cubes of this chunk: [g0, c1)
@@ -284,8 +337,8 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
         for (;;) {
             uint32_t k0 = kNoCand, k1 = kNoCand, k2 = kNoCand;
             int taken = 0;                                        // keys consumed this round
-            if (floorKey == 0u) boundsPhase<false>(sg, g0, c1, g1, r, 0u, k0, k1, k2);
-            else                boundsPhase<true>(sg, g0, c1, g1, r, floorKey, k0, k1, k2);
+            if (floorKey == 0u) boundsPhase<false, LEAVE>(sg, g0, c1, g1, r, 0u, skip - g0, k0, k1, k2);
+            else                boundsPhase<true, LEAVE>(sg, g0, c1, g1, r, floorKey, skip - g0, k0, k1, k2);
             if (!valid) k0 = kNoCand;
             uint32_t lastKey = 0u;
             bool exhausted = true;                                // all three keys consumed without the bound ending the walk
@@ -299,7 +352,9 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
                     lastKey = k0; ++taken;
                     k0 = k1; k1 = k2; k2 = kNoCand;
                     objectRay(sg[cand], o, d, qo, qu);
-                    bool miss = boxSureMiss(qo, qu);
+                    bool miss = false;
+                    if (!LEAVE || filters) {
+                    miss = boxSureMiss(qo, qu);
                     // The cube filter runs for every lane; the sphere filter runs for ALL the lanes of this walk step as
                     // soon as one of them holds a sphere (a vote among the lanes converged here) and a select keeps each
                     // lane's own answer -- there is no divergent arm, so the lanes arrive together at the loop exits.
@@ -312,6 +367,7 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
                     if (__any_sync(__activemask(), sph)) {
                         const bool sm = sphereSureMiss(qo, qu);
                         miss = sph ? sm : miss;
+                    }
                     }
                     if (miss) PTB_WALK_COUNT(taken, cand, 0);
                     if (!miss) { g = cand; break; }
@@ -593,10 +649,11 @@ namespace ptb {
 // One bounce of one CTA's segment: warp w of the CTA takes the 32-path chunks w, w + 8, ... of the segment's
 // `total` paths (FIRST: nChunks chunks of the CTA's camera-path tiles), and the warps pack the
 // survivors at the front of the CTA's segment of `pout`; *sOutCount ends up holding their number.
-template <bool FIRST, bool USE_BVH, bool EXT>
+// LEAVE (brute-force scenes): the leave codes of the paths are kept in PathPlanes::L and used by closestHitBrute<LEAVE>
+template <bool FIRST, bool USE_BVH, bool EXT, bool LEAVE = false>
 PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPlanes &pout, const int depth, const GeomRec *sgeoms,
                            const int numCubes, const CameraParams &cam, const int iterBase, const int iterStride,
-                           const uint32_t total, const uint32_t nChunks, uint32_t *sOutCount) {
+                           const uint32_t total, const uint32_t totalBack, const uint32_t nChunks, uint32_t *sOutCount) {
     const int remainingBefore = p.traceDepth - depth;
     const uint32_t pixMask = (1u << p.pixBits) - 1u;
     const uint32_t lane = threadIdx.x & 31u;
@@ -610,6 +667,9 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
         bool alive = false, valid;
         f3 o, d, c; uint32_t id = 0;
         uint32_t pix = 0, slot = 0, hitIndex = 0;
+        uint32_t leave = kNoLeave;                                 // LEAVE: the code read with the path, then the code of the scattered path
+        bool back = false;                                         // LEAVE: a chunk of the back of the segment (warp-uniform)
+        uint32_t src = 0;                                          // slot of this lane's path in `pin`
         o = d = c = mk3(0.f, 0.f, 0.f);
         if (FIRST) {
             const uint32_t tile = blockIdx.x + (chunk / (kBlock / 32)) * gridDim.x;
@@ -622,13 +682,19 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
                 cameraRayIter<EXT>(cam, pix, iterBase + (int)slot * iterStride, o, d);
             }
         } else {
-            const uint32_t k = chunk * 32u + lane;
-            valid = k < total;
-            if (valid) loadPathRay(pin, segBase + k, o, d);           // throughput and id follow after the search
+            // LEAVE: the segment is filled from both ends -- `total` settled paths (a leave code each) from the front, `totalBack`
+            // unsettled ones (kNoLeave) from the back, downwards; the chunks of the front come first
+            const uint32_t nFront = (total + 31u) / 32u;
+            back = LEAVE && chunk >= nFront;
+            const uint32_t k = (back ? chunk - nFront : chunk) * 32u + lane;
+            valid = k < (back ? totalBack : total);
+            src = back ? segBase + p.segCap - 1u - k : segBase + k;
+            if (valid) loadPathRay(pin, src, o, d);                    // throughput and id follow after the search
+            if (LEAVE && valid && !back) leave = pin.L[src];
         }
         Candidate best;
         const bool cached = FIRST && p.fbTn != nullptr;            // warp-uniform
-        if (!USE_BVH && !cached) closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
+        if (!USE_BVH && !cached) closestHitBrute<LEAVE && !FIRST>(sgeoms, p.numGeoms, numCubes, o, d, valid, leave, back, best);
         if (USE_BVH && !cached && valid) {
             // BVH scenes: trace_kernel ran before this launch and left the raw hit record of every path
             const uint32_t h = FIRST ? hitIndex : segBase + chunk * 32u + lane;
@@ -645,7 +711,7 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
                 id = pix | (slot << p.pixBits);
                 c = mk3(1.0f, 1.0f, 1.0f);                                    // src/pathtrace.cu:132
             } else {
-                loadPathTail(pin, segBase + chunk * 32u + lane, c, id);
+                loadPathTail(pin, src, c, id);
                 pix = id & pixMask;
                 slot = (id & ~kDeadBit) >> p.pixBits;
             }
@@ -661,16 +727,19 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
                     const float4 tn = __ldg(p.fbTn + pix);
                     best.t = tn.x; n = mk3(tn.y, tn.z, tn.w);
                     best.outside = (meta >> 30) & 1;
-                    matId = USE_BVH ? p.geoms[meta & 0x3fffffff].tag.y : sgeoms[meta & 0x3fffffff].tag.y;
+                    matId = USE_BVH ? p.geoms[meta & kFbSlotMask].tag.y : sgeoms[meta & kFbSlotMask].tag.y;
+                    if (LEAVE) leave = fbLeaveCode(meta);
                 }
             } else {
                 isHit = best.slot >= 0;
+                if (LEAVE) leave = kNoLeave;
                 if (isHit) {
                     if (USE_BVH) {
                         const GeomRec g = loadGeom(p.geoms + best.slot);
                         n = candidateNormal(g, best); matId = g.tag.y;
                     } else {
                         n = candidateNormal(sgeoms[best.slot], best); matId = sgeoms[best.slot].tag.y;
+                        if (LEAVE) leave = leaveCodeOf(sgeoms[best.slot].tag.x, best.slot, best.outside, best.a, best.b, best.c);
                     }
                 }
             }
@@ -680,7 +749,24 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
         }
         // CTA-local stream compaction: ballot + popc prefix, one shared-memory atomic per warp
         const unsigned ballot = __ballot_sync(0xffffffffu, alive);
-        if (ballot) {
+        if (LEAVE) {
+            // two-ended: survivors with a leave code go to the front of the segment, the others to its back; ONE 64-bit atomic
+            // reserves both runs (front count in the low word of sOutCount[0..1], back count in the high word)
+            if (ballot) {
+                const bool toBack = alive && leave == kNoLeave;
+                const unsigned ballotB = __ballot_sync(__activemask(), toBack), ballotF = ballot & ~ballotB;
+                unsigned long long off = 0;
+                if (lane == 0) off = atomicAdd(reinterpret_cast<unsigned long long *>(sOutCount), (unsigned long long)__popc(ballotF) | ((unsigned long long)__popc(ballotB) << 32));
+                off = __shfl_sync(0xffffffffu, off, 0);
+                if (alive) {
+                    const uint32_t below = (1u << lane) - 1u;
+                    const uint32_t dst = toBack ? segBase + p.segCap - 1u - ((uint32_t)(off >> 32) + (uint32_t)__popc(ballotB & below))
+                                                : segBase + (uint32_t)off + (uint32_t)__popc(ballotF & below);
+                    storePath(pout, dst, o, d, c, id);
+                    if (!toBack) pout.L[dst] = (uint16_t)leave;
+                }
+            }
+        } else if (ballot) {
             uint32_t off = 0;
             if (lane == 0) off = atomicAdd(sOutCount, (uint32_t)__popc(ballot));
             off = __shfl_sync(0xffffffffu, off, 0);
@@ -689,12 +775,12 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
     }
 }
 
-template <bool FIRST, bool USE_BVH, bool EXT>
+template <bool FIRST, bool USE_BVH, bool EXT, bool LEAVE = false>
 __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __grid_constant__ Params p, const int depth) {
     extern __shared__ float4 smem4[];
-    __shared__ uint32_t sOutCount;
+    __shared__ __align__(8) uint32_t sOutCount[2];                 // survivors of this CTA: front of its segment, back (LEAVE)
 
-    if (threadIdx.x == 0) sOutCount = 0u;
+    if (threadIdx.x == 0) sOutCount[0] = sOutCount[1] = 0u;
     const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
     // USE_BVH: the closest hits were found by trace_kernel (raw hit records in p.hits); nothing to stage
     if (USE_BVH) __syncthreads();
@@ -718,12 +804,14 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __g
         total = segIn[blockIdx.x];
         nChunks = (total + 31u) / 32u;
     }
-    bounceSegment<FIRST, USE_BVH, EXT>(p, p.in, p.out, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, nChunks, &sOutCount);
+    static_assert(!LEAVE || FIRST, "bounces >= 1 of the LEAVE pipeline are bounce_loop_kernel's");
+    bounceSegment<FIRST, USE_BVH, EXT, LEAVE>(p, p.in, p.out, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, 0u, nChunks, sOutCount);
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t n = sOutCount;
+        const uint32_t n = sOutCount[0], nb = sOutCount[1];
         segOut[blockIdx.x] = n;
-        if (n) atomicAdd(&ctrl->counts[depth + 1], n);
+        if (LEAVE) p.segCounts[2 * gridDim.x + blockIdx.x] = nb;      // back of the segment (read by bounce_loop_kernel<LEAVE>)
+        if (n + nb) atomicAdd(&ctrl->counts[depth + 1], n + nb);
     }
 }
 
@@ -865,8 +953,9 @@ constexpr uint32_t kSlotBlockBrute = 32, kSlotBlockBvh = 8;
 template <bool USE_BVH, bool EXT>
 __global__ void __launch_bounds__(kBlock, PTB_SHARED0_MINBLOCKS) bounce0_shared_kernel(const __grid_constant__ Params p) {
     extern __shared__ float4 smem4[];
-    __shared__ uint32_t sOutCount;
-    if (threadIdx.x == 0) sOutCount = 0u;
+    __shared__ __align__(8) uint32_t sOutCount[2];                 // survivors of this CTA: front of its segment, back (two-ended, below)
+    if (threadIdx.x == 0) sOutCount[0] = sOutCount[1] = 0u;
+    const bool twoEnded = !USE_BVH && p.out.L != nullptr;          // bounce_loop_kernel<LEAVE> follows: survivors without a leave code go to the back
     const int numCubes = USE_BVH ? 0 : p.hdr->numCubes;
     if (USE_BVH) __syncthreads();
     else         stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);      // ends with __syncthreads
@@ -891,6 +980,7 @@ __global__ void __launch_bounds__(kBlock, PTB_SHARED0_MINBLOCKS) bounce0_shared_
         if (valid) cameraRay(cam, pix, o, d);
         // ---- the hit of the pixel: once for all the slots of the tile
         float t = -1.0f; f3 n = mk3(0.f, 0.f, 0.f); int matId = 0, outside = 1; bool isHit = false;
+        uint32_t leave = kNoLeave;                                  // leave code of the paths that start on this hit (brute-force scenes, PathPlanes::L)
         if (cached) {
             if (valid) {
                 const int meta = __ldg(p.fbMeta + pix);
@@ -898,7 +988,8 @@ __global__ void __launch_bounds__(kBlock, PTB_SHARED0_MINBLOCKS) bounce0_shared_
                 if (isHit) {
                     const float4 tn = __ldg(p.fbTn + pix);
                     t = tn.x; n = mk3(tn.y, tn.z, tn.w); outside = (meta >> 30) & 1;
-                    matId = USE_BVH ? p.geoms[meta & 0x3fffffff].tag.y : sgeoms[meta & 0x3fffffff].tag.y;
+                    matId = USE_BVH ? p.geoms[meta & kFbSlotMask].tag.y : sgeoms[meta & kFbSlotMask].tag.y;
+                    if (!USE_BVH) leave = fbLeaveCode(meta);
                 }
             }
         } else if (USE_BVH) {
@@ -915,36 +1006,51 @@ __global__ void __launch_bounds__(kBlock, PTB_SHARED0_MINBLOCKS) bounce0_shared_
             }
         } else {
             Candidate best;
-            closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
+            closestHitBrute<false>(sgeoms, p.numGeoms, numCubes, o, d, valid, kNoLeave, true, best);
             isHit = valid && best.slot >= 0;
-            if (isHit) { t = best.t; n = candidateNormal(sgeoms[best.slot], best); matId = sgeoms[best.slot].tag.y; outside = best.outside; }
+            if (isHit) {
+                t = best.t; n = candidateNormal(sgeoms[best.slot], best); matId = sgeoms[best.slot].tag.y; outside = best.outside;
+                leave = leaveCodeOf(sgeoms[best.slot].tag.x, best.slot, best.outside, best.a, best.b, best.c);
+            }
         }
         // ---- the per-iteration part.  Whether a path survives bounce 0 does not depend on the iteration either (shadeStep: a hit on a
         // non-emissive material with bounces left always scatters), so the warp reserves the output slots of the WHOLE tile with one
         // shared-memory atomic and every slot of the wavefront packs its survivors at (slot - slot0) * n + rank -- no ballot, atomic and
         // shuffle per slot
         const bool survives = valid && isHit && p.traceDepth > 1 && !(__ldg(&p.mats[3 * matId]).w > 0.0f);
-        const unsigned ballot = __ballot_sync(0xffffffffu, survives);
+        const bool toBack = survives && twoEnded && leave == kNoLeave;
+        const unsigned ballotAll = __ballot_sync(0xffffffffu, survives), ballotB = __ballot_sync(0xffffffffu, toBack);
+        const unsigned ballot = toBack ? ballotB : ballotAll & ~ballotB;   // the survivors on this lane's side of the segment
         const uint32_t nSurv = (uint32_t)__popc(ballot), rank = (uint32_t)__popc(ballot & ((1u << lane) - 1u));
         uint32_t off = 0;
-        if (ballot) {
-            if (lane == 0) off = atomicAdd(&sOutCount, nSurv * (slot1 - slot0));
-            off = __shfl_sync(0xffffffffu, off, 0);
+        if (ballotAll) {
+            // one 64-bit atomic reserves both runs: front count in the low word of sOutCount[0..1], back count in the high word
+            unsigned long long o2 = 0;
+            const unsigned long long nF = (unsigned long long)__popc(ballotAll & ~ballotB) * (slot1 - slot0), nB = (unsigned long long)__popc(ballotB) * (slot1 - slot0);
+            if (lane == 0) o2 = atomicAdd(reinterpret_cast<unsigned long long *>(sOutCount), nF | (nB << 32));
+            o2 = __shfl_sync(0xffffffffu, o2, 0);
+            off = toBack ? (uint32_t)(o2 >> 32) : (uint32_t)o2;
         }
         for (uint32_t slot = slot0; slot < slot1; ++slot) {          // warp-uniform trip count
             f3 ro = o, rd = d, c = mk3(1.0f, 1.0f, 1.0f);           // src/pathtrace.cu:132
             if (valid) {
                 const bool alive = shadeStep<EXT>(p, 0, iterBase + (int)slot * iterStride, pix, isHit, matId, t, n, outside, ro, rd, c, p.traceDepth);
                 if (!alive) deposit(p, pix, slot, c);
-                else if (survives) storePath(p.out, segBase + off + (slot - slot0) * nSurv + rank, ro, rd, c, pix | (slot << p.pixBits));
+                else if (survives) {
+                    const uint32_t j = off + (slot - slot0) * nSurv + rank;
+                    const uint32_t dst = toBack ? segBase + p.segCap - 1u - j : segBase + j;
+                    storePath(p.out, dst, ro, rd, c, pix | (slot << p.pixBits));
+                    if (twoEnded && !toBack) p.out.L[dst] = (uint16_t)leave;
+                }
             }
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-        const uint32_t cnt = sOutCount;
+        const uint32_t cnt = sOutCount[0], cntBack = sOutCount[1];
         p.segCounts[blockIdx.x] = cnt;                              // depth 0: parity 0
-        if (cnt) atomicAdd(&ctrl->counts[1], cnt);
+        if (twoEnded) p.segCounts[2 * gridDim.x + blockIdx.x] = cntBack;
+        if (cnt + cntBack) atomicAdd(&ctrl->counts[1], cnt + cntBack);
     }
 }
 
@@ -955,12 +1061,12 @@ __global__ void __launch_bounds__(kBlock, PTB_SHARED0_MINBLOCKS) bounce0_shared_
 // slowest CTA until the wavefront is finished -- one launch tail per wavefront instead of one per
 // bounce, and the geoms are staged once.  Per path the arithmetic is bounce_kernel's, so the results are
 // identical; counts[d + 1] still receives one atomic per CTA and bounce.
-template <bool EXT>
+template <bool EXT, bool LEAVE>
 __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_loop_kernel(const __grid_constant__ Params p, const int depthBegin) {
     extern __shared__ float4 smem4[];
-    __shared__ uint32_t sOutCount;
+    __shared__ __align__(8) uint32_t sOutCount[2];                     // survivors of this CTA: front of its segment, back (LEAVE)
 
-    if (threadIdx.x == 0) sOutCount = 0u;
+    if (threadIdx.x == 0) sOutCount[0] = sOutCount[1] = 0u;
     const int numCubes = p.hdr->numCubes;
     stageShared(smem4, reinterpret_cast<const float4 *>(p.geoms), p.numGeoms * kGeomFloat4);      // ends with __syncthreads
     const GeomRec *sgeoms = heldSharedBase<GeomRec>(smem4);
@@ -968,16 +1074,18 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_loop_kernel(cons
     CameraParams cam;                                                  // never read: no camera rays after bounce 0
     const int iterBase = ctrl->iterBase, iterStride = ctrl->iterStride;
     uint32_t total = p.segCounts[((depthBegin + 1) & 1) * gridDim.x + blockIdx.x];
+    uint32_t totalBack = LEAVE ? p.segCounts[2 * gridDim.x + blockIdx.x] : 0u;
     PathPlanes pin = p.in, pout = p.out;
-    for (int depth = depthBegin; depth < p.traceDepth && total > 0u; ++depth) {
-        bounceSegment<false, false, EXT>(p, pin, pout, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, (total + 31u) / 32u, &sOutCount);
+    for (int depth = depthBegin; depth < p.traceDepth && total + totalBack > 0u; ++depth) {
+        bounceSegment<false, false, EXT, LEAVE>(p, pin, pout, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, totalBack,
+                                                (total + 31u) / 32u + (totalBack + 31u) / 32u, sOutCount);
         __syncthreads();                                               // the survivors are written and counted
-        total = sOutCount;
+        total = sOutCount[0]; totalBack = sOutCount[1];
         const PathPlanes t = pin; pin = pout; pout = t;
-        __syncthreads();                                               // everyone has read the count ...
-        if (threadIdx.x == 0) {                                        // ... before it is cleared for the next bounce
-            if (total) atomicAdd(&ctrl->counts[depth + 1], total);
-            sOutCount = 0u;
+        __syncthreads();                                               // everyone has read the counts ...
+        if (threadIdx.x == 0) {                                        // ... before they are cleared for the next bounce
+            if (total + totalBack) atomicAdd(&ctrl->counts[depth + 1], total + totalBack);
+            sOutCount[0] = sOutCount[1] = 0u;
         }
         __syncthreads();
     }
@@ -998,12 +1106,12 @@ __global__ void __launch_bounds__(kBlock) fb_cache_kernel(const __grid_constant_
         f3 o = mk3(0.f, 0.f, 0.f), d = o;
         if (valid) cameraRay(cam, pix, o, d);
         Candidate best;
-        closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
+        closestHitBrute<false>(sgeoms, p.numGeoms, numCubes, o, d, valid, kNoLeave, true, best);
         if (!valid) continue;
         if (best.slot < 0) { tnOut[pix] = make_float4(-1.0f, 0.f, 0.f, 0.f); metaOut[pix] = -1; continue; }
         const f3 n = candidateNormal(sgeoms[best.slot], best);
         tnOut[pix] = make_float4(best.t, n.x, n.y, n.z);
-        metaOut[pix] = best.slot | (best.outside << 30);
+        metaOut[pix] = best.slot | fbFaceBits(leaveCodeOf(sgeoms[best.slot].tag.x, best.slot, best.outside, best.a, best.b, best.c)) | (best.outside << 30);
     }
 }
 
@@ -1055,7 +1163,7 @@ __global__ void __launch_bounds__(kBlock) intersect_kernel(const __grid_constant
         if (i < nIn) loadPath(p.in, i, o, d, c, id);
         const bool valid = !(id & kDeadBit);                             // no-compaction mode: dead path stays in place
         Candidate best;
-        closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
+        closestHitBrute<false>(sgeoms, p.numGeoms, numCubes, o, d, valid, kNoLeave, true, best);
         if (i >= nIn) continue;
         if (!valid) { p.hits.meta[i] = -1; continue; }
         if (best.slot < 0) {
@@ -1329,7 +1437,7 @@ __global__ void __launch_bounds__(kBlock) stage_intersect_kernel(const __grid_co
             d = mk3(dirs[3 * (size_t)i], dirs[3 * (size_t)i + 1], dirs[3 * (size_t)i + 2]);
         }
         Candidate best;
-        closestHitBrute(sgeoms, p.numGeoms, numCubes, o, d, valid, best);
+        closestHitBrute<false>(sgeoms, p.numGeoms, numCubes, o, d, valid, kNoLeave, true, best);
         if (!valid) continue;
         if (best.slot < 0) {
             hit[i] = -1; t[i] = -1.0f; outside[i] = 1;

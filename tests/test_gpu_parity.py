@@ -270,6 +270,31 @@ def test_bounce_loop_launch_matches_one_launch_per_bounce(m, scene_dir, monkeypa
         assert out["1"][1]["kernel_launches"] < out["0"][1]["kernel_launches"], name
 
 
+def test_leave_test_is_bit_neutral(m, port, scene_dir, tmp_path):
+    """PtbOptions.leaveTest (default on): bounce rays carry the cube face they start on and the brute-force search drops that cube
+    after one row of the object-space ray instead of walking it (closestHitBrute<LEAVE>).  A pruning decision only: identical bits
+    and per-depth counts with the test off, with the first-bounce cache feeding the codes, with a jittered camera (bounce 0 through
+    bounce_kernel<FIRST>), on scenes where the test often FAILS (tilted anisotropic boxes: the face normal the reference builds from
+    `transform` is not the object-space axis; rays that start inside glass cubes), and against the oracle."""
+    rot = tmp_path / "tilted.txt"
+    rot.write_text(scenes.synthetic_text(n_objects=60, res=(320, 200), depth=8, seed=7))      # 58 random tilted spheres / cubes, 1/6 of them glass
+    cases = [(scene_dir + "/cornell.txt", {}), (scene_dir + "/glass.txt", {}), (scene_dir + "/glossy.txt", {}),
+             (scene_dir + "/cornell.txt", dict(first_bounce_cache=1)), (scene_dir + "/glass.txt", dict(antialias=1)),
+             (str(rot), dict(accel=m.ACCEL_BRUTE)), (str(rot), dict(accel=m.ACCEL_BRUTE, first_bounce_cache=1))]
+    for path, kw in cases:
+        s = m.Scene.load(path)
+        out = {}
+        for lt in (0, 1):
+            with m.Renderer(s, device=0, bsdf=m.BSDF_FULL, batch_iters=4, leave_test=lt, **kw) as r:
+                r.render(1, 6)                                  # a full wavefront and a partial one
+                out[lt] = (r.download(), r.stats())
+        assert same_bits(out[0][0], out[1][0]), (path, kw, int((bits(out[0][0]) != bits(out[1][0])).any(1).sum()))
+        assert out[0][1]["alive_per_depth"] == out[1][1]["alive_per_depth"], (path, kw)
+        if "antialias" not in kw and "glossy" not in path:      # (jittered camera and powf lobes: tests/test_gpu_extensions.py, to their tolerances)
+            want, walive, wseg = port.render(port.load_scene(path), orclib.MODE_FULL, 1, 6)
+            assert same_bits(out[1][0], want) and out[1][1]["alive_per_depth"] == list(walive), (path, kw)
+
+
 def test_batched_wavefront_matches_sequential(m, scene_dir):
     """B iterations per wavefront.  Ordered deposit (the default): every slot stores into its own partial image and the partial
     images are added in iteration order, so the accumulated SUM is bit for bit what one iteration per wavefront builds
