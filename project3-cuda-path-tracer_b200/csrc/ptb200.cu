@@ -549,8 +549,11 @@ void launchFusedBounces(PtbContext *c) {
                 else              LAUNCH(PTB_STAGE_FUSED_BOUNCE0, (bounce_kernel<true, false, EXT>), c->gridFused, kBlock, smem, p, d);
             } else if (c->loopBounces) {
                 // bounces 1 .. traceDepth-1 in one launch: every CTA walks its own segment through them
-                if (c->leaveTest) LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT, true>), c->gridFused, kBlock, smem, p, d);
-                else              LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT, false>), c->gridFused, kBlock, smem, p, d);
+                const bool one = c->numGeoms <= 32;               // a single chunk of the brute-force table
+                if (c->leaveTest) { if (one) LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT, true, true>), c->gridFused, kBlock, smem, p, d);
+                                    else     LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT, true, false>), c->gridFused, kBlock, smem, p, d); }
+                else              { if (one) LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT, false, true>), c->gridFused, kBlock, smem, p, d);
+                                    else     LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT, false, false>), c->gridFused, kBlock, smem, p, d); }
                 break;
             }
             else        LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_kernel<false, false, EXT>), c->gridFused, kBlock, smem, p, d);
@@ -861,8 +864,10 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
         int rc = PTB_OK;
         rc |= setSmem(bounce_kernel<true, false, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, false>, c->smemBrute);
         rc |= setSmem(bounce_kernel<true, false, true>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, true>, c->smemBrute);
-        rc |= setSmem(bounce_loop_kernel<false, false>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true, false>, c->smemBrute);
-        rc |= setSmem(bounce_loop_kernel<false, true>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true, true>, c->smemBrute);
+        rc |= setSmem(bounce_loop_kernel<false, false, false>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true, false, false>, c->smemBrute);
+        rc |= setSmem(bounce_loop_kernel<false, true, false>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true, true, false>, c->smemBrute);
+        rc |= setSmem(bounce_loop_kernel<false, false, true>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true, false, true>, c->smemBrute);
+        rc |= setSmem(bounce_loop_kernel<false, true, true>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true, true, true>, c->smemBrute);
         rc |= setSmem(bounce_kernel<true, false, false, true>, c->smemBrute); rc |= setSmem(bounce_kernel<true, false, true, true>, c->smemBrute);
         rc |= setSmem(bounce0_shared_kernel<false, false>, c->smemBrute); rc |= setSmem(bounce0_shared_kernel<false, true>, c->smemBrute);
         rc |= setSmem(intersect_kernel, c->smemBrute); rc |= setSmem(stage_intersect_kernel, c->smemBrute);

@@ -306,7 +306,9 @@ __device__ unsigned long long g_walkStats[4 * 8 * 4];
 // whose start surface the leave test cannot settle (kNoLeave: they left a sphere, the inside of a glass cube, ...) at the BACK of every
 // CTA's segment (two-ended compaction, bounceSegment), so a 32-path chunk is either all "settled" -- its walk is phase 1, then object ray +
 // exact test of the nearest candidate, no filter at all -- or all "unsettled" and walks with both filters as before.
-template <bool LEAVE>
+// ONE: the caller vouches for numGeoms <= 32 (bounce_loop_kernel<.., ONE>): the table is a single chunk, so the chunk loop with its g0 / g1 / c1
+// bookkeeping (spilled across the walk at the 64-register budget) is gone
+template <bool LEAVE, bool ONE = false>
 PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o, f3 d, bool valid, uint32_t leaveCode, const bool filters, Candidate &best) {
     best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
     int orig = 0x7fffffff;
@@ -330,8 +332,8 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
         const float quk = __uint_as_float(__float_as_uint(mvRow(row, d, 0.0f)) ^ flip);
         if (finiteRay && qok > 0.5f && quk > 0.0f) skip = lg;
     }
-    for (int g0 = 0; g0 < numGeoms; g0 += 32) {
-        const int g1 = min(numGeoms, g0 + 32);
+    for (int g0 = 0; g0 < (ONE ? 1 : numGeoms); g0 += 32) {
+        const int g1 = ONE ? numGeoms : min(numGeoms, g0 + 32);
         const int c1 = min(max(numCubes, g0), g1);                // cubes of this chunk: [g0, c1)
         uint32_t floorKey = 0u;                                   // keys below it were consumed by an earlier round
         for (;;) {
@@ -650,7 +652,7 @@ namespace ptb {
 // `total` paths (FIRST: nChunks chunks of the CTA's camera-path tiles), and the warps pack the
 // survivors at the front of the CTA's segment of `pout`; *sOutCount ends up holding their number.
 // LEAVE (brute-force scenes): the leave codes of the paths are kept in PathPlanes::L and used by closestHitBrute<LEAVE>
-template <bool FIRST, bool USE_BVH, bool EXT, bool LEAVE = false>
+template <bool FIRST, bool USE_BVH, bool EXT, bool LEAVE = false, bool ONE = false>
 PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPlanes &pout, const int depth, const GeomRec *sgeoms,
                            const int numCubes, const CameraParams &cam, const int iterBase, const int iterStride,
                            const uint32_t total, const uint32_t totalBack, const uint32_t nChunks, uint32_t *sOutCount) {
@@ -694,7 +696,7 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
         }
         Candidate best;
         const bool cached = FIRST && p.fbTn != nullptr;            // warp-uniform
-        if (!USE_BVH && !cached) closestHitBrute<LEAVE && !FIRST>(sgeoms, p.numGeoms, numCubes, o, d, valid, leave, back, best);
+        if (!USE_BVH && !cached) closestHitBrute<LEAVE && !FIRST, ONE>(sgeoms, p.numGeoms, numCubes, o, d, valid, leave, back, best);
         if (USE_BVH && !cached && valid) {
             // BVH scenes: trace_kernel ran before this launch and left the raw hit record of every path
             const uint32_t h = FIRST ? hitIndex : segBase + chunk * 32u + lane;
@@ -1061,7 +1063,8 @@ __global__ void __launch_bounds__(kBlock, PTB_SHARED0_MINBLOCKS) bounce0_shared_
 // slowest CTA until the wavefront is finished -- one launch tail per wavefront instead of one per
 // bounce, and the geoms are staged once.  Per path the arithmetic is bounce_kernel's, so the results are
 // identical; counts[d + 1] still receives one atomic per CTA and bounce.
-template <bool EXT, bool LEAVE>
+// ONE: the scene has at most 32 primitives (closestHitBrute<.., ONE>)
+template <bool EXT, bool LEAVE, bool ONE>
 __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_loop_kernel(const __grid_constant__ Params p, const int depthBegin) {
     extern __shared__ float4 smem4[];
     __shared__ __align__(8) uint32_t sOutCount[2];                     // survivors of this CTA: front of its segment, back (LEAVE)
@@ -1077,7 +1080,7 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_loop_kernel(cons
     uint32_t totalBack = LEAVE ? p.segCounts[2 * gridDim.x + blockIdx.x] : 0u;
     PathPlanes pin = p.in, pout = p.out;
     for (int depth = depthBegin; depth < p.traceDepth && total + totalBack > 0u; ++depth) {
-        bounceSegment<false, false, EXT, LEAVE>(p, pin, pout, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, totalBack,
+        bounceSegment<false, false, EXT, LEAVE, ONE>(p, pin, pout, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, totalBack,
                                                 (total + 31u) / 32u + (totalBack + 31u) / 32u, sOutCount);
         __syncthreads();                                               // the survivors are written and counted
         total = sOutCount[0]; totalBack = sOutCount[1];
