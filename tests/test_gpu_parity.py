@@ -295,6 +295,23 @@ def test_leave_test_is_bit_neutral(m, port, scene_dir, tmp_path):
             assert same_bits(out[1][0], want) and out[1][1]["alive_per_depth"] == list(walive), (path, kw)
 
 
+def test_one_chunk_search_switches_at_32_primitives(m, port, tmp_path):
+    """bounce_loop_kernel<.., ONE> (closestHitBrute<.., ONE>: no chunk loop over the brute-force table) serves scenes of at most 32
+    primitives, the chunked search everything above: both sides of the switch against the oracle, with and without the leave test."""
+    for n in (31, 32, 33, 34):                                # synthetic_text adds the light and the floor: n primitives in all
+        path = tmp_path / ("brute_%d.txt" % n)
+        path.write_text(scenes.synthetic_text(n_objects=n, res=(240, 160), depth=6, seed=11 + n))
+        s = m.Scene.load(str(path))
+        assert len(s.geoms) == n
+        want, walive, wseg = port.render(port.load_scene(str(path)), orclib.MODE_FULL, 1, 5)
+        for lt in (1, 0):
+            with m.Renderer(s, device=0, bsdf=m.BSDF_FULL, batch_iters=4, leave_test=lt, accel=m.ACCEL_BRUTE) as r:
+                r.render(1, 5)
+                got, st = r.download(), r.stats()
+            assert same_bits(got, want), (n, lt, int((bits(got) != bits(want)).any(1).sum()))
+            assert st["alive_per_depth"] == list(walive), (n, lt)
+
+
 def test_batched_wavefront_matches_sequential(m, scene_dir):
     """B iterations per wavefront.  Ordered deposit (the default): every slot stores into its own partial image and the partial
     images are added in iteration order, so the accumulated SUM is bit for bit what one iteration per wavefront builds
