@@ -907,6 +907,7 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     if (const char *e = tuningEnv("PTB_GRID_MULT")) gridMult = std::max(1, atoi(e));           // tuning knob (experiments)
     c->gridFused = c->numSMs * std::max(1, occ) * gridMult;
     c->gridFused = std::min(c->gridFused, c->gridTrace * kMaxVirtualSegs);      // trace_kernel serves at most kMaxVirtualSegs segments per CTA
+    if (const char *e = tuningEnv("PTB_GRID_FUSED")) c->gridFused = std::max(1, atoi(e));       // tuning knob (experiments): the grid itself
     c->gridStaged = c->numSMs * 8;
 
     // ---- state (src/pathtrace.cu:84-87, 95-96) ----

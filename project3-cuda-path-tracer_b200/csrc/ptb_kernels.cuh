@@ -231,6 +231,7 @@ constexpr uint32_t kMissKey = 0x7f800000u;                        // bits(+inf):
 struct BruteRay {                                                 // per-lane constants of phase 1
     f3 o, d, invD;                                                // o, d alias the ray's own registers
     float rinv, rdLen, slack;                                     // 1 / |d| (approximate), |d|
+    float scale;                                                  // 0.99998 |d|: a cube's entry parameter -> its lower-bound key in world units (pushBound)
 };
 
 // sorted insert of `key` into (k0 <= k1 <= k2); the largest of the four falls out
@@ -240,9 +241,10 @@ PTB_DEV void insertKey(uint32_t key, uint32_t &k0, uint32_t &k1, uint32_t &k2) {
     k0 = a; k1 = c; k2 = min(k2, f);
 }
 // lower-bound key of one primitive: e = entry distance (world units) or +inf for a sure miss (`reach` false)
+// `scale`: 0.99998 for a distance in world units, r.scale for a ray parameter (the multiply by |d| rides in the FMA)
 template <bool RESCAN>
-PTB_DEV void pushBound(float e, bool reach, int idx, const BruteRay &r, uint32_t floorKey, uint32_t &k0, uint32_t &k1, uint32_t &k2) {
-    const float lo = fmaxf(fmaf(e, 0.99998f, -r.slack), 0.0f);    // inf stays inf
+PTB_DEV void pushBound(float e, float scale, bool reach, int idx, const BruteRay &r, uint32_t floorKey, uint32_t &k0, uint32_t &k1, uint32_t &k2) {
+    const float lo = fmaxf(fmaf(e, scale, -r.slack), 0.0f);       // inf stays inf (a zero direction's inf * 0 = NaN becomes 0: reachable)
     uint32_t key = (__float_as_uint(lo) & ~31u) | (uint32_t)idx;
     if (RESCAN) { reach = reach && key >= floorKey; key = reach ? key : kNoCand; }
     insertKey(key, k0, k1, k2);
@@ -268,15 +270,25 @@ PTB_DEV void boundsPhase(const GeomRec *sg, int g0, int c1, int g1, const BruteR
         // that errs towards "reachable"
         const float tn = fmaxf(fmaxf(nx, ny), fmaxf(nz, 0.0f));
         const float tf = fminf(fminf(fx, fy), fz);
-        const bool reach = tn <= fmaf(tf, 1.00002f, 1e-6f) && !(LEAVE && i == skipIdx);
-        pushBound<RESCAN>(reach ? tn * r.rdLen : inf, reach, i, r, floorKey, k0, k1, k2);
+        const float lim = fmaf(tf, 1.00002f, 1e-6f);
+        if (LEAVE && !RESCAN) {
+            // reach = tn <= lim && i != skipIdx as ONE predicate (setp with a predicate operand) and one select; left to itself the
+            // compiler selects twice
+            float e;
+            asm("{ .reg .pred p, q;\n\tsetp.ne.s32 q, %3, %4;\n\tsetp.le.and.f32 p, %1, %2, q;\n\tselp.f32 %0, %1, 0f7F800000, p; }"
+                : "=f"(e) : "f"(tn), "f"(lim), "r"(i), "r"(skipIdx));
+            pushBound<false>(e, r.scale, true, i, r, floorKey, k0, k1, k2);
+        } else {
+            const bool reach = tn <= lim && !(LEAVE && i == skipIdx);
+            pushBound<RESCAN>(reach ? tn : inf, r.scale, reach, i, r, floorKey, k0, k1, k2);
+        }
     }
     // spheres [max(g0, c1), g1): padded bounding sphere
     const f3 dn = mk3(r.d.x * r.rinv, r.d.y * r.rinv, r.d.z * r.rinv);
 #pragma unroll 1
     for (int g = max(g0, c1); g < g1; ++g) {
         const float e = boundEntryRaw(false, sg[g].b0, sg[g].b1, r.o, r.invD, dn, r.rdLen);
-        pushBound<RESCAN>(e >= 0.0f ? e : inf, e >= 0.0f, g - g0, r, floorKey, k0, k1, k2);
+        pushBound<RESCAN>(e >= 0.0f ? e : inf, 0.99998f, e >= 0.0f, g - g0, r, floorKey, k0, k1, k2);
     }
 }
 
@@ -317,6 +329,7 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
     r.rinv = rsqrtApprox(dd);
     r.o = o; r.d = d;
     r.rdLen = dd * r.rinv;
+    r.scale = 0.99998f * r.rdLen;
     r.invD = mk3(rcpApprox(d.x), rcpApprox(d.y), rcpApprox(d.z));
     // slack on every lower bound: rounding of the bound itself plus the deviation of the exact hit
     // point from the ideal ray (a few ulp of the coordinates involved)
