@@ -66,6 +66,7 @@ struct Control {                 // device-resident loop control: no host round 
     unsigned long long aliveTotals[64];
     unsigned long long segments;
     unsigned long long iterations;
+    uint32_t traceNext[64];      // trace_kernel<SRC_SEGMENTS> (PTB_TRACE_DYNAMIC): next unclaimed path segment of the launch of depth d; zero between batches
 };
 
 struct CameraParams {
@@ -1142,11 +1143,13 @@ __global__ void advance_kernel(Control *ctrl, int traceDepth, uint32_t numPixels
     ctrl->segments += seg;
     ctrl->iterations += (unsigned long long)ctrl->batch;
     ctrl->iterBase += ctrl->batch * ctrl->iterStride;
+    for (int d = 0; d < 64; ++d) ctrl->traceNext[d] = 0u;
 }
 __global__ void set_control_kernel(Control *ctrl, int iterBase, int iterStride, int batch, int deferReduce) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ctrl->iterBase = iterBase; ctrl->iterStride = iterStride; ctrl->batch = batch; ctrl->deferReduce = deferReduce;
     for (int d = 0; d < 68; ++d) ctrl->counts[d] = 0;
+    for (int d = 0; d < 64; ++d) ctrl->traceNext[d] = 0u;
 }
 
 // ------------------------------------------------------------------------------------------------

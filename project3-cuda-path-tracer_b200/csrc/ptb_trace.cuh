@@ -65,6 +65,12 @@ namespace ptb {
 #ifndef PTB_TRACE_EXACT_LANES
 #define PTB_TRACE_EXACT_LANES 3
 #endif
+#ifndef PTB_TRACE_DYNAMIC
+#define PTB_TRACE_DYNAMIC 1            // 1: the warps of a SRC_SEGMENTS launch CLAIM pieces of the path segments (Control::traceNext) instead of their CTA owning segments
+#endif
+#ifndef PTB_TRACE_PIECE
+#define PTB_TRACE_PIECE 128            // rays per claimed piece at most (a power of two >= 32; launches with few rays take smaller pieces)
+#endif
 constexpr int kTraceBlock = PTB_TRACE_BLOCK;
 constexpr int kTraceRays = 1;          // ray slots per lane (spill-area sizing on the host)
 constexpr int kStackSmem = PTB_TRACE_STACK;
@@ -183,13 +189,40 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
     extern __shared__ float4 smem4[];
     __shared__ uint32_t sNextTicket, sTotal;
     __shared__ uint32_t sPrefix[kMaxVirtualSegs + 1];
+    // DYN (bounces >= 1 of the fused pipeline): the path segments are cut into PIECES of 32 .. kPieceMax consecutive rays and every WARP claims
+    // its next piece with one global atomic (Control::traceNext[depth]) when the one it holds is used up.  With segments owned by CTAs
+    // (blockIdx, + grid, ...) a CTA's share of the launch was fixed: the SMs were busy for 2.18 - 2.42 M of the 2.49 M cycles of a launch
+    // and ran 28.6 of their 32 warps while they were (ncu, profiles/r5z_trace_ncu.csv) -- now everybody finishes within one piece of
+    // everybody else.  Piece i of the launch is rays [q * piece, (q + 1) * piece) of segment v, q = i / vgrid, v = i % vgrid, for
+    // q < ceil(longest segment / piece): pieces beyond the end of a shorter segment are empty and skipped.
+    constexpr bool DYN = PTB_TRACE_DYNAMIC && SRC == SRC_SEGMENTS;
+    // Piece size: 32 << pieceShift rays, the largest power of two up to kPieceMax that still leaves every warp of the grid ~8 pieces of the
+    // counts[depth] rays of this launch -- the late bounces of a small wavefront have fewer rays than the grid has lanes, and with a fixed 512
+    // a 4-iteration wavefront ran 36 % slower than with CTA-owned segments (profiles/r5e_pieces_ab.txt).
+    constexpr uint32_t kPieceMax = PTB_TRACE_PIECE;
+    uint32_t pieceShift = 0;
+    if (DYN) {
+        const uint32_t perWarp = p.ctrl->counts[depth] / (gridDim.x * (kTraceBlock / 32) * 8u);
+        while ((64u << pieceShift) <= kPieceMax && (64u << pieceShift) <= perWarp) ++pieceShift;
+    }
+    __shared__ uint32_t sPiece[DYN ? kTraceBlock / 32 : 1][2];       // per warp: index of the next ray of its piece in the path buffers, rays left in it
     if (threadIdx.x == 0) sNextTicket = 0u;
 
     // ---- this CTA's rays.  Segment / camera sources: the virtual CTAs (segments) v = blockIdx.x, + gridDim.x, ... of the fused
     // pipeline's grid, served back to back as one queue; flat sources: one contiguous range.
     const uint32_t vgrid = p.vgrid;
     uint32_t flatLo = 0;
-    if (SRC == SRC_CAMERA || SRC == SRC_SEGMENTS) {
+    if (DYN) {
+        // the longest segment of the launch (sTotal): every CTA reads the vgrid counts (L2-resident, a few KB)
+        if (threadIdx.x == 0) sTotal = 0u;
+        if (threadIdx.x < 2 * (kTraceBlock / 32)) (&sPiece[0][0])[threadIdx.x] = 0u;
+        __syncthreads();
+        const uint32_t *cnts = p.segCounts + ((depth + 1) & 1) * vgrid;
+        uint32_t mx = 0;
+        for (uint32_t v = threadIdx.x; v < vgrid; v += kTraceBlock) mx = max(mx, cnts[v]);
+        for (int s = 16; s > 0; s >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+        if ((threadIdx.x & 31u) == 0u && mx > 0u) atomicMax(&sTotal, mx);
+    } else if (SRC == SRC_CAMERA || SRC == SRC_SEGMENTS) {
         const uint32_t nv = vgrid > blockIdx.x ? (vgrid - blockIdx.x + gridDim.x - 1) / gridDim.x : 0u;
         uint32_t cnt = 0;
         if (threadIdx.x < nv) {
@@ -217,7 +250,7 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
     __syncthreads();
     uint32_t *sw = reinterpret_cast<uint32_t *>(smem4);
     uint2 *stk = reinterpret_cast<uint2 *>(sw + kLaneWords * kTraceBlock);
-    const uint32_t nTickets = sTotal;
+    const uint32_t nTickets = DYN ? 0u : sTotal;                      // DYN: sTotal holds the longest segment, read where pieces are claimed
 #define SW(w) sw[(w) * kTraceBlock + threadIdx.x]
 #define SWF(w) __uint_as_float(SW(w))
     // shared-memory address of entry k of this lane's stack (only outside the step loop)
@@ -282,19 +315,54 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
         // ---- fetch: a new ray for every finished lane
         if (mIdle && ((int)__popc(mIdle) >= kFetchLanes || !(mStep | mLeaf | mCand))) {
             const uint32_t want = (uint32_t)__popc(mIdle);
+            bool have = false;
+            uint32_t idx = 0;
+            f3 ro = mk3(0.f, 0.f, 0.f), rd = ro;
+            if (DYN) {
+                // the idle lanes take the next rays of the warp's piece, in lane order; a used-up piece is replaced by the next unclaimed
+                // one of the launch
+                const uint32_t warp = threadIdx.x >> 5, rank = (uint32_t)__popc(mIdle & laneBelow);
+                uint32_t next = sPiece[warp][0], left = sPiece[warp][1], given = 0;
+                const uint32_t piece = 32u << pieceShift;
+                const uint32_t nPieces = ((sTotal + piece - 1u) >> (5u + pieceShift)) * vgrid;
+                for (;;) {
+                    if (left == 0u) {
+                        uint32_t i = 0;
+                        if (lane == 0) i = atomicAdd(&p.ctrl->traceNext[depth], 1u);
+                        i = __shfl_sync(0xffffffffu, i, 0);
+                        if (i >= nPieces) { drained = true; break; }
+                        const uint32_t q = i / vgrid, v = i - q * vgrid;
+                        const uint32_t cnt = p.segCounts[((depth + 1) & 1) * vgrid + v], lo = q * piece;
+                        if (lo >= cnt) continue;                      // beyond the end of this segment
+                        left = min(piece, cnt - lo); next = v * p.segCap + lo;
+                    }
+                    const uint32_t take = min(want - given, left);
+                    if (finished && rank - given < take) { have = true; idx = next + (rank - given); }     // (unsigned: rank < given is served already)
+                    next += take; left -= take; given += take;
+                    if (given == want) break;
+                }
+                __syncwarp();
+                if (lane == 0) { sPiece[warp][0] = next; sPiece[warp][1] = left; }
+                __syncwarp();
+                if (have) {
+                    const float4 a = p.in.A[idx];
+                    const float2 b = *reinterpret_cast<const float2 *>(&p.in.B[idx]);
+                    ro = mk3(a.x, a.y, a.z); rd = mk3(a.w, b.x, b.y);
+                }
+            }
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&sNextTicket, want);
-            base = __shfl_sync(0xffffffffu, base, 0);
-            drained = base + want >= nTickets;
-            if (SRC == SRC_CAMERA || SRC == SRC_SEGMENTS) {
+            if (!DYN) {
+                if (lane == 0) base = atomicAdd(&sNextTicket, want);
+                base = __shfl_sync(0xffffffffu, base, 0);
+                drained = base + want >= nTickets;
+            }
+            if (!DYN && (SRC == SRC_CAMERA || SRC == SRC_SEGMENTS)) {
                 // tickets only grow: the segment of the warp's first new ticket is found from the one of the previous fetch
                 while (segCur + 1 < kMaxVirtualSegs && sPrefix[segCur + 1] <= base) ++segCur;
             }
-            if (finished) {
+            if (!DYN && finished) {
                 const uint32_t k = base + (uint32_t)__popc(mIdle & laneBelow);
-                bool have = k < nTickets;
-                uint32_t idx = 0;
-                f3 ro = mk3(0.f, 0.f, 0.f), rd = ro;
+                have = k < nTickets;
                 if (have) {
                     if (SRC == SRC_CAMERA || SRC == SRC_SEGMENTS) {
                         // ticket -> (virtual segment j, offset): the segments of this CTA back to back
@@ -329,6 +397,8 @@ __global__ void __launch_bounds__(kTraceBlock, PTB_TRACE_MINBLOCKS) trace_kernel
                         }
                     }
                 }
+            }
+            {
                 if (have) {
                     p.hits.meta[idx] = -1;                            // a miss until a hit is accepted
                     SW(W_DX) = __float_as_uint(rd.x); SW(W_DY) = __float_as_uint(rd.y); SW(W_DZ) = __float_as_uint(rd.z);
