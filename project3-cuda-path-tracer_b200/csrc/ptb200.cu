@@ -1464,9 +1464,10 @@ int ptb_stage_intersect(PtbContext *c, int accel, const float *origins, const fl
             // raw hit records through trace_kernel (the traversal every BVH render runs), then normals / scene indices
             CU(rawTn.alloc(n)); CU(rawMeta.alloc(n));
             p.geoms = c->geoms.p; p.hits.tn = rawTn.p; p.hits.meta = rawMeta.p;
-            TRACE_KERNEL<SRC_RAYS, false, true><<<c->gridTrace, kTraceBlock, c->smemBvh, c->stream>>>(p, 0, TraceIO{o.p, d.p, n});
+            // (through LAUNCH: with PtbOptions.timeStages the traversal of the caller's rays shows up in PtbStats.stageUs[PTB_STAGE_INTERSECT],
+            // tools/gpu_ray_order.py)
+            LAUNCH(PTB_STAGE_INTERSECT, (TRACE_KERNEL<SRC_RAYS, false, true>), c->gridTrace, kTraceBlock, c->smemBvh, p, 0, TraceIO{o.p, d.p, n});
             stage_hits_out_kernel<<<c->gridStaged, kBlock, 0, c->stream>>>(p, n, dh.p, dt.p, dn.p, dout.p);
-            c->launches++;
         }
         else { p.geoms = c->geomsScene.p; stage_intersect_kernel<<<c->gridStaged, kBlock, c->smemBrute, c->stream>>>(p, o.p, d.p, n, dh.p, dt.p, dn.p, dout.p); }
         c->launches++;
