@@ -57,7 +57,7 @@ namespace ptb {
 #define PTB_TRACE_POP_ATTEMPTS 1       // stack entries a lane may pop per step while they turn out culled
 #endif
 #ifndef PTB_TRACE_FETCH_LANES
-#define PTB_TRACE_FETCH_LANES 8
+#define PTB_TRACE_FETCH_LANES 16     // (8 until the warps claimed their rays themselves: a fetch is one shuffle + address arithmetic now; profiles/r6d .. r6f)
 #endif
 #ifndef PTB_TRACE_PRUNE_LANES
 #define PTB_TRACE_PRUNE_LANES 8
