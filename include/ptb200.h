@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define PTB_ABI_VERSION 6
+#define PTB_ABI_VERSION 7
 
 /* ---- POD mirrors of src/sceneStructs.h (byte-identical; matrices column-major like glm) ---- */
 typedef struct PtbGeom {            /* struct Geom, src/sceneStructs.h:20-29, 236 bytes */
@@ -144,7 +144,13 @@ typedef struct PtbOptions {
                                        path state) and the closest-hit search settles that cube with one row of the object-space ray instead of
                                        walking it as its first candidate (src/intersections.h:48-78: both slab quotients of that axis are negative,
                                        so the reference's test misses).  A pruning decision only: identical images.  0 = the round-1 search */
+    int32_t hitQueue;               /* fused pipeline, brute-force scenes, bounces >= 1: PTB_HIT_QUEUE_AUTO (default), 0 or 1.  1 = a warp queues the
+                                       hits of its 32-path chunks in shared memory and shades 32 of them at a time, so the lanes whose ray left the
+                                       scene do not idle through normal / RNG / scatter (src/pathtrace.cu:227-266 shades path by path; the order in
+                                       which paths are shaded reaches no output).  Identical images.  AUTO: on for wavefronts of at least 16 tiles of
+                                       256 paths per CTA on scenes without refractive materials -- where it measured faster (cornell: 2.3 %) */
 } PtbOptions;
+#define PTB_HIT_QUEUE_AUTO (-1)
 /* antialias / lensRadius make the camera rays depend on the iteration, so they cannot be combined with
  * firstBounceCache (INSTRUCTION.md:113: "keep in mind how this influences the first-bounce cache"):
  * ptb_create returns PTB_ERR_UNSUPPORTED.  Materials with REFL > 0 and SPECEX > 0 scatter into a Phong

@@ -58,7 +58,7 @@ class PtbOptions(C.Structure):
                 ("firstBounceCache", C.c_int32), ("useGraphs", C.c_int32), ("antialias", C.c_int32),
                 ("stream", C.c_void_p), ("externalAccum", C.c_void_p),
                 ("lensRadius", C.c_float), ("focalDistance", C.c_float),
-                ("launchPerBounce", C.c_int32), ("depositMode", C.c_int32), ("timeStages", C.c_int32), ("lazyImage", C.c_int32), ("regroupMaterials", C.c_int32), ("lookahead", C.c_int32), ("leaveTest", C.c_int32)]
+                ("launchPerBounce", C.c_int32), ("depositMode", C.c_int32), ("timeStages", C.c_int32), ("lazyImage", C.c_int32), ("regroupMaterials", C.c_int32), ("lookahead", C.c_int32), ("leaveTest", C.c_int32), ("hitQueue", C.c_int32)]
 
 
 class PtbStats(C.Structure):
@@ -216,7 +216,7 @@ class Renderer:
     def __init__(self, scene, device=-1, bsdf=BSDF_FULL, pipeline=PIPELINE_FUSED, accel=ACCEL_AUTO,
                  batch_iters=0, compaction=1, sort_materials=0, first_bounce_cache=0, use_graphs=1,
                  stream=None, external_accum=None, trace_depth=None, antialias=0, lens_radius=0.0, focal_distance=0.0,
-                 launch_per_bounce=0, deposit_mode=DEPOSIT_ORDERED, time_stages=0, lazy_image=0, regroup_materials=None, lookahead=None, leave_test=None):
+                 launch_per_bounce=0, deposit_mode=DEPOSIT_ORDERED, time_stages=0, lazy_image=0, regroup_materials=None, lookahead=None, leave_test=None, hit_queue=None):
         L = lib()
         self.scene = scene
         self.trace_depth = scene.traceDepth if trace_depth is None else int(trace_depth)
@@ -236,6 +236,8 @@ class Renderer:
             opt.lookahead = int(lookahead)
         if leave_test is not None:
             opt.leaveTest = int(leave_test)
+        if hit_queue is not None:                                          # None: PTB_HIT_QUEUE_AUTO
+            opt.hitQueue = int(hit_queue)
         self._h = C.c_void_p()
         _check(L.ptb_create(C.byref(self._h), C.byref(desc), C.byref(opt)))
 

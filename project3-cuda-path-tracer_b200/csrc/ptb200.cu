@@ -169,6 +169,8 @@ struct PtbContext {
     DevBuf<uint16_t> L[2];               // leave codes of the paths (PathPlanes::L; brute-force scenes of the fused pipeline, PtbOptions.leaveTest)
     bool leaveWanted = false;            // ... decided at ptb_create: fused pipeline, brute force, one-launch bounce loop, PtbOptions.leaveTest
     bool leaveTest = false;              // the LEAVE kernel instantiations run: leaveWanted and the scene's matrices are finite and moderate
+    bool hitQueue = false;               // bounce_loop_kernel<.., QUEUE>: PtbOptions.hitQueue resolved against the wavefront and the materials
+    bool queueWavefront = false, refractive = false;      // ... at least 16 tiles of 256 paths per CTA; a material with REFR > 0 (full BSDF)
     DevBuf<float4> hitTn, fbTn;           // fbTn / fbMeta: first-bounce cache (INSTRUCTION.md:87-89)
     DevBuf<int> fbMeta;
     bool fbValid = false;
@@ -349,6 +351,16 @@ int validateScene(const PtbSceneDesc *scene) {
 
 // Packs the scene into the device layout inside the pinned staging buffer and copies it to the
 // device on the context's stream (src/pathtrace.cu:89-93 uploads the AoS structs instead).
+// PtbOptions.hitQueue against what the context knows.  AUTO: the queue measured faster where a warp has many chunks per bounce (wavefronts of
+// at least 16 tiles of 256 paths per CTA: cornell 800 x 800 from 32 iterations per wavefront; 2.3 % at 128, 1.7 % at 64) and slower on
+// small wavefronts (1.2 % at 16) and on the glass scene (4 %) (profiles/r7a_queue_ab.txt, r7c_queue_ab.txt, r7d_queue_ab.txt)
+void resolveHitQueue(PtbContext *c) {
+    bool hq = c->opt.hitQueue == 1;
+    if (c->opt.hitQueue == PTB_HIT_QUEUE_AUTO) hq = c->queueWavefront && !c->refractive;
+    if (hq != c->hitQueue) dropGraphs(c);                                                                 // another kernel: re-capture
+    c->hitQueue = hq;
+}
+
 int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
     const int G = scene->numGeoms, M = scene->numMaterials, Gp = std::max(1, G);
     // BVH primitives in scene order, the triangles of a mesh expanded in place: (geom index, triangle index or -1)
@@ -464,6 +476,9 @@ int uploadScene(PtbContext *c, const PtbSceneDesc *scene) {
         for (int i = 0; i < M; ++i) ext = ext || (scene->materials[i].hasReflective > 0.0f && scene->materials[i].specularExponent > 0.0f);
     if (ext != c->ext) dropGraphs(c);                                                                     // other kernels: re-capture
     c->ext = ext;
+    c->refractive = false;
+    if (c->opt.bsdfMode == PTB_BSDF_FULL) for (int i = 0; i < M; ++i) c->refractive = c->refractive || scene->materials[i].hasRefractive > 0.0f;
+    resolveHitQueue(c);
     hdr->numNodes = c->numNodes;
 
     if (bytesBrute) CU(cudaMemcpyAsync(c->geomsScene.p, bruteOrder, bytesBrute, cudaMemcpyHostToDevice, c->stream));
@@ -550,10 +565,12 @@ void launchFusedBounces(PtbContext *c) {
             } else if (c->loopBounces) {
                 // bounces 1 .. traceDepth-1 in one launch: every CTA walks its own segment through them
                 const bool one = c->numGeoms <= 32;               // a single chunk of the brute-force table
-                if (c->leaveTest) { if (one) LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT, true, true>), c->gridFused, kBlock, smem, p, d);
-                                    else     LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT, true, false>), c->gridFused, kBlock, smem, p, d); }
-                else              { if (one) LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT, false, true>), c->gridFused, kBlock, smem, p, d);
-                                    else     LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT, false, false>), c->gridFused, kBlock, smem, p, d); }
+#define PTB_LOOP(L, O, Q) LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_loop_kernel<EXT, L, O, Q>), c->gridFused, kBlock, smem, p, d)
+                if (c->hitQueue) { if (c->leaveTest) { if (one) PTB_LOOP(true, true, true); else PTB_LOOP(true, false, true); }
+                                   else              { if (one) PTB_LOOP(false, true, true); else PTB_LOOP(false, false, true); } }
+                else             { if (c->leaveTest) { if (one) PTB_LOOP(true, true, false); else PTB_LOOP(true, false, false); }
+                                   else              { if (one) PTB_LOOP(false, true, false); else PTB_LOOP(false, false, false); } }
+#undef PTB_LOOP
                 break;
             }
             else        LAUNCH(PTB_STAGE_FUSED_BOUNCES, (bounce_kernel<false, false, EXT>), c->gridFused, kBlock, smem, p, d);
@@ -769,6 +786,7 @@ void ptb_default_options(PtbOptions *o) {
     o->regroupMaterials = PTB_REGROUP_DEFAULT;
     o->lookahead = 1;                    // ptb_pathtrace traces whole wavefronts ahead (bit-identical images; only that entry point is affected)
     o->leaveTest = 1;                    // brute-force scenes: the cube face a bounce ray starts on is settled with one row of the object-space ray
+    o->hitQueue = PTB_HIT_QUEUE_AUTO;    // brute-force scenes: hits queued between search and shading where that measured faster
 }
 
 int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *optIn) {
@@ -864,10 +882,10 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
         int rc = PTB_OK;
         rc |= setSmem(bounce_kernel<true, false, false>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, false>, c->smemBrute);
         rc |= setSmem(bounce_kernel<true, false, true>, c->smemBrute); rc |= setSmem(bounce_kernel<false, false, true>, c->smemBrute);
-        rc |= setSmem(bounce_loop_kernel<false, false, false>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true, false, false>, c->smemBrute);
-        rc |= setSmem(bounce_loop_kernel<false, true, false>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true, true, false>, c->smemBrute);
-        rc |= setSmem(bounce_loop_kernel<false, false, true>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true, false, true>, c->smemBrute);
-        rc |= setSmem(bounce_loop_kernel<false, true, true>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<true, true, true>, c->smemBrute);
+#define PTB_LOOP_SMEM(E, L, O) rc |= setSmem(bounce_loop_kernel<E, L, O, false>, c->smemBrute); rc |= setSmem(bounce_loop_kernel<E, L, O, true>, c->smemBrute)
+        PTB_LOOP_SMEM(false, false, false); PTB_LOOP_SMEM(true, false, false); PTB_LOOP_SMEM(false, true, false); PTB_LOOP_SMEM(true, true, false);
+        PTB_LOOP_SMEM(false, false, true); PTB_LOOP_SMEM(true, false, true); PTB_LOOP_SMEM(false, true, true); PTB_LOOP_SMEM(true, true, true);
+#undef PTB_LOOP_SMEM
         rc |= setSmem(bounce_kernel<true, false, false, true>, c->smemBrute); rc |= setSmem(bounce_kernel<true, false, true, true>, c->smemBrute);
         rc |= setSmem(bounce0_shared_kernel<false, false>, c->smemBrute); rc |= setSmem(bounce0_shared_kernel<false, true>, c->smemBrute);
         rc |= setSmem(intersect_kernel, c->smemBrute); rc |= setSmem(stage_intersect_kernel, c->smemBrute);
@@ -909,6 +927,8 @@ int ptb_create(PtbContext **out, const PtbSceneDesc *scene, const PtbOptions *op
     c->gridFused = std::min(c->gridFused, c->gridTrace * kMaxVirtualSegs);      // trace_kernel serves at most kMaxVirtualSegs segments per CTA
     if (const char *e = tuningEnv("PTB_GRID_FUSED")) c->gridFused = std::max(1, atoi(e));       // tuning knob (experiments): the grid itself
     c->gridStaged = c->numSMs * 8;
+    c->queueWavefront = wavefrontTiles >= (size_t)c->gridFused * 16;
+    resolveHitQueue(c);
 
     // ---- state (src/pathtrace.cu:84-87, 95-96) ----
     if (opt.externalAccum) c->imagePtr = opt.externalAccum;

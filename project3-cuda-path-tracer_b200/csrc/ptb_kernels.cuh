@@ -791,6 +791,114 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// bounceSegmentQ: one bounce of one CTA's segment for bounce_loop_kernel, with a HIT QUEUE between the closest-hit search and the shading.
+// In bounceSegment a 32-path chunk goes through the search and then through normal / RNG / scatter / store together, and the lanes whose ray
+// left the scene (and the few that found nothing to do) idle through that second half: 23 - 25 of 32 lanes on the cornell box
+// (profiles/r5z_loop_blocks.txt: ~510 of a chunk's ~1 290 warp instructions).  Here a warp pushes the hits of a chunk -- path slot, t, geom |
+// outside, face code: six words -- into its own ring of 64 entries in shared memory and shades whenever 32 are waiting, one hit per lane, whichever
+// chunk they came from; what is left when its chunks are exhausted is shaded as one partial pass.  The shading lane reads the ray again from the
+// path buffer (two loads that hit L1 / L2) instead of carrying it through the queue.  Per path it is bounceSegment's arithmetic: same images,
+// same per-depth counts; only the order of the survivors inside a segment differs (nothing depends on it).  A ray that hit nothing has nothing
+// left to do (its radiance is zero and zero is never deposited), so it never enters the queue.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kQueueCap = 64;                                 // ring entries per warp (a power of two >= 63: 31 left over + 32 new)
+#ifndef PTB_QUEUE_RAY
+#define PTB_QUEUE_RAY 0                                            // 1: the ray travels through the queue (twelve words per hit) instead of being read again
+#endif
+enum { Q_SRC, Q_T, Q_META, Q_A, Q_B, Q_C, Q_OX, Q_OY, Q_OZ, Q_DX, Q_DY, Q_DZ, kQueueWords = PTB_QUEUE_RAY ? 12 : 6 };
+template <bool EXT, bool LEAVE, bool ONE>
+PTB_DEV void bounceSegmentQ(const Params &p, const PathPlanes &pin, const PathPlanes &pout, const int depth, const GeomRec *sgeoms,
+                            const int numCubes, const int iterBase, const int iterStride, const uint32_t total, const uint32_t totalBack,
+                            const uint32_t nChunks, uint32_t *sOutCount, uint32_t (*q)[kQueueCap]) {
+    const int remainingBefore = p.traceDepth - depth;
+    const uint32_t pixMask = (1u << p.pixBits) - 1u;
+    const uint32_t lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    const uint32_t segBase = blockIdx.x * p.segCap;
+    const uint32_t nFront = (total + 31u) / 32u;                   // LEAVE: the chunks of the front of the segment come first
+    uint32_t qHead = 0, qCount = 0;                                // warp-uniform
+    for (uint32_t chunk = threadIdx.x >> 5; ; chunk += kBlock / 32) {
+        const bool more = chunk < nChunks;                         // warp-uniform
+        if (more) {
+            // ---- closest hit of the chunk's 32 paths
+            const bool back = LEAVE && chunk >= nFront;
+            const uint32_t k = (back ? chunk - nFront : chunk) * 32u + lane;
+            const bool valid = k < (back ? totalBack : total);
+            const uint32_t src = back ? segBase + p.segCap - 1u - k : segBase + k;
+            f3 o = mk3(0.f, 0.f, 0.f), d = o;
+            uint32_t leave = kNoLeave;
+            if (valid) loadPathRay(pin, src, o, d);
+            if (LEAVE && valid && !back) leave = pin.L[src];
+            Candidate best;
+            closestHitBrute<LEAVE, ONE>(sgeoms, p.numGeoms, numCubes, o, d, valid, leave, back, best);
+            const bool hit = valid && best.slot >= 0;
+            const unsigned mHit = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const uint32_t e = (qHead + qCount + (uint32_t)__popc(mHit & below)) & (kQueueCap - 1u);
+                q[Q_SRC][e] = src; q[Q_T][e] = __float_as_uint(best.t); q[Q_META][e] = (uint32_t)best.slot | ((uint32_t)best.outside << 30);
+                q[Q_A][e] = __float_as_uint(best.a); q[Q_B][e] = __float_as_uint(best.b); q[Q_C][e] = __float_as_uint(best.c);
+                if (PTB_QUEUE_RAY) {
+                    q[Q_OX][e] = __float_as_uint(o.x); q[Q_OY][e] = __float_as_uint(o.y); q[Q_OZ][e] = __float_as_uint(o.z);
+                    q[Q_DX][e] = __float_as_uint(d.x); q[Q_DY][e] = __float_as_uint(d.y); q[Q_DZ][e] = __float_as_uint(d.z);
+                }
+            }
+            qCount += (uint32_t)__popc(mHit);
+            __syncwarp();
+        }
+        // ---- shading: full passes while 32 hits wait; the rest once the chunks are exhausted (pooling those leftovers over the CTA's
+        // eight warps measured no faster, profiles/r7b_queue_ab.txt)
+        while (qCount >= 32u || (!more && qCount > 0u)) {
+            const uint32_t n = min(qCount, 32u);
+            bool alive = false;
+            f3 o = mk3(0.f, 0.f, 0.f), d = o, c = o;
+            uint32_t id = 0, leave = kNoLeave;
+            if (lane < n) {
+                const uint32_t e = (qHead + lane) & (kQueueCap - 1u);
+                const uint32_t src = q[Q_SRC][e], meta = q[Q_META][e];
+                Candidate best;
+                best.t = __uint_as_float(q[Q_T][e]); best.slot = (int)(meta & 0x3fffffffu); best.outside = (int)(meta >> 30);
+                best.a = __uint_as_float(q[Q_A][e]); best.b = __uint_as_float(q[Q_B][e]); best.c = __uint_as_float(q[Q_C][e]);
+                loadPathTail(pin, src, c, id);
+                if (PTB_QUEUE_RAY) {
+                    o = mk3(__uint_as_float(q[Q_OX][e]), __uint_as_float(q[Q_OY][e]), __uint_as_float(q[Q_OZ][e]));
+                    d = mk3(__uint_as_float(q[Q_DX][e]), __uint_as_float(q[Q_DY][e]), __uint_as_float(q[Q_DZ][e]));
+                } else loadPathRay(pin, src, o, d);
+                const uint32_t pix = id & pixMask, slot = (id & ~kDeadBit) >> p.pixBits;
+                const f3 nrm = candidateNormal(sgeoms[best.slot], best);
+                const int matId = sgeoms[best.slot].tag.y;
+                if (LEAVE) leave = leaveCodeOf(sgeoms[best.slot].tag.x, best.slot, best.outside, best.a, best.b, best.c);
+                alive = shadeStep<EXT>(p, depth, iterBase + (int)slot * iterStride, pix, true, matId, best.t, nrm, best.outside, o, d, c, remainingBefore);
+                if (!alive) deposit(p, pix, slot, c);                     // gather at termination
+            }
+            // CTA-local stream compaction, as in bounceSegment
+            const unsigned ballot = __ballot_sync(0xffffffffu, alive);
+            if (LEAVE) {
+                if (ballot) {
+                    const bool toBack = alive && leave == kNoLeave;
+                    const unsigned ballotB = __ballot_sync(__activemask(), toBack), ballotF = ballot & ~ballotB;
+                    unsigned long long off = 0;
+                    if (lane == 0) off = atomicAdd(reinterpret_cast<unsigned long long *>(sOutCount), (unsigned long long)__popc(ballotF) | ((unsigned long long)__popc(ballotB) << 32));
+                    off = __shfl_sync(0xffffffffu, off, 0);
+                    if (alive) {
+                        const uint32_t dst = toBack ? segBase + p.segCap - 1u - ((uint32_t)(off >> 32) + (uint32_t)__popc(ballotB & below))
+                                                    : segBase + (uint32_t)off + (uint32_t)__popc(ballotF & below);
+                        storePath(pout, dst, o, d, c, id);
+                        if (!toBack) pout.L[dst] = (uint16_t)leave;
+                    }
+                }
+            } else if (ballot) {
+                uint32_t off = 0;
+                if (lane == 0) off = atomicAdd(sOutCount, (uint32_t)__popc(ballot));
+                off = __shfl_sync(0xffffffffu, off, 0);
+                if (alive) storePath(pout, segBase + off + (uint32_t)__popc(ballot & below), o, d, c, id);
+            }
+            qHead = (qHead + n) & (kQueueCap - 1u); qCount -= n;
+            __syncwarp();
+        }
+        if (!more) break;
+    }
+}
+
 template <bool FIRST, bool USE_BVH, bool EXT, bool LEAVE = false>
 __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_kernel(const __grid_constant__ Params p, const int depth) {
     extern __shared__ float4 smem4[];
@@ -1077,11 +1185,12 @@ __global__ void __launch_bounds__(kBlock, PTB_SHARED0_MINBLOCKS) bounce0_shared_
 // slowest CTA until the wavefront is finished -- one launch tail per wavefront instead of one per
 // bounce, and the geoms are staged once.  Per path the arithmetic is bounce_kernel's, so the results are
 // identical; counts[d + 1] still receives one atomic per CTA and bounce.
-// ONE: the scene has at most 32 primitives (closestHitBrute<.., ONE>)
-template <bool EXT, bool LEAVE, bool ONE>
+// ONE: the scene has at most 32 primitives (closestHitBrute<.., ONE>); QUEUE: bounceSegmentQ (PtbOptions.hitQueue)
+template <bool EXT, bool LEAVE, bool ONE, bool QUEUE>
 __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_loop_kernel(const __grid_constant__ Params p, const int depthBegin) {
     extern __shared__ float4 smem4[];
     __shared__ __align__(8) uint32_t sOutCount[2];                     // survivors of this CTA: front of its segment, back (LEAVE)
+    __shared__ uint32_t sQueue[QUEUE ? kBlock / 32 : 1][kQueueWords][QUEUE ? kQueueCap : 1];     // bounceSegmentQ: one ring of hits per warp, [word][entry] (12 KB)
 
     if (threadIdx.x == 0) sOutCount[0] = sOutCount[1] = 0u;
     const int numCubes = p.hdr->numCubes;
@@ -1094,8 +1203,11 @@ __global__ void __launch_bounds__(kBlock, PTB_MINBLOCKS) bounce_loop_kernel(cons
     uint32_t totalBack = LEAVE ? p.segCounts[2 * gridDim.x + blockIdx.x] : 0u;
     PathPlanes pin = p.in, pout = p.out;
     for (int depth = depthBegin; depth < p.traceDepth && total + totalBack > 0u; ++depth) {
-        bounceSegment<false, false, EXT, LEAVE, ONE>(p, pin, pout, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, totalBack,
-                                                (total + 31u) / 32u + (totalBack + 31u) / 32u, sOutCount);
+        if (QUEUE) bounceSegmentQ<EXT, LEAVE, ONE>(p, pin, pout, depth, sgeoms, numCubes, iterBase, iterStride, total, totalBack,
+                                                   (total + 31u) / 32u + (totalBack + 31u) / 32u, sOutCount,
+                                                   reinterpret_cast<uint32_t (*)[kQueueCap]>(&sQueue[QUEUE ? threadIdx.x >> 5 : 0][0][0]));
+        else       bounceSegment<false, false, EXT, LEAVE, ONE>(p, pin, pout, depth, sgeoms, numCubes, cam, iterBase, iterStride, total, totalBack,
+                                                                (total + 31u) / 32u + (totalBack + 31u) / 32u, sOutCount);
         __syncthreads();                                               // the survivors are written and counted
         total = sOutCount[0]; totalBack = sOutCount[1];
         const PathPlanes t = pin; pin = pout; pout = t;

@@ -295,6 +295,31 @@ def test_leave_test_is_bit_neutral(m, port, scene_dir, tmp_path):
             assert same_bits(out[1][0], want) and out[1][1]["alive_per_depth"] == list(walive), (path, kw)
 
 
+def test_hit_queue_is_bit_neutral(m, port, scene_dir, tmp_path):
+    """PtbOptions.hitQueue: bounce_loop_kernel<.., QUEUE> queues the hits of a warp's chunks in shared memory and shades 32 at a time
+    (bounceSegmentQ).  The order in which paths are shaded reaches no output: identical bits and per-depth counts with the queue on and
+    off -- cornell, glass, glossy (EXT), with and without the leave test, 60 tilted objects (the chunked search), a wavefront with a
+    partial last batch -- and against the oracle.  AUTO resolves to one of the two."""
+    rot = tmp_path / "tilted.txt"
+    rot.write_text(scenes.synthetic_text(n_objects=60, res=(320, 200), depth=8, seed=7))
+    cases = [(scene_dir + "/cornell.txt", {}), (scene_dir + "/glass.txt", {}), (scene_dir + "/glossy.txt", {}),
+             (scene_dir + "/cornell.txt", dict(leave_test=0)), (scene_dir + "/cornell.txt", dict(first_bounce_cache=1)),
+             (str(rot), dict(accel=m.ACCEL_BRUTE)), (str(rot), dict(accel=m.ACCEL_BRUTE, leave_test=0))]
+    for path, kw in cases:
+        s = m.Scene.load(path)
+        out = {}
+        for hq in (0, 1, None):
+            with m.Renderer(s, device=0, bsdf=m.BSDF_FULL, batch_iters=4, hit_queue=hq, **kw) as r:
+                r.render(1, 6)                                  # a full wavefront and a partial one
+                out[hq] = (r.download(), r.stats())
+        assert same_bits(out[0][0], out[1][0]), (path, kw, int((bits(out[0][0]) != bits(out[1][0])).any(1).sum()))
+        assert same_bits(out[0][0], out[None][0]), (path, kw)
+        assert out[0][1]["alive_per_depth"] == out[1][1]["alive_per_depth"] == out[None][1]["alive_per_depth"], (path, kw)
+        if "glossy" not in path:                                # (powf lobes: tests/test_gpu_extensions.py, to their tolerance)
+            want, walive, wseg = port.render(port.load_scene(path), orclib.MODE_FULL, 1, 6)
+            assert same_bits(out[1][0], want) and out[1][1]["alive_per_depth"] == list(walive), (path, kw)
+
+
 def test_one_chunk_search_switches_at_32_primitives(m, port, tmp_path):
     """bounce_loop_kernel<.., ONE> (closestHitBrute<.., ONE>: no chunk loop over the brute-force table) serves scenes of at most 32
     primitives, the chunked search everything above: both sides of the switch against the oracle, with and without the leave test."""

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), "libptb200.so does not export %s" % name
     L.ptb_abi_version.restype = C.c_int
-    assert L.ptb_abi_version() == 6      # PTB_ABI_VERSION: 2 added antialias / lens options, 3 triangle meshes in PtbSceneDesc, 4 deposit mode / stage timers / lazy image, 5 regroupMaterials, 6 leaveTest
+    assert L.ptb_abi_version() == 7      # PTB_ABI_VERSION: 2 added antialias / lens options, 3 triangle meshes in PtbSceneDesc, 4 deposit mode / stage timers / lazy image, 5 regroupMaterials, 6 leaveTest
 
 
 def test_struct_sizes_match_reference_layout():
