@@ -321,12 +321,10 @@ __device__ unsigned long long g_walkStats[4 * 8 * 4];
 // exact test of the nearest candidate, no filter at all -- or all "unsettled" and walks with both filters as before.
 // ONE: the caller vouches for numGeoms <= 32 (bounce_loop_kernel<.., ONE>): the table is a single chunk, so the chunk loop with its g0 / g1 / c1
 // bookkeeping (spilled across the walk at the 64-register budget) is gone
-template <bool LEAVE, bool ONE = false>
-PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o, f3 d, bool valid, uint32_t leaveCode, const bool filters, Candidate &best) {
-    best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
-    int orig = 0x7fffffff;
+// The per-ray constants of phase 1 (dd = d . d comes back for the leave test's finiteness check)
+PTB_DEV BruteRay bruteRay(f3 o, f3 d, float &dd) {
     BruteRay r;
-    const float dd = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
+    dd = fmaf(d.x, d.x, fmaf(d.y, d.y, d.z * d.z));
     r.rinv = rsqrtApprox(dd);
     r.o = o; r.d = d;
     r.rdLen = dd * r.rinv;
@@ -335,8 +333,12 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
     // slack on every lower bound: rounding of the bound itself plus the deviation of the exact hit
     // point from the ideal ray (a few ulp of the coordinates involved)
     r.slack = 2e-5f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z) + 1.0f);
-    int skip = -1;                                                // brute-force slot of the cube the ray provably leaves
-    if (LEAVE && leaveCode != kNoLeave) {
+    return r;
+}
+// The leave test (above): brute-force slot of the cube the ray provably leaves, -1 = none
+PTB_DEV int leaveSkip(const GeomRec *sg, const BruteRay &r, float dd, f3 o, f3 d, uint32_t leaveCode) {
+    int skip = -1;
+    if (leaveCode != kNoLeave) {
         // |o| < 1e6 per component and |d| < 1e6 (NaN fails both); the host vouches for the matrices (PtbContext::leaveTest)
         const bool finiteRay = r.slack < 20.0f && dd < 1e12f;
         const int lg = (int)(leaveCode & 0x7ffu);
@@ -346,59 +348,74 @@ PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o
         const float quk = __uint_as_float(__float_as_uint(mvRow(row, d, 0.0f)) ^ flip);
         if (finiteRay && qok > 0.5f && quk > 0.0f) skip = lg;
     }
+    return skip;
+}
+// Phase 2: the lane walks its keys nearest first through the exact test.  taken = keys consumed, lastKey = the last of them,
+// exhausted = all of them consumed without the bound ending the walk (with taken == 3: phase 1 has to look for more above lastKey).
+template <bool LEAVE>
+PTB_DEV void walkKeys(const GeomRec *sg, const int g0, f3 o, f3 d, const bool filters, uint32_t k0, uint32_t k1, uint32_t k2,
+                      Candidate &best, int &orig, int &taken, uint32_t &lastKey, bool &exhausted) {
+    taken = 0; lastKey = 0u; exhausted = true;
+    for (;;) {
+        int g = -1;
+        f3 qo, qu;
+        while (k0 != kNoCand) {
+            const float lo = __uint_as_float(k0 & ~31u);
+            if (!(lo <= best.t)) { exhausted = false; k0 = kNoCand; break; }   // sorted: nothing further can win (+inf = miss keys too)
+            const int cand = g0 + (int)(k0 & 31u);
+            lastKey = k0; ++taken;
+            k0 = k1; k1 = k2; k2 = kNoCand;
+            objectRay(sg[cand], o, d, qo, qu);
+            bool miss = false;
+            if (!LEAVE || filters) {
+            miss = boxSureMiss(qo, qu);
+            // The cube filter runs for every lane; the sphere filter runs for ALL the lanes of this walk step as
+            // soon as one of them holds a sphere (a vote among the lanes converged here) and a select keeps each
+            // lane's own answer -- there is no divergent arm, so the lanes arrive together at the loop exits.
+            // History: with the filters in the two arms of a type branch the sphere lanes (2 of 32 on the
+            // cornell box) went through the whole exact test as a separate pass; with the sphere filter as a
+            // plain `if` overriding the cube result they still left that arm on their own and ran the rest of
+            // the walk alone -- 2.61 object-ray + filter passes per warp where 2 are needed (ncu source
+            // counters, profiles/r01p_loop_regions.txt); the vote + select brought 112.9 -> 110.7 us/iteration.
+            const bool sph = sg[cand].tag.x != 1;
+            if (__any_sync(__activemask(), sph)) {
+                const bool sm = sphereSureMiss(qo, qu);
+                miss = sph ? sm : miss;
+            }
+            }
+            if (miss) PTB_WALK_COUNT(taken, cand, 0);
+            if (!miss) { g = cand; break; }
+        }
+        if (g < 0) break;
+        int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
+        const float t = exactTestQ(sg[g], o, qo, qu, outside, a, b, c);
+#ifdef PTB_WALK_STATS
+        const float before = best.t;
+#endif
+        acceptHit(sg[g], g, t, outside, a, b, c, best, orig);
+#ifdef PTB_WALK_STATS
+        PTB_WALK_COUNT(taken, g, !(t > 0.0f) ? 1 : (best.t != before ? 2 : 3));
+#endif
+    }
+}
+template <bool LEAVE, bool ONE = false>
+PTB_DEV void closestHitBrute(const GeomRec *sg, int numGeoms, int numCubes, f3 o, f3 d, bool valid, uint32_t leaveCode, const bool filters, Candidate &best) {
+    best.t = FLT_MAX; best.slot = -1; best.outside = 1; best.a = best.b = best.c = 0.f;
+    int orig = 0x7fffffff;
+    float dd;
+    const BruteRay r = bruteRay(o, d, dd);
+    const int skip = LEAVE ? leaveSkip(sg, r, dd, o, d, leaveCode) : -1;
     for (int g0 = 0; g0 < (ONE ? 1 : numGeoms); g0 += 32) {
         const int g1 = ONE ? numGeoms : min(numGeoms, g0 + 32);
         const int c1 = min(max(numCubes, g0), g1);                // cubes of this chunk: [g0, c1)
         uint32_t floorKey = 0u;                                   // keys below it were consumed by an earlier round
         for (;;) {
             uint32_t k0 = kNoCand, k1 = kNoCand, k2 = kNoCand;
-            int taken = 0;                                        // keys consumed this round
             if (floorKey == 0u) boundsPhase<false, LEAVE>(sg, g0, c1, g1, r, 0u, skip - g0, k0, k1, k2);
             else                boundsPhase<true, LEAVE>(sg, g0, c1, g1, r, floorKey, skip - g0, k0, k1, k2);
             if (!valid) k0 = kNoCand;
-            uint32_t lastKey = 0u;
-            bool exhausted = true;                                // all three keys consumed without the bound ending the walk
-            for (;;) {
-                int g = -1;
-                f3 qo, qu;
-                while (k0 != kNoCand) {
-                    const float lo = __uint_as_float(k0 & ~31u);
-                    if (!(lo <= best.t)) { exhausted = false; k0 = kNoCand; break; }   // sorted: nothing further can win (+inf = miss keys too)
-                    const int cand = g0 + (int)(k0 & 31u);
-                    lastKey = k0; ++taken;
-                    k0 = k1; k1 = k2; k2 = kNoCand;
-                    objectRay(sg[cand], o, d, qo, qu);
-                    bool miss = false;
-                    if (!LEAVE || filters) {
-                    miss = boxSureMiss(qo, qu);
-                    // The cube filter runs for every lane; the sphere filter runs for ALL the lanes of this walk step as
-                    // soon as one of them holds a sphere (a vote among the lanes converged here) and a select keeps each
-                    // lane's own answer -- there is no divergent arm, so the lanes arrive together at the loop exits.
-                    // History: with the filters in the two arms of a type branch the sphere lanes (2 of 32 on the
-                    // cornell box) went through the whole exact test as a separate pass; with the sphere filter as a
-                    // plain `if` overriding the cube result they still left that arm on their own and ran the rest of
-                    // the walk alone -- 2.61 object-ray + filter passes per warp where 2 are needed (ncu source
-                    // counters, profiles/r01p_loop_regions.txt); the vote + select brought 112.9 -> 110.7 us/iteration.
-                    const bool sph = sg[cand].tag.x != 1;
-                    if (__any_sync(__activemask(), sph)) {
-                        const bool sm = sphereSureMiss(qo, qu);
-                        miss = sph ? sm : miss;
-                    }
-                    }
-                    if (miss) PTB_WALK_COUNT(taken, cand, 0);
-                    if (!miss) { g = cand; break; }
-                }
-                if (g < 0) break;
-                int outside = 1; float a = 0.f, b = 0.f, c = 0.f;
-                const float t = exactTestQ(sg[g], o, qo, qu, outside, a, b, c);
-#ifdef PTB_WALK_STATS
-                const float before = best.t;
-#endif
-                acceptHit(sg[g], g, t, outside, a, b, c, best, orig);
-#ifdef PTB_WALK_STATS
-                PTB_WALK_COUNT(taken, g, !(t > 0.0f) ? 1 : (best.t != before ? 2 : 3));
-#endif
-            }
+            int taken; uint32_t lastKey; bool exhausted;
+            walkKeys<LEAVE>(sg, g0, o, d, filters, k0, k1, k2, best, orig, taken, lastKey, exhausted);
             if (!(valid && exhausted && taken == 3)) break;       // all three keys walked and the bound never ended the walk: look for more
             floorKey = lastKey + 1u;
         }
@@ -801,6 +818,8 @@ PTB_DEV void bounceSegment(const Params &p, const PathPlanes &pin, const PathPla
 // path buffer (two loads that hit L1 / L2) instead of carrying it through the queue.  Per path it is bounceSegment's arithmetic: same images,
 // same per-depth counts; only the order of the survivors inside a segment differs (nothing depends on it).  A ray that hit nothing has nothing
 // left to do (its radiance is zero and zero is never deposited), so it never enters the queue.
+// (The queue one stage earlier -- the lanes that have a candidate, between phase 1 and the walk -- measured 84.7 against 85.4 us on the bench
+// wavefront and no gain elsewhere: ~10 % of those lanes end up without a hit and idle through the shading again; profiles/r8a_candq_ab.txt.)
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t kQueueCap = 64;                                 // ring entries per warp (a power of two >= 63: 31 left over + 32 new)
 #ifndef PTB_QUEUE_RAY
