@@ -523,7 +523,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "reference cornell scene regenerated from tests/scenes.py; no external data",
             "config": {"workload": WORKLOAD, "bsdf": "full", "iterations_per_step_per_gpu": spp, "batch_iters": st1["batch_iters"],
                        "deposit": "ordered (bit-identical to one iteration per wavefront; tests/test_gpu_parity.py::test_bench_configuration_against_the_oracle)",
-                       "pipeline": "fused bounce kernels + CUDA graph", "parallelism": "spp split x%d, 1 ncclReduce/frame inside libptb200.so" % world,
+                       "pipeline": "fused bounce kernels + CUDA graph", "options": "library defaults (leaveTest 1, hitQueue AUTO: on at this wavefront size)",
+                       "parallelism": "spp split x%d, 1 ncclReduce/frame inside libptb200.so" % world,
                        "l2": "inputs larger than L2: %.0f MB of path state per wavefront vs 126 MB L2" % (st1["path_state_bytes"] / 2 / 1e6)},
             "iters_per_s": iters_all / (ms * 1e-3),
             "segments_per_iter": seg_all / iters_all,
