@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), "libptb200.so does not export %s" % name
     L.ptb_abi_version.restype = C.c_int
-    assert L.ptb_abi_version() == 7      # PTB_ABI_VERSION: 2 added antialias / lens options, 3 triangle meshes in PtbSceneDesc, 4 deposit mode / stage timers / lazy image, 5 regroupMaterials, 6 leaveTest
+    assert L.ptb_abi_version() == 7      # PTB_ABI_VERSION: 2 added antialias / lens options, 3 triangle meshes in PtbSceneDesc, 4 deposit mode / stage timers / lazy image, 5 regroupMaterials, 6 leaveTest, 7 hitQueue
 
 
 def test_struct_sizes_match_reference_layout():
@@ -34,6 +34,23 @@ def test_struct_sizes_match_reference_layout():
     o = m.PtbOptions()
     m.lib().ptb_default_options(C.byref(o))
     assert o.device == -1 and o.bsdfMode == m.BSDF_FULL and o.pipeline == m.PIPELINE_FUSED and o.useGraphs == 1
+
+
+def test_options_mirror_matches_the_header():
+    """The ctypes mirror of PtbOptions has the header's fields, in the header's order (ptb_default_options writes the whole C struct), and
+    the defaults of the image-neutral options are the documented ones."""
+    m = pkg()
+    header = open(os.path.join(ROOT, "include", "ptb200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    body = re.search(r"typedef struct PtbOptions\s*\{(.*?)\}\s*PtbOptions;", header, flags=re.S)
+    if body is None:
+        body = re.search(r"typedef struct\s*\{([^{}]*?)\}\s*PtbOptions;", header, flags=re.S)
+    assert body, "PtbOptions not found in include/ptb200.h"
+    declared = re.findall(r"\b([A-Za-z_][A-Za-z0-9_]*)\s*;", body.group(1))
+    assert declared == [n for n, _ in m.PtbOptions._fields_], (declared, [n for n, _ in m.PtbOptions._fields_])
+    o = m.PtbOptions()
+    m.lib().ptb_default_options(C.byref(o))
+    assert (o.leaveTest, o.hitQueue, o.lookahead, o.depositMode) == (1, -1, 1, m.DEPOSIT_ORDERED)
 
 
 def test_scene_loader_matches_reference_pod(scene_dir):
