@@ -517,6 +517,19 @@ def main():
                 traffic_src = os.path.relpath(profs[-1], ROOT)
             except Exception:
                 traffic = None
+        # issue-slot view of the same kernels, from the newest committed ncu --set full summary (recorded, not measured live: ncu replays kernels)
+        issue = None
+        try:
+            import csv
+            csvs = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_bounce_ncu.csv")))
+            rows = list(csv.reader(open(csvs[-1])))
+            col = lambda key: [i for i, h in enumerate(rows[0]) if h.startswith(key)][0]
+            iB, iL, iT = col("smsp__issue_active.avg.pct"), col("smsp__thread_inst_executed_per_inst_executed"), col("gpu__time_duration")
+            issue = {"source": os.path.relpath(csvs[-1], ROOT),
+                     "kernels": [{"kernel": r[0].split("(")[0].replace("void ", ""), "issue_slots_busy_pct": float(r[iB]), "lanes_per_instruction": float(r[iL]),
+                                  "ms_under_ncu": float(r[iT])} for r in rows[1:]]}
+        except Exception:
+            issue = None
         line = {
             "metric": METRIC, "value": seg_all / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -542,6 +555,7 @@ def main():
                          "algorithmic_bytes": "88 B/segment + 24 B/pixel/iteration (SURVEY.md 8(d))",
                          "bounce_launches_in_timed_region_per_gpu": bounce_launches,
                          "avg_launch_us": ms * 1e3 / max(1.0, bounce_launches),
+                         "issue": issue,
                          "fp32": {"achieved_tflops": FLOP_PER_SEGMENT * seg_all / (ms * 1e-3) / 1e12 / world,
                                   "peak_tflops": 148 * 128 * 2 * sm_max * 1e6 / 1e12, "flop_per_segment": FLOP_PER_SEGMENT,
                                   "note": "the bounce kernel is instruction-issue bound, not HBM bound: bit-exact parity forbids FFMA in the exact tests (DESIGN.md 4.4)"}},
